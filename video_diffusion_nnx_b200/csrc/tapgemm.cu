@@ -1,0 +1,618 @@
+// Tap-GEMM: TMA-fed implicit-GEMM on tcgen05 tensor cores with TMEM accumulators.
+//
+// One kernel family serves every convolution / projection of the Unet3D hot path
+// (reference call sites: modules.py:71-91,162-165,219-222,261-276; utils.py:113,125):
+//
+//   out[m, n] = sum_{tap, src, c} A_src[pixel(m) + shift(tap), c] * Wp[n, (tap,src,c)]
+//
+// Rows m are pixels of an (n_img, H, W) grid, 128 per CTA. For each (tap, src, 64-channel
+// chunk) the producer warp issues ONE 4-D TMA box load (chunk, bw, bh, bn) at the shifted
+// coordinate; out-of-image elements are zero-filled by the TMA unit (SAME padding), and the
+// box lands in shared memory already in the canonical K-major 128B-swizzled UMMA layout.
+// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2-5 = epilogue
+// (tcgen05.ld -> bias / residual / GroupNorm partial sums -> bf16 or fp32 store).
+#include <algorithm>
+#include <cstring>
+
+#include "vdn_common.cuh"
+#include "vdn_host.h"
+
+namespace vdn {
+
+constexpr int kTileM = 128;
+constexpr int kMaxStages = 8;
+constexpr int kGemmThreads = 192;
+
+struct TapMaps {
+  CUtensorMap a[4];
+  CUtensorMap b;
+};
+
+struct TapArgs {
+  int M, N, BN;
+  int H, W;          // row grid
+  int bw, bh, bn;    // TMA box (pixels); bw*bh*bn == 128
+  int n_taps, n_src, chunks;  // chunks of BK channels per source
+  int stages;
+  int tmem_cols;
+  int n_maps;
+  signed char tap_dx[16], tap_dy[16], tap_map[16];
+  // epilogue
+  const float* bias;
+  const void* res;
+  void* out;
+  void* out2;
+  int split_col;
+  int ld_out, ld_out2;
+  int out_f32;
+  int scatter, py, px;  // VDN_TAP_UP parity scatter into a 2H x 2W grid
+  float* gn_sums;
+  int gn_groups, cpg, rows_per_sample;
+};
+
+// ---------------------------------------------------------------------------------------
+// epilogue helpers
+// ---------------------------------------------------------------------------------------
+template <int CPG16>
+__device__ __forceinline__ void gn_accumulate16(const float (&v)[16], bool valid, float* gsum_base, int group0,
+                                                int lane) {
+  // v: 16 consecutive output channels of this thread's row; groups of CPG16 channels.
+#pragma unroll
+  for (int j = 0; j < 16; j += CPG16) {
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < CPG16; ++k) {
+      float x = valid ? v[j + k] : 0.f;
+      s1 += x;
+      s2 += x * x;
+    }
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    if (lane == 0) {
+      float* p = gsum_base + 2 * (group0 + j / CPG16);
+      atomicAdd(p, s1);
+      atomicAdd(p + 1, s2);
+    }
+  }
+}
+
+template <int BK>
+__global__ void __launch_bounds__(kGemmThreads) tapgemm_kernel(const __grid_constant__ TapMaps maps,
+                                                               const TapArgs args) {
+  constexpr int kSwizzle = BK * 2;                 // bytes per smem row == swizzle span
+  constexpr int kABytes = kTileM * BK * 2;         // 16 KB / 8 KB / 4 KB
+  constexpr uint32_t kLayout = umma_layout_type(kSwizzle);
+  constexpr uint32_t kSBO = 8 * kSwizzle;          // byte stride between 8-row groups
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t tmem_full_bar;
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int BN = args.BN;
+  const int b_bytes = (BN * BK * 2 + 1023) & ~1023;
+  const int stage_bytes = kABytes + b_bytes;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+  const int n_tile = blockIdx.x;
+  const int m0 = blockIdx.y * kTileM;
+  const int S = args.stages;
+  const int n_steps = args.n_taps * args.n_src * args.chunks;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < args.n_maps; ++i) tma_prefetch_desc(&maps.a[i]);
+    tma_prefetch_desc(&maps.b);
+    for (int s = 0; s < S; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&tmem_full_bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(&tmem_base_smem, (uint32_t)args.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      const int hw = args.H * args.W;
+      const int n0 = m0 / hw;
+      const int rem = m0 - n0 * hw;
+      const int y0 = rem / args.W;
+      const int x0 = rem - y0 * args.W;
+      int it = 0;
+      for (int t = 0; t < args.n_taps; ++t) {
+        const int cx = x0 + args.tap_dx[t];
+        const int cy = y0 + args.tap_dy[t];
+        for (int s = 0; s < args.n_src; ++s) {
+          const CUtensorMap* am = &maps.a[args.tap_map[t] + s];
+          for (int c = 0; c < args.chunks; ++c, ++it) {
+            const int st = it % S;
+            const uint32_t ph = (uint32_t)(it / S) & 1u;
+            mbar_wait(&empty_bar[st], ph ^ 1u);
+            uint8_t* sa = smem + st * stage_bytes;
+            uint8_t* sb = sa + kABytes;
+            mbar_expect_tx(&full_bar[st], (uint32_t)(kABytes + BN * BK * 2));
+            tma_load_4d(sa, am, &full_bar[st], c * BK, cx, cy, n0);
+            tma_load_2d(sb, &maps.b, &full_bar[st], it * BK, n_tile * BN);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(kTileM, BN, 0, 0);
+      for (int it = 0; it < n_steps; ++it) {
+        const int st = it % S;
+        const uint32_t ph = (uint32_t)(it / S) & 1u;
+        mbar_wait(&full_bar[st], ph);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + st * stage_bytes);
+        const uint32_t sb = sa + kABytes;
+        const uint64_t da = umma_smem_desc(sa, 16, kSBO, kLayout);
+        const uint64_t db = umma_smem_desc(sb, 16, kSBO, kLayout);
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          // advance 16 K-elements = 32 bytes inside the swizzle span (encoded >> 4)
+          umma_bf16(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (it | k) != 0 ? 1u : 0u);
+        }
+        tc_commit(&empty_bar[st]);  // frees the smem slot when these MMAs retire
+      }
+      tc_commit(&tmem_full_bar);
+    }
+    __syncwarp();
+  } else {
+    // ================= epilogue (warps 2..5) =================
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    const int r = quarter * 32 + lane;
+    const int m = m0 + r;
+    const bool valid = m < args.M;
+    mbar_wait(&tmem_full_bar, 0);
+    tc_fence_after();
+
+    // output row index
+    long orow = m;
+    if (args.scatter) {
+      const int hw = args.H * args.W;
+      const int n = m / hw;
+      const int rem = m - n * hw;
+      const int y = rem / args.W;
+      const int x = rem - y * args.W;
+      orow = ((long)n * (2 * args.H) + (2 * y + args.py)) * (2 * args.W) + (2 * x + args.px);
+    }
+    const int col_base = n_tile * BN;
+    uint8_t* outp;
+    int ld, col_o;
+    if (args.split_col > 0 && col_base >= args.split_col) {
+      outp = reinterpret_cast<uint8_t*>(args.out2);
+      ld = args.ld_out2;
+      col_o = col_base - args.split_col;
+    } else {
+      outp = reinterpret_cast<uint8_t*>(args.out);
+      ld = args.ld_out;
+      col_o = col_base;
+    }
+    const uint8_t* resp = reinterpret_cast<const uint8_t*>(args.res);
+    const int esz = args.out_f32 ? 4 : 2;
+    float* gsum = nullptr;
+    if (args.gn_sums) {
+      // all 32 rows of a warp belong to one sample (rows_per_sample % 32 == 0 enforced on host)
+      const int sample = min(m0 + quarter * 32, args.M - 1) / args.rows_per_sample;
+      gsum = args.gn_sums + (long)sample * args.gn_groups * 2;
+    }
+    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t raw[32];
+      const bool wide = (BN - c0) >= 32;
+      if (wide) {
+        tmem_ld_32x32(taddr + (uint32_t)c0, raw);
+      } else {
+        tmem_ld_32x16(taddr + (uint32_t)c0, *reinterpret_cast<uint32_t(*)[16]>(&raw[0]));
+      }
+      tmem_ld_wait();
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        if (h == 1 && !wide) break;
+        float v[16];
+        const int cg = col_base + c0 + h * 16;  // global output column of v[0]
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[h * 16 + j]);
+        if (args.bias) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(args.bias + cg + j));
+            v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+          }
+        }
+        const long eoff = orow * ld + (col_o + c0 + h * 16);
+        if (resp && valid) {
+          if (args.out_f32) {
+            const float4* rp = reinterpret_cast<const float4*>(resp + eoff * 4);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float4 q = rp[j];
+              v[4 * j] += q.x; v[4 * j + 1] += q.y; v[4 * j + 2] += q.z; v[4 * j + 3] += q.w;
+            }
+          } else {
+            const uint4* rp = reinterpret_cast<const uint4*>(resp + eoff * 2);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              const uint4 q = rp[j];
+              float2 f;
+              f = unpack_bf16x2(q.x); v[8 * j + 0] += f.x; v[8 * j + 1] += f.y;
+              f = unpack_bf16x2(q.y); v[8 * j + 2] += f.x; v[8 * j + 3] += f.y;
+              f = unpack_bf16x2(q.z); v[8 * j + 4] += f.x; v[8 * j + 5] += f.y;
+              f = unpack_bf16x2(q.w); v[8 * j + 6] += f.x; v[8 * j + 7] += f.y;
+            }
+          }
+        }
+        if (gsum) {
+          const int cpg = args.cpg;
+          const int g0 = cg / cpg;
+          if (cpg >= 16) gn_accumulate16<16>(v, valid, gsum, g0, lane);
+          else if (cpg == 8) gn_accumulate16<8>(v, valid, gsum, g0, lane);
+          else if (cpg == 4) gn_accumulate16<4>(v, valid, gsum, g0, lane);
+          else gn_accumulate16<2>(v, valid, gsum, g0, lane);
+        }
+        if (valid) {
+          if (args.out_f32) {
+            float4* op = reinterpret_cast<float4*>(outp + eoff * 4);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          } else {
+            uint4* op = reinterpret_cast<uint4*>(outp + eoff * 2);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              uint4 q;
+              q.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
+              q.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+              q.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+              q.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+              op[j] = q;
+            }
+          }
+        }
+      }
+    }
+    (void)esz;
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)args.tmem_cols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Reference kernel (CUDA cores, one thread per output element). Test-only.
+// ---------------------------------------------------------------------------------------
+struct RefArgs {
+  int kind, M, N, H, W, n_src, C, n_taps;
+  int tap_dy[16], tap_dx[16];
+  const bf16* src[2];
+  const bf16* wp;
+  const float* bias;
+  const void* res;
+  void* out;
+  void* out2;
+  int split_col, ld_out, ld_out2, out_f32, py, px;
+  float* gn_sums;
+  int gn_groups, cpg, rows_per_sample;
+};
+
+__global__ void tapgemm_ref_kernel(const RefArgs a) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long)a.M * a.N) return;
+  const int m = (int)(idx / a.N);
+  const int n = (int)(idx % a.N);
+  const int hw = a.H * a.W;
+  const int img = m / hw;
+  const int rem = m % hw;
+  const int y = rem / a.W, x = rem % a.W;
+  const int ktot = a.n_taps * a.n_src * a.C;
+  float acc = 0.f;
+  for (int t = 0; t < a.n_taps; ++t) {
+    int sy, sx, SH, SW;
+    if (a.kind == VDN_TAP_DOWN) {
+      SH = 2 * a.H; SW = 2 * a.W;
+      sy = 2 * y + a.tap_dy[t] - 1;
+      sx = 2 * x + a.tap_dx[t] - 1;
+    } else {
+      SH = a.H; SW = a.W;
+      sy = y + a.tap_dy[t];
+      sx = x + a.tap_dx[t];
+    }
+    if (sy < 0 || sy >= SH || sx < 0 || sx >= SW) continue;
+    for (int s = 0; s < a.n_src; ++s) {
+      const bf16* ap = a.src[s] + (((long)img * SH + sy) * SW + sx) * a.C;
+      const bf16* wp = a.wp + (long)n * ktot + (long)(t * a.n_src + s) * a.C;
+      for (int c = 0; c < a.C; ++c) acc += __bfloat162float(ap[c]) * __bfloat162float(wp[c]);
+    }
+  }
+  if (a.bias) acc += a.bias[n];
+  long orow = m;
+  if (a.kind == VDN_TAP_UP) orow = ((long)img * (2 * a.H) + (2 * y + a.py)) * (2 * a.W) + (2 * x + a.px);
+  void* outp = a.out;
+  int ld = a.ld_out, col = n;
+  if (a.split_col > 0 && n >= a.split_col) {
+    outp = a.out2; ld = a.ld_out2; col = n - a.split_col;
+  }
+  const long eoff = orow * ld + col;
+  if (a.res) {
+    acc += a.out_f32 ? reinterpret_cast<const float*>(a.res)[eoff]
+                     : __bfloat162float(reinterpret_cast<const bf16*>(a.res)[eoff]);
+  }
+  if (a.gn_sums) {
+    float* p = a.gn_sums + ((long)(m / a.rows_per_sample) * a.gn_groups + n / a.cpg) * 2;
+    atomicAdd(p, acc);
+    atomicAdd(p + 1, acc * acc);
+  }
+  if (a.out_f32) reinterpret_cast<float*>(outp)[eoff] = acc;
+  else reinterpret_cast<bf16*>(outp)[eoff] = __float2bfloat16(acc);
+}
+
+// ---------------------------------------------------------------------------------------
+// weight packing
+// ---------------------------------------------------------------------------------------
+struct PackArgs {
+  int taps, cin, cout, mode, ld, n_off, k_off;
+  int perm[16];
+};
+__global__ void pack_weight_kernel(const float* __restrict__ src, bf16* __restrict__ dst, const PackArgs a) {
+  const long total = (long)a.taps * a.cin * a.cout;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    // iterate in DESTINATION order so that writes coalesce: (n, t, k)
+    int nrows = a.mode == 0 ? a.cout : a.cin;
+    int kin = a.mode == 0 ? a.cin : a.cout;
+    (void)nrows;
+    const int k = (int)(i % kin);
+    const int t = (int)((i / kin) % a.taps);
+    const int n = (int)(i / ((long)kin * a.taps));
+    const int ci = a.mode == 0 ? k : n;
+    const int co = a.mode == 0 ? n : k;
+    const float v = src[((long)a.perm[t] * a.cin + ci) * a.cout + co];
+    dst[(long)(a.n_off + n) * a.ld + a.k_off + (long)t * kin + k] = __float2bfloat16(v);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------
+static bool is_pow2(int x) { return x > 0 && (x & (x - 1)) == 0; }
+
+static int validate_desc(const vdn_tapgemm_desc* d) {
+  VDN_REQUIRE(d != nullptr, VDN_E_SHAPE, "tapgemm: null desc");
+  VDN_REQUIRE(d->kind >= 0 && d->kind <= 2, VDN_E_SHAPE, "tapgemm: bad kind %d", d->kind);
+  VDN_REQUIRE(d->n_img > 0 && d->H > 0 && d->W > 0, VDN_E_SHAPE, "tapgemm: empty grid");
+  VDN_REQUIRE(is_pow2(d->W) || d->W % 128 == 0, VDN_E_SHAPE, "tapgemm: W=%d must be a power of two or a multiple of 128", d->W);
+  VDN_REQUIRE(is_pow2(d->H) || d->W >= 128, VDN_E_SHAPE, "tapgemm: H=%d must be a power of two when W < 128", d->H);
+  VDN_REQUIRE(d->n_src == 1 || d->n_src == 2, VDN_E_SHAPE, "tapgemm: n_src must be 1 or 2");
+  VDN_REQUIRE(d->src_c >= 16 && d->src_c % 16 == 0, VDN_E_SHAPE, "tapgemm: src_c=%d must be a multiple of 16", d->src_c);
+  VDN_REQUIRE(d->n_taps >= 1 && d->n_taps <= 16, VDN_E_SHAPE, "tapgemm: n_taps=%d out of range", d->n_taps);
+  VDN_REQUIRE(d->n_out >= 16 && d->n_out % 16 == 0, VDN_E_SHAPE, "tapgemm: n_out=%d must be a multiple of 16", d->n_out);
+  VDN_REQUIRE(d->kind != VDN_TAP_DOWN || d->n_src == 1, VDN_E_SHAPE, "tapgemm: DOWN supports one source");
+  if (d->gn_groups > 0) {
+    VDN_REQUIRE(d->n_out % d->gn_groups == 0, VDN_E_SHAPE, "tapgemm: n_out %% gn_groups != 0");
+    const int cpg = d->n_out / d->gn_groups;
+    VDN_REQUIRE(cpg >= 2 && is_pow2(cpg < 16 ? cpg : 16) && (cpg < 16 || cpg % 16 == 0), VDN_E_SHAPE,
+                "tapgemm: channels per group %d unsupported", cpg);
+    VDN_REQUIRE(d->rows_per_sample > 0 && d->rows_per_sample % 32 == 0, VDN_E_SHAPE,
+                "tapgemm: rows_per_sample=%d must be a multiple of 32", d->rows_per_sample);
+    VDN_REQUIRE(d->kind != VDN_TAP_UP && d->split_col == 0, VDN_E_SHAPE, "tapgemm: gn stats need a plain output");
+  }
+  return VDN_OK;
+}
+
+static int pick_bn(int N) {
+  if (N <= 256) return N;
+  if (N % 256 == 0) return 256;
+  if (N % 192 == 0) return 192;
+  if (N % 128 == 0) return 128;
+  if (N % 64 == 0) return 64;
+  if (N % 32 == 0) return 32;
+  return 16;
+}
+
+template <int BK>
+static int launch_tapgemm(const TapMaps& maps, const TapArgs& args, int smem_bytes, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(tapgemm_kernel<BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    VDN_REQUIRE(e == cudaSuccess, VDN_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  dim3 grid(args.N / args.BN, ceil_div(args.M, kTileM));
+  tapgemm_kernel<BK><<<grid, kGemmThreads, smem_bytes, st>>>(maps, args);
+  return check_launch("tapgemm_kernel");
+}
+
+}  // namespace vdn
+
+using namespace vdn;
+
+extern "C" int vdn_tapgemm(const vdn_tapgemm_desc* d, const void* src0, const void* src1, const void* wp,
+                           const float* bias, const void* residual, void* out, void* out2, float* gn_sums,
+                           void* stream) {
+  int rc = validate_desc(d);
+  if (rc) return rc;
+  VDN_REQUIRE(src0 && wp && out, VDN_E_SHAPE, "tapgemm: null operand");
+  VDN_REQUIRE(d->n_src == 1 || src1, VDN_E_SHAPE, "tapgemm: src1 missing");
+  VDN_REQUIRE(d->split_col == 0 || out2, VDN_E_SHAPE, "tapgemm: out2 missing");
+
+  const int C = d->src_c;
+  const int BK = (C % 64 == 0) ? 64 : (C % 32 == 0) ? 32 : 16;
+  TapArgs a;
+  memset(&a, 0, sizeof(a));
+  a.M = d->n_img * d->H * d->W;
+  a.N = d->n_out;
+  a.BN = pick_bn(d->n_out);
+  if (d->split_col > 0) {
+    while (d->split_col % a.BN != 0) a.BN /= 2;
+    VDN_REQUIRE(a.BN >= 16, VDN_E_SHAPE, "tapgemm: split_col %d not tileable", d->split_col);
+  }
+  a.H = d->H;
+  a.W = d->W;
+  a.bw = std::min(d->W, 128);
+  a.bh = std::min(d->H, 128 / a.bw);
+  a.bn = 128 / (a.bw * a.bh);
+  a.n_taps = d->n_taps;
+  a.n_src = d->n_src;
+  a.chunks = C / BK;
+  a.bias = bias;
+  a.res = residual;
+  a.out = out;
+  a.out2 = out2;
+  a.split_col = d->split_col;
+  a.ld_out = d->split_col > 0 ? d->split_col : d->n_out;
+  a.ld_out2 = d->n_out - d->split_col;
+  a.out_f32 = d->out_dtype == VDN_F32;
+  a.scatter = d->kind == VDN_TAP_UP;
+  a.py = d->py;
+  a.px = d->px;
+  a.gn_sums = gn_sums;
+  a.gn_groups = gn_sums ? d->gn_groups : 0;
+  a.cpg = d->gn_groups > 0 ? d->n_out / d->gn_groups : 1;
+  a.rows_per_sample = d->rows_per_sample > 0 ? d->rows_per_sample : 1;
+  if (!gn_sums) a.gn_sums = nullptr;
+
+  TapMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  const int swz = BK * 2;
+  const uint32_t box[4] = {(uint32_t)BK, (uint32_t)a.bw, (uint32_t)a.bh, (uint32_t)a.bn};
+  if (d->kind == VDN_TAP_DOWN) {
+    // four parity views of the (n_img, 2H, 2W, C) source; view (ry,rx)[n][y][x] = src[n][2y+ry][2x+rx]
+    const uint64_t SW = 2 * (uint64_t)d->W, SH = 2 * (uint64_t)d->H;
+    for (int ry = 0; ry < 2; ++ry)
+      for (int rx = 0; rx < 2; ++rx) {
+        const uint64_t dims[4] = {(uint64_t)C, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->n_img};
+        const uint64_t str[3] = {2 * (uint64_t)C * 2, 2 * SW * C * 2, SH * SW * C * 2};
+        const uint8_t* base = reinterpret_cast<const uint8_t*>(src0) + ((uint64_t)ry * SW + rx) * C * 2;
+        rc = encode_tmap_bf16(&maps.a[ry * 2 + rx], base, 4, dims, str, box, swz);
+        if (rc) return rc;
+      }
+    for (int t = 0; t < d->n_taps; ++t) {
+      const int ky = d->tap_dy[t], kx = d->tap_dx[t];
+      VDN_REQUIRE(ky >= 0 && ky < 4 && kx >= 0 && kx < 4, VDN_E_SHAPE, "tapgemm: DOWN tap out of range");
+      const int ry = (ky + 1) & 1, rx = (kx + 1) & 1;
+      a.tap_map[t] = (signed char)(ry * 2 + rx);
+      a.tap_dy[t] = (signed char)((ky - 1) >> 1);
+      a.tap_dx[t] = (signed char)((kx - 1) >> 1);
+    }
+  } else {
+    const void* srcs[2] = {src0, src1};
+    for (int s = 0; s < d->n_src; ++s) {
+      const uint64_t dims[4] = {(uint64_t)C, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->n_img};
+      const uint64_t str[3] = {(uint64_t)C * 2, (uint64_t)d->W * C * 2, (uint64_t)d->H * d->W * C * 2};
+      rc = encode_tmap_bf16(&maps.a[s], srcs[s], 4, dims, str, box, swz);
+      if (rc) return rc;
+    }
+    for (int t = 0; t < d->n_taps; ++t) {
+      VDN_REQUIRE(d->tap_dy[t] >= -64 && d->tap_dy[t] <= 64 && d->tap_dx[t] >= -64 && d->tap_dx[t] <= 64,
+                  VDN_E_SHAPE, "tapgemm: tap shift out of range");
+      a.tap_map[t] = 0;
+      a.tap_dy[t] = (signed char)d->tap_dy[t];
+      a.tap_dx[t] = (signed char)d->tap_dx[t];
+    }
+  }
+  a.n_maps = d->kind == VDN_TAP_DOWN ? 4 : d->n_src;
+  {
+    const uint64_t ktot = (uint64_t)d->n_taps * d->n_src * C;
+    const uint64_t dims[2] = {ktot, (uint64_t)d->n_out};
+    const uint64_t str[1] = {ktot * 2};
+    const uint32_t bbox[2] = {(uint32_t)BK, (uint32_t)a.BN};
+    rc = encode_tmap_bf16(&maps.b, wp, 2, dims, str, bbox, swz);
+    if (rc) return rc;
+  }
+
+  const int a_bytes = kTileM * BK * 2;
+  const int b_bytes = (a.BN * BK * 2 + 1023) & ~1023;
+  const int stage_bytes = a_bytes + b_bytes;
+  const int budget = stage_bytes >= 24 * 1024 ? 192 * 1024 : 96 * 1024;
+  const int n_steps = d->n_taps * d->n_src * a.chunks;
+  a.stages = std::max(2, std::min(std::min(kMaxStages, budget / stage_bytes), std::max(n_steps, 2)));
+  int cols = 32;
+  while (cols < a.BN) cols *= 2;
+  a.tmem_cols = cols;
+  const int smem_bytes = a.stages * stage_bytes + 1024;
+
+  // alignment of epilogue vector accesses
+  VDN_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0 && (!residual || (reinterpret_cast<uintptr_t>(residual) & 15) == 0) &&
+                  (!bias || (reinterpret_cast<uintptr_t>(bias) & 15) == 0),
+              VDN_E_ALIGN, "tapgemm: out/residual/bias must be 16B aligned");
+
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (BK == 64) return launch_tapgemm<64>(maps, a, smem_bytes, st);
+  if (BK == 32) return launch_tapgemm<32>(maps, a, smem_bytes, st);
+  return launch_tapgemm<16>(maps, a, smem_bytes, st);
+}
+
+extern "C" int vdn_tapgemm_ref(const vdn_tapgemm_desc* d, const void* src0, const void* src1, const void* wp,
+                               const float* bias, const void* residual, void* out, void* out2, float* gn_sums,
+                               void* stream) {
+  int rc = validate_desc(d);
+  if (rc) return rc;
+  RefArgs a;
+  memset(&a, 0, sizeof(a));
+  a.kind = d->kind;
+  a.M = d->n_img * d->H * d->W;
+  a.N = d->n_out;
+  a.H = d->H;
+  a.W = d->W;
+  a.n_src = d->n_src;
+  a.C = d->src_c;
+  a.n_taps = d->n_taps;
+  for (int t = 0; t < d->n_taps; ++t) {
+    a.tap_dy[t] = d->tap_dy[t];
+    a.tap_dx[t] = d->tap_dx[t];
+  }
+  a.src[0] = reinterpret_cast<const bf16*>(src0);
+  a.src[1] = reinterpret_cast<const bf16*>(src1);
+  a.wp = reinterpret_cast<const bf16*>(wp);
+  a.bias = bias;
+  a.res = residual;
+  a.out = out;
+  a.out2 = out2;
+  a.split_col = d->split_col;
+  a.ld_out = d->split_col > 0 ? d->split_col : d->n_out;
+  a.ld_out2 = d->n_out - d->split_col;
+  a.out_f32 = d->out_dtype == VDN_F32;
+  a.py = d->py;
+  a.px = d->px;
+  a.gn_sums = gn_sums;
+  a.gn_groups = d->gn_groups;
+  a.cpg = d->gn_groups > 0 ? d->n_out / d->gn_groups : 1;
+  a.rows_per_sample = d->rows_per_sample > 0 ? d->rows_per_sample : 1;
+  const long total = (long)a.M * a.N;
+  const int threads = 256;
+  tapgemm_ref_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a);
+  return check_launch("tapgemm_ref_kernel");
+}
+
+extern "C" int vdn_pack_weight(const float* src, void* dst, int taps, int cin, int cout, int mode,
+                               const int* perm_host, int ld, int n_off, int k_off, void* stream) {
+  VDN_REQUIRE(src && dst, VDN_E_SHAPE, "pack_weight: null pointer");
+  VDN_REQUIRE(taps >= 1 && taps <= 16 && cin > 0 && cout > 0 && (mode == 0 || mode == 1), VDN_E_SHAPE,
+              "pack_weight: bad arguments");
+  PackArgs a;
+  a.taps = taps; a.cin = cin; a.cout = cout; a.mode = mode; a.ld = ld; a.n_off = n_off; a.k_off = k_off;
+  for (int t = 0; t < 16; ++t) a.perm[t] = (perm_host && t < taps) ? perm_host[t] : t;
+  const long total = (long)taps * cin * cout;
+  const int threads = 256;
+  const int blocks = (int)std::min<long>((total + threads - 1) / threads, 148 * 8);
+  pack_weight_kernel<<<blocks, threads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(src, reinterpret_cast<bf16*>(dst), a);
+  return check_launch("pack_weight_kernel");
+}
