@@ -90,15 +90,17 @@ typedef struct {
 } vdn_tapgemm_desc;
 
 /* src0/src1: bf16 (n_img, Hs, Ws, src_c). wp: packed bf16 [n_out][n_taps*n_src*src_c].
- * bias: fp32 [n_out] or NULL. residual: same dtype/shape as out, or NULL.
+ * bias: fp32 [n_out] or NULL. residual (residual2 for the out2 part): same dtype/shape as out, or NULL.
+ * residual may alias out (each element is read then written by the same thread).
  * gn_sums: fp32 [B][gn_groups][2], must be zeroed by the caller; or NULL. */
 int vdn_tapgemm(const vdn_tapgemm_desc* d, const void* src0, const void* src1, const void* wp, const float* bias,
-                const void* residual, void* out, void* out2, float* gn_sums, void* stream);
+                const void* residual, const void* residual2, void* out, void* out2, float* gn_sums, void* stream);
 
 /* Reference (non tensor-core) implementation of the same contract, used only by the GPU
  * tests to localise faults. Not on any product path. */
 int vdn_tapgemm_ref(const vdn_tapgemm_desc* d, const void* src0, const void* src1, const void* wp,
-                    const float* bias, const void* residual, void* out, void* out2, float* gn_sums, void* stream);
+                    const float* bias, const void* residual, const void* residual2, void* out, void* out2,
+                    float* gn_sums, void* stream);
 
 #ifdef __cplusplus
 }

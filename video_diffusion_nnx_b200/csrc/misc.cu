@@ -1,0 +1,708 @@
+// Small / bandwidth-bound kernels of the hot path:
+//   init_conv (1,k,k) with tiny Cin (unet3d.py:110-115) fwd + wgrad, final 1x1 conv to `channels`
+//   (unet3d.py:251) fwd + bwd, time-embedding MLP and the per-ResnetBlock time heads
+//   (unet3d.py:128-133, modules.py:202-208,233-238) fwd + bwd, q_sample / loss / p_sample
+//   (gaussian_diffusion.py:401-470,120-261), bias-gradient column sums, fused Adam + EMA
+//   (trainer.py:367-382).
+#include <algorithm>
+
+#include "vdn_common.cuh"
+#include "vdn_host.h"
+
+namespace vdn {
+
+__device__ __forceinline__ float block_sum(float v, float* red /*>=32 floats*/) {
+  v = warp_sum(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) red[w] = v;
+  __syncthreads();
+  const int nw = (blockDim.x + 31) >> 5;
+  float r = (threadIdx.x < nw) ? red[threadIdx.x] : 0.f;
+  if (w == 0) r = warp_sum(r);
+  if (threadIdx.x == 0) red[0] = r;
+  __syncthreads();
+  r = red[0];
+  return r;
+}
+
+// ---------------------------------------------------------------------------------------
+// init conv: x fp32 (B,Cin,F,H,W) -> out bf16 (B*F,H,W,Cout); 16x16 pixel tile per block.
+// ---------------------------------------------------------------------------------------
+constexpr int kIT = 16;
+__global__ void __launch_bounds__(256) init_conv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                            const float* __restrict__ bias, bf16* __restrict__ out,
+                                                            int B, int Cin, int F, int H, int W, int Cout, int ks) {
+  extern __shared__ float sm[];
+  const int pad = ks / 2, hs = kIT + ks - 1;
+  float* sW = sm;                             // [ks*ks*Cin][Cout]
+  float* sX = sm + ks * ks * Cin * Cout;      // [Cin][hs][hs]
+  const int tiles_x = W / kIT;
+  const int ty = blockIdx.x / tiles_x, tx = blockIdx.x % tiles_x;
+  const int img = blockIdx.y, b = img / F, f = img % F;
+  for (int i = threadIdx.x; i < ks * ks * Cin * Cout; i += blockDim.x) sW[i] = w[i];
+  for (int i = threadIdx.x; i < Cin * hs * hs; i += blockDim.x) {
+    const int ci = i / (hs * hs), r = i % (hs * hs);
+    const int yy = ty * kIT + r / hs - pad, xx = tx * kIT + r % hs - pad;
+    float v = 0.f;
+    if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = x[((((long)b * Cin + ci) * F + f) * H + yy) * W + xx];
+    sX[i] = v;
+  }
+  __syncthreads();
+  const int py = threadIdx.x / kIT, px = threadIdx.x % kIT;
+  const long opix = ((long)img * H + ty * kIT + py) * W + tx * kIT + px;
+  for (int co0 = 0; co0 < Cout; co0 += 32) {
+    float acc[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc[j] = bias[co0 + j];
+    for (int ci = 0; ci < Cin; ++ci)
+      for (int t = 0; t < ks * ks; ++t) {
+        const float xv = sX[(ci * hs + py + t / ks) * hs + px + t % ks];
+        const float* wp = sW + (t * Cin + ci) * Cout + co0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[j] = fmaf(xv, wp[j], acc[j]);
+      }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint4 u;
+      u.x = pack_bf16x2(acc[8 * q + 0], acc[8 * q + 1]);
+      u.y = pack_bf16x2(acc[8 * q + 2], acc[8 * q + 3]);
+      u.z = pack_bf16x2(acc[8 * q + 4], acc[8 * q + 5]);
+      u.w = pack_bf16x2(acc[8 * q + 6], acc[8 * q + 7]);
+      reinterpret_cast<uint4*>(out + opix * Cout + co0)[q] = u;
+    }
+  }
+}
+
+// wgrad + bias grad of the init conv. grid (tile groups, n_img); thread -> (co lane = tid%32, tap group tid/32).
+__global__ void __launch_bounds__(256) init_conv_wgrad_kernel(const float* __restrict__ x, const bf16* __restrict__ dy,
+                                                              float* __restrict__ dw, float* __restrict__ dbias, int B,
+                                                              int Cin, int F, int H, int W, int Cout, int ks,
+                                                              int tiles_per_block) {
+  extern __shared__ float sm[];
+  const int pad = ks / 2, hs = kIT + ks - 1;
+  float* sX = sm;                       // [Cin][hs][hs]
+  float* sD = sm + Cin * hs * hs;       // [256][33]
+  const int tiles_x = W / kIT, n_tiles = tiles_x * (H / kIT);
+  const int img = blockIdx.y, b = img / F, f = img % F;
+  const int col = threadIdx.x & 31, grp = threadIdx.x >> 5;
+  const int n_tc = ks * ks * Cin;             // (tap, ci) pairs
+  const int per_thr = (n_tc + 7) / 8;         // pairs per thread (<= 19 for ks=7,Cin=3)
+  for (int co0 = 0; co0 < Cout; co0 += 32) {
+    float acc[20];
+#pragma unroll
+    for (int j = 0; j < 20; ++j) acc[j] = 0.f;
+    float bsum = 0.f;
+    for (int tt = 0; tt < tiles_per_block; ++tt) {
+      const int tile = blockIdx.x * tiles_per_block + tt;
+      if (tile >= n_tiles) break;
+      const int ty = tile / tiles_x, tx = tile % tiles_x;
+      __syncthreads();
+      for (int i = threadIdx.x; i < Cin * hs * hs; i += blockDim.x) {
+        const int ci = i / (hs * hs), r = i % (hs * hs);
+        const int yy = ty * kIT + r / hs - pad, xx = tx * kIT + r % hs - pad;
+        float v = 0.f;
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = x[((((long)b * Cin + ci) * F + f) * H + yy) * W + xx];
+        sX[i] = v;
+      }
+      for (int i = threadIdx.x; i < 256 * 32; i += blockDim.x) {
+        const int p = i >> 5, c = i & 31;
+        const long opix = ((long)img * H + ty * kIT + p / kIT) * W + tx * kIT + p % kIT;
+        sD[p * 33 + c] = __bfloat162float(dy[opix * Cout + co0 + c]);
+      }
+      __syncthreads();
+      if (grp == 0)
+        for (int p = 0; p < 256; ++p) bsum += sD[p * 33 + col];
+#pragma unroll
+      for (int j = 0; j < 20; ++j) {
+        const int tc = grp + 8 * j;
+        if (j < per_thr && tc < n_tc) {
+          const int t = tc / Cin, ci = tc % Cin;
+          const float* xr = sX + (ci * hs + t / ks) * hs + t % ks;
+          float a = 0.f;
+          for (int p = 0; p < 256; ++p) a = fmaf(xr[(p / kIT) * hs + p % kIT], sD[p * 33 + col], a);
+          acc[j] += a;
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 20; ++j) {
+      const int tc = grp + 8 * j;
+      if (j < per_thr && tc < n_tc) atomicAdd(&dw[(long)tc * Cout + co0 + col], acc[j]);
+    }
+    if (grp == 0) atomicAdd(&dbias[co0 + col], bsum);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// final 1x1 conv: h bf16 [P][C] -> out fp32 [P][Co] (Co = image channels, <= 4)
+// ---------------------------------------------------------------------------------------
+template <int CO>
+__global__ void __launch_bounds__(256) final_conv_fwd_kernel(const bf16* __restrict__ h, const float* __restrict__ w,
+                                                             const float* __restrict__ bias, float* __restrict__ out,
+                                                             long P, int C) {
+  extern __shared__ float sW[];  // [C][CO]
+  for (int i = threadIdx.x; i < C * CO; i += blockDim.x) sW[i] = w[i];
+  __syncthreads();
+  for (long p = (long)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (long)gridDim.x * blockDim.x) {
+    float acc[CO];
+#pragma unroll
+    for (int o = 0; o < CO; ++o) acc[o] = bias[o];
+    for (int c0 = 0; c0 < C; c0 += 8) {
+      const uint4 u = *reinterpret_cast<const uint4*>(h + p * C + c0);
+      float v[8];
+      float2 f2;
+      f2 = unpack_bf16x2(u.x); v[0] = f2.x; v[1] = f2.y;
+      f2 = unpack_bf16x2(u.y); v[2] = f2.x; v[3] = f2.y;
+      f2 = unpack_bf16x2(u.z); v[4] = f2.x; v[5] = f2.y;
+      f2 = unpack_bf16x2(u.w); v[6] = f2.x; v[7] = f2.y;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int o = 0; o < CO; ++o) acc[o] = fmaf(v[j], sW[(c0 + j) * CO + o], acc[o]);
+    }
+#pragma unroll
+    for (int o = 0; o < CO; ++o) out[p * CO + o] = acc[o];
+  }
+}
+
+// dh = dout W^T (bf16), dW[c][o] += sum_p h[p][c] dout[p][o], db[o] += sum_p dout[p][o].
+// Threads are organised as (pixel lane, channel-vector): tid = pl * (C/8) + ci.
+template <int CO>
+__global__ void __launch_bounds__(256) final_conv_bwd_kernel(const bf16* __restrict__ h, const float* __restrict__ dout,
+                                                             const float* __restrict__ w, bf16* __restrict__ dh,
+                                                             float* __restrict__ dw, float* __restrict__ db, long P,
+                                                             int C) {
+  extern __shared__ float sm[];
+  float* sW = sm;            // [C][CO]
+  float* red = sm + C * CO;  // [256][8*CO]
+  for (int i = threadIdx.x; i < C * CO; i += blockDim.x) sW[i] = w[i];
+  __syncthreads();
+  const int c8n = C / 8, pl_n = blockDim.x / c8n;
+  const int ci = threadIdx.x % c8n, pl = threadIdx.x / c8n, c0 = ci * 8;
+  float gw[8][CO], gb[CO];
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+#pragma unroll
+    for (int o = 0; o < CO; ++o) gw[j][o] = 0.f;
+#pragma unroll
+  for (int o = 0; o < CO; ++o) gb[o] = 0.f;
+  if (pl < pl_n) {
+    for (long p = (long)blockIdx.x * pl_n + pl; p < P; p += (long)gridDim.x * pl_n) {
+      float d[CO];
+#pragma unroll
+      for (int o = 0; o < CO; ++o) d[o] = dout[p * CO + o];
+      const uint4 u = *reinterpret_cast<const uint4*>(h + p * C + c0);
+      float v[8], g[8];
+      float2 f2;
+      f2 = unpack_bf16x2(u.x); v[0] = f2.x; v[1] = f2.y;
+      f2 = unpack_bf16x2(u.y); v[2] = f2.x; v[3] = f2.y;
+      f2 = unpack_bf16x2(u.z); v[4] = f2.x; v[5] = f2.y;
+      f2 = unpack_bf16x2(u.w); v[6] = f2.x; v[7] = f2.y;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float a = 0.f;
+#pragma unroll
+        for (int o = 0; o < CO; ++o) {
+          a = fmaf(d[o], sW[(c0 + j) * CO + o], a);
+          gw[j][o] = fmaf(v[j], d[o], gw[j][o]);
+        }
+        g[j] = a;
+      }
+      uint4 q;
+      q.x = pack_bf16x2(g[0], g[1]); q.y = pack_bf16x2(g[2], g[3]);
+      q.z = pack_bf16x2(g[4], g[5]); q.w = pack_bf16x2(g[6], g[7]);
+      *reinterpret_cast<uint4*>(dh + p * C + c0) = q;
+      if (ci == 0) {
+#pragma unroll
+        for (int o = 0; o < CO; ++o) gb[o] += d[o];
+      }
+    }
+  }
+  float* my = red + (long)threadIdx.x * 8 * CO;
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+#pragma unroll
+    for (int o = 0; o < CO; ++o) my[j * CO + o] = gw[j][o];
+  __syncthreads();
+  for (int i = threadIdx.x; i < C * CO; i += blockDim.x) {
+    const int c = i / CO, o = i % CO;
+    float a = 0.f;
+    for (int q = 0; q < pl_n; ++q) a += red[(long)(q * c8n + c / 8) * 8 * CO + (c % 8) * CO + o];
+    atomicAdd(&dw[i], a);
+  }
+  __syncthreads();
+  if (ci == 0 && pl < pl_n) {
+#pragma unroll
+    for (int o = 0; o < CO; ++o) red[pl * CO + o] = gb[o];
+  }
+  __syncthreads();
+  if (threadIdx.x < CO) {
+    float a = 0.f;
+    for (int q = 0; q < pl_n; ++q) a += red[q * CO + threadIdx.x];
+    atomicAdd(&db[threadIdx.x], a);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// time embedding MLP: sinusoid(dim) -> Linear(dim,4dim) -> gelu_tanh -> Linear(4dim,4dim)
+// One block per batch row. Saves emb, h1 (pre-GELU) for the backward.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ float gelu_tanh_f(float x) {
+  const float k = 0.7978845608028654f;
+  return 0.5f * x * (1.f + tanhf(k * (x + 0.044715f * x * x * x)));
+}
+__device__ __forceinline__ float gelu_tanh_grad_f(float x) {
+  const float k = 0.7978845608028654f;
+  const float u = k * (x + 0.044715f * x * x * x);
+  const float th = tanhf(u);
+  const float du = k * (1.f + 3.f * 0.044715f * x * x);
+  return 0.5f * (1.f + th) + 0.5f * x * (1.f - th * th) * du;
+}
+
+__global__ void __launch_bounds__(256) time_mlp_fwd_kernel(const int* __restrict__ time, const float* __restrict__ w1,
+                                                           const float* __restrict__ b1, const float* __restrict__ w2,
+                                                           const float* __restrict__ b2, float* __restrict__ emb_out,
+                                                           float* __restrict__ h1_out, float* __restrict__ t_out,
+                                                           int dim) {
+  extern __shared__ float sm[];
+  const int td = 4 * dim;
+  float* emb = sm;        // [dim]
+  float* g = sm + dim;    // [4dim]
+  const int b = blockIdx.x;
+  const float tv = (float)time[b];
+  const int half = dim / 2;
+  const float ef = logf(10000.f) / (float)(half - 1);
+  for (int i = threadIdx.x; i < half; i += blockDim.x) {
+    const float ang = tv * expf((float)i * -ef);
+    emb[i] = sinf(ang);
+    emb[half + i] = cosf(ang);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < dim; i += blockDim.x) emb_out[(long)b * dim + i] = emb[i];
+  for (int j = threadIdx.x; j < td; j += blockDim.x) {
+    float a = b1[j];
+    for (int k = 0; k < dim; ++k) a = fmaf(emb[k], w1[(long)k * td + j], a);
+    h1_out[(long)b * td + j] = a;
+    g[j] = gelu_tanh_f(a);
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < td; j += blockDim.x) {
+    float a = b2[j];
+    for (int k = 0; k < td; ++k) a = fmaf(g[k], w2[(long)k * td + j], a);
+    t_out[(long)b * td + j] = a;
+  }
+}
+
+// dt [B][4dim] -> grads of w1,b1,w2,b2. Single block (B is the per-GPU batch, tiny).
+__global__ void __launch_bounds__(256) time_mlp_bwd_kernel(const float* __restrict__ dt, const float* __restrict__ emb,
+                                                           const float* __restrict__ h1, const float* __restrict__ w2,
+                                                           float* __restrict__ dw1, float* __restrict__ db1,
+                                                           float* __restrict__ dw2, float* __restrict__ db2,
+                                                           float* __restrict__ dh1_ws /*[B][4dim]*/, int B, int dim) {
+  const int td = 4 * dim;
+  // dw2[k][j] = sum_b gelu(h1[b][k]) dt[b][j] ; db2[j] = sum_b dt[b][j]
+  for (long i = threadIdx.x; i < (long)td * td; i += blockDim.x) {
+    const int k = (int)(i / td), j = (int)(i % td);
+    float a = 0.f;
+    for (int b = 0; b < B; ++b) a = fmaf(gelu_tanh_f(h1[(long)b * td + k]), dt[(long)b * td + j], a);
+    dw2[i] += a;
+  }
+  for (int j = threadIdx.x; j < td; j += blockDim.x) {
+    float a = 0.f;
+    for (int b = 0; b < B; ++b) a += dt[(long)b * td + j];
+    db2[j] += a;
+  }
+  // dh1[b][k] = gelu'(h1) * sum_j w2[k][j] dt[b][j]
+  for (int i = threadIdx.x; i < B * td; i += blockDim.x) {
+    const int b = i / td, k = i % td;
+    float a = 0.f;
+    for (int j = 0; j < td; ++j) a = fmaf(w2[(long)k * td + j], dt[(long)b * td + j], a);
+    dh1_ws[i] = a * gelu_tanh_grad_f(h1[i]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < dim * td; i += blockDim.x) {
+    const int k = i / td, j = i % td;
+    float a = 0.f;
+    for (int b = 0; b < B; ++b) a = fmaf(emb[(long)b * dim + k], dh1_ws[(long)b * td + j], a);
+    dw1[i] += a;
+  }
+  for (int j = threadIdx.x; j < td; j += blockDim.x) {
+    float a = 0.f;
+    for (int b = 0; b < B; ++b) a += dh1_ws[(long)b * td + j];
+    db1[j] += a;
+  }
+}
+
+}  // namespace vdn
+
+// Per-ResnetBlock time head: e = LayerNorm(Linear(silu(t))) -> (scale | shift)  (modules.py:233-238)
+struct vdn_time_head {
+  const float* w;     // [4dim][n_out]
+  const float* b;     // [n_out]
+  const float* ln_g;  // [n_out]
+  const float* ln_b;  // [n_out]
+  float* dw;          // grads (may be null in forward-only use)
+  float* db;
+  float* dln_g;
+  float* dln_b;
+  int n_out;          // 2 * cout
+  int off;            // column offset into the [B][ss_ld] scale/shift buffer
+};
+
+namespace vdn {
+
+// grid (n_heads, B)
+__global__ void __launch_bounds__(256) time_heads_fwd_kernel(const float* __restrict__ t, const vdn_time_head* __restrict__ heads,
+                                                             float* __restrict__ e_pre, float* __restrict__ ss, int ss_ld,
+                                                             int td) {
+  extern __shared__ float sm[];
+  float* st = sm;          // silu(t_b) [td]
+  float* red = sm + td;    // [32]
+  const vdn_time_head hd = heads[blockIdx.x];
+  const int b = blockIdx.y;
+  for (int k = threadIdx.x; k < td; k += blockDim.x) st[k] = silu_f(t[(long)b * td + k]);
+  __syncthreads();
+  float s1 = 0.f, s2 = 0.f;
+  for (int j = threadIdx.x; j < hd.n_out; j += blockDim.x) {
+    float a = hd.b[j];
+    for (int k = 0; k < td; ++k) a = fmaf(st[k], hd.w[(long)k * hd.n_out + j], a);
+    e_pre[(long)b * ss_ld + hd.off + j] = a;
+    s1 += a;
+    s2 += a * a;
+  }
+  s1 = block_sum(s1, red);
+  s2 = block_sum(s2, red);
+  const float mean = s1 / (float)hd.n_out;
+  const float rstd = rsqrtf(fmaxf(s2 / (float)hd.n_out - mean * mean, 0.f) + 1e-6f);
+  for (int j = threadIdx.x; j < hd.n_out; j += blockDim.x) {
+    const float a = e_pre[(long)b * ss_ld + hd.off + j];
+    ss[(long)b * ss_ld + hd.off + j] = (a - mean) * rstd * hd.ln_g[j] + hd.ln_b[j];
+  }
+}
+
+// grid (n_heads): LN backward, dW/db accumulation over the batch, dt_silu accumulation (atomics).
+__global__ void __launch_bounds__(256) time_heads_bwd_kernel(const float* __restrict__ t, const vdn_time_head* __restrict__ heads,
+                                                             const float* __restrict__ e_pre, const float* __restrict__ dss,
+                                                             int ss_ld, float* __restrict__ de_ws /*[B][ss_ld]*/,
+                                                             float* __restrict__ dt /*[B][td], zeroed*/, int B, int td) {
+  extern __shared__ float sm[];
+  float* red = sm;  // [32]
+  const vdn_time_head hd = heads[blockIdx.x];
+  const int n = hd.n_out;
+  for (int b = 0; b < B; ++b) {
+    const float* e = e_pre + (long)b * ss_ld + hd.off;
+    const float* dy = dss + (long)b * ss_ld + hd.off;
+    float s1 = 0.f, s2 = 0.f;
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+      s1 += e[j];
+      s2 += e[j] * e[j];
+    }
+    s1 = block_sum(s1, red);
+    s2 = block_sum(s2, red);
+    const float mean = s1 / (float)n;
+    const float rstd = rsqrtf(fmaxf(s2 / (float)n - mean * mean, 0.f) + 1e-6f);
+    float a1 = 0.f, a2 = 0.f;
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+      const float eh = (e[j] - mean) * rstd;
+      const float gd = hd.ln_g[j] * dy[j];
+      a1 += gd;
+      a2 += gd * eh;
+      hd.dln_g[j] += dy[j] * eh;   // single block per head: plain accumulation is race free
+      hd.dln_b[j] += dy[j];
+    }
+    a1 = block_sum(a1, red) / (float)n;
+    a2 = block_sum(a2, red) / (float)n;
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+      const float eh = (e[j] - mean) * rstd;
+      const float v = rstd * (hd.ln_g[j] * dy[j] - a1 - eh * a2);
+      de_ws[(long)b * ss_ld + hd.off + j] = v;
+      hd.db[j] += v;
+    }
+  }
+  __syncthreads();
+  // dW[k][j] += sum_b silu(t[b][k]) de[b][j]
+  for (long i = threadIdx.x; i < (long)td * n; i += blockDim.x) {
+    const int k = (int)(i / n), j = (int)(i % n);
+    float a = 0.f;
+    for (int b = 0; b < B; ++b) a = fmaf(silu_f(t[(long)b * td + k]), de_ws[(long)b * ss_ld + hd.off + j], a);
+    hd.dw[i] += a;
+  }
+  // dt[b][k] += silu'(t[b][k]) * sum_j W[k][j] de[b][j]
+  for (int i = threadIdx.x; i < B * td; i += blockDim.x) {
+    const int b = i / td, k = i % td;
+    float a = 0.f;
+    for (int j = 0; j < n; ++j) a = fmaf(hd.w[(long)k * n + j], de_ws[(long)b * ss_ld + hd.off + j], a);
+    atomicAdd(&dt[i], a * silu_grad_f(t[i]));
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// diffusion elementwise math. Images are fp32 (B,C,F,H,W); the Unet output is (B,F,H,W,C).
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ long bfhwc_index(long i, int C, long FHW) {
+  // i indexes (b,c,r) with r in [0,FHW); returns the index of the same element in (b,r,c)
+  const long r = i % FHW;
+  const long bc = i / FHW;
+  const long b = bc / C, c = bc % C;
+  return (b * FHW + r) * C + c;
+}
+
+__global__ void q_sample_kernel(const float* __restrict__ x, const float* __restrict__ noise, const int* __restrict__ t,
+                                const float* __restrict__ sa, const float* __restrict__ sb, float* __restrict__ out,
+                                long n, long per_sample, int normalize) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const int tb = t[i / per_sample];
+    float xv = x[i];
+    if (normalize) xv = xv * 2.f - 1.f;
+    out[i] = sa[tb] * xv + sb[tb] * noise[i];
+  }
+}
+
+// loss += mean(|pred-noise|^p); dpred = d loss / d pred (fp32, Unet output layout)
+__global__ void __launch_bounds__(256) loss_kernel(const float* __restrict__ pred, const float* __restrict__ noise,
+                                                   float* __restrict__ loss, float* __restrict__ dpred, long n, int C,
+                                                   long FHW, int l1) {
+  __shared__ float red[32];
+  float acc = 0.f;
+  const float inv_n = 1.f / (float)n;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const long j = (C == 1) ? i : bfhwc_index(i, C, FHW);
+    const float d = pred[j] - noise[i];
+    if (l1) {
+      acc += fabsf(d);
+      if (dpred) dpred[j] = (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f)) * inv_n;
+    } else {
+      acc += d * d;
+      if (dpred) dpred[j] = 2.f * d * inv_n;
+    }
+  }
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) atomicAdd(loss, acc * inv_n);
+}
+
+// x_{t-1} = c1*clip(rc*x - rm1*eps) + c2*x + (t!=0)*exp(0.5*logvar)*z   (gaussian_diffusion.py:120-261)
+__global__ void p_sample_kernel(const float* __restrict__ x, const float* __restrict__ eps, const float* __restrict__ z,
+                                const int* __restrict__ t, const float* __restrict__ rc, const float* __restrict__ rm1,
+                                const float* __restrict__ c1, const float* __restrict__ c2,
+                                const float* __restrict__ logvar, float* __restrict__ out, long n, long per_sample,
+                                int C, long FHW, int clip) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const int tb = t[i / per_sample];
+    const long j = (C == 1) ? i : bfhwc_index(i, C, FHW);
+    const float xv = x[i];
+    float x0 = rc[tb] * xv - rm1[tb] * eps[j];
+    if (clip) x0 = fminf(fmaxf(x0, -1.f), 1.f);
+    const float mean = c1[tb] * x0 + c2[tb] * xv;
+    const float nz = (tb == 0) ? 0.f : 1.f;
+    out[i] = mean + nz * expf(0.5f * logvar[tb]) * z[i];
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// column sums (bias gradients): db[c] += sum_p dy[p][c], dy bf16 [P][C]
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ dy, float* __restrict__ db, long P, int C) {
+  extern __shared__ float red[];  // [256][8]
+  const int c8n = C / 8, pl_n = blockDim.x / c8n;
+  const int ci = threadIdx.x % c8n, pl = threadIdx.x / c8n;
+  float a[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a[j] = 0.f;
+  if (pl < pl_n) {
+    for (long p = (long)blockIdx.x * pl_n + pl; p < P; p += (long)gridDim.x * pl_n) {
+      const uint4 u = *reinterpret_cast<const uint4*>(dy + p * C + ci * 8);
+      float2 f2;
+      f2 = unpack_bf16x2(u.x); a[0] += f2.x; a[1] += f2.y;
+      f2 = unpack_bf16x2(u.y); a[2] += f2.x; a[3] += f2.y;
+      f2 = unpack_bf16x2(u.z); a[4] += f2.x; a[5] += f2.y;
+      f2 = unpack_bf16x2(u.w); a[6] += f2.x; a[7] += f2.y;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[threadIdx.x * 8 + j] = a[j];
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f;
+    for (int q = 0; q < pl_n; ++q) s += red[(q * c8n + c / 8) * 8 + (c & 7)];
+    atomicAdd(&db[c], s);
+  }
+}
+
+__global__ void add_bf16_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b, bf16* __restrict__ out, long n8) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long)gridDim.x * blockDim.x) {
+    const uint4 ua = reinterpret_cast<const uint4*>(a)[i], ub = reinterpret_cast<const uint4*>(b)[i];
+    float2 x, y;
+    uint4 o;
+    x = unpack_bf16x2(ua.x); y = unpack_bf16x2(ub.x); o.x = pack_bf16x2(x.x + y.x, x.y + y.y);
+    x = unpack_bf16x2(ua.y); y = unpack_bf16x2(ub.y); o.y = pack_bf16x2(x.x + y.x, x.y + y.y);
+    x = unpack_bf16x2(ua.z); y = unpack_bf16x2(ub.z); o.z = pack_bf16x2(x.x + y.x, x.y + y.y);
+    x = unpack_bf16x2(ua.w); y = unpack_bf16x2(ub.w); o.w = pack_bf16x2(x.x + y.x, x.y + y.y);
+    reinterpret_cast<uint4*>(out)[i] = o;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Fused Adam (optax.adam defaults, bias-corrected) + EMA (trainer.py:367-382) over the flat state.
+// hp (device): {lr, b1, b2, eps, 1-b1^t, 1-b2^t, ema_decay, do_ema, grad_scale}
+// ---------------------------------------------------------------------------------------
+__global__ void adam_ema_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                float* __restrict__ v, float* __restrict__ ema, const float* __restrict__ hp, long n) {
+  const float lr = hp[0], b1 = hp[1], b2 = hp[2], eps = hp[3], bc1 = hp[4], bc2 = hp[5], decay = hp[6];
+  const bool do_ema = hp[7] != 0.f;
+  const float gs = hp[8];
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const float gi = g[i] * gs;
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    const float pi = p[i] - lr * (mi / bc1) / (sqrtf(vi / bc2) + eps);
+    p[i] = pi;
+    if (do_ema) ema[i] = decay * ema[i] + (1.f - decay) * pi;
+  }
+}
+
+static int ew_grid(long n, int threads = 256) {
+  return (int)std::max<long>(1, std::min<long>((n + threads - 1) / threads, (long)num_sms() * 8));
+}
+
+}  // namespace vdn
+
+using namespace vdn;
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+
+extern "C" int vdn_init_conv_fwd(const float* x, const float* w, const float* bias, void* out, int B, int Cin, int F,
+                                 int H, int W, int Cout, int ks, void* stream) {
+  VDN_REQUIRE(H % kIT == 0 && W % kIT == 0 && Cout % 32 == 0 && (ks & 1) && ks <= 7 && Cin >= 1 && Cin <= 4, VDN_E_SHAPE,
+              "init_conv_fwd: unsupported shape H=%d W=%d Cout=%d ks=%d Cin=%d", H, W, Cout, ks, Cin);
+  const int hs = kIT + ks - 1;
+  const size_t smem = (size_t)(ks * ks * Cin * Cout + Cin * hs * hs) * sizeof(float);
+  cudaFuncSetAttribute(init_conv_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024));
+  init_conv_fwd_kernel<<<dim3((H / kIT) * (W / kIT), B * F), 256, smem, ST(stream)>>>(
+      x, w, bias, reinterpret_cast<bf16*>(out), B, Cin, F, H, W, Cout, ks);
+  return check_launch("init_conv_fwd");
+}
+
+extern "C" int vdn_init_conv_wgrad(const float* x, const void* dy, float* dw, float* dbias, int B, int Cin, int F,
+                                   int H, int W, int Cout, int ks, void* stream) {
+  VDN_REQUIRE(H % kIT == 0 && W % kIT == 0 && Cout % 32 == 0 && (ks & 1) && ks <= 7 && Cin >= 1 && Cin <= 3, VDN_E_SHAPE,
+              "init_conv_wgrad: unsupported shape");
+  const int hs = kIT + ks - 1;
+  const size_t smem = (size_t)(Cin * hs * hs + 256 * 33) * sizeof(float);
+  const int n_tiles = (H / kIT) * (W / kIT);
+  const int tpb = std::max(1, std::min(4, n_tiles));
+  init_conv_wgrad_kernel<<<dim3(ceil_div(n_tiles, tpb), B * F), 256, smem, ST(stream)>>>(
+      x, reinterpret_cast<const bf16*>(dy), dw, dbias, B, Cin, F, H, W, Cout, ks, tpb);
+  return check_launch("init_conv_wgrad");
+}
+
+extern "C" int vdn_final_conv_fwd(const void* h, const float* w, const float* bias, float* out, long P, int C, int Co,
+                                  void* stream) {
+  VDN_REQUIRE(C % 8 == 0 && Co >= 1 && Co <= 4, VDN_E_SHAPE, "final_conv_fwd: C=%d Co=%d unsupported", C, Co);
+  const int grid = ew_grid(P);
+  const size_t smem = (size_t)C * Co * sizeof(float);
+  const bf16* hp = reinterpret_cast<const bf16*>(h);
+  switch (Co) {
+    case 1: final_conv_fwd_kernel<1><<<grid, 256, smem, ST(stream)>>>(hp, w, bias, out, P, C); break;
+    case 2: final_conv_fwd_kernel<2><<<grid, 256, smem, ST(stream)>>>(hp, w, bias, out, P, C); break;
+    case 3: final_conv_fwd_kernel<3><<<grid, 256, smem, ST(stream)>>>(hp, w, bias, out, P, C); break;
+    default: final_conv_fwd_kernel<4><<<grid, 256, smem, ST(stream)>>>(hp, w, bias, out, P, C); break;
+  }
+  return check_launch("final_conv_fwd");
+}
+
+extern "C" int vdn_final_conv_bwd(const void* h, const float* dout, const float* w, void* dh, float* dw, float* db,
+                                  long P, int C, int Co, void* stream) {
+  VDN_REQUIRE(C % 8 == 0 && 256 % (C / 8) == 0 && Co >= 1 && Co <= 4, VDN_E_SHAPE, "final_conv_bwd: C=%d Co=%d unsupported", C, Co);
+  const int pl_n = 256 / (C / 8);
+  const int grid = (int)std::max<long>(1, std::min<long>((P + pl_n * 16 - 1) / (pl_n * 16), num_sms() * 4));
+  const size_t smem = (size_t)(C * Co + 256 * 8 * Co) * sizeof(float);
+  const bf16* hp = reinterpret_cast<const bf16*>(h);
+  bf16* dhp = reinterpret_cast<bf16*>(dh);
+  switch (Co) {
+    case 1: final_conv_bwd_kernel<1><<<grid, 256, smem, ST(stream)>>>(hp, dout, w, dhp, dw, db, P, C); break;
+    case 2: final_conv_bwd_kernel<2><<<grid, 256, smem, ST(stream)>>>(hp, dout, w, dhp, dw, db, P, C); break;
+    case 3: final_conv_bwd_kernel<3><<<grid, 256, smem, ST(stream)>>>(hp, dout, w, dhp, dw, db, P, C); break;
+    default: final_conv_bwd_kernel<4><<<grid, 256, smem, ST(stream)>>>(hp, dout, w, dhp, dw, db, P, C); break;
+  }
+  return check_launch("final_conv_bwd");
+}
+
+extern "C" int vdn_time_mlp_fwd(const int* time, const float* w1, const float* b1, const float* w2, const float* b2,
+                                float* emb_out, float* h1_out, float* t_out, int B, int dim, void* stream) {
+  VDN_REQUIRE(B > 0 && dim >= 4 && dim % 2 == 0, VDN_E_SHAPE, "time_mlp_fwd: bad shape");
+  time_mlp_fwd_kernel<<<B, 256, (size_t)5 * dim * sizeof(float), ST(stream)>>>(time, w1, b1, w2, b2, emb_out, h1_out,
+                                                                                t_out, dim);
+  return check_launch("time_mlp_fwd");
+}
+
+extern "C" int vdn_time_mlp_bwd(const float* dt, const float* emb, const float* h1, const float* w2, float* dw1,
+                                float* db1, float* dw2, float* db2, float* dh1_ws, int B, int dim, void* stream) {
+  time_mlp_bwd_kernel<<<1, 256, 0, ST(stream)>>>(dt, emb, h1, w2, dw1, db1, dw2, db2, dh1_ws, B, dim);
+  return check_launch("time_mlp_bwd");
+}
+
+extern "C" int vdn_time_heads_fwd(const float* t, const void* heads_dev, int n_heads, float* e_pre, float* ss,
+                                  int ss_ld, int B, int td, void* stream) {
+  VDN_REQUIRE(n_heads > 0 && B > 0, VDN_E_SHAPE, "time_heads_fwd: bad shape");
+  time_heads_fwd_kernel<<<dim3(n_heads, B), 256, (size_t)(td + 32) * sizeof(float), ST(stream)>>>(
+      t, reinterpret_cast<const vdn_time_head*>(heads_dev), e_pre, ss, ss_ld, td);
+  return check_launch("time_heads_fwd");
+}
+
+extern "C" int vdn_time_heads_bwd(const float* t, const void* heads_dev, int n_heads, const float* e_pre,
+                                  const float* dss, int ss_ld, float* de_ws, float* dt, int B, int td, void* stream) {
+  cudaError_t e = cudaMemsetAsync(dt, 0, (size_t)B * td * sizeof(float), ST(stream));
+  VDN_REQUIRE(e == cudaSuccess, VDN_E_CUDA, "time_heads_bwd memset: %s", cudaGetErrorString(e));
+  time_heads_bwd_kernel<<<n_heads, 256, 32 * sizeof(float), ST(stream)>>>(
+      t, reinterpret_cast<const vdn_time_head*>(heads_dev), e_pre, dss, ss_ld, de_ws, dt, B, td);
+  return check_launch("time_heads_bwd");
+}
+
+extern "C" int vdn_q_sample(const float* x_start, const float* noise, const int* t, const float* sqrt_ac,
+                            const float* sqrt_1mac, float* out, int B, long per_sample, int normalize, void* stream) {
+  const long n = (long)B * per_sample;
+  q_sample_kernel<<<ew_grid(n), 256, 0, ST(stream)>>>(x_start, noise, t, sqrt_ac, sqrt_1mac, out, n, per_sample, normalize);
+  return check_launch("q_sample");
+}
+
+extern "C" int vdn_loss(const float* pred, const float* noise, float* loss, float* dpred, int B, int C, long FHW,
+                        int l1, void* stream) {
+  const long n = (long)B * C * FHW;
+  cudaError_t e = cudaMemsetAsync(loss, 0, sizeof(float), ST(stream));
+  VDN_REQUIRE(e == cudaSuccess, VDN_E_CUDA, "loss memset: %s", cudaGetErrorString(e));
+  loss_kernel<<<ew_grid(n), 256, 0, ST(stream)>>>(pred, noise, loss, dpred, n, C, FHW, l1);
+  return check_launch("loss");
+}
+
+extern "C" int vdn_p_sample(const float* x, const float* eps, const float* z, const int* t, const float* recip,
+                            const float* recipm1, const float* coef1, const float* coef2, const float* logvar,
+                            float* out, int B, int C, long FHW, int clip, void* stream) {
+  const long n = (long)B * C * FHW;
+  p_sample_kernel<<<ew_grid(n), 256, 0, ST(stream)>>>(x, eps, z, t, recip, recipm1, coef1, coef2, logvar, out, n,
+                                                      (long)C * FHW, C, FHW, clip);
+  return check_launch("p_sample");
+}
+
+extern "C" int vdn_colsum(const void* dy, float* db, long P, int C, void* stream) {
+  VDN_REQUIRE(C % 8 == 0 && C / 8 <= 256 && 256 % (C / 8) == 0, VDN_E_SHAPE, "colsum: C=%d unsupported", C);
+  const int pl_n = 256 / (C / 8);
+  const int grid = (int)std::max<long>(1, std::min<long>((P + pl_n * 16 - 1) / (pl_n * 16), num_sms() * 4));
+  colsum_kernel<<<grid, 256, 256 * 8 * sizeof(float), ST(stream)>>>(reinterpret_cast<const bf16*>(dy), db, P, C);
+  return check_launch("colsum");
+}
+
+extern "C" int vdn_add_bf16(const void* a, const void* b, void* out, long n, void* stream) {
+  VDN_REQUIRE(n % 8 == 0, VDN_E_SHAPE, "add_bf16: n must be a multiple of 8");
+  add_bf16_kernel<<<ew_grid(n / 8), 256, 0, ST(stream)>>>(reinterpret_cast<const bf16*>(a),
+                                                          reinterpret_cast<const bf16*>(b),
+                                                          reinterpret_cast<bf16*>(out), n / 8);
+  return check_launch("add_bf16");
+}
+
+extern "C" int vdn_adam_ema(float* p, const float* g, float* m, float* v, float* ema, const float* hp_dev, long n,
+                            void* stream) {
+  adam_ema_kernel<<<ew_grid(n), 256, 0, ST(stream)>>>(p, g, m, v, ema, hp_dev, n);
+  return check_launch("adam_ema");
+}

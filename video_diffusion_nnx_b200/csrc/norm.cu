@@ -1,0 +1,512 @@
+// GroupNorm / LayerNorm / SiLU kernels of Block and ResnetBlock (modules.py:150-243), forward
+// and backward. HBM/L2-bound elementwise + reduction work: 16-byte vector accesses, per-sample
+// affine coefficients staged in shared memory, warp-shuffle reductions.
+//
+// GroupNorm statistics (per sample, per group, over F*H*W*C/G elements - flax semantics, eps 1e-6,
+// fast variance) arrive as raw sums [B][G][2] = (sum x, sum x^2) accumulated by the producing
+// conv's epilogue (tapgemm.cu).
+#include <algorithm>
+
+#include "vdn_common.cuh"
+#include "vdn_host.h"
+
+namespace vdn {
+
+constexpr float kEps = 1e-6f;
+constexpr int kNormThreads = 256;
+
+struct GnArgs {
+  const bf16* x;        // raw conv output [B][rows][C]
+  const float* sums;    // [B][G][2]
+  const float* gamma;   // [C]
+  const float* beta;    // [C]
+  const float* ss;      // [B][ss_ld] scale = [0,C), shift = [C,2C); or null
+  int ss_ld;
+  int B, rows, C, G;
+};
+
+// Per-sample affine in smem: y = x * A[c] + Bc[c]  (GN * gamma + beta, then *(scale+1)+shift)
+__device__ __forceinline__ void gn_affine_to_smem(const GnArgs& a, int b, float* sA, float* sB) {
+  const int cpg = a.C / a.G;
+  const float inv_n = 1.f / ((float)a.rows * (float)cpg);
+  for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
+    const int g = c / cpg;
+    const float s1 = a.sums[((long)b * a.G + g) * 2];
+    const float s2 = a.sums[((long)b * a.G + g) * 2 + 1];
+    const float mean = s1 * inv_n;
+    const float var = fmaxf(s2 * inv_n - mean * mean, 0.f);
+    const float rstd = rsqrtf(var + kEps);
+    float A = rstd * a.gamma[c];
+    float Bc = a.beta[c] - mean * A;
+    if (a.ss) {
+      const float sc = a.ss[(long)b * a.ss_ld + c] + 1.f;
+      const float sh = a.ss[(long)b * a.ss_ld + a.C + c];
+      A *= sc;
+      Bc = Bc * sc + sh;
+    }
+    sA[c] = A;
+    sB[c] = Bc;
+  }
+}
+
+__device__ __forceinline__ void load8(const bf16* p, float (&v)[8]) {
+  const uint4 q = *reinterpret_cast<const uint4*>(p);
+  float2 f;
+  f = unpack_bf16x2(q.x); v[0] = f.x; v[1] = f.y;
+  f = unpack_bf16x2(q.y); v[2] = f.x; v[3] = f.y;
+  f = unpack_bf16x2(q.z); v[4] = f.x; v[5] = f.y;
+  f = unpack_bf16x2(q.w); v[6] = f.x; v[7] = f.y;
+}
+__device__ __forceinline__ void store8(bf16* p, const float (&v)[8]) {
+  uint4 q;
+  q.x = pack_bf16x2(v[0], v[1]);
+  q.y = pack_bf16x2(v[2], v[3]);
+  q.z = pack_bf16x2(v[4], v[5]);
+  q.w = pack_bf16x2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(p) = q;
+}
+
+// ---------------------------------------------------------------------------------------
+// out = silu(GN(x) [* (scale+1) + shift])            (Block, modules.py:171-179)
+// grid (chunks, B); each thread streams 8-channel vectors of its sample.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kNormThreads) gn_silu_fwd_kernel(const GnArgs a, bf16* __restrict__ out) {
+  extern __shared__ float sm[];
+  float* sA = sm;
+  float* sB = sm + a.C;
+  const int b = blockIdx.y;
+  gn_affine_to_smem(a, b, sA, sB);
+  __syncthreads();
+  const int c8n = a.C / 8;
+  const long nvec = (long)a.rows * c8n;
+  const bf16* xb = a.x + (long)b * a.rows * a.C;
+  bf16* ob = out + (long)b * a.rows * a.C;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long)gridDim.x * blockDim.x) {
+    const int c0 = (int)(i % c8n) * 8;
+    float v[8];
+    load8(xb + i * 8, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = silu_f(fmaf(v[j], sA[c0 + j], sB[c0 + j]));
+    store8(ob + i * 8, v);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// ResnetBlock tail (modules.py:241-242): out = silu(GN(b_raw)) + LayerNorm_C(s)
+// One lane group of LG = min(32, C/8) lanes per pixel; each lane owns 8*(C/(8*LG)) channels.
+// ---------------------------------------------------------------------------------------
+template <int VPL>  // 8-channel vectors per lane
+__global__ void __launch_bounds__(kNormThreads) resblock_tail_fwd_kernel(const GnArgs a, const bf16* __restrict__ s,
+                                                                         const float* __restrict__ ln_g,
+                                                                         const float* __restrict__ ln_b,
+                                                                         bf16* __restrict__ out) {
+  extern __shared__ float sm[];
+  float* sA = sm;
+  float* sB = sm + a.C;
+  float* sG = sm + 2 * a.C;
+  float* sBt = sm + 3 * a.C;
+  const int b = blockIdx.y;
+  gn_affine_to_smem(a, b, sA, sB);
+  for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
+    sG[c] = ln_g[c];
+    sBt[c] = ln_b[c];
+  }
+  __syncthreads();
+  const int lg = a.C / (8 * VPL);  // lanes per pixel (power of two <= 32)
+  const int sub = threadIdx.x % lg;
+  const int ppb = blockDim.x / lg;  // pixels per block iteration
+  const float inv_c = 1.f / (float)a.C;
+  const long base = (long)b * a.rows;
+  const long n_it = (a.rows + (long)gridDim.x * ppb - 1) / ((long)gridDim.x * ppb);
+  for (long it = 0; it < n_it; ++it) {  // uniform trip count: the shuffles below need whole warps
+    const long p_raw = (it * gridDim.x + blockIdx.x) * ppb + threadIdx.x / lg;
+    const bool valid = p_raw < a.rows;
+    const long p = valid ? p_raw : (long)a.rows - 1;
+    const long roff = (base + p) * a.C;
+    float sv[VPL][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      load8(s + roff + (k * lg + sub) * 8, sv[k]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s1 += sv[k][j];
+        s2 += sv[k][j] * sv[k][j];
+      }
+    }
+    for (int o = lg >> 1; o > 0; o >>= 1) {
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    const float mean = s1 * inv_c;
+    const float rstd = rsqrtf(fmaxf(s2 * inv_c - mean * mean, 0.f) + kEps);
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      const int c0 = (k * lg + sub) * 8;
+      float xv[8], o8[8];
+      load8(a.x + roff + c0, xv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float y = silu_f(fmaf(xv[j], sA[c0 + j], sB[c0 + j]));
+        o8[j] = y + (sv[k][j] - mean) * rstd * sG[c0 + j] + sBt[c0 + j];
+      }
+      if (valid) store8(out + roff + c0, o8);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Backward.
+//   z = x*A + Bc ; y = silu(z) ; dz = dy * silu'(z)
+//   T1[b,c] = sum_pix dz ; T2[b,c] = sum_pix dz * xhat      (xhat = (x - mean_g) * rstd_g)
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kNormThreads) gn_bwd_reduce_kernel(const GnArgs a, const bf16* __restrict__ dy,
+                                                                     float* __restrict__ T /*[B][C][2]*/) {
+  extern __shared__ float sm[];
+  float* sA = sm;
+  float* sB = sm + a.C;
+  float* sMean = sm + 2 * a.C;   // per channel (group value replicated)
+  float* sRstd = sm + 3 * a.C;
+  float* red = sm + 4 * a.C;     // [blockDim][16]
+  const int b = blockIdx.y;
+  gn_affine_to_smem(a, b, sA, sB);
+  {
+    const int cpg = a.C / a.G;
+    const float inv_n = 1.f / ((float)a.rows * (float)cpg);
+    for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
+      const int g = c / cpg;
+      const float mean = a.sums[((long)b * a.G + g) * 2] * inv_n;
+      const float var = fmaxf(a.sums[((long)b * a.G + g) * 2 + 1] * inv_n - mean * mean, 0.f);
+      sMean[c] = mean;
+      sRstd[c] = rsqrtf(var + kEps);
+    }
+  }
+  __syncthreads();
+  const int c8n = a.C / 8;              // vectors per pixel
+  const int pl_n = blockDim.x / c8n;    // pixel lanes (>= 1 when C <= 2048)
+  const int ci = threadIdx.x % c8n;
+  const int pl = threadIdx.x / c8n;
+  const int c0 = ci * 8;
+  float t1[8], t2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) t1[j] = t2[j] = 0.f;
+  const long base = (long)b * a.rows;
+  if (pl < pl_n) {
+    for (long p = (long)blockIdx.x * pl_n + pl; p < a.rows; p += (long)gridDim.x * pl_n) {
+      const long off = (base + p) * a.C + c0;
+      float xv[8], dv[8];
+      load8(a.x + off, xv);
+      load8(dy + off, dv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float z = fmaf(xv[j], sA[c0 + j], sB[c0 + j]);
+        const float dz = dv[j] * silu_grad_f(z);
+        const float xh = (xv[j] - sMean[c0 + j]) * sRstd[c0 + j];
+        t1[j] += dz;
+        t2[j] += dz * xh;
+      }
+    }
+  }
+  // reduce over pixel lanes through smem, then one atomic per (c, {T1,T2}) per block
+  float* my = red + (long)threadIdx.x * 16;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    my[j] = t1[j];
+    my[8 + j] = t2[j];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < c8n * 16; i += blockDim.x) {
+    const int cc = i / 16, j = i % 16;
+    float acc = 0.f;
+    for (int q = 0; q < pl_n; ++q) acc += red[(long)(q * c8n + cc) * 16 + j];
+    const int c = cc * 8 + (j & 7);
+    atomicAdd(&T[((long)b * a.C + c) * 2 + (j >> 3)], acc);
+  }
+}
+
+// dgamma/dbeta (accumulated), dscale/dshift per (b,c) from T.  One block per launch is plenty.
+__global__ void gn_bwd_finalize_kernel(const GnArgs a, const float* __restrict__ T, float* __restrict__ dgamma,
+                                       float* __restrict__ dbeta, float* __restrict__ dss /*[B][dss_ld] or null*/,
+                                       int dss_ld) {
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < a.C; c += gridDim.x * blockDim.x) {
+    float dg = 0.f, db = 0.f;
+    const float gam = a.gamma[c], bet = a.beta[c];
+    for (int b = 0; b < a.B; ++b) {
+      const float t1 = T[((long)b * a.C + c) * 2], t2 = T[((long)b * a.C + c) * 2 + 1];
+      const float sc = a.ss ? a.ss[(long)b * a.ss_ld + c] + 1.f : 1.f;
+      dg += sc * t2;
+      db += sc * t1;
+      if (dss) {
+        dss[(long)b * dss_ld + c] = gam * t2 + bet * t1;  // dscale = sum dz * (xhat*gamma + beta)
+        dss[(long)b * dss_ld + a.C + c] = t1;             // dshift
+      }
+    }
+    dgamma[c] += dg;
+    dbeta[c] += db;
+  }
+}
+
+// dx = rstd_g * (gamma_c*(s+1)*dz - m1_g - xhat*m2_g),  m1_g = mean_g(dxhat), m2_g = mean_g(dxhat*xhat)
+__global__ void __launch_bounds__(kNormThreads) gn_bwd_apply_kernel(const GnArgs a, const bf16* __restrict__ dy,
+                                                                    const float* __restrict__ T,
+                                                                    bf16* __restrict__ dx) {
+  extern __shared__ float sm[];
+  float* sA = sm;
+  float* sB = sm + a.C;
+  float* sMean = sm + 2 * a.C;
+  float* sRstd = sm + 3 * a.C;
+  float* sK = sm + 4 * a.C;    // gamma*(s+1)
+  float* sM1 = sm + 5 * a.C;   // per channel copy of m1_g
+  float* sM2 = sm + 6 * a.C;
+  const int b = blockIdx.y;
+  const int cpg = a.C / a.G;
+  gn_affine_to_smem(a, b, sA, sB);
+  const float inv_n = 1.f / ((float)a.rows * (float)cpg);
+  for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
+    const int g = c / cpg;
+    const float mean = a.sums[((long)b * a.G + g) * 2] * inv_n;
+    const float var = fmaxf(a.sums[((long)b * a.G + g) * 2 + 1] * inv_n - mean * mean, 0.f);
+    sMean[c] = mean;
+    sRstd[c] = rsqrtf(var + kEps);
+    const float sc = a.ss ? a.ss[(long)b * a.ss_ld + c] + 1.f : 1.f;
+    sK[c] = a.gamma[c] * sc;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
+    const int g0 = (c / cpg) * cpg;
+    float m1 = 0.f, m2 = 0.f;
+    for (int k = 0; k < cpg; ++k) {
+      m1 += sK[g0 + k] * T[((long)b * a.C + g0 + k) * 2];
+      m2 += sK[g0 + k] * T[((long)b * a.C + g0 + k) * 2 + 1];
+    }
+    sM1[c] = m1 * inv_n;
+    sM2[c] = m2 * inv_n;
+  }
+  __syncthreads();
+  const int c8n = a.C / 8;
+  const long nvec = (long)a.rows * c8n;
+  const long boff = (long)b * a.rows * a.C;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long)gridDim.x * blockDim.x) {
+    const int c0 = (int)(i % c8n) * 8;
+    float xv[8], dv[8], o[8];
+    load8(a.x + boff + i * 8, xv);
+    load8(dy + boff + i * 8, dv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = c0 + j;
+      const float z = fmaf(xv[j], sA[c], sB[c]);
+      const float dz = dv[j] * silu_grad_f(z);
+      const float xh = (xv[j] - sMean[c]) * sRstd[c];
+      o[j] = sRstd[c] * (sK[c] * dz - sM1[c] - xh * sM2[c]);
+    }
+    store8(dx + boff + i * 8, o);
+  }
+}
+
+// LayerNorm over channels, backward (norm_2 of ResnetBlock, modules.py:223,242):
+//   y = shat*g + b ; ds = rstd * (g*dy - mean_c(g*dy) - shat*mean_c(g*dy*shat)) ; dg += dy*shat ; db += dy
+template <int VPL>
+__global__ void __launch_bounds__(kNormThreads) ln_bwd_kernel(const bf16* __restrict__ s, const bf16* __restrict__ dy,
+                                                              const float* __restrict__ ln_g, bf16* __restrict__ ds,
+                                                              float* __restrict__ dg, float* __restrict__ db, long P,
+                                                              int C) {
+  extern __shared__ float sm[];
+  float* sG = sm;            // [C]
+  float* accG = sm + C;      // [C] block-level accumulators
+  float* accB = sm + 2 * C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    sG[c] = ln_g[c];
+    accG[c] = 0.f;
+    accB[c] = 0.f;
+  }
+  __syncthreads();
+  const int lg = C / (8 * VPL);
+  const int sub = threadIdx.x % lg;
+  const int ppb = blockDim.x / lg;
+  const float inv_c = 1.f / (float)C;
+  float pg[VPL][8], pb[VPL][8];
+#pragma unroll
+  for (int k = 0; k < VPL; ++k)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) pg[k][j] = pb[k][j] = 0.f;
+  const long n_it = (P + (long)gridDim.x * ppb - 1) / ((long)gridDim.x * ppb);
+  for (long it = 0; it < n_it; ++it) {  // uniform trip count (warp shuffles inside)
+    const long p_raw = (it * gridDim.x + blockIdx.x) * ppb + threadIdx.x / lg;
+    const bool valid = p_raw < P;
+    const long p = valid ? p_raw : P - 1;
+    const long roff = p * C;
+    float sv[VPL][8], dv[VPL][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      load8(s + roff + (k * lg + sub) * 8, sv[k]);
+      load8(dy + roff + (k * lg + sub) * 8, dv[k]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (!valid) dv[k][j] = 0.f;
+        s1 += sv[k][j];
+        s2 += sv[k][j] * sv[k][j];
+      }
+    }
+    for (int o = lg >> 1; o > 0; o >>= 1) {
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    const float mean = s1 * inv_c;
+    const float rstd = rsqrtf(fmaxf(s2 * inv_c - mean * mean, 0.f) + kEps);
+    float a1 = 0.f, a2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      const int c0 = (k * lg + sub) * 8;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float sh = (sv[k][j] - mean) * rstd;
+        const float gd = sG[c0 + j] * dv[k][j];
+        a1 += gd;
+        a2 += gd * sh;
+        pg[k][j] += dv[k][j] * sh;
+        pb[k][j] += dv[k][j];
+        sv[k][j] = sh;  // keep shat
+      }
+    }
+    for (int o = lg >> 1; o > 0; o >>= 1) {
+      a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+      a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+    }
+    a1 *= inv_c;
+    a2 *= inv_c;
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      const int c0 = (k * lg + sub) * 8;
+      float o8[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o8[j] = rstd * (sG[c0 + j] * dv[k][j] - a1 - sv[k][j] * a2);
+      if (valid) store8(ds + roff + c0, o8);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) {
+    const int c0 = (k * lg + sub) * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(&accG[c0 + j], pg[k][j]);
+      atomicAdd(&accB[c0 + j], pb[k][j]);
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    atomicAdd(&dg[c], accG[c]);
+    atomicAdd(&db[c], accB[c]);
+  }
+}
+
+static int vpl_for(int C) {
+  // lanes per pixel = C / (8*VPL) must be a power of two <= 32
+  int vpl = 1;
+  while (C / (8 * vpl) > 32) vpl *= 2;
+  return vpl;
+}
+static bool pow2(int x) { return x > 0 && (x & (x - 1)) == 0; }
+
+static int check_gn(const char* who, int B, int rows, int C, int G) {
+  VDN_REQUIRE(B > 0 && rows > 0 && C >= 8 && C % 8 == 0 && G > 0 && C % G == 0, VDN_E_SHAPE,
+              "%s: bad shape B=%d rows=%d C=%d G=%d", who, B, rows, C, G);
+  VDN_REQUIRE(C <= 2048, VDN_E_SHAPE, "%s: C=%d > 2048 unsupported", who, C);
+  return VDN_OK;
+}
+
+static int grid_x_for(long work_items, int per_block, int B) {
+  long want = (work_items + per_block - 1) / per_block;
+  long cap = std::max<long>(1, (long)num_sms() * 8 / std::max(B, 1));
+  return (int)std::max<long>(1, std::min(want, cap));
+}
+
+}  // namespace vdn
+
+using namespace vdn;
+
+extern "C" int vdn_gn_silu_fwd(const void* x_raw, const float* gn_sums, const float* gamma, const float* beta,
+                               const float* scale_shift, int ss_ld, void* out, int B, int rows_per_sample, int C,
+                               int G, void* stream) {
+  int rc = check_gn("gn_silu_fwd", B, rows_per_sample, C, G);
+  if (rc) return rc;
+  GnArgs a{reinterpret_cast<const bf16*>(x_raw), gn_sums, gamma, beta, scale_shift, ss_ld, B, rows_per_sample, C, G};
+  const long nvec = (long)rows_per_sample * (C / 8);
+  dim3 grid(grid_x_for(nvec, kNormThreads * 4, B), B);
+  gn_silu_fwd_kernel<<<grid, kNormThreads, 2 * C * sizeof(float), reinterpret_cast<cudaStream_t>(stream)>>>(
+      a, reinterpret_cast<bf16*>(out));
+  return check_launch("gn_silu_fwd");
+}
+
+extern "C" int vdn_resblock_tail_fwd(const void* b_raw, const float* gn_sums, const float* gamma, const float* beta,
+                                     const void* s, const float* ln_gamma, const float* ln_beta, void* out, int B,
+                                     int rows_per_sample, int C, int G, void* stream) {
+  int rc = check_gn("resblock_tail_fwd", B, rows_per_sample, C, G);
+  if (rc) return rc;
+  const int vpl = vpl_for(C);
+  VDN_REQUIRE(pow2(C / (8 * vpl)), VDN_E_SHAPE, "resblock_tail_fwd: C=%d must be 8 * power of two", C);
+  GnArgs a{reinterpret_cast<const bf16*>(b_raw), gn_sums, gamma, beta, nullptr, 0, B, rows_per_sample, C, G};
+  const int lg = C / (8 * vpl);
+  const int ppb = kNormThreads / lg;
+  dim3 grid(grid_x_for(rows_per_sample, ppb * 4, B), B);
+  const size_t smem = 4 * C * sizeof(float);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const bf16* sp = reinterpret_cast<const bf16*>(s);
+  bf16* op = reinterpret_cast<bf16*>(out);
+  switch (vpl) {
+    case 1: resblock_tail_fwd_kernel<1><<<grid, kNormThreads, smem, st>>>(a, sp, ln_gamma, ln_beta, op); break;
+    case 2: resblock_tail_fwd_kernel<2><<<grid, kNormThreads, smem, st>>>(a, sp, ln_gamma, ln_beta, op); break;
+    case 4: resblock_tail_fwd_kernel<4><<<grid, kNormThreads, smem, st>>>(a, sp, ln_gamma, ln_beta, op); break;
+    default: resblock_tail_fwd_kernel<8><<<grid, kNormThreads, smem, st>>>(a, sp, ln_gamma, ln_beta, op); break;
+  }
+  return check_launch("resblock_tail_fwd");
+}
+
+extern "C" int vdn_gn_silu_bwd(const void* dy, const void* x_raw, const float* gn_sums, const float* gamma,
+                               const float* beta, const float* scale_shift, int ss_ld, float* T_ws, void* dx_raw,
+                               float* dgamma, float* dbeta, float* dss, int dss_ld, int B, int rows_per_sample, int C,
+                               int G, void* stream) {
+  int rc = check_gn("gn_silu_bwd", B, rows_per_sample, C, G);
+  if (rc) return rc;
+  VDN_REQUIRE(pow2(C / 8) && C / 8 <= kNormThreads, VDN_E_SHAPE, "gn_silu_bwd: C=%d must be 8 * power of two <= 2048", C);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  GnArgs a{reinterpret_cast<const bf16*>(x_raw), gn_sums, gamma, beta, scale_shift, ss_ld, B, rows_per_sample, C, G};
+  cudaError_t e = cudaMemsetAsync(T_ws, 0, (size_t)B * C * 2 * sizeof(float), st);
+  VDN_REQUIRE(e == cudaSuccess, VDN_E_CUDA, "gn_silu_bwd memset: %s", cudaGetErrorString(e));
+  const int pl_n = kNormThreads / (C / 8);
+  dim3 grid(grid_x_for(rows_per_sample, pl_n * 16, B), B);
+  const size_t smem_r = (4 * C + kNormThreads * 16) * sizeof(float);
+  gn_bwd_reduce_kernel<<<grid, kNormThreads, smem_r, st>>>(a, reinterpret_cast<const bf16*>(dy), T_ws);
+  rc = check_launch("gn_bwd_reduce");
+  if (rc) return rc;
+  gn_bwd_finalize_kernel<<<ceil_div(C, 128), 128, 0, st>>>(a, T_ws, dgamma, dbeta, dss, dss_ld);
+  rc = check_launch("gn_bwd_finalize");
+  if (rc) return rc;
+  const long nvec = (long)rows_per_sample * (C / 8);
+  dim3 grid2(grid_x_for(nvec, kNormThreads * 4, B), B);
+  gn_bwd_apply_kernel<<<grid2, kNormThreads, 7 * C * sizeof(float), st>>>(a, reinterpret_cast<const bf16*>(dy), T_ws,
+                                                                          reinterpret_cast<bf16*>(dx_raw));
+  return check_launch("gn_bwd_apply");
+}
+
+extern "C" int vdn_ln_bwd(const void* s, const void* dy, const float* ln_gamma, void* ds, float* dgamma, float* dbeta,
+                          long P, int C, void* stream) {
+  VDN_REQUIRE(P > 0 && C >= 8 && C % 8 == 0 && C <= 2048, VDN_E_SHAPE, "ln_bwd: bad shape P=%ld C=%d", P, C);
+  const int vpl = vpl_for(C);
+  VDN_REQUIRE(pow2(C / (8 * vpl)), VDN_E_SHAPE, "ln_bwd: C=%d must be 8 * power of two", C);
+  const int lg = C / (8 * vpl);
+  const int ppb = kNormThreads / lg;
+  const int grid = (int)std::max<long>(1, std::min<long>((P + ppb * 8 - 1) / (ppb * 8), num_sms() * 4));
+  const size_t smem = 3 * C * sizeof(float);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const bf16* sp = reinterpret_cast<const bf16*>(s);
+  const bf16* dp = reinterpret_cast<const bf16*>(dy);
+  bf16* op = reinterpret_cast<bf16*>(ds);
+  switch (vpl) {
+    case 1: ln_bwd_kernel<1><<<grid, kNormThreads, smem, st>>>(sp, dp, ln_gamma, op, dgamma, dbeta, P, C); break;
+    case 2: ln_bwd_kernel<2><<<grid, kNormThreads, smem, st>>>(sp, dp, ln_gamma, op, dgamma, dbeta, P, C); break;
+    case 4: ln_bwd_kernel<4><<<grid, kNormThreads, smem, st>>>(sp, dp, ln_gamma, op, dgamma, dbeta, P, C); break;
+    default: ln_bwd_kernel<8><<<grid, kNormThreads, smem, st>>>(sp, dp, ln_gamma, op, dgamma, dbeta, P, C); break;
+  }
+  return check_launch("ln_bwd");
+}

@@ -40,6 +40,7 @@ struct TapArgs {
   // epilogue
   const float* bias;
   const void* res;
+  const void* res2;
   void* out;
   void* out2;
   int split_col;
@@ -193,17 +194,19 @@ __global__ void __launch_bounds__(kGemmThreads) tapgemm_kernel(const __grid_cons
     }
     const int col_base = n_tile * BN;
     uint8_t* outp;
+    const uint8_t* resp;
     int ld, col_o;
     if (args.split_col > 0 && col_base >= args.split_col) {
       outp = reinterpret_cast<uint8_t*>(args.out2);
+      resp = reinterpret_cast<const uint8_t*>(args.res2);
       ld = args.ld_out2;
       col_o = col_base - args.split_col;
     } else {
       outp = reinterpret_cast<uint8_t*>(args.out);
+      resp = reinterpret_cast<const uint8_t*>(args.res);
       ld = args.ld_out;
       col_o = col_base;
     }
-    const uint8_t* resp = reinterpret_cast<const uint8_t*>(args.res);
     const int esz = args.out_f32 ? 4 : 2;
     float* gsum = nullptr;
     if (args.gn_sums) {
@@ -307,6 +310,7 @@ struct RefArgs {
   const bf16* wp;
   const float* bias;
   const void* res;
+  const void* res2;
   void* out;
   void* out2;
   int split_col, ld_out, ld_out2, out_f32, py, px;
@@ -347,14 +351,15 @@ __global__ void tapgemm_ref_kernel(const RefArgs a) {
   long orow = m;
   if (a.kind == VDN_TAP_UP) orow = ((long)img * (2 * a.H) + (2 * y + a.py)) * (2 * a.W) + (2 * x + a.px);
   void* outp = a.out;
+  const void* resp = a.res;
   int ld = a.ld_out, col = n;
   if (a.split_col > 0 && n >= a.split_col) {
-    outp = a.out2; ld = a.ld_out2; col = n - a.split_col;
+    outp = a.out2; resp = a.res2; ld = a.ld_out2; col = n - a.split_col;
   }
   const long eoff = orow * ld + col;
-  if (a.res) {
-    acc += a.out_f32 ? reinterpret_cast<const float*>(a.res)[eoff]
-                     : __bfloat162float(reinterpret_cast<const bf16*>(a.res)[eoff]);
+  if (resp) {
+    acc += a.out_f32 ? reinterpret_cast<const float*>(resp)[eoff]
+                     : __bfloat162float(reinterpret_cast<const bf16*>(resp)[eoff]);
   }
   if (a.gn_sums) {
     float* p = a.gn_sums + ((long)(m / a.rows_per_sample) * a.gn_groups + n / a.cpg) * 2;
@@ -376,9 +381,7 @@ __global__ void pack_weight_kernel(const float* __restrict__ src, bf16* __restri
   const long total = (long)a.taps * a.cin * a.cout;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     // iterate in DESTINATION order so that writes coalesce: (n, t, k)
-    int nrows = a.mode == 0 ? a.cout : a.cin;
     int kin = a.mode == 0 ? a.cin : a.cout;
-    (void)nrows;
     const int k = (int)(i % kin);
     const int t = (int)((i / kin) % a.taps);
     const int n = (int)(i / ((long)kin * a.taps));
@@ -445,8 +448,8 @@ static int launch_tapgemm(const TapMaps& maps, const TapArgs& args, int smem_byt
 using namespace vdn;
 
 extern "C" int vdn_tapgemm(const vdn_tapgemm_desc* d, const void* src0, const void* src1, const void* wp,
-                           const float* bias, const void* residual, void* out, void* out2, float* gn_sums,
-                           void* stream) {
+                           const float* bias, const void* residual, const void* residual2, void* out, void* out2,
+                           float* gn_sums, void* stream) {
   int rc = validate_desc(d);
   if (rc) return rc;
   VDN_REQUIRE(src0 && wp && out, VDN_E_SHAPE, "tapgemm: null operand");
@@ -474,6 +477,7 @@ extern "C" int vdn_tapgemm(const vdn_tapgemm_desc* d, const void* src0, const vo
   a.chunks = C / BK;
   a.bias = bias;
   a.res = residual;
+  a.res2 = residual2;
   a.out = out;
   a.out2 = out2;
   a.split_col = d->split_col;
@@ -561,8 +565,8 @@ extern "C" int vdn_tapgemm(const vdn_tapgemm_desc* d, const void* src0, const vo
 }
 
 extern "C" int vdn_tapgemm_ref(const vdn_tapgemm_desc* d, const void* src0, const void* src1, const void* wp,
-                               const float* bias, const void* residual, void* out, void* out2, float* gn_sums,
-                               void* stream) {
+                               const float* bias, const void* residual, const void* residual2, void* out,
+                               void* out2, float* gn_sums, void* stream) {
   int rc = validate_desc(d);
   if (rc) return rc;
   RefArgs a;
@@ -584,6 +588,7 @@ extern "C" int vdn_tapgemm_ref(const vdn_tapgemm_desc* d, const void* src0, cons
   a.wp = reinterpret_cast<const bf16*>(wp);
   a.bias = bias;
   a.res = residual;
+  a.res2 = residual2;
   a.out = out;
   a.out2 = out2;
   a.split_col = d->split_col;

@@ -42,7 +42,7 @@ def pack_weight(src: torch.Tensor, dst: torch.Tensor, taps: int, cin: int, cout:
 
 
 def tapgemm(kind: int, srcs: Sequence[torch.Tensor], wp: torch.Tensor, taps, *, bias=None, residual=None,
-            out=None, out2=None, split_col: int = 0, gn_sums=None, gn_groups: int = 0, rows_per_sample: int = 0,
+            residual2=None, out=None, out2=None, split_col: int = 0, gn_sums=None, gn_groups: int = 0, rows_per_sample: int = 0,
             py: int = 0, px: int = 0, out_dtype=torch.bfloat16, ref: bool = False) -> torch.Tensor:
     x0 = srcs[0]
     assert x0.dtype == torch.bfloat16 and x0.is_contiguous() and x0.dim() == 4
@@ -67,5 +67,183 @@ def tapgemm(kind: int, srcs: Sequence[torch.Tensor], wp: torch.Tensor, taps, *, 
         out = torch.empty((n_img, oh, ow, split_col if split_col else n_out), dtype=out_dtype, device=x0.device)
     fn = lib.vdn_tapgemm_ref if ref else lib.vdn_tapgemm
     check(fn(C.byref(d), ptr(x0), ptr(srcs[1]) if len(srcs) > 1 else None, ptr(wp), ptr(bias), ptr(residual),
-             ptr(out), ptr(out2), ptr(gn_sums), stream_ptr()), "vdn_tapgemm")
+             ptr(residual2), ptr(out), ptr(out2), ptr(gn_sums), stream_ptr()), "vdn_tapgemm")
     return out
+
+
+# ------------------------------------------------------------------------------------------
+# wgrad
+# ------------------------------------------------------------------------------------------
+def wgrad(kind: int, srcs: Sequence[torch.Tensor], g: torch.Tensor, dw: torch.Tensor, taps, ref: bool = False) -> None:
+    """dw[tap][n_src*C][Cout] (fp32, reference kernel layout) += sum_pixels src[p + tap]^T g[p]."""
+    x0 = srcs[0]
+    assert x0.dtype == torch.bfloat16 and g.dtype == torch.bfloat16 and dw.dtype == torch.float32
+    assert x0.is_contiguous() and g.is_contiguous() and dw.is_contiguous()
+    n_img, Hs, Ws, Cs = x0.shape
+    cout = g.shape[-1]
+    if kind == VDN_TAP_DOWN:
+        H, W = Hs // 2, Ws // 2
+        assert g.shape[1] == H and g.shape[2] == W
+    elif kind == VDN_TAP_UP:
+        H, W = Hs, Ws
+        assert g.shape[1] == 2 * H and g.shape[2] == 2 * W
+    else:
+        H, W = Hs, Ws
+        assert g.shape[1] == H and g.shape[2] == W
+    assert dw.numel() == len(taps) * len(srcs) * Cs * cout
+    dy = (C.c_int * len(taps))(*[t[0] for t in taps])
+    dx = (C.c_int * len(taps))(*[t[1] for t in taps])
+    fn = lib.vdn_wgrad_ref if ref else lib.vdn_wgrad
+    check(fn(kind, ptr(x0), ptr(srcs[1]) if len(srcs) > 1 else None, ptr(g), ptr(dw), n_img, H, W, len(srcs), Cs,
+             cout, len(taps), dy, dx, stream_ptr()), "vdn_wgrad")
+
+
+# ------------------------------------------------------------------------------------------
+# norms
+# ------------------------------------------------------------------------------------------
+def gn_silu_fwd(x_raw, sums, gamma, beta, ss, out, B, rows, Cc, G=8):
+    ss_ld = ss.stride(0) if ss is not None else 0
+    check(lib.vdn_gn_silu_fwd(ptr(x_raw), ptr(sums), ptr(gamma), ptr(beta), ptr(ss), ss_ld, ptr(out), B, rows, Cc, G,
+                              stream_ptr()), "vdn_gn_silu_fwd")
+
+
+def resblock_tail_fwd(b_raw, sums, gamma, beta, s, ln_g, ln_b, out, B, rows, Cc, G=8):
+    check(lib.vdn_resblock_tail_fwd(ptr(b_raw), ptr(sums), ptr(gamma), ptr(beta), ptr(s), ptr(ln_g), ptr(ln_b),
+                                    ptr(out), B, rows, Cc, G, stream_ptr()), "vdn_resblock_tail_fwd")
+
+
+def gn_silu_bwd(dy, x_raw, sums, gamma, beta, ss, T_ws, dx_raw, dgamma, dbeta, dss, B, rows, Cc, G=8):
+    ss_ld = ss.stride(0) if ss is not None else 0
+    dss_ld = dss.stride(0) if dss is not None else 0
+    check(lib.vdn_gn_silu_bwd(ptr(dy), ptr(x_raw), ptr(sums), ptr(gamma), ptr(beta), ptr(ss), ss_ld, ptr(T_ws),
+                              ptr(dx_raw), ptr(dgamma), ptr(dbeta), ptr(dss), dss_ld, B, rows, Cc, G, stream_ptr()),
+          "vdn_gn_silu_bwd")
+
+
+def ln_bwd(s, dy, ln_g, ds, dg, db, P, Cc):
+    check(lib.vdn_ln_bwd(ptr(s), ptr(dy), ptr(ln_g), ptr(ds), ptr(dg), ptr(db), C.c_long(P), Cc, stream_ptr()),
+          "vdn_ln_bwd")
+
+
+# ------------------------------------------------------------------------------------------
+# attention cores
+# ------------------------------------------------------------------------------------------
+MHA_TEMPORAL, MHA_SPATIAL = 0, 1
+
+
+def mha_core_fwd(qkv, o, lse, mode, B, F, HW):
+    check(lib.vdn_mha_core_fwd(ptr(qkv), ptr(o), ptr(lse), mode, B, F, HW, stream_ptr()), "vdn_mha_core_fwd")
+
+
+def mha_core_bwd(qkv, o, d_o, lse, D_ws, dqkv, mode, B, F, HW):
+    check(lib.vdn_mha_core_bwd(ptr(qkv), ptr(o), ptr(d_o), ptr(lse), ptr(D_ws), ptr(dqkv), mode, B, F, HW,
+                               stream_ptr()), "vdn_mha_core_bwd")
+
+
+lib.vdn_sla_workspace_floats.restype = C.c_size_t
+
+
+def sla_workspace_floats(n_img, N) -> int:
+    return int(lib.vdn_sla_workspace_floats(n_img, N))
+
+
+def sla_core_fwd(qkv, tok_out, ctx, kstat, ws, n_img, N):
+    check(lib.vdn_sla_core_fwd(ptr(qkv), ptr(tok_out), ptr(ctx), ptr(kstat), ptr(ws), n_img, N, stream_ptr()),
+          "vdn_sla_core_fwd")
+
+
+def sla_core_bwd(qkv, d_tok, ctx, kstat, dctx, dqkv, n_img, N):
+    check(lib.vdn_sla_core_bwd(ptr(qkv), ptr(d_tok), ptr(ctx), ptr(kstat), ptr(dctx), ptr(dqkv), n_img, N,
+                               stream_ptr()), "vdn_sla_core_bwd")
+
+
+# ------------------------------------------------------------------------------------------
+# small kernels
+# ------------------------------------------------------------------------------------------
+def init_conv_fwd(x, w, bias, out, B, Cin, F, H, W, Cout, ks):
+    check(lib.vdn_init_conv_fwd(ptr(x), ptr(w), ptr(bias), ptr(out), B, Cin, F, H, W, Cout, ks, stream_ptr()),
+          "vdn_init_conv_fwd")
+
+
+def init_conv_wgrad(x, dy, dw, dbias, B, Cin, F, H, W, Cout, ks):
+    check(lib.vdn_init_conv_wgrad(ptr(x), ptr(dy), ptr(dw), ptr(dbias), B, Cin, F, H, W, Cout, ks, stream_ptr()),
+          "vdn_init_conv_wgrad")
+
+
+def final_conv_fwd(h, w, bias, out, P, Cc, Co):
+    check(lib.vdn_final_conv_fwd(ptr(h), ptr(w), ptr(bias), ptr(out), C.c_long(P), Cc, Co, stream_ptr()),
+          "vdn_final_conv_fwd")
+
+
+def final_conv_bwd(h, dout, w, dh, dw, db, P, Cc, Co):
+    check(lib.vdn_final_conv_bwd(ptr(h), ptr(dout), ptr(w), ptr(dh), ptr(dw), ptr(db), C.c_long(P), Cc, Co,
+                                 stream_ptr()), "vdn_final_conv_bwd")
+
+
+def time_mlp_fwd(time, w1, b1, w2, b2, emb, h1, t_out, B, dim):
+    check(lib.vdn_time_mlp_fwd(ptr(time), ptr(w1), ptr(b1), ptr(w2), ptr(b2), ptr(emb), ptr(h1), ptr(t_out), B, dim,
+                               stream_ptr()), "vdn_time_mlp_fwd")
+
+
+def time_mlp_bwd(dt, emb, h1, w2, dw1, db1, dw2, db2, dh1_ws, B, dim):
+    check(lib.vdn_time_mlp_bwd(ptr(dt), ptr(emb), ptr(h1), ptr(w2), ptr(dw1), ptr(db1), ptr(dw2), ptr(db2),
+                               ptr(dh1_ws), B, dim, stream_ptr()), "vdn_time_mlp_bwd")
+
+
+class TimeHead(C.Structure):
+    _fields_ = [("w", C.c_void_p), ("b", C.c_void_p), ("ln_g", C.c_void_p), ("ln_b", C.c_void_p),
+                ("dw", C.c_void_p), ("db", C.c_void_p), ("dln_g", C.c_void_p), ("dln_b", C.c_void_p),
+                ("n_out", C.c_int), ("off", C.c_int)]
+
+
+def make_time_head_table(entries, device) -> torch.Tensor:
+    """entries: list of dicts with tensors w,b,ln_g,ln_b,(dw,db,dln_g,dln_b) and ints n_out, off.
+    Returns a device uint8 tensor holding the vdn_time_head array."""
+    arr = (TimeHead * len(entries))()
+    for i, e in enumerate(entries):
+        for k in ("w", "b", "ln_g", "ln_b", "dw", "db", "dln_g", "dln_b"):
+            t = e.get(k)
+            setattr(arr[i], k, t.data_ptr() if t is not None else None)
+        arr[i].n_out, arr[i].off = e["n_out"], e["off"]
+    raw = bytes(arr)
+    host = torch.frombuffer(bytearray(raw), dtype=torch.uint8)
+    return host.to(device)
+
+
+def time_heads_fwd(t, table, n_heads, e_pre, ss, B, td):
+    check(lib.vdn_time_heads_fwd(ptr(t), ptr(table), n_heads, ptr(e_pre), ptr(ss), ss.stride(0), B, td, stream_ptr()),
+          "vdn_time_heads_fwd")
+
+
+def time_heads_bwd(t, table, n_heads, e_pre, dss, de_ws, dt, B, td):
+    check(lib.vdn_time_heads_bwd(ptr(t), ptr(table), n_heads, ptr(e_pre), ptr(dss), dss.stride(0), ptr(de_ws),
+                                 ptr(dt), B, td, stream_ptr()), "vdn_time_heads_bwd")
+
+
+def q_sample(x_start, noise, t, sqrt_ac, sqrt_1mac, out, normalize: bool):
+    B = x_start.shape[0]
+    check(lib.vdn_q_sample(ptr(x_start), ptr(noise), ptr(t), ptr(sqrt_ac), ptr(sqrt_1mac), ptr(out), B,
+                           C.c_long(x_start.numel() // B), int(normalize), stream_ptr()), "vdn_q_sample")
+
+
+def loss_fwd_bwd(pred, noise, loss, dpred, B, Cc, FHW, l1: bool):
+    check(lib.vdn_loss(ptr(pred), ptr(noise), ptr(loss), ptr(dpred), B, Cc, C.c_long(FHW), int(l1), stream_ptr()),
+          "vdn_loss")
+
+
+def p_sample(x, eps, z, t, recip, recipm1, coef1, coef2, logvar, out, B, Cc, FHW, clip: bool = True):
+    check(lib.vdn_p_sample(ptr(x), ptr(eps), ptr(z), ptr(t), ptr(recip), ptr(recipm1), ptr(coef1), ptr(coef2),
+                           ptr(logvar), ptr(out), B, Cc, C.c_long(FHW), int(clip), stream_ptr()), "vdn_p_sample")
+
+
+def colsum(dy, db, P, Cc):
+    check(lib.vdn_colsum(ptr(dy), ptr(db), C.c_long(P), Cc, stream_ptr()), "vdn_colsum")
+
+
+def add_bf16(a, b, out):
+    check(lib.vdn_add_bf16(ptr(a), ptr(b), ptr(out), C.c_long(a.numel()), stream_ptr()), "vdn_add_bf16")
+
+
+def adam_ema(p, g, m, v, ema, hp):
+    check(lib.vdn_adam_ema(ptr(p), ptr(g), ptr(m), ptr(v), ptr(ema), ptr(hp), C.c_long(p.numel()), stream_ptr()),
+          "vdn_adam_ema")
