@@ -6,6 +6,8 @@
 //   (trainer.py:367-382).
 #include <algorithm>
 
+#include <curand_kernel.h>
+
 #include "vdn_common.cuh"
 #include "vdn_host.h"
 
@@ -563,6 +565,25 @@ __global__ void adam_ema_kernel(float* __restrict__ p, const float* __restrict__
   }
 }
 
+// Standard normal draws (Philox4x32-10 counter RNG): element i of stream (seed, subsequence) is a pure
+// function of (seed, subsequence, i), so results do not depend on the launch geometry or on how a
+// sample batch is sharded over GPUs (gaussian_diffusion.py:254,309,445 draw these with jax.random).
+__global__ void randn_kernel(float* __restrict__ out, long n, unsigned long long seed, unsigned long long subseq,
+                             unsigned long long elem_offset) {
+  const long n4 = (n + 3) / 4;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
+    curandStatePhilox4_32_10_t st;
+    // one Philox counter block (4 x 32-bit outputs) per group of 4 elements; `offset` counts outputs
+    curand_init(seed, subseq, 4ull * (unsigned long long)(elem_offset / 4 + i), &st);
+    const float4 z = curand_normal4(&st);
+    const long b = i * 4;
+    if (b + 0 < n) out[b + 0] = z.x;
+    if (b + 1 < n) out[b + 1] = z.y;
+    if (b + 2 < n) out[b + 2] = z.z;
+    if (b + 3 < n) out[b + 3] = z.w;
+  }
+}
+
 static int ew_grid(long n, int threads = 256) {
   return (int)std::max<long>(1, std::min<long>((n + threads - 1) / threads, (long)num_sms() * 8));
 }
@@ -578,7 +599,11 @@ extern "C" int vdn_init_conv_fwd(const float* x, const float* w, const float* bi
               "init_conv_fwd: unsupported shape H=%d W=%d Cout=%d ks=%d Cin=%d", H, W, Cout, ks, Cin);
   const int hs = kIT + ks - 1;
   const size_t smem = (size_t)(ks * ks * Cin * Cout + Cin * hs * hs) * sizeof(float);
-  cudaFuncSetAttribute(init_conv_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024));
+  static bool cfg = false;
+  if (!cfg) {
+    cudaFuncSetAttribute(init_conv_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    cfg = true;
+  }
   init_conv_fwd_kernel<<<dim3((H / kIT) * (W / kIT), B * F), 256, smem, ST(stream)>>>(
       x, w, bias, reinterpret_cast<bf16*>(out), B, Cin, F, H, W, Cout, ks);
   return check_launch("init_conv_fwd");
@@ -686,7 +711,7 @@ extern "C" int vdn_p_sample(const float* x, const float* eps, const float* z, co
 }
 
 extern "C" int vdn_colsum(const void* dy, float* db, long P, int C, void* stream) {
-  VDN_REQUIRE(C % 8 == 0 && C / 8 <= 256 && 256 % (C / 8) == 0, VDN_E_SHAPE, "colsum: C=%d unsupported", C);
+  VDN_REQUIRE(C % 8 == 0 && C / 8 <= 256, VDN_E_SHAPE, "colsum: C=%d unsupported", C);
   const int pl_n = 256 / (C / 8);
   const int grid = (int)std::max<long>(1, std::min<long>((P + pl_n * 16 - 1) / (pl_n * 16), num_sms() * 4));
   colsum_kernel<<<grid, 256, 256 * 8 * sizeof(float), ST(stream)>>>(reinterpret_cast<const bf16*>(dy), db, P, C);
@@ -699,6 +724,13 @@ extern "C" int vdn_add_bf16(const void* a, const void* b, void* out, long n, voi
                                                           reinterpret_cast<const bf16*>(b),
                                                           reinterpret_cast<bf16*>(out), n / 8);
   return check_launch("add_bf16");
+}
+
+extern "C" int vdn_randn(float* out, long n, unsigned long long seed, unsigned long long subseq,
+                         unsigned long long elem_offset, void* stream) {
+  VDN_REQUIRE(out && n > 0 && elem_offset % 4 == 0, VDN_E_SHAPE, "randn: bad args (elem_offset must be a multiple of 4)");
+  randn_kernel<<<ew_grid((n + 3) / 4), 256, 0, ST(stream)>>>(out, n, seed, subseq, elem_offset);
+  return check_launch("randn");
 }
 
 extern "C" int vdn_adam_ema(float* p, const float* g, float* m, float* v, float* ema, const float* hp_dev, long n,

@@ -1,0 +1,718 @@
+"""Host-side execution engine for the Unet3D hot path.
+
+Mirrors the module tree of the reference (unet3d.py:58-252, modules.py) as a static plan for one
+(B, F, H, W): every activation / saved tensor is allocated once (stable addresses, so a whole
+forward+backward can be captured in a CUDA graph), and forward / backward are sequences of C-ABI
+kernel launches (include/vdn.h) on the current CUDA stream. torch is used for device memory only.
+
+Effective graph = SURVEY.md Appendix A.1 (PreNorm's LayerNorm result is discarded, attention sees
+the un-normalised input and no mask / bias: modules.py:146-148).
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import ops
+from .ops import TAPS_1x1, TAPS_3x3, TAPS_4x4, VDN_TAP_DOWN, VDN_TAP_UNIT, VDN_TAP_UP
+
+HEADS = 8
+DIM_HEAD = 32
+HD = HEADS * DIM_HEAD  # 256; also SLA's heads * D (unet3d.py:174,225)
+GROUPS = 8
+BF16 = torch.bfloat16
+F32 = torch.float32
+
+
+# ------------------------------------------------------------------------------------------
+# parameters
+# ------------------------------------------------------------------------------------------
+def internal_param_spec(dim: int, channels: int, dim_mults=(1, 2, 4, 8), init_kernel_size: int = 7,
+                        out_dim: Optional[int] = None) -> List[Tuple[str, tuple]]:
+    """Internal flat layout. q/k/v kernels are stored fused as [C][768] (q | k | v) so that one
+    GEMM produces qkv; state_dict()/load_state_dict() translate to the reference's nnx paths."""
+    s: List[Tuple[str, tuple]] = []
+    td = dim * 4
+    out_dim = channels if out_dim is None else out_dim
+
+    def mha(p, c):
+        s.extend([(p + ".norm.scale", (c,)), (p + ".norm.bias", (c,)), (p + ".qkv.kernel", (c, 3 * HD)),
+                  (p + ".qkv.bias", (3 * HD,)), (p + ".out.kernel", (HD, c)), (p + ".out.bias", (c,))])
+
+    def sla(p, c):
+        s.extend([(p + ".norm.scale", (c,)), (p + ".norm.bias", (c,)), (p + ".qkv.kernel", (c, 3 * HD)),
+                  (p + ".to_out.kernel", (HD, c))])
+
+    def resnet(p, cin, cout, time=True):
+        if time:
+            s.extend([(p + ".mlp.kernel", (td, 2 * cout)), (p + ".mlp.bias", (2 * cout,))])
+        s.extend([(p + ".norm_1.scale", (2 * cout,)), (p + ".norm_1.bias", (2 * cout,))])
+        for b, ci in (("block_1", cin), ("block_2", cout)):
+            s.extend([(f"{p}.{b}.proj.kernel", (9, ci, cout)), (f"{p}.{b}.proj.bias", (cout,)),
+                      (f"{p}.{b}.norm.scale", (cout,)), (f"{p}.{b}.norm.bias", (cout,))])
+        if cin != cout:
+            s.extend([(p + ".res_conv.kernel", (1, cin, cout)), (p + ".res_conv.bias", (cout,))])
+        s.extend([(p + ".norm_2.scale", (cout,)), (p + ".norm_2.bias", (cout,))])
+
+    k = init_kernel_size
+    s.append(("time_rel_pos_bias.embedding", (32, HEADS)))
+    s.extend([("init_conv.kernel", (k * k, channels, dim)), ("init_conv.bias", (dim,))])
+    mha("init_temporal_attn", dim)
+    s.extend([("time_mlp.1.kernel", (dim, td)), ("time_mlp.1.bias", (td,)),
+              ("time_mlp.3.kernel", (td, td)), ("time_mlp.3.bias", (td,))])
+    dims = [dim] + [dim * m for m in dim_mults]
+    in_out = list(zip(dims[:-1], dims[1:]))
+    n = len(in_out)
+    for l, (ci, co) in enumerate(in_out):
+        resnet(f"downs.{l}.0", ci, co)
+        resnet(f"downs.{l}.1", co, co)
+        sla(f"downs.{l}.2", co)
+        mha(f"downs.{l}.3", co)
+        if l < n - 1:
+            s.extend([(f"downs.{l}.4.kernel", (16, co, co)), (f"downs.{l}.4.bias", (co,))])
+    mid = dims[-1]
+    resnet("mid_block1", mid, mid)
+    mha("mid_spatial_attn", mid)
+    mha("mid_temporal_attn", mid)
+    resnet("mid_block2", mid, mid)
+    for i, (ci, co) in enumerate(reversed(in_out)):
+        resnet(f"ups.{i}.0", co * 2, ci)
+        resnet(f"ups.{i}.1", ci, ci)
+        sla(f"ups.{i}.2", ci)
+        mha(f"ups.{i}.3", ci)
+        if i < n - 1:
+            s.extend([(f"ups.{i}.4.kernel", (16, ci, ci)), (f"ups.{i}.4.bias", (ci,))])
+    resnet("final_conv.0", dim * 2, dim, time=False)
+    s.extend([("final_conv.1.kernel", (dim, out_dim)), ("final_conv.1.bias", (out_dim,))])
+
+    # "late" parameters (their gradients are completed by the LAST backward stage) go first, the rest
+    # stays in execution order: see UnetEngine.backward_stages / grad_slices.
+    return [e for e in s if is_late_param(e[0])] + [e for e in s if not is_late_param(e[0])]
+
+
+def is_late_param(name: str) -> bool:
+    return name.startswith(("time_", "init_")) or ".mlp." in name or ".norm_1." in name
+
+
+class ParamStore:
+    """Flat fp32 master parameters (+ gradients) with named views; 16-byte aligned segments."""
+
+    def __init__(self, spec: Sequence[Tuple[str, tuple]], device, with_grad: bool):
+        self.spec = list(spec)
+        self.offsets: Dict[str, Tuple[int, tuple]] = {}
+        off = 0
+        for name, shape in self.spec:
+            n = 1
+            for d in shape:
+                n *= d
+            self.offsets[name] = (off, shape)
+            off += (n + 3) // 4 * 4
+        self.total = off
+        self.flat = torch.zeros(off, dtype=F32, device=device)
+        self.grad = torch.zeros(off, dtype=F32, device=device) if with_grad else None
+
+    def view(self, name: str) -> torch.Tensor:
+        off, shape = self.offsets[name]
+        n = 1
+        for d in shape:
+            n *= d
+        return self.flat[off:off + n].view(shape)
+
+    def gview(self, name: str) -> torch.Tensor:
+        off, shape = self.offsets[name]
+        n = 1
+        for d in shape:
+            n *= d
+        return self.grad[off:off + n].view(shape)
+
+
+# ------------------------------------------------------------------------------------------
+# building blocks
+# ------------------------------------------------------------------------------------------
+class _Pool:
+    """Exact-shape scratch pool. The get/put sequence of a step is static, so after the first eager
+    step no allocation happens and buffer addresses are stable (CUDA-graph safe)."""
+
+    def __init__(self, device):
+        self.device = device
+        self.free: Dict[tuple, List[torch.Tensor]] = {}
+
+    def get(self, shape, dtype=BF16) -> torch.Tensor:
+        key = (tuple(shape), dtype)
+        lst = self.free.get(key)
+        if lst:
+            return lst.pop()
+        return torch.empty(shape, dtype=dtype, device=self.device)
+
+    def put(self, t: torch.Tensor) -> None:
+        self.free.setdefault((tuple(t.shape), t.dtype), []).append(t)
+
+
+class GemmConv:
+    """A conv / projection with its packed tensor-core operands (forward and dgrad)."""
+
+    def __init__(self, eng: "UnetEngine", wname: str, bname: Optional[str], taps, n_src: int, c_src: int, cout: int):
+        self.eng, self.taps, self.n_src, self.c_src, self.cout = eng, list(taps), n_src, c_src, cout
+        self.cin = n_src * c_src
+        st = eng.store
+        self.w = st.view(wname)
+        self.bias = st.view(bname) if bname else None
+        nt = len(self.taps)
+        self.wp = torch.empty(cout, nt * self.cin, dtype=BF16, device=eng.device)
+        self.wd = torch.empty(self.cin, nt * cout, dtype=BF16, device=eng.device) if eng.training else None
+        if eng.training:
+            self.dw = st.gview(wname)
+            self.dbias = st.gview(bname) if bname else None
+        self.flip = [nt - 1 - t for t in range(nt)]
+        eng.packers.append(self.repack)
+
+    def repack(self):
+        nt = len(self.taps)
+        ops.pack_weight(self.w, self.wp, nt, self.cin, self.cout, 0)
+        if self.wd is not None:
+            ops.pack_weight(self.w, self.wd, nt, self.cin, self.cout, 1, self.flip)
+
+    def fwd(self, srcs, out, residual=None, gn_sums=None, rows_per_sample=0, out_dtype=BF16):
+        return ops.tapgemm(VDN_TAP_UNIT, srcs, self.wp, self.taps, bias=self.bias, residual=residual, out=out,
+                           gn_sums=gn_sums, gn_groups=GROUPS if gn_sums is not None else 0,
+                           rows_per_sample=rows_per_sample, out_dtype=out_dtype)
+
+    def dgrad(self, dy, outs, residuals=None):
+        """dsrc(s) = dy (*) W^T (+ residuals). outs: 1 or 2 tensors (concat split)."""
+        r = residuals or [None] * len(outs)
+        if len(outs) == 1:
+            ops.tapgemm(VDN_TAP_UNIT, [dy], self.wd, self.taps, residual=r[0], out=outs[0])
+        else:
+            ops.tapgemm(VDN_TAP_UNIT, [dy], self.wd, self.taps, residual=r[0], residual2=r[1], out=outs[0],
+                        out2=outs[1], split_col=self.c_src)
+
+    def wgrad(self, srcs, dy):
+        ops.wgrad(VDN_TAP_UNIT, srcs, dy, self.dw, self.taps)
+        if self.dbias is not None:
+            ops.colsum(dy, self.dbias, dy.numel() // self.cout, self.cout)
+
+
+class ResBlock:
+    """ResnetBlock (modules.py:182-243)."""
+
+    def __init__(self, eng, prefix, n_src, c_src, cout, n_img, H, W, time=True):
+        self.eng, self.prefix = eng, prefix
+        self.n_src, self.c_src, self.cout, self.n_img, self.H, self.W = n_src, c_src, cout, n_img, H, W
+        cin = n_src * c_src
+        st = eng.store
+        self.conv1 = GemmConv(eng, prefix + ".block_1.proj.kernel", prefix + ".block_1.proj.bias", TAPS_3x3, n_src, c_src, cout)
+        self.conv2 = GemmConv(eng, prefix + ".block_2.proj.kernel", prefix + ".block_2.proj.bias", TAPS_3x3, 1, cout, cout)
+        self.res = (GemmConv(eng, prefix + ".res_conv.kernel", prefix + ".res_conv.bias", TAPS_1x1, n_src, c_src, cout)
+                    if cin != cout else None)
+        self.p = {k: st.view(f"{prefix}.{k}") for k in ("block_1.norm.scale", "block_1.norm.bias", "block_2.norm.scale",
+                                                         "block_2.norm.bias", "norm_2.scale", "norm_2.bias")}
+        if eng.training:
+            self.g = {k: st.gview(f"{prefix}.{k}") for k in self.p}
+        shape = (n_img, H, W, cout)
+        self.a_raw, self.a, self.b_raw, self.out = (eng.new(shape) for _ in range(4))
+        self.s = eng.new(shape) if self.res is not None else None
+        self.sums1, self.sums2 = eng.new_gn_sums(), eng.new_gn_sums()
+        self.rows = n_img // eng.B * H * W
+        self.ss_off = eng.register_time_head(prefix, cout) if time else None
+        self.srcs = None
+
+    def _ss(self):
+        if self.ss_off is None:
+            return None
+        return self.eng.ss[:, self.ss_off:self.ss_off + 2 * self.cout]
+
+    def forward(self, srcs):
+        eng, B = self.eng, self.eng.B
+        self.srcs = list(srcs)
+        self.conv1.fwd(srcs, self.a_raw, gn_sums=self.sums1, rows_per_sample=self.rows)
+        ops.gn_silu_fwd(self.a_raw, self.sums1, self.p["block_1.norm.scale"], self.p["block_1.norm.bias"], self._ss(),
+                        self.a, B, self.rows, self.cout)
+        self.conv2.fwd([self.a], self.b_raw, gn_sums=self.sums2, rows_per_sample=self.rows)
+        if self.res is not None:
+            self.res.fwd(srcs, self.s)
+            s = self.s
+        else:
+            s = srcs[0]
+        ops.resblock_tail_fwd(self.b_raw, self.sums2, self.p["block_2.norm.scale"], self.p["block_2.norm.bias"], s,
+                              self.p["norm_2.scale"], self.p["norm_2.bias"], self.out, B, self.rows, self.cout)
+        return self.out
+
+    def backward(self, dout, extra=None):
+        """Returns the list of source gradients (freshly pooled buffers; caller releases). `extra`
+        (optional) is added to the first source's gradient."""
+        eng, B, C = self.eng, self.eng.B, self.cout
+        pool = eng.pool
+        shape = (self.n_img, self.H, self.W, C)
+        P = self.n_img * self.H * self.W
+        s = self.s if self.res is not None else self.srcs[0]
+        ds = pool.get(shape)
+        ops.ln_bwd(s, dout, self.p["norm_2.scale"], ds, self.g["norm_2.scale"], self.g["norm_2.bias"], P, C)
+        T = pool.get((B, C, 2), F32)
+        db_raw = pool.get(shape)
+        ops.gn_silu_bwd(dout, self.b_raw, self.sums2, self.p["block_2.norm.scale"], self.p["block_2.norm.bias"], None,
+                        T, db_raw, self.g["block_2.norm.scale"], self.g["block_2.norm.bias"], None, B, self.rows, C)
+        self.conv2.wgrad([self.a], db_raw)
+        da = pool.get(shape)
+        self.conv2.dgrad(db_raw, [da])
+        pool.put(db_raw)
+        da_raw = pool.get(shape)
+        dss = eng.dss[:, self.ss_off:self.ss_off + 2 * C] if self.ss_off is not None else None
+        ops.gn_silu_bwd(da, self.a_raw, self.sums1, self.p["block_1.norm.scale"], self.p["block_1.norm.bias"],
+                        self._ss(), T, da_raw, self.g["block_1.norm.scale"], self.g["block_1.norm.bias"], dss, B,
+                        self.rows, C)
+        pool.put(da)
+        pool.put(T)
+        self.conv1.wgrad(self.srcs, da_raw)
+        sshape = (self.n_img, self.H, self.W, self.c_src)
+        dsrc = [pool.get(sshape) for _ in range(self.n_src)]
+        if self.res is not None:
+            self.res.wgrad(self.srcs, ds)
+            self.conv1.dgrad(da_raw, dsrc)
+            self.res.dgrad(ds, dsrc, residuals=dsrc)  # in-place accumulate
+        else:
+            self.conv1.dgrad(da_raw, dsrc, residuals=[ds])
+        pool.put(ds)
+        pool.put(da_raw)
+        if extra is not None:
+            ops.add_bf16(dsrc[0], extra, dsrc[0])
+        return dsrc
+
+
+class MHABlock:
+    """x + MultiheadAttention(x) over frames (mode 0) or over pixels of a frame (mode 1)
+    (unet3d.py:86-96,118-120,196-208; modules.py:247-326 without mask / bias)."""
+
+    def __init__(self, eng, prefix, C, n_img, H, W, mode):
+        self.eng, self.C, self.n_img, self.H, self.W, self.mode = eng, C, n_img, H, W, mode
+        self.qkv_proj = GemmConv(eng, prefix + ".qkv.kernel", prefix + ".qkv.bias", TAPS_1x1, 1, C, 3 * HD)
+        self.out_proj = GemmConv(eng, prefix + ".out.kernel", prefix + ".out.bias", TAPS_1x1, 1, HD, C)
+        self.qkv = eng.new((n_img, H, W, 3 * HD))
+        self.o = eng.new((n_img, H, W, HD))
+        self.lse = eng.new((n_img * H * W, HEADS), F32)
+        self.out = eng.new((n_img, H, W, C))
+        self.x = None
+
+    def forward(self, x):
+        eng = self.eng
+        self.x = x
+        self.qkv_proj.fwd([x], self.qkv)
+        ops.mha_core_fwd(self.qkv, self.o, self.lse, self.mode, eng.B, self.n_img // eng.B, self.H * self.W)
+        self.out_proj.fwd([self.o], self.out, residual=x)
+        return self.out
+
+    def backward(self, dout):
+        eng, pool = self.eng, self.eng.pool
+        self.out_proj.wgrad([self.o], dout)
+        do = pool.get(self.o.shape)
+        self.out_proj.dgrad(dout, [do])
+        dqkv = pool.get(self.qkv.shape)
+        D = pool.get(self.lse.shape, F32)
+        ops.mha_core_bwd(self.qkv, self.o, do, self.lse, D, dqkv, self.mode, eng.B, self.n_img // eng.B, self.H * self.W)
+        pool.put(do)
+        pool.put(D)
+        self.qkv_proj.wgrad([self.x], dqkv)
+        dx = pool.get(self.x.shape)
+        self.qkv_proj.dgrad(dqkv, [dx], residuals=[dout])
+        pool.put(dqkv)
+        return dx
+
+
+class SLABlock:
+    """x + SpatialLinearAttention(x) (modules.py:64-129; unet3d.py:170-178)."""
+
+    def __init__(self, eng, prefix, C, n_img, H, W):
+        self.eng, self.C, self.n_img, self.H, self.W = eng, C, n_img, H, W
+        self.qkv_proj = GemmConv(eng, prefix + ".qkv.kernel", None, TAPS_1x1, 1, C, 3 * HD)
+        self.out_proj = GemmConv(eng, prefix + ".to_out.kernel", None, TAPS_1x1, 1, HD, C)
+        N = H * W
+        self.qkv = eng.new((n_img, H, W, 3 * HD))
+        self.tok = eng.new((n_img, H, W, HD))
+        self.ctx = eng.new((n_img, HEADS, 32, 32), F32)
+        self.kstat = eng.new((n_img, HEADS, 2, 32), F32)
+        self.ws = eng.shared_ws(ops.sla_workspace_floats(n_img, N))
+        self.out = eng.new((n_img, H, W, C))
+        self.x = None
+
+    def forward(self, x):
+        self.x = x
+        self.qkv_proj.fwd([x], self.qkv)
+        ops.sla_core_fwd(self.qkv, self.tok, self.ctx, self.kstat, self.ws, self.n_img, self.H * self.W)
+        self.out_proj.fwd([self.tok], self.out, residual=x)
+        return self.out
+
+    def backward(self, dout):
+        pool = self.eng.pool
+        self.out_proj.wgrad([self.tok], dout)
+        dtok = pool.get(self.tok.shape)
+        self.out_proj.dgrad(dout, [dtok])
+        dqkv = pool.get(self.qkv.shape)
+        dctx = pool.get(self.ctx.shape, F32)
+        ops.sla_core_bwd(self.qkv, dtok, self.ctx, self.kstat, dctx, dqkv, self.n_img, self.H * self.W)
+        pool.put(dtok)
+        pool.put(dctx)
+        self.qkv_proj.wgrad([self.x], dqkv)
+        dx = pool.get(self.x.shape)
+        self.qkv_proj.dgrad(dqkv, [dx], residuals=[dout])
+        pool.put(dqkv)
+        return dx
+
+
+class DownConv:
+    """nnx.Conv(dim,dim,(1,4,4),(1,2,2)) SAME (utils.py:125)."""
+
+    def __init__(self, eng, prefix, C, n_img, H, W):
+        self.eng, self.C, self.n_img, self.H, self.W = eng, C, n_img, H, W
+        st = eng.store
+        self.w, self.bias = st.view(prefix + ".kernel"), st.view(prefix + ".bias")
+        self.wp = torch.empty(C, 16 * C, dtype=BF16, device=eng.device)
+        self.out = eng.new((n_img, H // 2, W // 2, C))
+        self.cls = []
+        if eng.training:
+            self.dw, self.dbias = st.gview(prefix + ".kernel"), st.gview(prefix + ".bias")
+            for py in range(2):
+                for px in range(2):
+                    kys, kxs = (1 - py, 3 - py), (1 - px, 3 - px)
+                    shifts = [((py + 1 - ky) // 2, (px + 1 - kx) // 2) for ky in kys for kx in kxs]
+                    kidx = [ky * 4 + kx for ky in kys for kx in kxs]
+                    self.cls.append((py, px, shifts, kidx, torch.empty(C, 4 * C, dtype=BF16, device=eng.device)))
+        eng.packers.append(self.repack)
+        self.x = None
+
+    def repack(self):
+        ops.pack_weight(self.w, self.wp, 16, self.C, self.C, 0)
+        for _, _, _, kidx, wd in self.cls:
+            ops.pack_weight(self.w, wd, 4, self.C, self.C, 1, kidx)
+
+    def forward(self, x):
+        self.x = x
+        ops.tapgemm(VDN_TAP_DOWN, [x], self.wp, TAPS_4x4, bias=self.bias, out=self.out)
+        return self.out
+
+    def backward(self, dy, acc):
+        """acc (same shape as x) += dgrad(dy); returns acc."""
+        ops.wgrad(VDN_TAP_DOWN, [self.x], dy, self.dw, TAPS_4x4)
+        ops.colsum(dy, self.dbias, dy.numel() // self.C, self.C)
+        for py, px, shifts, _, wd in self.cls:
+            ops.tapgemm(VDN_TAP_UP, [dy], wd, shifts, residual=acc, out=acc, py=py, px=px)
+        return acc
+
+
+class UpConv:
+    """nnx.ConvTranspose(dim,dim,(1,4,4),(1,2,2)) SAME, unflipped kernel (utils.py:113)."""
+
+    def __init__(self, eng, prefix, C, n_img, H, W):
+        self.eng, self.C, self.n_img, self.H, self.W = eng, C, n_img, H, W
+        st = eng.store
+        self.w, self.bias = st.view(prefix + ".kernel"), st.view(prefix + ".bias")
+        self.out = eng.new((n_img, 2 * H, 2 * W, C))
+        self.cls = []
+        for py in range(2):
+            for px in range(2):
+                shifts, kidx = ops.up_class_taps(py, px)
+                self.cls.append((py, px, shifts, kidx, torch.empty(C, 4 * C, dtype=BF16, device=eng.device)))
+        self.wd = None
+        if eng.training:
+            self.dw, self.dbias = st.gview(prefix + ".kernel"), st.gview(prefix + ".bias")
+            self.wd = torch.empty(C, 16 * C, dtype=BF16, device=eng.device)
+        eng.packers.append(self.repack)
+        self.x = None
+
+    def repack(self):
+        for _, _, _, kidx, wp in self.cls:
+            ops.pack_weight(self.w, wp, 4, self.C, self.C, 0, kidx)
+        if self.wd is not None:
+            ops.pack_weight(self.w, self.wd, 16, self.C, self.C, 1, [15 - k for k in range(16)])
+
+    def forward(self, x):
+        self.x = x
+        for py, px, shifts, _, wp in self.cls:
+            ops.tapgemm(VDN_TAP_UP, [x], wp, shifts, bias=self.bias, out=self.out, py=py, px=px)
+        return self.out
+
+    def backward(self, dy):
+        pool = self.eng.pool
+        ops.wgrad(VDN_TAP_UP, [self.x], dy, self.dw, TAPS_4x4)
+        ops.colsum(dy, self.dbias, dy.numel() // self.C, self.C)
+        dx = pool.get(self.x.shape)
+        ops.tapgemm(VDN_TAP_DOWN, [dy], self.wd, TAPS_4x4, out=dx)
+        return dx
+
+
+# ------------------------------------------------------------------------------------------
+# the engine
+# ------------------------------------------------------------------------------------------
+class UnetEngine:
+    def __init__(self, store: ParamStore, *, dim: int, channels: int, dim_mults=(1, 2, 4, 8), init_kernel_size=7,
+                 B: int, F: int, H: int, W: int, training: bool, out_dim: Optional[int] = None):
+        self.store, self.device, self.training = store, store.flat.device, training
+        self.dim, self.channels, self.B, self.F, self.H, self.W = dim, channels, B, F, H, W
+        self.out_dim = channels if out_dim is None else out_dim
+        self.ks = init_kernel_size
+        self.packers = []
+        self.pool = _Pool(self.device)
+        self._gn_slots: List[torch.Tensor] = []
+        self._gn_count = 0
+        self._heads: List[dict] = []
+        self._ss_total = 0
+        self._ws = None
+        self._ws_floats = 0
+        n_img = B * F
+        self.n_img = n_img
+        td = dim * 4
+        self.td = td
+        dims = [dim] + [dim * m for m in dim_mults]
+        in_out = list(zip(dims[:-1], dims[1:]))
+        n = len(in_out)
+        self.n_res = n
+        # count GroupNorm slots first (2 per ResnetBlock) so one buffer can be zeroed per forward
+        n_blocks = 4 * n + 2 + 1
+        self.gn_all = torch.zeros(n_blocks * 2, B, GROUPS, 2, dtype=F32, device=self.device)
+
+        self.h0 = self.new((n_img, H, W, dim))
+        self.init_attn = MHABlock(self, "init_temporal_attn", dim, n_img, H, W, 0)
+        self.downs, self.ups = [], []
+        h, w = H, W
+        for l, (ci, co) in enumerate(in_out):
+            blk = [ResBlock(self, f"downs.{l}.0", 1, ci, co, n_img, h, w),
+                   ResBlock(self, f"downs.{l}.1", 1, co, co, n_img, h, w),
+                   SLABlock(self, f"downs.{l}.2", co, n_img, h, w),
+                   MHABlock(self, f"downs.{l}.3", co, n_img, h, w, 0),
+                   DownConv(self, f"downs.{l}.4", co, n_img, h, w) if l < n - 1 else None]
+            self.downs.append(blk)
+            if l < n - 1:
+                h, w = h // 2, w // 2
+        mid = dims[-1]
+        self.mid1 = ResBlock(self, "mid_block1", 1, mid, mid, n_img, h, w)
+        self.mid_sattn = MHABlock(self, "mid_spatial_attn", mid, n_img, h, w, 1)
+        self.mid_tattn = MHABlock(self, "mid_temporal_attn", mid, n_img, h, w, 0)
+        self.mid2 = ResBlock(self, "mid_block2", 1, mid, mid, n_img, h, w)
+        for i, (ci, co) in enumerate(reversed(in_out)):
+            blk = [ResBlock(self, f"ups.{i}.0", 2, co, ci, n_img, h, w),
+                   ResBlock(self, f"ups.{i}.1", 1, ci, ci, n_img, h, w),
+                   SLABlock(self, f"ups.{i}.2", ci, n_img, h, w),
+                   MHABlock(self, f"ups.{i}.3", ci, n_img, h, w, 0),
+                   UpConv(self, f"ups.{i}.4", ci, n_img, h, w) if i < n - 1 else None]
+            self.ups.append(blk)
+            if i < n - 1:
+                h, w = h * 2, w * 2
+        self.final_block = ResBlock(self, "final_conv.0", 2, dim, dim, n_img, H, W, time=False)
+        self.out = self.new((B, F, H, W, self.out_dim), F32)
+
+        # time embedding buffers + head table
+        st = store
+        self.emb = self.new((B, dim), F32)
+        self.h1 = self.new((B, td), F32)
+        self.t_emb = self.new((B, td), F32)
+        self.ss = self.new((B, max(self._ss_total, 4)), F32)
+        self.e_pre = self.new((B, max(self._ss_total, 4)), F32)
+        if training:
+            self.dss = torch.zeros((B, max(self._ss_total, 4)), dtype=F32, device=self.device)
+            self.de_ws = self.new((B, max(self._ss_total, 4)), F32)
+            self.dt = self.new((B, td), F32)
+            self.dh1_ws = self.new((B, td), F32)
+        entries = []
+        for hd in self._heads:
+            p = hd["prefix"]
+            e = dict(w=st.view(p + ".mlp.kernel"), b=st.view(p + ".mlp.bias"), ln_g=st.view(p + ".norm_1.scale"),
+                     ln_b=st.view(p + ".norm_1.bias"), n_out=2 * hd["cout"], off=hd["off"])
+            if training:
+                e.update(dw=st.gview(p + ".mlp.kernel"), db=st.gview(p + ".mlp.bias"),
+                         dln_g=st.gview(p + ".norm_1.scale"), dln_b=st.gview(p + ".norm_1.bias"))
+            entries.append(e)
+        self.head_table = ops.make_time_head_table(entries, self.device)
+        self.n_heads = len(entries)
+        self.x_in = None
+        self.repack()
+
+    # -- allocation helpers ------------------------------------------------------------------
+    def new(self, shape, dtype=BF16):
+        return torch.empty(shape, dtype=dtype, device=self.device)
+
+    def new_gn_sums(self):
+        t = self.gn_all[self._gn_count]
+        self._gn_count += 1
+        return t
+
+    def shared_ws(self, n_floats):
+        if self._ws is None or n_floats > self._ws_floats:
+            self._ws_floats = max(n_floats, self._ws_floats)
+            self._ws = torch.empty(self._ws_floats, dtype=F32, device=self.device)
+            self._ws_owner = True
+        return _WsRef(self)
+
+    def register_time_head(self, prefix, cout):
+        off = self._ss_total
+        self._heads.append(dict(prefix=prefix, cout=cout, off=off))
+        self._ss_total += 2 * cout
+        return off
+
+    def repack(self):
+        """Refresh every packed bf16 GEMM operand from the fp32 master weights."""
+        for f in self.packers:
+            f()
+
+    # -- forward -----------------------------------------------------------------------------
+    def forward(self, x: torch.Tensor, time: torch.Tensor) -> torch.Tensor:
+        """x fp32 (B,C,F,H,W), time int32 (B,) -> fp32 (B,F,H,W,C) (unet3d.py:262-387)."""
+        st = self.store
+        B, Fr, H, W = self.B, self.F, self.H, self.W
+        self.x_in = x
+        self.gn_all.zero_()
+        ops.init_conv_fwd(x, st.view("init_conv.kernel"), st.view("init_conv.bias"), self.h0, B, self.channels, Fr, H,
+                          W, self.dim, self.ks)
+        h = self.init_attn.forward(self.h0)
+        r = h
+        ops.time_mlp_fwd(time, st.view("time_mlp.1.kernel"), st.view("time_mlp.1.bias"), st.view("time_mlp.3.kernel"),
+                         st.view("time_mlp.3.bias"), self.emb, self.h1, self.t_emb, B, self.dim)
+        ops.time_heads_fwd(self.t_emb, self.head_table, self.n_heads, self.e_pre, self.ss, B, self.td)
+        skips = []
+        for b1, b2, sla, mha, down in self.downs:
+            h = b1.forward([h])
+            h = b2.forward([h])
+            h = sla.forward(h)
+            h = mha.forward(h)
+            skips.append(h)
+            if down is not None:
+                h = down.forward(h)
+        h = self.mid1.forward([h])
+        h = self.mid_sattn.forward(h)
+        h = self.mid_tattn.forward(h)
+        h = self.mid2.forward([h])
+        for b1, b2, sla, mha, up in self.ups:
+            h = b1.forward([h, skips.pop()])
+            h = b2.forward([h])
+            h = sla.forward(h)
+            h = mha.forward(h)
+            if up is not None:
+                h = up.forward(h)
+        h = self.final_block.forward([h, r])
+        self.h_last = h
+        P = self.n_img * H * W
+        ops.final_conv_fwd(h, st.view("final_conv.1.kernel"), st.view("final_conv.1.bias"), self.out, P, self.dim,
+                           self.out_dim)
+        return self.out
+
+    # -- backward ----------------------------------------------------------------------------
+    # Gradient completion order (reverse execution): final -> ups.{n-1..0} -> mid -> downs.{n-1..0} -> late
+    # ("late" = init conv / init attention / time MLP / all time heads, finished by the last stage).
+    # The flat parameter layout is [late | downs.0.. | mid | ups.0.. | final], so each stage completes one
+    # contiguous slice of store.grad; trainer.py reduces those slices while later stages still run.
+    def backward_stages(self):
+        """List of (stage_name, fn). fn() enqueues that stage's kernels; stages must run in order."""
+        assert self.training
+        st, pool = self.store, self.pool
+        P = self.n_img * self.H * self.W
+        S = {}
+        n = self.n_res
+
+        def step(mod_backward, *a, **k):
+            d2 = mod_backward(S["d"], *a, **k)
+            if isinstance(d2, (list, tuple)):
+                (d2,) = d2
+            pool.put(S["d"])
+            S["d"] = d2
+
+        def st_final():
+            self.dss.zero_()
+            dh = pool.get(self.h_last.shape)
+            ops.final_conv_bwd(self.h_last, S["dout"], st.view("final_conv.1.kernel"), dh,
+                               st.gview("final_conv.1.kernel"), st.gview("final_conv.1.bias"), P, self.dim, self.out_dim)
+            S["d"], S["dr"] = self.final_block.backward(dh)
+            pool.put(dh)
+            S["dskips"] = [None] * n
+
+        def make_up(i):
+            def f():
+                b1, b2, sla, mha, up = self.ups[i]
+                if up is not None:
+                    step(up.backward)
+                step(mha.backward)
+                step(sla.backward)
+                step(b2.backward)
+                d2, dsk = b1.backward(S["d"])
+                pool.put(S["d"])
+                S["d"] = d2
+                S["dskips"][n - 1 - i] = dsk
+            return f
+
+        def st_mid():
+            step(self.mid2.backward)
+            step(self.mid_tattn.backward)
+            step(self.mid_sattn.backward)
+            step(self.mid1.backward, extra=S["dskips"][n - 1])
+            pool.put(S["dskips"][n - 1])
+
+        def make_down(l):
+            def f():
+                b1, b2, sla, mha, down = self.downs[l]
+                if down is not None:
+                    acc = down.backward(S["d"], S["dskips"][l])
+                    pool.put(S["d"])
+                    S["d"] = acc
+                step(mha.backward)
+                step(sla.backward)
+                step(b2.backward)
+                step(b1.backward, extra=S["dr"] if l == 0 else None)
+            return f
+
+        def st_late():
+            pool.put(S["dr"])
+            step(self.init_attn.backward)
+            ops.init_conv_wgrad(self.x_in, S["d"], st.gview("init_conv.kernel"), st.gview("init_conv.bias"), self.B,
+                                self.channels, self.F, self.H, self.W, self.dim, self.ks)
+            pool.put(S["d"])
+            ops.time_heads_bwd(self.t_emb, self.head_table, self.n_heads, self.e_pre, self.dss, self.de_ws, self.dt,
+                               self.B, self.td)
+            ops.time_mlp_bwd(self.dt, self.emb, self.h1, st.view("time_mlp.3.kernel"), st.gview("time_mlp.1.kernel"),
+                             st.gview("time_mlp.1.bias"), st.gview("time_mlp.3.kernel"), st.gview("time_mlp.3.bias"),
+                             self.dh1_ws, self.B, self.dim)
+
+        stages = [("final", st_final)]
+        stages += [(f"ups.{i}", make_up(i)) for i in reversed(range(n))]
+        stages += [("mid", st_mid)]
+        stages += [(f"downs.{l}", make_down(l)) for l in reversed(range(n))]
+        stages += [("late", st_late)]
+        self._bw_state = S
+        return stages
+
+    def backward(self, dout: torch.Tensor) -> None:
+        """dout fp32 (B,F,H,W,C): accumulates every parameter gradient into store.grad (+=)."""
+        if not hasattr(self, "_stages"):
+            self._stages = self.backward_stages()
+        self._bw_state["dout"] = dout
+        for _, fn in self._stages:
+            fn()
+
+    def grad_slices(self):
+        """{stage_name: (begin, end)} offsets into store.grad completed by each backward stage."""
+        offs = self.store.offsets
+        names = [nm for nm, _ in self.store.spec if not is_late_param(nm)]
+
+        def first(prefix):
+            for nm in names:
+                if nm.startswith(prefix):
+                    return offs[nm][0]
+            raise KeyError(prefix)
+
+        n = self.n_res
+        marks = [("late", 0)]
+        marks += [(f"downs.{l}", first(f"downs.{l}.")) for l in range(n)]
+        marks += [("mid", first("mid_block1."))]
+        marks += [(f"ups.{i}", first(f"ups.{i}.")) for i in range(n)]
+        marks += [("final", first("final_conv."))]
+        out = {}
+        for j, (nm, b) in enumerate(marks):
+            e = marks[j + 1][1] if j + 1 < len(marks) else self.store.total
+            out[nm] = (b, e)
+        return out
+
+
+class _WsRef:
+    """Late-bound reference to the engine's shared workspace (it may grow while the plan is built)."""
+
+    def __init__(self, eng):
+        self.eng = eng
+
+    def data_ptr(self):
+        return self.eng._ws.data_ptr()

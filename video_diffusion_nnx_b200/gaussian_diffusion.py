@@ -1,0 +1,223 @@
+"""GaussianDiffusion with the reference's method surface (gaussian_diffusion.py:53-65 and
+:120-502), executed by the sm_100a kernels behind include/vdn.h.
+
+`key` arguments: the reference threads jax.random PRNG keys; here a key is an integer seed (or a
+`Key`), consumed by a counter-based Philox normal generator (csrc/misc.cu) so that every draw is a
+pure function of (seed, stream, element index) - independent of how a batch is sharded over GPUs.
+JAX's threefry streams cannot be reproduced without JAX, so parity tests pass t / noise explicitly.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import ops
+
+SCHEDULE_NAMES = ("alphas_cumprod", "sqrt_alphas_cumprod", "sqrt_one_minus_alphas_cumprod",
+                  "log_one_minus_alphas_cumprod", "sqrt_recip_alphas_cumprod", "sqrt_recipm1_alphas_cumprod",
+                  "posterior_variance", "posterior_log_variance_clipped", "posterior_mean_coef1",
+                  "posterior_mean_coef2")
+
+
+def cosine_beta_schedule(timesteps: int, s: float = 0.008) -> np.ndarray:
+    """utils.py:241-256, in float32 (the reference runs with jax x64 disabled)."""
+    f = np.float32
+    x = np.linspace(0, timesteps, timesteps + 1, dtype=f)
+    ac = np.cos(((x / f(timesteps)) + f(s)) / f(1 + s) * f(math.pi) * f(0.5)).astype(f) ** 2
+    ac = ac / ac[0]
+    return np.clip(f(1) - (ac[1:] / ac[:-1]), f(0), f(0.9999)).astype(f)
+
+
+def make_schedule(timesteps: int) -> Dict[str, np.ndarray]:
+    """The ten float32 tables of gaussian_diffusion.py:77-98."""
+    f = np.float32
+    betas = cosine_beta_schedule(timesteps)
+    alphas = f(1) - betas
+    ac = np.cumprod(alphas, axis=0, dtype=f)
+    ac_prev = np.concatenate([np.ones(1, f), ac[:-1]])
+    pv = betas * (f(1) - ac_prev) / (f(1) - ac)
+    return {
+        "alphas_cumprod": ac,
+        "sqrt_alphas_cumprod": np.sqrt(ac),
+        "sqrt_one_minus_alphas_cumprod": np.sqrt(f(1) - ac),
+        "log_one_minus_alphas_cumprod": np.log(f(1) - ac),
+        "sqrt_recip_alphas_cumprod": np.sqrt(f(1) / ac),
+        "sqrt_recipm1_alphas_cumprod": np.sqrt(f(1) / ac - f(1)),
+        "posterior_variance": pv,
+        "posterior_log_variance_clipped": np.log(np.maximum(pv, f(1e-20))),
+        "posterior_mean_coef1": betas * np.sqrt(ac_prev) / (f(1) - ac),
+        "posterior_mean_coef2": (f(1) - ac_prev) * np.sqrt(alphas) / (f(1) - ac),
+    }
+
+
+class Key:
+    """Minimal stand-in for a jax PRNG key: (seed, stream counter)."""
+
+    def __init__(self, seed: int, stream: int = 0):
+        self.seed, self.stream = int(seed), int(stream)
+
+    def split(self, n: int = 2):
+        return [Key(self.seed, self.stream * 1000003 + i + 1) for i in range(n)]
+
+
+def as_key(key) -> Key:
+    return key if isinstance(key, Key) else Key(int(key))
+
+
+class GaussianDiffusion:
+    def __init__(self, denoise_fn, *, image_size: int, num_frames: int, text_use_bert_cls: bool = False,
+                 channels: int = 3, timesteps: int = 1000, loss_type: str = "l1", use_dynamic_thres: bool = False,
+                 dynamic_thres_percentile: float = 0.9):
+        if use_dynamic_thres:
+            raise NotImplementedError("dynamic thresholding (off in every reference config) is out of scope")
+        if loss_type not in ("l1", "l2"):
+            raise ValueError(f"Unsupported loss type: {loss_type}")
+        self.denoise_fn = denoise_fn
+        self.image_size, self.num_frames, self.channels = image_size, num_frames, channels
+        self.loss_type = loss_type
+        self.text_use_bert_cls = text_use_bert_cls
+        self.use_dynamic_thres = use_dynamic_thres
+        self.dynamic_thres_percentile = dynamic_thres_percentile
+        self.num_timesteps = int(timesteps)
+        self._host_tables = make_schedule(self.num_timesteps)
+        self._dev_tables: Dict[str, torch.Tensor] = {}
+
+    # schedule tables as attributes, like the reference's nnx.Variables
+    def __getattr__(self, name):
+        if name in SCHEDULE_NAMES:
+            return self.table(name)
+        raise AttributeError(name)
+
+    def table(self, name: str) -> torch.Tensor:
+        if name not in self._dev_tables:
+            self._dev_tables[name] = torch.from_numpy(self._host_tables[name]).to(self.denoise_fn.device)
+        return self._dev_tables[name]
+
+    @property
+    def device(self):
+        return self.denoise_fn.device
+
+    def _f32(self, x):
+        return x.to(device=self.device, dtype=torch.float32).contiguous()
+
+    def _i32(self, t):
+        return t.to(device=self.device, dtype=torch.int32).contiguous()
+
+    def _normal(self, shape, key: Key, elem_offset: int = 0) -> torch.Tensor:
+        out = torch.empty(shape, dtype=torch.float32, device=self.device)
+        ops.randn(out, key.seed, key.stream, elem_offset)
+        return out
+
+    # ---- forward process --------------------------------------------------------------
+    def q_sample(self, x_start, t, key=None, noise=None, *, _normalize: bool = False):
+        """gaussian_diffusion.py:401-420."""
+        x_start = self._f32(x_start)
+        if noise is None:
+            assert key is not None, "A PRNGKey must be provided to q_sample if noise is not."
+            noise = self._normal(x_start.shape, as_key(key))
+        out = torch.empty_like(x_start)
+        ops.q_sample(x_start, self._f32(noise), self._i32(t), self.table("sqrt_alphas_cumprod"),
+                     self.table("sqrt_one_minus_alphas_cumprod"), out, _normalize)
+        return out
+
+    def p_losses(self, x_start, t, key=None, cond=None, noise=None, *, _normalize: bool = False, **kwargs):
+        """gaussian_diffusion.py:423-470 (forward only; the training step in trainer.py adds backward)."""
+        key = as_key(0 if key is None else key)
+        _, noise_key, q_key = key.split(3)
+        x_start = self._f32(x_start)
+        if noise is None:
+            noise = self._normal(x_start.shape, noise_key)
+        noise = self._f32(noise)
+        t = self._i32(t)
+        x_noisy = self.q_sample(x_start, t, key=q_key, noise=noise, _normalize=_normalize)
+        pred = self.denoise_fn(x_noisy, t, cond=cond, **kwargs)  # (b f h w c)
+        B, C = x_start.shape[0], x_start.shape[1]
+        loss = torch.zeros(1, dtype=torch.float32, device=self.device)
+        ops.loss_fwd_bwd(pred, noise, loss, None, B, C, x_start.numel() // (B * C), self.loss_type == "l1")
+        return loss[0]
+
+    def __call__(self, x, key, *args, **kwargs):
+        """gaussian_diffusion.py:473-502: random t, normalise to [-1,1], p_losses."""
+        B = x.shape[0]
+        assert tuple(x.shape[1:]) == (self.channels, self.num_frames, self.image_size, self.image_size), \
+            "expected (b, c, f, h, w) matching the configured channels / frames / size"
+        key = as_key(key)
+        _, t_key, loss_key = key.split(3)
+        g = torch.Generator(device="cpu").manual_seed(t_key.seed * 7919 + t_key.stream)
+        t = torch.randint(0, self.num_timesteps, (B,), generator=g, dtype=torch.int32)
+        return self.p_losses(x, t, loss_key, *args, _normalize=True, **kwargs)
+
+    # ---- reverse process --------------------------------------------------------------
+    def predict_start_from_noise(self, x_t, t, noise):
+        """gaussian_diffusion.py:120-136 (host-visible helper; the fused kernel is p_sample)."""
+        rc = self.table("sqrt_recip_alphas_cumprod")[self._i32(t).long()].view(-1, 1, 1, 1, 1)
+        rm = self.table("sqrt_recipm1_alphas_cumprod")[self._i32(t).long()].view(-1, 1, 1, 1, 1)
+        return rc * self._f32(x_t) - rm * self._f32(noise)
+
+    def p_sample(self, x, t, key=None, cond=None, cond_scale: float = 1.0, clip_denoised: bool = True, *, z=None):
+        """gaussian_diffusion.py:231-261: one Unet forward + the fused posterior update kernel."""
+        x = self._f32(x)
+        t = self._i32(t)
+        eps = self.denoise_fn.forward_with_cond_scale(x, t, cond=cond, cond_scale=cond_scale)
+        if z is None:
+            z = self._normal(x.shape, as_key(key))
+        out = torch.empty_like(x)
+        B, C = x.shape[0], x.shape[1]
+        ops.p_sample(x, eps, self._f32(z), t, self.table("sqrt_recip_alphas_cumprod"),
+                     self.table("sqrt_recipm1_alphas_cumprod"), self.table("posterior_mean_coef1"),
+                     self.table("posterior_mean_coef2"), self.table("posterior_log_variance_clipped"), out, B, C,
+                     x.numel() // (B * C), clip_denoised)
+        return out
+
+    def p_sample_loop(self, shape, key, cond=None, cond_scale: float = 1.0, *, sample_offset: int = 0,
+                      use_graph: bool = True, timesteps: Optional[int] = None):
+        """gaussian_diffusion.py:264-320. The T host iterations replay ONE captured CUDA graph
+        (Unet forward + Philox z + posterior update); `sample_offset` is the global index of this
+        shard's first sample, so a sharded batch draws the same noise as the unsharded one."""
+        key = as_key(key)
+        B = shape[0]
+        shape = (B, self.channels, self.num_frames, self.image_size, self.image_size)
+        per_sample = shape[1] * shape[2] * shape[3] * shape[4]
+        assert per_sample % 4 == 0
+        loop_key, init_key = key.split(2)
+        img = self._normal(shape, init_key, sample_offset * per_sample)
+        T = self.num_timesteps if timesteps is None else timesteps
+        eng = self.denoise_fn.engine(B, self.num_frames, self.image_size, self.image_size, training=False)
+        t_dev = torch.empty(B, dtype=torch.int32, device=self.device)
+        z = torch.empty(shape, dtype=torch.float32, device=self.device)
+        nxt = torch.empty_like(img)
+        tabs = [self.table(n) for n in ("sqrt_recip_alphas_cumprod", "sqrt_recipm1_alphas_cumprod",
+                                        "posterior_mean_coef1", "posterior_mean_coef2",
+                                        "posterior_log_variance_clipped")]
+        FHW = per_sample // shape[1]
+
+        def body():
+            eps = eng.forward(img, t_dev)
+            ops.p_sample(img, eps, z, t_dev, *tabs, nxt, B, shape[1], FHW, True)
+            img.copy_(nxt)
+
+        graph = None
+        for n, i in enumerate(reversed(range(T))):
+            t_dev.fill_(i)
+            ops.randn(z, loop_key.seed, loop_key.stream * 4099 + i + 1, sample_offset * per_sample)
+            if use_graph and n == 1 and graph is None:
+                torch.cuda.synchronize()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    body()
+                graph.replay()
+            elif graph is not None:
+                graph.replay()
+            else:
+                body()
+        return (img + 1) * 0.5  # unnormalize_img, utils.py:259-268
+
+    def sample(self, key, cond=None, cond_scale: float = 1.0, batch_size: int = 16, **kw):
+        """gaussian_diffusion.py:323-357."""
+        if cond is not None:
+            raise NotImplementedError("conditioning is outside the accelerated hot path")
+        shape = (batch_size, self.channels, self.num_frames, self.image_size, self.image_size)
+        return self.p_sample_loop(shape, key, cond=cond, cond_scale=cond_scale, **kw)

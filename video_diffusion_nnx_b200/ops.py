@@ -247,3 +247,9 @@ def add_bf16(a, b, out):
 def adam_ema(p, g, m, v, ema, hp):
     check(lib.vdn_adam_ema(ptr(p), ptr(g), ptr(m), ptr(v), ptr(ema), ptr(hp), C.c_long(p.numel()), stream_ptr()),
           "vdn_adam_ema")
+
+
+def randn(out, seed: int, subseq: int = 0, elem_offset: int = 0):
+    """Fill `out` (fp32) with N(0,1) draws: element i = Philox(seed, subseq, elem_offset + i)."""
+    check(lib.vdn_randn(ptr(out), C.c_long(out.numel()), C.c_ulonglong(seed & (2 ** 64 - 1)), C.c_ulonglong(subseq),
+                        C.c_ulonglong(elem_offset), stream_ptr()), "vdn_randn")
