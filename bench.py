@@ -1,0 +1,365 @@
+#!/usr/bin/env python
+"""Benchmark of the B200-native Unet3D / GaussianDiffusion hot path (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+Default workload: configs/config_v2_2.yaml data-parallel TRAINING step (Unet3D dim 32, 1 channel,
+10 frames, 64x64, T=1000, L2 loss, Adam + EMA), per-GPU batch 4 (the config's train_batch_size),
+synthetic clips, random-init weights, bf16 tensor-core compute with fp32 master weights.
+One JSON line is printed by rank 0. `value` = clips/s with inputs resident in HBM (device-timed,
+max over ranks); `e2e` = the same step through the public TrainStep.step API with the batch coming
+from pinned host memory and the loss read back every step. The sampling metric (frames/s of the
+full T-step p_sample_loop) is reported under "sampling".
+
+--impl reference times the reference's algorithm on the host CPU cores (the oracle port of the JAX
+code: JAX/flax are not installable in this image), one clip per step as a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CFG = dict(dim=32, channels=1, frames=10, size=64, timesteps=1000, loss="l2", lr=1e-4, lr_decay_start_step=20000,
+           lr_decay_steps=80000, lr_decay_coeff=0.1, step_start_ema=2000, update_ema_every=10, ema_decay=0.9999,
+           per_gpu_batch=4)
+TRAIN_GFLOP_PER_CLIP = 159.3   # 3 x 53.1 GFLOP forward (SURVEY.md 8d / BASELINE.md section 4)
+FWD_GFLOP_PER_CLIP = 53.1
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sust=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.idx, self.rows, self._stop, self._th = gpu_index, [], threading.Event(), None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.idx)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._th = threading.Thread(target=self._run, daemon=True)
+        self._th.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._th.join(timeout=6)
+
+    def summary(self):
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        mx = max((float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()), default=None)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(self.rows)}
+
+
+def run_reference(args):
+    """The reference's own algorithm on the host cores (oracle port; JAX is not installable here)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+
+    from oracle import diffusion_oracle as D
+    from oracle import unet3d_oracle as U
+
+    cores = os.cpu_count()
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    p = U.init_params(CFG["dim"], CFG["channels"])
+    for v in p.values():
+        v.requires_grad_(True)
+    gd = D.GaussianDiffusionOracle(lambda xx, tt: U.unet3d_forward(p, xx, tt, CFG["dim"]), image_size=CFG["size"],
+                                   num_frames=CFG["frames"], channels=CFG["channels"], timesteps=CFG["timesteps"],
+                                   loss_type=CFG["loss"])
+    Bs = 1  # bounded sample: one clip per step
+    x = torch.rand(Bs, 1, CFG["frames"], CFG["size"], CFG["size"])
+
+    def step():
+        for v in p.values():
+            v.grad = None
+        t = torch.randint(0, CFG["timesteps"], (Bs,), dtype=torch.int32)
+        loss = gd(x, t, torch.randn_like(x))
+        loss.backward()
+        return loss.item()
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    val = Bs * args.steps / dt
+    line = {"impl": "reference", "metric": "train clips/sec (Unet3D config_v2_2)", "value": val, "unit": "clips/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "config_v2_2 train step (fwd+bwd), 1 clip per step (bounded sample), CPU"},
+            "cpu_baseline": {"value": val, "unit": "clips/s", "cores": cores, "kind": "port",
+                             "sample": f"{args.steps} steps x 1 clip, fwd+bwd (no optimizer), torch fp32 oracle port of the JAX reference"},
+            "e2e": {"value": val, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_sample():
+    import torch
+
+    from oracle import diffusion_oracle as D
+    from oracle import unet3d_oracle as U
+
+    cores = os.cpu_count()
+    torch.set_num_threads(cores)
+    p = U.init_params(CFG["dim"], CFG["channels"])
+    for v in p.values():
+        v.requires_grad_(True)
+    gd = D.GaussianDiffusionOracle(lambda xx, tt: U.unet3d_forward(p, xx, tt, CFG["dim"]), image_size=CFG["size"],
+                                   num_frames=CFG["frames"], channels=CFG["channels"], timesteps=CFG["timesteps"],
+                                   loss_type=CFG["loss"])
+    x = torch.rand(1, 1, CFG["frames"], CFG["size"], CFG["size"])
+    ts = []
+    for i in range(4):
+        t = torch.randint(0, CFG["timesteps"], (1,), dtype=torch.int32)
+        t0 = time.perf_counter()
+        loss = gd(x, t, torch.randn_like(x))
+        loss.backward()
+        ts.append(time.perf_counter() - t0)
+    best = sorted(ts[1:])[len(ts[1:]) // 2]
+    return {"value": 1.0 / best, "unit": "clips/s", "cores": cores, "kind": "port",
+            "sample": "median of 3 training steps (fwd+bwd) of 1 clip after 1 warm-up, torch fp32 oracle port of the JAX reference"}
+
+
+def conv_roofline(torch, ops, pk):
+    """Times the dominant tensor-core kernel class of the step - the (1,3,3) implicit-GEMM conv of the
+    64x64 level (M = B*F*64*64 = 163840 pixels, 32 -> 32 channels, K = 288) - in isolation with CUDA
+    events, rotating over enough distinct buffers to exceed L2."""
+    dev = "cuda"
+    n_img, H, W, C = CFG["per_gpu_batch"] * CFG["frames"], CFG["size"], CFG["size"], CFG["dim"]
+    nbuf = 16  # 16 x (10.5 MB in + 10.5 MB out) = 336 MB > 126 MB L2
+    xs = [torch.randn(n_img, H, W, C, device=dev).to(torch.bfloat16) for _ in range(nbuf)]
+    outs = [torch.empty(n_img, H, W, C, device=dev, dtype=torch.bfloat16) for _ in range(nbuf)]
+    w = torch.randn(9, C, C, device=dev) * (9 * C) ** -0.5
+    wp = torch.empty(C, 9 * C, dtype=torch.bfloat16, device=dev)
+    ops.pack_weight(w, wp, 9, C, C, 0)
+    bias = torch.zeros(C, device=dev)
+    sums = torch.zeros(CFG["per_gpu_batch"], 8, 2, device=dev)
+    rows = CFG["frames"] * H * W
+
+    def run(i):
+        ops.tapgemm(ops.VDN_TAP_UNIT, [xs[i % nbuf]], wp, ops.TAPS_3x3, bias=bias, out=outs[i % nbuf], gn_sums=sums,
+                    gn_groups=8, rows_per_sample=rows)
+
+    for i in range(8):
+        run(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n = 64
+    e0.record()
+    for i in range(n):
+        run(i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    M = n_img * H * W
+    flops = 2.0 * M * C * 9 * C
+    bytes_alg = 2.0 * M * C * 2 + 9 * C * C * 2
+    tf = flops / (ms * 1e-3) / 1e12
+    gbs = bytes_alg / (ms * 1e-3) / 1e9
+    # this layer is below the ridge (AI = flops/bytes ~ 144 FLOP/B < 212): HBM is the binding roofline
+    return {"kernel": "tapgemm_kernel<32> conv(1,3,3) 32->32 @64x64 (M=163840,N=32,K=288)", "bound": "hbm",
+            "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"], "traffic": None,
+            "us_per_launch": ms * 1e3, "tensor_tflops": tf, "tensor_frac_of_burst": tf / pk["tf_burst"],
+            "peak_source": pk["src"]}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=CFG["per_gpu_batch"], help="per-GPU batch")
+    ap.add_argument("--no-sampling", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sample-timesteps", type=int, default=CFG["timesteps"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    pg = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        pg = dist.group.WORLD
+
+    from video_diffusion_nnx_b200 import _lib, ops
+    from video_diffusion_nnx_b200.gaussian_diffusion import GaussianDiffusion
+    from video_diffusion_nnx_b200.trainer import TrainStep
+    from video_diffusion_nnx_b200.unet3d import Unet3D
+
+    pk = peaks()
+    B = args.batch
+    dev = torch.device("cuda", local)
+    net = Unet3D(dim=CFG["dim"], channels=CFG["channels"], rngs=0, device=dev)
+    gd = GaussianDiffusion(net, image_size=CFG["size"], num_frames=CFG["frames"], channels=CFG["channels"],
+                           timesteps=CFG["timesteps"], loss_type=CFG["loss"])
+    ts = TrainStep(gd, batch_size=B, train_lr=CFG["lr"], lr_decay_start_step=CFG["lr_decay_start_step"],
+                   lr_decay_steps=CFG["lr_decay_steps"], lr_decay_coeff=CFG["lr_decay_coeff"],
+                   step_start_ema=0, update_ema_every=CFG["update_ema_every"], ema_decay=CFG["ema_decay"],
+                   use_graph=True, process_group=pg)
+    shape = (B, CFG["channels"], CFG["frames"], CFG["size"], CFG["size"])
+    g = torch.Generator().manual_seed(1234 + rank)
+    K, Wm = args.steps, args.warmup
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident timing (`value`) ----------------
+    x_dev = torch.rand(shape, generator=g).to(dev)
+    t_all = torch.randint(0, CFG["timesteps"], (K + Wm + 2, B), generator=g, dtype=torch.int32).to(dev)
+    ts.x.copy_(x_dev)
+    l0 = _lib.lib.vdn_launch_count()
+    ts.t.copy_(t_all[0])
+    ops.randn(ts.noise, 7 + rank, 0)
+    ts.step_device(0)  # eager warm-up step + graph capture + one replayed step
+    launches_capture = _lib.lib.vdn_launch_count() - l0
+    # the first call ran the step eagerly once and captured it once: launches per step is half of that (+2 randn)
+    launches_per_step = (launches_capture - 1) // 2 + 1
+    for i in range(Wm):
+        ts.t.copy_(t_all[1 + i])
+        ops.randn(ts.noise, 7 + rank, 1 + i)
+        ts.step_device(1 + i)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        e0.record()
+        for i in range(K):
+            ts.t.copy_(t_all[1 + Wm + i])
+            ops.randn(ts.noise, 7 + rank, 1 + Wm + i)
+            ts.step_device(1 + Wm + i)
+        e1.record()
+        barrier()
+    ms = e0.elapsed_time(e1)
+    loss_last = float(ts.loss.item())
+    tms = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms = float(tms.item())
+    ms_per_step = ms / K
+    value = world * B / (ms_per_step * 1e-3)
+
+    # ---------------- end-to-end through the public API (`e2e`) ----------------
+    hosts = [torch.rand(shape, generator=g).pin_memory() for _ in range(4)]
+    for i in range(2):
+        float(ts.step(hosts[i % 4], 100 + i, 2000 + i).item())
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(K):
+        loss = ts.step(hosts[i % 4], 1000 + i, 3000 + i)
+        _ = float(loss.item())  # device -> host read of the step's result, every step
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * K / float(te.item())
+    h2d = hosts[0].numel() * 4 + B * 4 + 16 * 4
+    d2h = 4
+
+    line = None
+    if rank == 0:
+        act_mb = sum(t.numel() * t.element_size() for t in ts.eng.__dict__.values() if isinstance(t, torch.Tensor)) / 1e6
+        line = {
+            "metric": "train clips/sec (Unet3D config_v2_2 p_losses fwd+bwd+allreduce+Adam/EMA, device-timed)",
+            "value": value, "unit": "clips/s", "n_gpus": world, "steps": K, "warmup": Wm,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"configs/config_v2_2.yaml training step: Unet3D dim 32, 1 ch, 10 frames, 64x64, "
+                                   f"T=1000, L2, Adam+EMA; per-GPU batch {B}, global batch {B * world}",
+                       "parallelism": f"dp{world}", "global_batch": B * world,
+                       "l2": "no explicit flush: one step streams > 2 GB of activations / saved tensors, far beyond the 126 MB L2",
+                       "timing": "CUDA events on the launch stream around K CUDA-graph-replayed steps, max over ranks"},
+            "loss_last": loss_last,
+            "e2e": {"value": e2e_value, "unit": "clips/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "how": "TrainStep.step(pinned host batch, key, step) + loss.item() every step, wall clock"},
+            "gpu_launches": int(launches_per_step * K),
+            "launches_per_step": int(launches_per_step),
+            "clocks": clk.summary(),
+            "train_tflops": value * TRAIN_GFLOP_PER_CLIP / 1e3,
+            "train_frac_of_sustained_bf16_peak": value / world * TRAIN_GFLOP_PER_CLIP / 1e3 / pk["tf_sust"],
+        }
+
+    # ---------------- sampling metric (frames/s of the full T-step loop) ----------------
+    if not args.no_sampling:
+        net.train(False)
+        sb = B
+        T = args.sample_timesteps
+        gd.p_sample_loop((sb,), 11, sample_offset=rank * sb, timesteps=4)  # warm-up + capture path
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        vid = gd.p_sample_loop((sb,), 12, sample_offset=rank * sb, timesteps=T)
+        s1.record()
+        barrier()
+        sms = torch.tensor([s0.elapsed_time(s1)], device=dev)
+        if world > 1:
+            dist.all_reduce(sms, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            fps = world * sb * CFG["frames"] / (float(sms.item()) * 1e-3) * (CFG["timesteps"] / T) / (CFG["timesteps"] / T)
+            fps_full = world * sb * CFG["frames"] / (float(sms.item()) * 1e-3 * CFG["timesteps"] / T)
+            line["sampling"] = {"metric": "sampling frames/sec (p_sample_loop, T=1000, config_v2_2)", "value": fps_full,
+                                "unit": "frames/s", "timesteps_run": T, "ms_per_timestep": float(sms.item()) / T,
+                                "sample_batch_per_gpu": sb, "finite": bool(torch.isfinite(vid).all().item()),
+                                "sampling_tflops": fps_full * 5.31,
+                                "frac_of_sustained_bf16_peak": fps_full / world * 5.31 / pk["tf_sust"]}
+            del fps
+
+    if rank == 0:
+        line["roofline"] = conv_roofline(torch, ops, pk)
+        if not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline_sample()
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -38,6 +38,8 @@ typedef enum {
 
 int vdn_version(void);
 const char* vdn_last_error(void);
+/* kernels launched (or recorded into a CUDA graph under capture) by this library so far */
+unsigned long long vdn_launch_count(void);
 
 /* ---------------------------------------------------------------------------------
  * Weight repacking (fp32 reference layout -> bf16 K-major GEMM operand).

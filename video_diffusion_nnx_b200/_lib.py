@@ -53,6 +53,7 @@ def _load():
 lib = _load()
 lib.vdn_last_error.restype = C.c_char_p
 lib.vdn_version.restype = C.c_int
+lib.vdn_launch_count.restype = C.c_ulonglong
 
 
 def check(rc: int, what: str = "") -> None:

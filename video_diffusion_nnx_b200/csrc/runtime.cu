@@ -1,5 +1,6 @@
 // Host-side runtime glue: error reporting, driver entry points (TMA descriptor encode),
 // version query. No allocation, no synchronisation.
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <mutex>
@@ -18,7 +19,10 @@ void set_last_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static std::atomic<unsigned long long> g_launches{0};
+
 int check_launch(const char* what) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
   cudaError_t e = cudaPeekAtLastError();
   if (e != cudaSuccess) {
     set_last_error("%s: %s", what, cudaGetErrorString(e));
@@ -80,4 +84,6 @@ int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_
 }  // namespace vdn
 
 extern "C" int vdn_version(void) { return 100; }
+// Number of kernels this library has launched (or recorded into a CUDA graph) in this process.
+extern "C" unsigned long long vdn_launch_count(void) { return vdn::g_launches.load(); }
 extern "C" const char* vdn_last_error(void) { return vdn::g_err; }
