@@ -170,7 +170,7 @@ def conv_roofline(torch, ops, pk):
     wp = torch.empty(C, 9 * C, dtype=torch.bfloat16, device=dev)
     ops.pack_weight(w, wp, 9, C, C, 0)
     bias = torch.zeros(C, device=dev)
-    sums = torch.zeros(CFG["per_gpu_batch"], 8, 2, device=dev)
+    sums = torch.zeros(ops.GN_REPLICAS, CFG["per_gpu_batch"], 8, 2, device=dev)
     rows = CFG["frames"] * H * W
 
     def run(i):

@@ -22,6 +22,15 @@ def _bf(*shape, scale=1.0):
     return (torch.randn(*shape, device=DEV) * scale).to(torch.bfloat16)
 
 
+def _replicated(sums):
+    """[B][G][2] -> the kernels' [R][B][G][2] replica layout (all mass in replica 3)."""
+    from video_diffusion_nnx_b200 import ops
+
+    out = torch.zeros((ops.GN_REPLICAS,) + tuple(sums.shape), device=sums.device)
+    out[3] = sums
+    return out.contiguous()
+
+
 def _rel(a, b):
     return ((a.float() - b.float()).abs().max() / (b.float().abs().max() + 1e-6)).item()
 
@@ -120,7 +129,7 @@ def test_gn_silu_fwd_bwd(B, R, Cc, with_ss):
     dy = _bf(B, R, Cc)
     y.backward(dy.float())
     xg = xf.detach().reshape(B, R, 8, Cc // 8)
-    sums = torch.stack([xg.sum(dim=(1, 3)), (xg * xg).sum(dim=(1, 3))], -1).contiguous()
+    sums = _replicated(torch.stack([xg.sum(dim=(1, 3)), (xg * xg).sum(dim=(1, 3))], -1))
     out = torch.empty_like(x)
     ops.gn_silu_fwd(x, sums, gamma.detach(), beta.detach(), ss.detach() if with_ss else None, out, B, R, Cc)
     assert _rel(out, y) < 1e-2  # bf16 output rounding
@@ -152,7 +161,7 @@ def test_resblock_tail_and_ln_bwd(B, R, Cc):
     ln = _ln_ref(sf, lg, lb)
     ref = F.silu(_gn_ref(b_raw.float(), gamma, beta)) + ln
     xg = b_raw.float().reshape(B, R, 8, Cc // 8)
-    sums = torch.stack([xg.sum(dim=(1, 3)), (xg * xg).sum(dim=(1, 3))], -1).contiguous()
+    sums = _replicated(torch.stack([xg.sum(dim=(1, 3)), (xg * xg).sum(dim=(1, 3))], -1))
     out = torch.empty_like(s)
     ops.resblock_tail_fwd(b_raw, sums, gamma, beta, s, lg.detach(), lb.detach(), out, B, R, Cc)
     assert _rel(out, ref) < 1e-2

@@ -84,16 +84,31 @@ def test_concat_two_sources_residual_and_gn_sums():
     bias = torch.randn(cout, device="cuda")
     res = _rand_bf16(n_img, H, W, cout)
     wp = _pack(w)
-    ref = _conv_ref([x0, x1], w, 3, 3) + bias + res.float()
-    sums = torch.zeros(B, 8, 2, device="cuda")
-    out = ops.tapgemm(ops.VDN_TAP_UNIT, [x0, x1], wp, ops.TAPS_3x3, bias=bias, residual=res, gn_sums=sums,
-                      gn_groups=8, rows_per_sample=Fr * H * W)  # residual shares the output dtype (bf16)
+    ref = _conv_ref([x0, x1], w, 3, 3) + bias
+    sums = torch.zeros(ops.GN_REPLICAS, B, 8, 2, device="cuda")
+    out = ops.tapgemm(ops.VDN_TAP_UNIT, [x0, x1], wp, ops.TAPS_3x3, bias=bias, gn_sums=sums,
+                      gn_groups=8, rows_per_sample=Fr * H * W)
     _check(out, ref, 1e-2)
     g = ref.view(B, Fr * H * W, 8, cout // 8)
     s1 = g.sum(dim=(1, 3))
     s2 = (g * g).sum(dim=(1, 3))
-    assert torch.allclose(sums[..., 0], s1, rtol=1e-3, atol=1e-1)
-    assert torch.allclose(sums[..., 1], s2, rtol=1e-3, atol=1e-1)
+    tot = sums.sum(0)
+    assert torch.allclose(tot[..., 0], s1, rtol=1e-3, atol=1e-1)
+    assert torch.allclose(tot[..., 1], s2, rtol=1e-3, atol=1e-1)
+    # residual (bf16, same dtype as the output) through the staged epilogue; in-place aliasing allowed
+    out2 = ops.tapgemm(ops.VDN_TAP_UNIT, [x0, x1], wp, ops.TAPS_3x3, bias=bias, residual=res)
+    _check(out2, ref + res.float(), 1e-2)
+    acc = res.clone()
+    ops.tapgemm(ops.VDN_TAP_UNIT, [x0, x1], wp, ops.TAPS_3x3, bias=bias, residual=acc, out=acc)
+    _check(acc, ref + res.float(), 1e-2)
+    # GroupNorm sums when a 128-row tile spans two samples (rows_per_sample = 96 -> per-warp path)
+    xs = _rand_bf16(3, 4, 8, c)
+    w1 = _rand_bf16(1, c, cout, scale=c ** -0.5).float()
+    sums2 = torch.zeros(ops.GN_REPLICAS, 1, 8, 2, device="cuda")
+    o3 = ops.tapgemm(ops.VDN_TAP_UNIT, [xs], _pack(w1), ops.TAPS_1x1, gn_sums=sums2, gn_groups=8,
+                     rows_per_sample=96, out_dtype=torch.float32)
+    g3 = o3.view(1, 96, 8, cout // 8)
+    assert torch.allclose(sums2.sum(0)[..., 0], g3.sum(dim=(1, 3)), rtol=1e-3, atol=1e-2)
 
 
 def test_split_output_dgrad_of_concat():

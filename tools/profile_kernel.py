@@ -1,0 +1,43 @@
+"""Runs one hot kernel in isolation for `ncu --set full` captures.
+  python tools/profile_kernel.py conv_l0 | qkv_l0 | wgrad_l0 | conv_l3
+"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from video_diffusion_nnx_b200 import ops  # noqa: E402
+
+what = sys.argv[1] if len(sys.argv) > 1 else "conv_l0"
+dev = "cuda"
+B, F = 4, 10
+
+
+def bf(*s):
+    return torch.randn(*s, device=dev).to(torch.bfloat16)
+
+
+if what in ("conv_l0", "conv_l3", "qkv_l0"):
+    H, C, N, taps = {"conv_l0": (64, 32, 32, ops.TAPS_3x3), "conv_l3": (8, 256, 256, ops.TAPS_3x3),
+                     "qkv_l0": (64, 32, 768, ops.TAPS_1x1)}[what]
+    x = bf(B * F, H, H, C)
+    w = torch.randn(len(taps), C, N, device=dev) * (len(taps) * C) ** -0.5
+    wp = torch.empty(N, len(taps) * C, dtype=torch.bfloat16, device=dev)
+    ops.pack_weight(w, wp, len(taps), C, N, 0)
+    out = torch.empty(B * F, H, H, N, dtype=torch.bfloat16, device=dev)
+    bias = torch.zeros(N, device=dev)
+    sums = torch.zeros(ops.GN_REPLICAS, B, 8, 2, device=dev)
+    for _ in range(5):
+        if what == "qkv_l0":
+            ops.tapgemm(ops.VDN_TAP_UNIT, [x], wp, taps, bias=bias, out=out)
+        else:
+            ops.tapgemm(ops.VDN_TAP_UNIT, [x], wp, taps, bias=bias, out=out, gn_sums=sums, gn_groups=8,
+                        rows_per_sample=F * H * H)
+elif what == "wgrad_l0":
+    x, g = bf(B * F, 64, 64, 32), bf(B * F, 64, 64, 32)
+    dw = torch.zeros(9, 32, 32, device=dev)
+    for _ in range(5):
+        ops.wgrad(ops.VDN_TAP_UNIT, [x], g, dw, ops.TAPS_3x3)
+torch.cuda.synchronize()
+print("done")

@@ -17,7 +17,7 @@ constexpr int kNormThreads = 256;
 
 struct GnArgs {
   const bf16* x;        // raw conv output [B][rows][C]
-  const float* sums;    // [B][G][2]
+  const float* sums;    // [kGnReplicas][B][G][2]
   const float* gamma;   // [C]
   const float* beta;    // [C]
   const float* ss;      // [B][ss_ld] scale = [0,C), shift = [C,2C); or null
@@ -25,14 +25,25 @@ struct GnArgs {
   int B, rows, C, G;
 };
 
+__device__ __forceinline__ void gn_read_sums(const GnArgs& a, int b, int g, float& s1, float& s2) {
+  s1 = 0.f;
+  s2 = 0.f;
+#pragma unroll
+  for (int r = 0; r < kGnReplicas; ++r) {
+    const float2 v = *reinterpret_cast<const float2*>(a.sums + ((long)(r * a.B + b) * a.G + g) * 2);
+    s1 += v.x;
+    s2 += v.y;
+  }
+}
+
 // Per-sample affine in smem: y = x * A[c] + Bc[c]  (GN * gamma + beta, then *(scale+1)+shift)
 __device__ __forceinline__ void gn_affine_to_smem(const GnArgs& a, int b, float* sA, float* sB) {
   const int cpg = a.C / a.G;
   const float inv_n = 1.f / ((float)a.rows * (float)cpg);
   for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
     const int g = c / cpg;
-    const float s1 = a.sums[((long)b * a.G + g) * 2];
-    const float s2 = a.sums[((long)b * a.G + g) * 2 + 1];
+    float s1, s2;
+    gn_read_sums(a, b, g, s1, s2);
     const float mean = s1 * inv_n;
     const float var = fmaxf(s2 * inv_n - mean * mean, 0.f);
     const float rstd = rsqrtf(var + kEps);
@@ -175,8 +186,10 @@ __global__ void __launch_bounds__(kNormThreads) gn_bwd_reduce_kernel(const GnArg
     const float inv_n = 1.f / ((float)a.rows * (float)cpg);
     for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
       const int g = c / cpg;
-      const float mean = a.sums[((long)b * a.G + g) * 2] * inv_n;
-      const float var = fmaxf(a.sums[((long)b * a.G + g) * 2 + 1] * inv_n - mean * mean, 0.f);
+      float s1, s2;
+      gn_read_sums(a, b, g, s1, s2);
+      const float mean = s1 * inv_n;
+      const float var = fmaxf(s2 * inv_n - mean * mean, 0.f);
       sMean[c] = mean;
       sRstd[c] = rsqrtf(var + kEps);
     }
@@ -264,8 +277,10 @@ __global__ void __launch_bounds__(kNormThreads) gn_bwd_apply_kernel(const GnArgs
   const float inv_n = 1.f / ((float)a.rows * (float)cpg);
   for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
     const int g = c / cpg;
-    const float mean = a.sums[((long)b * a.G + g) * 2] * inv_n;
-    const float var = fmaxf(a.sums[((long)b * a.G + g) * 2 + 1] * inv_n - mean * mean, 0.f);
+    float s1, s2;
+    gn_read_sums(a, b, g, s1, s2);
+    const float mean = s1 * inv_n;
+    const float var = fmaxf(s2 * inv_n - mean * mean, 0.f);
     sMean[c] = mean;
     sRstd[c] = rsqrtf(var + kEps);
     const float sc = a.ss ? a.ss[(long)b * a.ss_ld + c] + 1.f : 1.f;

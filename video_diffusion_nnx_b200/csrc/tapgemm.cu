@@ -12,6 +12,7 @@
 // Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2-5 = epilogue
 // (tcgen05.ld -> bias / residual / GroupNorm partial sums -> bf16 or fp32 store).
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "vdn_common.cuh"
@@ -48,7 +49,7 @@ struct TapArgs {
   int out_f32;
   int scatter, py, px;  // VDN_TAP_UP parity scatter into a 2H x 2W grid
   float* gn_sums;
-  int gn_groups, cpg, rows_per_sample;
+  int gn_groups, cpg, rows_per_sample, n_samples;
 };
 
 // ---------------------------------------------------------------------------------------
@@ -77,6 +78,27 @@ __device__ __forceinline__ void gn_accumulate16(const float (&v)[16], bool valid
   }
 }
 
+// Same reduction, but lane 0 accumulates into this warp's private smem slots (no atomics).
+template <int CPG16>
+__device__ __forceinline__ void gn_accumulate16_warp(const float (&v)[16], bool valid, float* slot, int lane) {
+#pragma unroll
+  for (int j = 0; j < 16; j += CPG16) {
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < CPG16; ++k) {
+      float x = valid ? v[j + k] : 0.f;
+      s1 += x;
+      s2 += x * x;
+    }
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    if (lane == 0) {
+      slot[2 * (j / CPG16)] += s1;
+      slot[2 * (j / CPG16) + 1] += s2;
+    }
+  }
+}
+
 template <int BK>
 __global__ void __launch_bounds__(kGemmThreads) tapgemm_kernel(const __grid_constant__ TapMaps maps,
                                                                const TapArgs args) {
@@ -90,6 +112,7 @@ __global__ void __launch_bounds__(kGemmThreads) tapgemm_kernel(const __grid_cons
   __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
   __shared__ __align__(8) uint64_t tmem_full_bar;
   __shared__ uint32_t tmem_base_smem;
+  __shared__ float s_gn[4][16];  // per epilogue warp: (sum, sumsq) of up to 8 groups of this N tile
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -179,19 +202,12 @@ __global__ void __launch_bounds__(kGemmThreads) tapgemm_kernel(const __grid_cons
     const int r = quarter * 32 + lane;
     const int m = m0 + r;
     const bool valid = m < args.M;
+    const int et = threadIdx.x - 64;  // epilogue thread id 0..127
+    if (et < 64) s_gn[et >> 4][et & 15] = 0.f;
+    asm volatile("bar.sync 1, 128;" ::: "memory");
     mbar_wait(&tmem_full_bar, 0);
     tc_fence_after();
 
-    // output row index
-    long orow = m;
-    if (args.scatter) {
-      const int hw = args.H * args.W;
-      const int n = m / hw;
-      const int rem = m - n * hw;
-      const int y = rem / args.W;
-      const int x = rem - y * args.W;
-      orow = ((long)n * (2 * args.H) + (2 * y + args.py)) * (2 * args.W) + (2 * x + args.px);
-    }
     const int col_base = n_tile * BN;
     uint8_t* outp;
     const uint8_t* resp;
@@ -208,12 +224,29 @@ __global__ void __launch_bounds__(kGemmThreads) tapgemm_kernel(const __grid_cons
       col_o = col_base;
     }
     const int esz = args.out_f32 ? 4 : 2;
-    float* gsum = nullptr;
-    if (args.gn_sums) {
-      // all 32 rows of a warp belong to one sample (rows_per_sample % 32 == 0 enforced on host)
-      const int sample = min(m0 + quarter * 32, args.M - 1) / args.rows_per_sample;
-      gsum = args.gn_sums + (long)sample * args.gn_groups * 2;
+    const bool staged = !args.scatter;  // stage the tile in smem and store coalesced rows
+    // direct (scatter) mode: output row of this thread
+    long orow = m;
+    if (args.scatter) {
+      const int hw = args.H * args.W;
+      const int n = m / hw;
+      const int rem = m - n * hw;
+      const int y = rem / args.W;
+      const int x = rem - y * args.W;
+      orow = ((long)n * (2 * args.H) + (2 * y + args.py)) * (2 * args.W) + (2 * x + args.px);
     }
+    // GroupNorm partial sums: CTA-level reduction in smem when the tile lies in one sample, else per warp
+    const bool gn_on = args.gn_sums != nullptr;
+    const bool gn_cta = gn_on && (args.rows_per_sample % kTileM == 0);
+    float* gdst = nullptr;
+    if (gn_on) {
+      const int sample = min(m0 + (gn_cta ? 0 : quarter * 32), args.M - 1) / args.rows_per_sample;
+      const int rep = blockIdx.y % kGnReplicas;
+      gdst = args.gn_sums + ((long)(rep * args.n_samples + sample) * args.gn_groups) * 2;
+    }
+    const int g_tile0 = col_base / args.cpg;  // first group covered by this N tile
+    const int pitch = BN * esz + 16;          // smem row pitch of the staged tile (bytes)
+    uint8_t* srow = smem + (size_t)r * pitch;
     const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
 
     for (int c0 = 0; c0 < BN; c0 += 32) {
@@ -229,7 +262,8 @@ __global__ void __launch_bounds__(kGemmThreads) tapgemm_kernel(const __grid_cons
       for (int h = 0; h < 2; ++h) {
         if (h == 1 && !wide) break;
         float v[16];
-        const int cg = col_base + c0 + h * 16;  // global output column of v[0]
+        const int cl = c0 + h * 16;        // column inside the tile
+        const int cg = col_base + cl;      // global output column of v[0]
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[h * 16 + j]);
         if (args.bias) {
@@ -239,43 +273,29 @@ __global__ void __launch_bounds__(kGemmThreads) tapgemm_kernel(const __grid_cons
             v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
           }
         }
-        const long eoff = orow * ld + (col_o + c0 + h * 16);
-        if (resp && valid) {
-          if (args.out_f32) {
-            const float4* rp = reinterpret_cast<const float4*>(resp + eoff * 4);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float4 q = rp[j];
-              v[4 * j] += q.x; v[4 * j + 1] += q.y; v[4 * j + 2] += q.z; v[4 * j + 3] += q.w;
-            }
+        if (gn_on) {
+          const int cpg = args.cpg;
+          if (gn_cta) {
+            float* slot = &s_gn[warp - 2][2 * (cg / cpg - g_tile0)];
+            if (cpg >= 16) gn_accumulate16_warp<16>(v, valid, slot, lane);
+            else if (cpg == 8) gn_accumulate16_warp<8>(v, valid, slot, lane);
+            else if (cpg == 4) gn_accumulate16_warp<4>(v, valid, slot, lane);
+            else gn_accumulate16_warp<2>(v, valid, slot, lane);
           } else {
-            const uint4* rp = reinterpret_cast<const uint4*>(resp + eoff * 2);
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-              const uint4 q = rp[j];
-              float2 f;
-              f = unpack_bf16x2(q.x); v[8 * j + 0] += f.x; v[8 * j + 1] += f.y;
-              f = unpack_bf16x2(q.y); v[8 * j + 2] += f.x; v[8 * j + 3] += f.y;
-              f = unpack_bf16x2(q.z); v[8 * j + 4] += f.x; v[8 * j + 5] += f.y;
-              f = unpack_bf16x2(q.w); v[8 * j + 6] += f.x; v[8 * j + 7] += f.y;
-            }
+            float* base = gdst + 2 * (cg / cpg);
+            if (cpg >= 16) gn_accumulate16<16>(v, valid, base, 0, lane);
+            else if (cpg == 8) gn_accumulate16<8>(v, valid, base, 0, lane);
+            else if (cpg == 4) gn_accumulate16<4>(v, valid, base, 0, lane);
+            else gn_accumulate16<2>(v, valid, base, 0, lane);
           }
         }
-        if (gsum) {
-          const int cpg = args.cpg;
-          const int g0 = cg / cpg;
-          if (cpg >= 16) gn_accumulate16<16>(v, valid, gsum, g0, lane);
-          else if (cpg == 8) gn_accumulate16<8>(v, valid, gsum, g0, lane);
-          else if (cpg == 4) gn_accumulate16<4>(v, valid, gsum, g0, lane);
-          else gn_accumulate16<2>(v, valid, gsum, g0, lane);
-        }
-        if (valid) {
+        if (staged) {
           if (args.out_f32) {
-            float4* op = reinterpret_cast<float4*>(outp + eoff * 4);
+            float4* sp = reinterpret_cast<float4*>(srow + cl * 4);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            for (int j = 0; j < 4; ++j) sp[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
           } else {
-            uint4* op = reinterpret_cast<uint4*>(outp + eoff * 2);
+            uint4* sp = reinterpret_cast<uint4*>(srow + cl * 2);
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
               uint4 q;
@@ -283,13 +303,84 @@ __global__ void __launch_bounds__(kGemmThreads) tapgemm_kernel(const __grid_cons
               q.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
               q.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
               q.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
-              op[j] = q;
+              sp[j] = q;
+            }
+          }
+        } else {
+          const long eoff = orow * ld + (col_o + cl);
+          if (resp && valid) {
+            if (args.out_f32) {
+              const float4* rp = reinterpret_cast<const float4*>(resp + eoff * 4);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float4 q = rp[j];
+                v[4 * j] += q.x; v[4 * j + 1] += q.y; v[4 * j + 2] += q.z; v[4 * j + 3] += q.w;
+              }
+            } else {
+              const uint4* rp = reinterpret_cast<const uint4*>(resp + eoff * 2);
+#pragma unroll
+              for (int j = 0; j < 2; ++j) {
+                const uint4 q = rp[j];
+                float2 f;
+                f = unpack_bf16x2(q.x); v[8 * j + 0] += f.x; v[8 * j + 1] += f.y;
+                f = unpack_bf16x2(q.y); v[8 * j + 2] += f.x; v[8 * j + 3] += f.y;
+                f = unpack_bf16x2(q.z); v[8 * j + 4] += f.x; v[8 * j + 5] += f.y;
+                f = unpack_bf16x2(q.w); v[8 * j + 6] += f.x; v[8 * j + 7] += f.y;
+              }
+            }
+          }
+          if (valid) {
+            if (args.out_f32) {
+              float4* op = reinterpret_cast<float4*>(outp + eoff * 4);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            } else {
+              uint4* op = reinterpret_cast<uint4*>(outp + eoff * 2);
+#pragma unroll
+              for (int j = 0; j < 2; ++j) {
+                uint4 q;
+                q.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
+                q.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+                q.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+                q.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+                op[j] = q;
+              }
             }
           }
         }
       }
     }
-    (void)esz;
+    if (staged) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      // coalesced write-out: consecutive threads store consecutive 16-byte segments of a row
+      const int spr = (BN * esz) >> 4;  // 16B segments per row
+      const int total = kTileM * spr;
+      for (int idx = et; idx < total; idx += 128) {
+        const int rr = idx / spr, sg = idx - rr * spr;
+        const int mm = m0 + rr;
+        if (mm >= args.M) break;
+        uint4 q = *reinterpret_cast<const uint4*>(smem + (size_t)rr * pitch + sg * 16);
+        const long goff = ((long)mm * ld + col_o) * esz + sg * 16;
+        if (resp) {
+          const uint4 rq = *reinterpret_cast<const uint4*>(resp + goff);
+          if (args.out_f32) {
+            q.x = __float_as_uint(__uint_as_float(q.x) + __uint_as_float(rq.x));
+            q.y = __float_as_uint(__uint_as_float(q.y) + __uint_as_float(rq.y));
+            q.z = __float_as_uint(__uint_as_float(q.z) + __uint_as_float(rq.z));
+            q.w = __float_as_uint(__uint_as_float(q.w) + __uint_as_float(rq.w));
+          } else {
+            float2 a, b;
+            a = unpack_bf16x2(q.x); b = unpack_bf16x2(rq.x); q.x = pack_bf16x2(a.x + b.x, a.y + b.y);
+            a = unpack_bf16x2(q.y); b = unpack_bf16x2(rq.y); q.y = pack_bf16x2(a.x + b.x, a.y + b.y);
+            a = unpack_bf16x2(q.z); b = unpack_bf16x2(rq.z); q.z = pack_bf16x2(a.x + b.x, a.y + b.y);
+            a = unpack_bf16x2(q.w); b = unpack_bf16x2(rq.w); q.w = pack_bf16x2(a.x + b.x, a.y + b.y);
+          }
+        }
+        *reinterpret_cast<uint4*>(outp + goff) = q;
+      }
+      if (gn_cta && et < 2 * ((BN + args.cpg - 1) / args.cpg))
+        atomicAdd(gdst + 2 * g_tile0 + et, s_gn[0][et] + s_gn[1][et] + s_gn[2][et] + s_gn[3][et]);
+    }
   }
 
   tc_fence_before();
@@ -420,13 +511,17 @@ static int validate_desc(const vdn_tapgemm_desc* d) {
   return VDN_OK;
 }
 
-static int pick_bn(int N) {
+// N tile: as wide as possible (fewer re-reads of the A tile) while still giving every SM a CTA.
+static int pick_bn(int N, int m_tiles) {
+  int best = -1;
+  for (int bn = 256; bn >= 32; bn >>= 1) {
+    if (bn > N || N % bn != 0) continue;
+    if (best < 0) best = bn;
+    if (m_tiles * (N / bn) >= num_sms()) return bn;
+    best = bn;
+  }
+  if (best > 0) return best;
   if (N <= 256) return N;
-  if (N % 256 == 0) return 256;
-  if (N % 192 == 0) return 192;
-  if (N % 128 == 0) return 128;
-  if (N % 64 == 0) return 64;
-  if (N % 32 == 0) return 32;
   return 16;
 }
 
@@ -462,7 +557,11 @@ extern "C" int vdn_tapgemm(const vdn_tapgemm_desc* d, const void* src0, const vo
   memset(&a, 0, sizeof(a));
   a.M = d->n_img * d->H * d->W;
   a.N = d->n_out;
-  a.BN = pick_bn(d->n_out);
+  a.BN = pick_bn(d->n_out, ceil_div(a.M, kTileM));
+  if (const char* e = getenv("VDN_BN")) {  // tuning override (experiments only)
+    const int v = atoi(e);
+    if (v >= 16 && v <= 256 && d->n_out % v == 0) a.BN = v;
+  }
   if (d->split_col > 0) {
     while (d->split_col % a.BN != 0) a.BN /= 2;
     VDN_REQUIRE(a.BN >= 16, VDN_E_SHAPE, "tapgemm: split_col %d not tileable", d->split_col);
@@ -491,7 +590,9 @@ extern "C" int vdn_tapgemm(const vdn_tapgemm_desc* d, const void* src0, const vo
   a.gn_groups = gn_sums ? d->gn_groups : 0;
   a.cpg = d->gn_groups > 0 ? d->n_out / d->gn_groups : 1;
   a.rows_per_sample = d->rows_per_sample > 0 ? d->rows_per_sample : 1;
+  a.n_samples = std::max(1, a.M / a.rows_per_sample);
   if (!gn_sums) a.gn_sums = nullptr;
+  VDN_REQUIRE(!(gn_sums && residual), VDN_E_SHAPE, "tapgemm: gn_sums and residual are mutually exclusive");
 
   TapMaps maps;
   memset(&maps, 0, sizeof(maps));
@@ -545,13 +646,16 @@ extern "C" int vdn_tapgemm(const vdn_tapgemm_desc* d, const void* src0, const vo
   const int a_bytes = kTileM * BK * 2;
   const int b_bytes = (a.BN * BK * 2 + 1023) & ~1023;
   const int stage_bytes = a_bytes + b_bytes;
-  const int budget = stage_bytes >= 24 * 1024 ? 192 * 1024 : 96 * 1024;
+  // small tiles are latency bound: keep shared memory low so that many CTAs share an SM
+  const int budget = stage_bytes > 24 * 1024 ? 192 * 1024 : (stage_bytes > 12 * 1024 ? 64 * 1024 : 32 * 1024);
   const int n_steps = d->n_taps * d->n_src * a.chunks;
   a.stages = std::max(2, std::min(std::min(kMaxStages, budget / stage_bytes), std::max(n_steps, 2)));
+  if (const char* e = getenv("VDN_STAGES")) a.stages = std::max(1, std::min(kMaxStages, atoi(e)));
   int cols = 32;
   while (cols < a.BN) cols *= 2;
   a.tmem_cols = cols;
-  const int smem_bytes = a.stages * stage_bytes + 1024;
+  const int tile_bytes = d->kind == VDN_TAP_UP ? 0 : kTileM * (a.BN * (a.out_f32 ? 4 : 2) + 16);
+  const int smem_bytes = std::max(a.stages * stage_bytes, tile_bytes) + 1024;
 
   // alignment of epilogue vector accesses
   VDN_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0 && (!residual || (reinterpret_cast<uintptr_t>(residual) & 15) == 0) &&

@@ -13,6 +13,10 @@ namespace vdn {
 
 typedef __nv_bfloat16 bf16;
 
+// GroupNorm partial sums are spread over this many replica slots ([R][B][G][2]) to keep same-address
+// atomic contention low; consumers add the replicas up.
+constexpr int kGnReplicas = 16;
+
 // ----------------------------------------------------------------------------
 // error plumbing (host)
 // ----------------------------------------------------------------------------

@@ -467,7 +467,7 @@ class UnetEngine:
         self.n_res = n
         # count GroupNorm slots first (2 per ResnetBlock) so one buffer can be zeroed per forward
         n_blocks = 4 * n + 2 + 1
-        self.gn_all = torch.zeros(n_blocks * 2, B, GROUPS, 2, dtype=F32, device=self.device)
+        self.gn_all = torch.zeros(n_blocks * 2, ops.GN_REPLICAS, B, GROUPS, 2, dtype=F32, device=self.device)
 
         self.h0 = self.new((n_img, H, W, dim))
         self.init_attn = MHABlock(self, "init_temporal_attn", dim, n_img, H, W, 0)

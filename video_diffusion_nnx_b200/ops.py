@@ -10,6 +10,7 @@ import torch
 from . import _lib
 from ._lib import VDN_BF16, VDN_F32, VDN_TAP_DOWN, VDN_TAP_UNIT, VDN_TAP_UP, TapGemmDesc, check, lib, ptr, stream_ptr
 
+GN_REPLICAS = 16  # kGnReplicas in csrc/vdn_common.cuh: GroupNorm partial sums are [R][B][G][2]
 TAPS_1x1 = [(0, 0)]
 TAPS_3x3 = [(dy, dx) for dy in (-1, 0, 1) for dx in (-1, 0, 1)]  # kernel (kh,kw) row-major, SAME padding
 TAPS_4x4 = [(ky, kx) for ky in range(4) for kx in range(4)]  # VDN_TAP_DOWN: kernel indices
