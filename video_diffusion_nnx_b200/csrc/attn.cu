@@ -55,16 +55,21 @@ __device__ __forceinline__ void store32(bf16* p, const float (&v)[32]) {
   }
 }
 __device__ __forceinline__ float dot32(const float (&a)[32], const float (&b)[32]) {
-  float s = 0.f;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;  // 4 independent chains (ILP)
 #pragma unroll
-  for (int e = 0; e < 32; ++e) s = fmaf(a[e], b[e], s);
-  return s;
+  for (int e = 0; e < 32; e += 4) {
+    s0 = fmaf(a[e], b[e], s0);
+    s1 = fmaf(a[e + 1], b[e + 1], s1);
+    s2 = fmaf(a[e + 2], b[e + 2], s2);
+    s3 = fmaf(a[e + 3], b[e + 3], s3);
+  }
+  return (s0 + s1) + (s2 + s3);
 }
 
 // ---------------------------------------------------------------------------------------
 // MHA core forward: one thread per (sequence, query token, head); online softmax over keys.
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) mha_core_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ o,
+__global__ void __launch_bounds__(256, 2) mha_core_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ o,
                                                            float* __restrict__ lse, const SeqMap m) {
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const long total = m.n_seq * m.S * kHeads;
@@ -104,7 +109,7 @@ __global__ void __launch_bounds__(256) mha_core_fwd_kernel(const bf16* __restric
 }
 
 // Backward, phase 1: dq (and D_i = do_i . o_i for phase 2).
-__global__ void __launch_bounds__(256) mha_core_bwd_dq_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o,
+__global__ void __launch_bounds__(256, 2) mha_core_bwd_dq_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o,
                                                               const bf16* __restrict__ d_o,
                                                               const float* __restrict__ lse, float* __restrict__ Dws,
                                                               bf16* __restrict__ dqkv, const SeqMap m) {
@@ -140,7 +145,7 @@ __global__ void __launch_bounds__(256) mha_core_bwd_dq_kernel(const bf16* __rest
 }
 
 // Backward, phase 2: dk_j, dv_j; one thread per (sequence, key token, head).
-__global__ void __launch_bounds__(256) mha_core_bwd_dkv_kernel(const bf16* __restrict__ qkv,
+__global__ void __launch_bounds__(256, 2) mha_core_bwd_dkv_kernel(const bf16* __restrict__ qkv,
                                                                const bf16* __restrict__ d_o,
                                                                const float* __restrict__ lse,
                                                                const float* __restrict__ Dws,
@@ -337,7 +342,11 @@ __global__ void __launch_bounds__(256) sla_apply_kernel(const bf16* __restrict__
     for (int d = 0; d < 32; ++d) {
       const float qd = q[d];
 #pragma unroll
-      for (int e = 0; e < 32; ++e) o[e] = fmaf(qd, ch[d * 32 + e], o[e]);
+      for (int e = 0; e < 32; e += 4) {
+        const float4 c4 = *reinterpret_cast<const float4*>(&ch[d * 32 + e]);
+        o[e] = fmaf(qd, c4.x, o[e]); o[e + 1] = fmaf(qd, c4.y, o[e + 1]);
+        o[e + 2] = fmaf(qd, c4.z, o[e + 2]); o[e + 3] = fmaf(qd, c4.w, o[e + 3]);
+      }
     }
     store32(out + row * kHD + h * kDh, o);
   }
@@ -435,9 +444,14 @@ __global__ void __launch_bounds__(256) sla_bwd_tokens_kernel(const bf16* __restr
     float dotq = 0.f;
 #pragma unroll 4
     for (int d = 0; d < 32; ++d) {
-      float t = 0.f;
+      float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
 #pragma unroll
-      for (int e = 0; e < 32; ++e) t = fmaf(ch[d * 32 + e], g[e], t);
+      for (int e = 0; e < 32; e += 4) {
+        const float4 c4 = *reinterpret_cast<const float4*>(&ch[d * 32 + e]);
+        t0 = fmaf(c4.x, g[e], t0); t1 = fmaf(c4.y, g[e + 1], t1);
+        t2 = fmaf(c4.z, g[e + 2], t2); t3 = fmaf(c4.w, g[e + 3], t3);
+      }
+      const float t = (t0 + t1) + (t2 + t3);
       r[d] = t;  // dq~[d]
       dotq = fmaf(a[d], t, dotq);
     }
@@ -451,10 +465,14 @@ __global__ void __launch_bounds__(256) sla_bwd_tokens_kernel(const bf16* __restr
     for (int d = 0; d < 32; ++d) a[d] = __expf(a[d] - sm_m[h * 32 + d]) * sm_is[h * 32 + d];  // k~
 #pragma unroll 4
     for (int d = 0; d < 32; ++d) {
-      float t = 0.f;
+      float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
 #pragma unroll
-      for (int e = 0; e < 32; ++e) t = fmaf(dch[d * 32 + e], g[e], t);
-      r[d] = a[d] * (t - sm_r[h * 32 + d]);
+      for (int e = 0; e < 32; e += 4) {
+        const float4 c4 = *reinterpret_cast<const float4*>(&dch[d * 32 + e]);
+        t0 = fmaf(c4.x, g[e], t0); t1 = fmaf(c4.y, g[e + 1], t1);
+        t2 = fmaf(c4.z, g[e + 2], t2); t3 = fmaf(c4.w, g[e + 3], t3);
+      }
+      r[d] = a[d] * (((t0 + t1) + (t2 + t3)) - sm_r[h * 32 + d]);
     }
     store32(dqkv + row * kQKV + kHD + h * kDh, r);
     // ---- dv[e] = sum_d k~[d] dctx[d][e] ----
@@ -464,7 +482,11 @@ __global__ void __launch_bounds__(256) sla_bwd_tokens_kernel(const bf16* __restr
     for (int d = 0; d < 32; ++d) {
       const float kd = a[d];
 #pragma unroll
-      for (int e = 0; e < 32; ++e) r[e] = fmaf(kd, dch[d * 32 + e], r[e]);
+      for (int e = 0; e < 32; e += 4) {
+        const float4 c4 = *reinterpret_cast<const float4*>(&dch[d * 32 + e]);
+        r[e] = fmaf(kd, c4.x, r[e]); r[e + 1] = fmaf(kd, c4.y, r[e + 1]);
+        r[e + 2] = fmaf(kd, c4.z, r[e + 2]); r[e + 3] = fmaf(kd, c4.w, r[e + 3]);
+      }
     }
     store32(dqkv + row * kQKV + 2 * kHD + h * kDh, r);
   }
@@ -541,7 +563,7 @@ extern "C" int vdn_sla_core_fwd(const void* qkv, void* tok_out, float* ctx, floa
     cudaFuncSetAttribute(sla_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 1024 * 4);
     cfg = true;
   }
-  const int gx = std::max(1, std::min((N + 31) / 32, std::max(1, 148 * 4 / n_img)));
+  const int gx = std::max(1, std::min((N + 31) / 32, std::max(1, 148 * 8 / n_img)));
   sla_apply_kernel<<<dim3(gx, n_img), 256, 8 * 1024 * sizeof(float), st>>>(reinterpret_cast<const bf16*>(qkv), ctx,
                                                                            reinterpret_cast<bf16*>(tok_out), N);
   return check_launch("sla_apply");
@@ -566,7 +588,7 @@ extern "C" int vdn_sla_core_bwd(const void* qkv, const void* d_tok, const float*
     cudaFuncSetAttribute(sla_bwd_tokens_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cfg = true;
   }
-  const int gx = std::max(1, std::min((N + 31) / 32, std::max(1, 148 * 2 / n_img)));
+  const int gx = std::max(1, std::min((N + 31) / 32, std::max(1, 148 * 6 / n_img)));
   sla_bwd_tokens_kernel<<<dim3(gx, n_img), 256, smem, st>>>(reinterpret_cast<const bf16*>(qkv),
                                                             reinterpret_cast<const bf16*>(d_tok), ctx, dctx, kstat,
                                                             reinterpret_cast<bf16*>(dqkv), N);

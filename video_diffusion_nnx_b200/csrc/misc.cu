@@ -383,59 +383,89 @@ __global__ void __launch_bounds__(256) time_heads_fwd_kernel(const float* __rest
   }
 }
 
-// grid (n_heads): LN backward, dW/db accumulation over the batch, dt_silu accumulation (atomics).
-__global__ void __launch_bounds__(256) time_heads_bwd_kernel(const float* __restrict__ t, const vdn_time_head* __restrict__ heads,
-                                                             const float* __restrict__ e_pre, const float* __restrict__ dss,
-                                                             int ss_ld, float* __restrict__ de_ws /*[B][ss_ld]*/,
-                                                             float* __restrict__ dt /*[B][td], zeroed*/, int B, int td) {
-  extern __shared__ float sm[];
-  float* red = sm;  // [32]
+// Backward of the time heads, two kernels.
+// A: grid (n_heads, B): LayerNorm backward of one (head, sample) row -> de; db / dln accumulate (atomics over B).
+__global__ void __launch_bounds__(256) time_heads_bwd_ln_kernel(const vdn_time_head* __restrict__ heads,
+                                                                const float* __restrict__ e_pre,
+                                                                const float* __restrict__ dss, int ss_ld,
+                                                                float* __restrict__ de_ws /*[B][ss_ld]*/) {
+  __shared__ float red[32];
+  const vdn_time_head hd = heads[blockIdx.x];
+  const int b = blockIdx.y, n = hd.n_out;
+  const float* e = e_pre + (long)b * ss_ld + hd.off;
+  const float* dy = dss + (long)b * ss_ld + hd.off;
+  float s1 = 0.f, s2 = 0.f;
+  for (int j = threadIdx.x; j < n; j += blockDim.x) {
+    s1 += e[j];
+    s2 += e[j] * e[j];
+  }
+  s1 = block_sum(s1, red);
+  s2 = block_sum(s2, red);
+  const float mean = s1 / (float)n;
+  const float rstd = rsqrtf(fmaxf(s2 / (float)n - mean * mean, 0.f) + 1e-6f);
+  float a1 = 0.f, a2 = 0.f;
+  for (int j = threadIdx.x; j < n; j += blockDim.x) {
+    const float eh = (e[j] - mean) * rstd;
+    const float gd = hd.ln_g[j] * dy[j];
+    a1 += gd;
+    a2 += gd * eh;
+    atomicAdd(&hd.dln_g[j], dy[j] * eh);
+    atomicAdd(&hd.dln_b[j], dy[j]);
+  }
+  a1 = block_sum(a1, red) / (float)n;
+  a2 = block_sum(a2, red) / (float)n;
+  for (int j = threadIdx.x; j < n; j += blockDim.x) {
+    const float eh = (e[j] - mean) * rstd;
+    const float v = rstd * (hd.ln_g[j] * dy[j] - a1 - eh * a2);
+    de_ws[(long)b * ss_ld + hd.off + j] = v;
+    atomicAdd(&hd.db[j], v);
+  }
+}
+
+// B: grid (n_heads, td/8): 8 rows k of the head's weight: dW[k][:] += sum_b silu(t[b][k]) de[b][:],
+//    dt[b][k] += silu'(t[b][k]) * sum_j W[k][j] de[b][j] (one warp per k, atomics over heads).
+constexpr int kTHB = 8;  // max batch rows held in registers per pass
+__global__ void __launch_bounds__(256) time_heads_bwd_w_kernel(const float* __restrict__ t,
+                                                               const vdn_time_head* __restrict__ heads,
+                                                               const float* __restrict__ de_ws, int ss_ld,
+                                                               float* __restrict__ dt, int B, int td) {
   const vdn_time_head hd = heads[blockIdx.x];
   const int n = hd.n_out;
-  for (int b = 0; b < B; ++b) {
-    const float* e = e_pre + (long)b * ss_ld + hd.off;
-    const float* dy = dss + (long)b * ss_ld + hd.off;
-    float s1 = 0.f, s2 = 0.f;
+  const int k0 = blockIdx.y * 8;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int b0 = 0; b0 < B; b0 += kTHB) {
+    const int nb = min(kTHB, B - b0);
+    // dW rows k0..k0+7
     for (int j = threadIdx.x; j < n; j += blockDim.x) {
-      s1 += e[j];
-      s2 += e[j] * e[j];
+      float de[kTHB];
+#pragma unroll
+      for (int q = 0; q < kTHB; ++q) de[q] = q < nb ? de_ws[(long)(b0 + q) * ss_ld + hd.off + j] : 0.f;
+      for (int kk = 0; kk < 8 && k0 + kk < td; ++kk) {
+        float a = 0.f;
+#pragma unroll
+        for (int q = 0; q < kTHB; ++q)
+          if (q < nb) a = fmaf(silu_f(t[(long)(b0 + q) * td + k0 + kk]), de[q], a);
+        hd.dw[(long)(k0 + kk) * n + j] += a;
+      }
     }
-    s1 = block_sum(s1, red);
-    s2 = block_sum(s2, red);
-    const float mean = s1 / (float)n;
-    const float rstd = rsqrtf(fmaxf(s2 / (float)n - mean * mean, 0.f) + 1e-6f);
-    float a1 = 0.f, a2 = 0.f;
-    for (int j = threadIdx.x; j < n; j += blockDim.x) {
-      const float eh = (e[j] - mean) * rstd;
-      const float gd = hd.ln_g[j] * dy[j];
-      a1 += gd;
-      a2 += gd * eh;
-      hd.dln_g[j] += dy[j] * eh;   // single block per head: plain accumulation is race free
-      hd.dln_b[j] += dy[j];
+    // dt: warp `warp` owns row k0 + warp
+    const int k = k0 + warp;
+    if (k < td) {
+      float acc[kTHB];
+#pragma unroll
+      for (int q = 0; q < kTHB; ++q) acc[q] = 0.f;
+      for (int j = lane; j < n; j += 32) {
+        const float w = hd.w[(long)k * n + j];
+#pragma unroll
+        for (int q = 0; q < kTHB; ++q)
+          if (q < nb) acc[q] = fmaf(w, de_ws[(long)(b0 + q) * ss_ld + hd.off + j], acc[q]);
+      }
+#pragma unroll
+      for (int q = 0; q < kTHB; ++q) {
+        const float v = warp_sum(acc[q]);
+        if (lane == 0 && q < nb) atomicAdd(&dt[(long)(b0 + q) * td + k], v * silu_grad_f(t[(long)(b0 + q) * td + k]));
+      }
     }
-    a1 = block_sum(a1, red) / (float)n;
-    a2 = block_sum(a2, red) / (float)n;
-    for (int j = threadIdx.x; j < n; j += blockDim.x) {
-      const float eh = (e[j] - mean) * rstd;
-      const float v = rstd * (hd.ln_g[j] * dy[j] - a1 - eh * a2);
-      de_ws[(long)b * ss_ld + hd.off + j] = v;
-      hd.db[j] += v;
-    }
-  }
-  __syncthreads();
-  // dW[k][j] += sum_b silu(t[b][k]) de[b][j]
-  for (long i = threadIdx.x; i < (long)td * n; i += blockDim.x) {
-    const int k = (int)(i / n), j = (int)(i % n);
-    float a = 0.f;
-    for (int b = 0; b < B; ++b) a = fmaf(silu_f(t[(long)b * td + k]), de_ws[(long)b * ss_ld + hd.off + j], a);
-    hd.dw[i] += a;
-  }
-  // dt[b][k] += silu'(t[b][k]) * sum_j W[k][j] de[b][j]
-  for (int i = threadIdx.x; i < B * td; i += blockDim.x) {
-    const int b = i / td, k = i % td;
-    float a = 0.f;
-    for (int j = 0; j < n; ++j) a = fmaf(hd.w[(long)k * n + j], de_ws[(long)b * ss_ld + hd.off + j], a);
-    atomicAdd(&dt[i], a * silu_grad_f(t[i]));
   }
 }
 
@@ -512,6 +542,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ dy
 #pragma unroll
   for (int j = 0; j < 8; ++j) a[j] = 0.f;
   if (pl < pl_n) {
+#pragma unroll 4
     for (long p = (long)blockIdx.x * pl_n + pl; p < P; p += (long)gridDim.x * pl_n) {
       const uint4 u = *reinterpret_cast<const uint4*>(dy + p * C + ci * 8);
       float2 f2;
@@ -680,9 +711,12 @@ extern "C" int vdn_time_heads_bwd(const float* t, const void* heads_dev, int n_h
                                   const float* dss, int ss_ld, float* de_ws, float* dt, int B, int td, void* stream) {
   cudaError_t e = cudaMemsetAsync(dt, 0, (size_t)B * td * sizeof(float), ST(stream));
   VDN_REQUIRE(e == cudaSuccess, VDN_E_CUDA, "time_heads_bwd memset: %s", cudaGetErrorString(e));
-  time_heads_bwd_kernel<<<n_heads, 256, 32 * sizeof(float), ST(stream)>>>(
-      t, reinterpret_cast<const vdn_time_head*>(heads_dev), e_pre, dss, ss_ld, de_ws, dt, B, td);
-  return check_launch("time_heads_bwd");
+  const vdn_time_head* hd = reinterpret_cast<const vdn_time_head*>(heads_dev);
+  time_heads_bwd_ln_kernel<<<dim3(n_heads, B), 256, 0, ST(stream)>>>(hd, e_pre, dss, ss_ld, de_ws);
+  int rc = check_launch("time_heads_bwd_ln");
+  if (rc) return rc;
+  time_heads_bwd_w_kernel<<<dim3(n_heads, (td + 7) / 8), 256, 0, ST(stream)>>>(t, hd, de_ws, ss_ld, dt, B, td);
+  return check_launch("time_heads_bwd_w");
 }
 
 extern "C" int vdn_q_sample(const float* x_start, const float* noise, const int* t, const float* sqrt_ac,

@@ -92,6 +92,7 @@ __global__ void __launch_bounds__(kNormThreads) gn_silu_fwd_kernel(const GnArgs 
   const long nvec = (long)a.rows * c8n;
   const bf16* xb = a.x + (long)b * a.rows * a.C;
   bf16* ob = out + (long)b * a.rows * a.C;
+#pragma unroll 2
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long)gridDim.x * blockDim.x) {
     const int c0 = (int)(i % c8n) * 8;
     float v[8];
@@ -205,6 +206,7 @@ __global__ void __launch_bounds__(kNormThreads) gn_bwd_reduce_kernel(const GnArg
   for (int j = 0; j < 8; ++j) t1[j] = t2[j] = 0.f;
   const long base = (long)b * a.rows;
   if (pl < pl_n) {
+#pragma unroll 2
     for (long p = (long)blockIdx.x * pl_n + pl; p < a.rows; p += (long)gridDim.x * pl_n) {
       const long off = (base + p) * a.C + c0;
       float xv[8], dv[8];

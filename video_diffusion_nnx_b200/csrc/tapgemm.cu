@@ -483,6 +483,43 @@ __global__ void pack_weight_kernel(const float* __restrict__ src, bf16* __restri
   }
 }
 
+}  // namespace vdn
+
+// One entry of the batched repack table (device memory). `begin` = exclusive prefix sum of the job sizes.
+struct vdn_pack_job {
+  const float* src;
+  void* dst;
+  int taps, cin, cout, mode, ld, n_off, k_off;
+  int perm[16];
+  long long begin;
+};
+
+namespace vdn {
+
+// All weight repacks of a model in ONE launch: each 256-element chunk locates its job by binary search.
+__global__ void __launch_bounds__(256) pack_batched_kernel(const vdn_pack_job* __restrict__ jobs, int n_jobs,
+                                                           long long total) {
+  for (long long c0 = (long long)blockIdx.x * 256; c0 < total; c0 += (long long)gridDim.x * 256) {
+    const long long i = c0 + threadIdx.x;
+    if (i >= total) continue;
+    int lo = 0, hi = n_jobs - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (jobs[mid].begin <= i) lo = mid; else hi = mid - 1;
+    }
+    const vdn_pack_job& a = jobs[lo];
+    const long long r = i - a.begin;
+    const int kin = a.mode == 0 ? a.cin : a.cout;
+    const int k = (int)(r % kin);
+    const int t = (int)((r / kin) % a.taps);
+    const int n = (int)(r / ((long long)kin * a.taps));
+    const int ci = a.mode == 0 ? k : n;
+    const int co = a.mode == 0 ? n : k;
+    const float v = a.src[((long)a.perm[t] * a.cin + ci) * a.cout + co];
+    reinterpret_cast<bf16*>(a.dst)[(long)(a.n_off + n) * a.ld + a.k_off + (long)t * kin + k] = __float2bfloat16(v);
+  }
+}
+
 // ---------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------
@@ -709,6 +746,14 @@ extern "C" int vdn_tapgemm_ref(const vdn_tapgemm_desc* d, const void* src0, cons
   const int threads = 256;
   tapgemm_ref_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a);
   return check_launch("tapgemm_ref_kernel");
+}
+
+extern "C" int vdn_pack_batched(const void* jobs_dev, int n_jobs, long long total, void* stream) {
+  VDN_REQUIRE(jobs_dev && n_jobs > 0 && total > 0, VDN_E_SHAPE, "pack_batched: bad args");
+  const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 16);
+  pack_batched_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const vdn_pack_job*>(jobs_dev), n_jobs, total);
+  return check_launch("pack_batched_kernel");
 }
 
 extern "C" int vdn_pack_weight(const float* src, void* dst, int taps, int cin, int cout, int mode,

@@ -165,13 +165,9 @@ class GemmConv:
             self.dw = st.gview(wname)
             self.dbias = st.gview(bname) if bname else None
         self.flip = [nt - 1 - t for t in range(nt)]
-        eng.packers.append(self.repack)
-
-    def repack(self):
-        nt = len(self.taps)
-        ops.pack_weight(self.w, self.wp, nt, self.cin, self.cout, 0)
+        eng.pack_jobs.append((self.w, self.wp, nt, self.cin, self.cout, 0, None))
         if self.wd is not None:
-            ops.pack_weight(self.w, self.wd, nt, self.cin, self.cout, 1, self.flip)
+            eng.pack_jobs.append((self.w, self.wd, nt, self.cin, self.cout, 1, self.flip))
 
     def fwd(self, srcs, out, residual=None, gn_sums=None, rows_per_sample=0, out_dtype=BF16):
         return ops.tapgemm(VDN_TAP_UNIT, srcs, self.wp, self.taps, bias=self.bias, residual=residual, out=out,
@@ -376,13 +372,10 @@ class DownConv:
                     shifts = [((py + 1 - ky) // 2, (px + 1 - kx) // 2) for ky in kys for kx in kxs]
                     kidx = [ky * 4 + kx for ky in kys for kx in kxs]
                     self.cls.append((py, px, shifts, kidx, torch.empty(C, 4 * C, dtype=BF16, device=eng.device)))
-        eng.packers.append(self.repack)
-        self.x = None
-
-    def repack(self):
-        ops.pack_weight(self.w, self.wp, 16, self.C, self.C, 0)
+        eng.pack_jobs.append((self.w, self.wp, 16, C, C, 0, None))
         for _, _, _, kidx, wd in self.cls:
-            ops.pack_weight(self.w, wd, 4, self.C, self.C, 1, kidx)
+            eng.pack_jobs.append((self.w, wd, 4, C, C, 1, kidx))
+        self.x = None
 
     def forward(self, x):
         self.x = x
@@ -415,14 +408,11 @@ class UpConv:
         if eng.training:
             self.dw, self.dbias = st.gview(prefix + ".kernel"), st.gview(prefix + ".bias")
             self.wd = torch.empty(C, 16 * C, dtype=BF16, device=eng.device)
-        eng.packers.append(self.repack)
-        self.x = None
-
-    def repack(self):
         for _, _, _, kidx, wp in self.cls:
-            ops.pack_weight(self.w, wp, 4, self.C, self.C, 0, kidx)
+            eng.pack_jobs.append((self.w, wp, 4, C, C, 0, kidx))
         if self.wd is not None:
-            ops.pack_weight(self.w, self.wd, 16, self.C, self.C, 1, [15 - k for k in range(16)])
+            eng.pack_jobs.append((self.w, self.wd, 16, C, C, 1, [15 - k for k in range(16)]))
+        self.x = None
 
     def forward(self, x):
         self.x = x
@@ -449,7 +439,7 @@ class UnetEngine:
         self.dim, self.channels, self.B, self.F, self.H, self.W = dim, channels, B, F, H, W
         self.out_dim = channels if out_dim is None else out_dim
         self.ks = init_kernel_size
-        self.packers = []
+        self.pack_jobs = []
         self.pool = _Pool(self.device)
         self._gn_slots: List[torch.Tensor] = []
         self._gn_count = 0
@@ -523,6 +513,7 @@ class UnetEngine:
         self.head_table = ops.make_time_head_table(entries, self.device)
         self.n_heads = len(entries)
         self.x_in = None
+        self.pack_table, self.n_pack_jobs, self.pack_total = ops.make_pack_table(self.pack_jobs, self.device)
         self.repack()
 
     # -- allocation helpers ------------------------------------------------------------------
@@ -548,9 +539,8 @@ class UnetEngine:
         return off
 
     def repack(self):
-        """Refresh every packed bf16 GEMM operand from the fp32 master weights."""
-        for f in self.packers:
-            f()
+        """Refresh every packed bf16 GEMM operand from the fp32 master weights (one batched launch)."""
+        ops.pack_batched(self.pack_table, self.n_pack_jobs, self.pack_total)
 
     # -- forward -----------------------------------------------------------------------------
     def forward(self, x: torch.Tensor, time: torch.Tensor) -> torch.Tensor:

@@ -254,3 +254,30 @@ def randn(out, seed: int, subseq: int = 0, elem_offset: int = 0):
     """Fill `out` (fp32) with N(0,1) draws: element i = Philox(seed, subseq, elem_offset + i)."""
     check(lib.vdn_randn(ptr(out), C.c_long(out.numel()), C.c_ulonglong(seed & (2 ** 64 - 1)), C.c_ulonglong(subseq),
                         C.c_ulonglong(elem_offset), stream_ptr()), "vdn_randn")
+
+
+class PackJob(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("taps", C.c_int), ("cin", C.c_int), ("cout", C.c_int),
+                ("mode", C.c_int), ("ld", C.c_int), ("n_off", C.c_int), ("k_off", C.c_int), ("perm", C.c_int * 16),
+                ("begin", C.c_longlong)]
+
+
+def make_pack_table(jobs, device):
+    """jobs: list of (src fp32 tensor, dst bf16 2-D tensor, taps, cin, cout, mode, perm|None). Returns
+    (device table, n_jobs, total elements) for pack_batched()."""
+    arr = (PackJob * len(jobs))()
+    begin = 0
+    for i, (src, dst, taps, cin, cout, mode, perm) in enumerate(jobs):
+        a = arr[i]
+        a.src, a.dst = src.data_ptr(), dst.data_ptr()
+        a.taps, a.cin, a.cout, a.mode, a.ld, a.n_off, a.k_off = taps, cin, cout, mode, dst.shape[-1], 0, 0
+        for t in range(16):
+            a.perm[t] = perm[t] if (perm is not None and t < len(perm)) else t
+        a.begin = begin
+        begin += taps * cin * cout
+    host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+    return host.to(device), len(jobs), begin
+
+
+def pack_batched(table, n_jobs: int, total: int):
+    check(lib.vdn_pack_batched(ptr(table), n_jobs, C.c_longlong(total), stream_ptr()), "vdn_pack_batched")
