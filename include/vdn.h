@@ -104,6 +104,146 @@ int vdn_tapgemm_ref(const vdn_tapgemm_desc* d, const void* src0, const void* src
                     const float* bias, const void* residual, const void* residual2, void* out, void* out2,
                     float* gn_sums, void* stream);
 
+/* ---------------------------------------------------------------------------------
+ * Batched repack: every packed operand of a model in one launch. jobs_dev points to a device
+ * array of vdn_pack_job (begin = exclusive prefix sum of taps*cin*cout); total = sum of sizes.
+ * --------------------------------------------------------------------------------- */
+typedef struct {
+  const float* src; /* fp32 [taps][cin][cout] */
+  void* dst;        /* bf16 packed operand */
+  int taps, cin, cout, mode, ld, n_off, k_off;
+  int perm[16];
+  long long begin;
+} vdn_pack_job;
+int vdn_pack_batched(const void* jobs_dev, int n_jobs, long long total, void* stream);
+
+/* ---------------------------------------------------------------------------------
+ * Weight gradient of every conv / projection (tcgen05, MN-major operands, split-K + fp32 atomics):
+ *   dw[tap][n_src*C][Cout] += sum_pixels src[p + tap]^T g[p]     (reference kernel layout)
+ * Replaces the XLA transpose of the call sites listed for vdn_tapgemm under
+ * jax.value_and_grad (trainer.py:361). kind as in vdn_tapgemm:
+ *   UNIT: src (n_img,H,W,C) x n_src, g (n_img,H,W,Cout), taps = (dy,dx) shifts
+ *   DOWN: src (n_img,2H,2W,C), g (n_img,H,W,Cout), taps = kernel indices (ky,kx) in 0..3
+ *   UP  : src (n_img,H,W,C), g (n_img,2H,2W,Cout), taps = kernel indices (a,b) in 0..3
+ * --------------------------------------------------------------------------------- */
+int vdn_wgrad(int kind, const void* src0, const void* src1, const void* g, float* dw, int n_img, int H, int W,
+              int n_src, int C, int Cout, int n_taps, const int* tap_dy, const int* tap_dx, void* stream);
+/* test-only CUDA-core reference of the same contract */
+int vdn_wgrad_ref(int kind, const void* src0, const void* src1, const void* g, float* dw, int n_img, int H, int W,
+                  int n_src, int C, int Cout, int n_taps, const int* tap_dy, const int* tap_dx, void* stream);
+
+/* ---------------------------------------------------------------------------------
+ * Block / ResnetBlock normalisation (modules.py:150-243). gn_sums: fp32 [16][B][G][2] replica
+ * slots of (sum x, sum x^2) per (sample, group) as accumulated by vdn_tapgemm. flax semantics:
+ * statistics over (F,H,W,C/G), eps 1e-6, var = max(0, E[x^2]-E[x]^2).
+ *   gn_silu_fwd:        out = silu( GN(x_raw)*gamma+beta [ *(scale+1)+shift ] )     modules.py:171-179
+ *   resblock_tail_fwd:  out = silu(GN(b_raw)*gamma+beta) + LayerNorm_C(s)           modules.py:241-242
+ *   gn_silu_bwd:        dx_raw, dgamma+=, dbeta+=, dss = (dscale | dshift) [B][2C]; T_ws fp32 [B][C][2]
+ *   ln_bwd:             ds, dgamma+=, dbeta+= of the per-pixel LayerNorm (norm_2)
+ * scale_shift: fp32 rows [B][ss_ld], scale = [0,C), shift = [C,2C); NULL when the block has no time
+ * embedding. All activation tensors bf16 [B][rows_per_sample][C].
+ * --------------------------------------------------------------------------------- */
+int vdn_gn_silu_fwd(const void* x_raw, const float* gn_sums, const float* gamma, const float* beta,
+                    const float* scale_shift, int ss_ld, void* out, int B, int rows_per_sample, int C, int G,
+                    void* stream);
+int vdn_resblock_tail_fwd(const void* b_raw, const float* gn_sums, const float* gamma, const float* beta,
+                          const void* s, const float* ln_gamma, const float* ln_beta, void* out, int B,
+                          int rows_per_sample, int C, int G, void* stream);
+int vdn_gn_silu_bwd(const void* dy, const void* x_raw, const float* gn_sums, const float* gamma, const float* beta,
+                    const float* scale_shift, int ss_ld, float* T_ws, void* dx_raw, float* dgamma, float* dbeta,
+                    float* dss, int dss_ld, int B, int rows_per_sample, int C, int G, void* stream);
+int vdn_ln_bwd(const void* s, const void* dy, const float* ln_gamma, void* ds, float* dgamma, float* dbeta, long P,
+               int C, void* stream);
+
+/* ---------------------------------------------------------------------------------
+ * Attention cores on the fused projection qkv bf16 [P][768] = (q | k | v), 8 heads x 32.
+ *   mha_core: MultiheadAttention core, modules.py:285-324 (q / sqrt(32), softmax over keys; the mask
+ *     and bias branches never run inside Unet3D because PreNorm drops kwargs, modules.py:146-148).
+ *     mode 0: sequences over frames per pixel ('b f h w c -> b (h w) f c', unet3d.py:86-96);
+ *     mode 1: sequences over the pixels of a frame ('b f (h w) c', unet3d.py:196-205).
+ *     o bf16 [P][256], lse fp32 [P][8]. bwd: D_ws fp32 [P][8] scratch, dqkv bf16 [P][768].
+ *   sla_core: SpatialLinearAttention core, modules.py:105-123: q softmax over the 32 features
+ *     (unscaled), k softmax over the N = H*W tokens, ctx = k~^T v, out = q~ ctx.
+ *     tok_out bf16 [P][256], ctx fp32 [n_img][8][32][32], kstat fp32 [n_img][8][2][32] (col max, col sum),
+ *     ws: fp32 scratch of vdn_sla_workspace_floats(n_img, N). bwd: dctx fp32 scratch like ctx.
+ * --------------------------------------------------------------------------------- */
+int vdn_mha_core_fwd(const void* qkv, void* o, float* lse, int mode, int B, int F, int HW, void* stream);
+int vdn_mha_core_bwd(const void* qkv, const void* o, const void* d_o, const float* lse, float* D_ws, void* dqkv,
+                     int mode, int B, int F, int HW, void* stream);
+size_t vdn_sla_workspace_floats(int n_img, int N);
+int vdn_sla_core_fwd(const void* qkv, void* tok_out, float* ctx, float* kstat, float* ws, int n_img, int N,
+                     void* stream);
+int vdn_sla_core_bwd(const void* qkv, const void* d_tok, const float* ctx, const float* kstat, float* dctx,
+                     void* dqkv, int n_img, int N, void* stream);
+
+/* ---------------------------------------------------------------------------------
+ * Small layers. init conv: nnx.Conv(channels, dim, (1,k,k)) on x fp32 (B,Cin,F,H,W) (unet3d.py:110-115,
+ * :280-282) -> bf16 (B*F,H,W,Cout); w fp32 [k*k][Cin][Cout]. final conv: nnx.Conv(dim, out, 1)
+ * (unet3d.py:251): h bf16 [P][C] -> fp32 [P][Co]. time MLP: SinusoidalPosEmb -> Linear -> gelu(tanh) ->
+ * Linear (modules.py:30-45, unet3d.py:128-133). time heads: per ResnetBlock
+ * LayerNorm(Linear(silu(t))) -> (scale | shift) (modules.py:202-208,233-238), all heads in one launch
+ * through a device table of vdn_time_head.
+ * --------------------------------------------------------------------------------- */
+typedef struct {
+  const float* w;    /* [4*dim][n_out] */
+  const float* b;    /* [n_out] */
+  const float* ln_g; /* [n_out] */
+  const float* ln_b; /* [n_out] */
+  float* dw;         /* gradients (+=); may be NULL for forward-only use */
+  float* db;
+  float* dln_g;
+  float* dln_b;
+  int n_out;         /* 2 * cout */
+  int off;           /* column offset into the [B][ss_ld] scale/shift buffer */
+} vdn_time_head;
+
+int vdn_init_conv_fwd(const float* x, const float* w, const float* bias, void* out, int B, int Cin, int F, int H,
+                      int W, int Cout, int ks, void* stream);
+int vdn_init_conv_wgrad(const float* x, const void* dy, float* dw, float* dbias, int B, int Cin, int F, int H, int W,
+                        int Cout, int ks, void* stream);
+int vdn_final_conv_fwd(const void* h, const float* w, const float* bias, float* out, long P, int C, int Co,
+                       void* stream);
+int vdn_final_conv_bwd(const void* h, const float* dout, const float* w, void* dh, float* dw, float* db, long P,
+                       int C, int Co, void* stream);
+int vdn_time_mlp_fwd(const int* time, const float* w1, const float* b1, const float* w2, const float* b2,
+                     float* emb_out, float* h1_out, float* t_out, int B, int dim, void* stream);
+int vdn_time_mlp_bwd(const float* dt, const float* emb, const float* h1, const float* w2, float* dw1, float* db1,
+                     float* dw2, float* db2, float* dh1_ws, int B, int dim, void* stream);
+int vdn_time_heads_fwd(const float* t, const void* heads_dev, int n_heads, float* e_pre, float* ss, int ss_ld,
+                       int B, int td, void* stream);
+int vdn_time_heads_bwd(const float* t, const void* heads_dev, int n_heads, const float* e_pre, const float* dss,
+                       int ss_ld, float* de_ws, float* dt, int B, int td, void* stream);
+
+/* ---------------------------------------------------------------------------------
+ * Diffusion math on fp32 images (B,C,F,H,W); Unet output eps is (B,F,H,W,C).
+ *   q_sample: sqrt_ac[t]*x + sqrt_1mac[t]*noise, optionally x <- 2x-1 first
+ *             (gaussian_diffusion.py:401-420, :499 / utils.py:271-280)
+ *   loss:     mean |pred-noise| (l1) or mean (pred-noise)^2 (l2) and d loss / d pred
+ *             (gaussian_diffusion.py:460-466); *loss is overwritten
+ *   p_sample: predict_start_from_noise -> clip -> q_posterior mean -> + (t!=0) exp(logvar/2) z
+ *             (gaussian_diffusion.py:120-261)
+ *   randn:    N(0,1) from Philox4x32-10 (seed, subsequence, element offset): stands in for
+ *             jax.random.normal (gaussian_diffusion.py:254,309,445)
+ * --------------------------------------------------------------------------------- */
+int vdn_q_sample(const float* x_start, const float* noise, const int* t, const float* sqrt_ac, const float* sqrt_1mac,
+                 float* out, int B, long per_sample, int normalize, void* stream);
+int vdn_loss(const float* pred, const float* noise, float* loss, float* dpred, int B, int C, long FHW, int l1,
+             void* stream);
+int vdn_p_sample(const float* x, const float* eps, const float* z, const int* t, const float* recip,
+                 const float* recipm1, const float* coef1, const float* coef2, const float* logvar, float* out, int B,
+                 int C, long FHW, int clip, void* stream);
+int vdn_randn(float* out, long n, unsigned long long seed, unsigned long long subseq, unsigned long long elem_offset,
+              void* stream);
+
+/* ---------------------------------------------------------------------------------
+ * Training glue: bias gradients (column sums of a bf16 [P][C] gradient, +=), bf16 add, and the fused
+ * optax.adam + EMA update over the flat fp32 state (trainer.py:367-382).
+ * hp_dev (device, 9 floats): lr, b1, b2, eps, 1-b1^t, 1-b2^t, ema_decay, do_ema, grad_scale.
+ * --------------------------------------------------------------------------------- */
+int vdn_colsum(const void* dy, float* db, long P, int C, void* stream);
+int vdn_add_bf16(const void* a, const void* b, void* out, long n, void* stream);
+int vdn_adam_ema(float* p, const float* g, float* m, float* v, float* ema, const float* hp_dev, long n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -338,20 +338,6 @@ __global__ void __launch_bounds__(256) time_mlp_bwd_kernel(const float* __restri
 
 }  // namespace vdn
 
-// Per-ResnetBlock time head: e = LayerNorm(Linear(silu(t))) -> (scale | shift)  (modules.py:233-238)
-struct vdn_time_head {
-  const float* w;     // [4dim][n_out]
-  const float* b;     // [n_out]
-  const float* ln_g;  // [n_out]
-  const float* ln_b;  // [n_out]
-  float* dw;          // grads (may be null in forward-only use)
-  float* db;
-  float* dln_g;
-  float* dln_b;
-  int n_out;          // 2 * cout
-  int off;            // column offset into the [B][ss_ld] scale/shift buffer
-};
-
 namespace vdn {
 
 // grid (n_heads, B)

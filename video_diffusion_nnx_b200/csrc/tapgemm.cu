@@ -485,15 +485,6 @@ __global__ void pack_weight_kernel(const float* __restrict__ src, bf16* __restri
 
 }  // namespace vdn
 
-// One entry of the batched repack table (device memory). `begin` = exclusive prefix sum of the job sizes.
-struct vdn_pack_job {
-  const float* src;
-  void* dst;
-  int taps, cin, cout, mode, ld, n_off, k_off;
-  int perm[16];
-  long long begin;
-};
-
 namespace vdn {
 
 // All weight repacks of a model in ONE launch: each 256-element chunk locates its job by binary search.

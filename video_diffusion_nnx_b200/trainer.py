@@ -40,6 +40,43 @@ def piecewise_cosine_lr(step: int, init_value: float, decay_start: int, decay_st
     return v1 + (v0 - v1) / 2.0 * (math.cos(math.pi * pct) + 1.0)
 
 
+def plan_buckets(stage_order, slices, bucket_elems: int):
+    """Group consecutive backward stages into gradient buckets. stage_order: stage names in backward
+    order; slices: {name: (begin, end)} element ranges of the flat gradient each stage completes.
+    Returns [(stage_names, (lo, hi))]: a bucket closes once it holds >= bucket_elems elements (and at the
+    last stage). Buckets are contiguous because the flat layout mirrors the completion order."""
+    out, cur, lo, hi = [], [], None, None
+    for i, name in enumerate(stage_order):
+        b, e = slices[name]
+        cur.append(name)
+        lo = b if lo is None else min(lo, b)
+        hi = e if hi is None else max(hi, e)
+        if (hi - lo) >= bucket_elems or i == len(stage_order) - 1:
+            out.append((cur, (lo, hi)))
+            cur, lo, hi = [], None, None
+    return out
+
+
+def shard_range(global_batch: int, world: int, rank: int):
+    """Batch shard of `rank` (trainer.py:163 requires divisibility; gaussian_diffusion.py:281)."""
+    assert global_batch % world == 0, "batch_size must be divisible by number of devices"
+    per = global_batch // world
+    return rank * per, (rank + 1) * per
+
+
+def allreduce_mean_(flat_grad, buckets, group=None, async_streams=None):
+    """Sum-reduce each bucket slice of the flat gradient over the data-parallel group and scale by
+    1/world (the GSPMD-implicit mean of trainer.py:363-364 made explicit). Used by the CPU gloo tests;
+    TrainStep issues the same reductions per bucket on a side stream and folds the 1/world into Adam."""
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    for _, (lo, hi) in buckets:
+        dist.all_reduce(flat_grad[lo:hi], group=group)
+    flat_grad.mul_(1.0 / world)
+    return flat_grad
+
+
 class TrainStep:
     def __init__(self, diffusion: GaussianDiffusion, *, batch_size: int, train_lr: float = 1e-4,
                  lr_decay_start_step: int = 0, lr_decay_steps: int = 0, lr_decay_coeff: float = 1.0,
@@ -81,16 +118,9 @@ class TrainStep:
     def _plan_segments(self, bucket_bytes: int):
         stages = self.eng.backward_stages()
         self.eng._stages = stages
-        slices = self.eng.grad_slices()
-        segs, cur, lo, hi = [], [], None, None
-        for name, fn in stages:
-            b, e = slices[name]
-            cur.append(fn)
-            lo = b if lo is None else min(lo, b)
-            hi = e if hi is None else max(hi, e)
-            if (hi - lo) * 4 >= bucket_bytes or name == "late":
-                segs.append((cur, (lo, hi)))
-                cur, lo, hi = [], None, None
+        fn_of = dict(stages)
+        plan = plan_buckets([n for n, _ in stages], self.eng.grad_slices(), bucket_bytes // 4)
+        segs = [([fn_of[n] for n in names], rng) for names, rng in plan]
         if self.world == 1:  # no exchange: one segment
             fns = [f for s, _ in segs for f in s]
             segs = [(fns, (0, self.net.store.total))]
