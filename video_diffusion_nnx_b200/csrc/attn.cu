@@ -67,117 +67,164 @@ __device__ __forceinline__ float dot32(const float (&a)[32], const float (&b)[32
 }
 
 // ---------------------------------------------------------------------------------------
-// MHA core forward: one thread per (sequence, query token, head); online softmax over keys.
+// MHA core. Two adjacent lanes share one (sequence, token, head): each owns 16 of the 32 head
+// features (32 B loads, ~64 live registers), dot products are completed with one shuffle.
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256, 2) mha_core_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ o,
+__device__ __forceinline__ void load16(const bf16* p, float (&v)[16]) {
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const uint4 u = reinterpret_cast<const uint4*>(p)[q];
+    float2 f;
+    f = unpack_bf16x2(u.x); v[8 * q + 0] = f.x; v[8 * q + 1] = f.y;
+    f = unpack_bf16x2(u.y); v[8 * q + 2] = f.x; v[8 * q + 3] = f.y;
+    f = unpack_bf16x2(u.z); v[8 * q + 4] = f.x; v[8 * q + 5] = f.y;
+    f = unpack_bf16x2(u.w); v[8 * q + 6] = f.x; v[8 * q + 7] = f.y;
+  }
+}
+__device__ __forceinline__ void store16(bf16* p, const float (&v)[16]) {
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    uint4 u;
+    u.x = pack_bf16x2(v[8 * q + 0], v[8 * q + 1]);
+    u.y = pack_bf16x2(v[8 * q + 2], v[8 * q + 3]);
+    u.z = pack_bf16x2(v[8 * q + 4], v[8 * q + 5]);
+    u.w = pack_bf16x2(v[8 * q + 6], v[8 * q + 7]);
+    reinterpret_cast<uint4*>(p)[q] = u;
+  }
+}
+// full 32-wide dot product of the lane pair
+__device__ __forceinline__ float dot_pair(const float (&a)[16], const float (&b)[16]) {
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+  for (int e = 0; e < 16; e += 4) {
+    s0 = fmaf(a[e], b[e], s0);
+    s1 = fmaf(a[e + 1], b[e + 1], s1);
+    s2 = fmaf(a[e + 2], b[e + 2], s2);
+    s3 = fmaf(a[e + 3], b[e + 3], s3);
+  }
+  const float s = (s0 + s1) + (s2 + s3);
+  return s + __shfl_xor_sync(0xffffffffu, s, 1);
+}
+
+struct MhaIdx {
+  bool valid;
+  int h, tok, half;
+  long seq;
+};
+__device__ __forceinline__ MhaIdx mha_index(const SeqMap& m) {
+  const long total = m.n_seq * m.S * kHeads * 2;
+  long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  MhaIdx r;
+  r.valid = idx < total;
+  if (!r.valid) idx = total - 2 + (idx & 1);  // keep whole warps alive for the shuffles
+  r.half = (int)(idx & 1);
+  idx >>= 1;
+  r.h = (int)(idx % kHeads);
+  r.tok = (int)((idx / kHeads) % m.S);
+  r.seq = idx / ((long)kHeads * m.S);
+  return r;
+}
+
+__global__ void __launch_bounds__(256) mha_core_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ o,
                                                            float* __restrict__ lse, const SeqMap m) {
-  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long total = m.n_seq * m.S * kHeads;
-  if (idx >= total) return;
-  const int h = (int)(idx % kHeads);
-  const int i = (int)((idx / kHeads) % m.S);
-  const long seq = idx / ((long)kHeads * m.S);
-  const long row_i = seq_row(m, seq, i);
+  const MhaIdx t = mha_index(m);
+  const int col = t.h * kDh + t.half * 16;
+  const long row_i = seq_row(m, t.seq, t.tok);
   const float scale = rsqrtf((float)kDh);
-  float q[32];
-  load32(qkv + row_i * kQKV + h * kDh, q);
+  float q[16], acc[16];
+  load16(qkv + row_i * kQKV + col, q);
 #pragma unroll
-  for (int e = 0; e < 32; ++e) q[e] *= scale;
-  float acc[32];
-#pragma unroll
-  for (int e = 0; e < 32; ++e) acc[e] = 0.f;
+  for (int e = 0; e < 16; ++e) {
+    q[e] *= scale;
+    acc[e] = 0.f;
+  }
   float mx = -INFINITY, l = 0.f;
   for (int j = 0; j < m.S; ++j) {
-    const long row_j = seq_row(m, seq, j);
-    float kv[32];
-    load32(qkv + row_j * kQKV + kHD + h * kDh, kv);
-    const float s = dot32(q, kv);
-    const float mn = fmaxf(mx, s);
+    const long row_j = seq_row(m, t.seq, j);
+    float kv[16];
+    load16(qkv + row_j * kQKV + kHD + col, kv);
+    const float sc = dot_pair(q, kv);
+    const float mn = fmaxf(mx, sc);
     const float corr = __expf(mx - mn);
-    const float p = __expf(s - mn);
-    load32(qkv + row_j * kQKV + 2 * kHD + h * kDh, kv);
+    const float p = __expf(sc - mn);
+    load16(qkv + row_j * kQKV + 2 * kHD + col, kv);
     l = l * corr + p;
 #pragma unroll
-    for (int e = 0; e < 32; ++e) acc[e] = fmaf(acc[e], corr, p * kv[e]);
+    for (int e = 0; e < 16; ++e) acc[e] = fmaf(acc[e], corr, p * kv[e]);
     mx = mn;
   }
   const float inv = 1.f / l;
 #pragma unroll
-  for (int e = 0; e < 32; ++e) acc[e] *= inv;
-  store32(o + row_i * kHD + h * kDh, acc);
-  lse[row_i * kHeads + h] = mx + __logf(l);
+  for (int e = 0; e < 16; ++e) acc[e] *= inv;
+  if (t.valid) {
+    store16(o + row_i * kHD + col, acc);
+    if (t.half == 0) lse[row_i * kHeads + t.h] = mx + __logf(l);
+  }
 }
 
 // Backward, phase 1: dq (and D_i = do_i . o_i for phase 2).
-__global__ void __launch_bounds__(256, 2) mha_core_bwd_dq_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o,
+__global__ void __launch_bounds__(256) mha_core_bwd_dq_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o,
                                                               const bf16* __restrict__ d_o,
                                                               const float* __restrict__ lse, float* __restrict__ Dws,
                                                               bf16* __restrict__ dqkv, const SeqMap m) {
-  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long total = m.n_seq * m.S * kHeads;
-  if (idx >= total) return;
-  const int h = (int)(idx % kHeads);
-  const int i = (int)((idx / kHeads) % m.S);
-  const long seq = idx / ((long)kHeads * m.S);
-  const long row_i = seq_row(m, seq, i);
+  const MhaIdx t = mha_index(m);
+  const int col = t.h * kDh + t.half * 16;
+  const long row_i = seq_row(m, t.seq, t.tok);
   const float scale = rsqrtf((float)kDh);
-  float q[32], dov[32], tmp[32];
-  load32(qkv + row_i * kQKV + h * kDh, q);
-  load32(d_o + row_i * kHD + h * kDh, dov);
-  load32(o + row_i * kHD + h * kDh, tmp);
-  const float D = dot32(dov, tmp);
-  Dws[row_i * kHeads + h] = D;
-  const float L = lse[row_i * kHeads + h];
-  float dq[32];
+  float q[16], dov[16], tmp[16], dq[16];
+  load16(qkv + row_i * kQKV + col, q);
+  load16(d_o + row_i * kHD + col, dov);
+  load16(o + row_i * kHD + col, tmp);
+  const float D = dot_pair(dov, tmp);
+  if (t.valid && t.half == 0) Dws[row_i * kHeads + t.h] = D;
+  const float L = lse[row_i * kHeads + t.h];
 #pragma unroll
-  for (int e = 0; e < 32; ++e) dq[e] = 0.f;
+  for (int e = 0; e < 16; ++e) dq[e] = 0.f;
   for (int j = 0; j < m.S; ++j) {
-    const long row_j = seq_row(m, seq, j);
-    float kv[32];
-    load32(qkv + row_j * kQKV + kHD + h * kDh, kv);
-    const float p = __expf(dot32(q, kv) * scale - L);
-    load32(qkv + row_j * kQKV + 2 * kHD + h * kDh, tmp);
-    const float ds = p * (dot32(dov, tmp) - D) * scale;
+    const long row_j = seq_row(m, t.seq, j);
+    float kv[16];
+    load16(qkv + row_j * kQKV + kHD + col, kv);
+    const float p = __expf(dot_pair(q, kv) * scale - L);
+    load16(qkv + row_j * kQKV + 2 * kHD + col, tmp);
+    const float ds = p * (dot_pair(dov, tmp) - D) * scale;
 #pragma unroll
-    for (int e = 0; e < 32; ++e) dq[e] = fmaf(ds, kv[e], dq[e]);
+    for (int e = 0; e < 16; ++e) dq[e] = fmaf(ds, kv[e], dq[e]);
   }
-  store32(dqkv + row_i * kQKV + h * kDh, dq);
+  if (t.valid) store16(dqkv + row_i * kQKV + col, dq);
 }
 
-// Backward, phase 2: dk_j, dv_j; one thread per (sequence, key token, head).
-__global__ void __launch_bounds__(256, 2) mha_core_bwd_dkv_kernel(const bf16* __restrict__ qkv,
+// Backward, phase 2: dk_j, dv_j; lane pair per (sequence, key token, head).
+__global__ void __launch_bounds__(256) mha_core_bwd_dkv_kernel(const bf16* __restrict__ qkv,
                                                                const bf16* __restrict__ d_o,
                                                                const float* __restrict__ lse,
                                                                const float* __restrict__ Dws,
                                                                bf16* __restrict__ dqkv, const SeqMap m) {
-  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long total = m.n_seq * m.S * kHeads;
-  if (idx >= total) return;
-  const int h = (int)(idx % kHeads);
-  const int j = (int)((idx / kHeads) % m.S);
-  const long seq = idx / ((long)kHeads * m.S);
-  const long row_j = seq_row(m, seq, j);
+  const MhaIdx t = mha_index(m);
+  const int col = t.h * kDh + t.half * 16;
+  const long row_j = seq_row(m, t.seq, t.tok);
   const float scale = rsqrtf((float)kDh);
-  float kj[32], vj[32], dk[32], dv[32];
-  load32(qkv + row_j * kQKV + kHD + h * kDh, kj);
-  load32(qkv + row_j * kQKV + 2 * kHD + h * kDh, vj);
+  float kj[16], vj[16], dk[16], dv[16];
+  load16(qkv + row_j * kQKV + kHD + col, kj);
+  load16(qkv + row_j * kQKV + 2 * kHD + col, vj);
 #pragma unroll
-  for (int e = 0; e < 32; ++e) dk[e] = dv[e] = 0.f;
+  for (int e = 0; e < 16; ++e) dk[e] = dv[e] = 0.f;
   for (int i = 0; i < m.S; ++i) {
-    const long row_i = seq_row(m, seq, i);
-    float qi[32], doi[32];
-    load32(qkv + row_i * kQKV + h * kDh, qi);
-    load32(d_o + row_i * kHD + h * kDh, doi);
-    const float p = __expf(dot32(qi, kj) * scale - lse[row_i * kHeads + h]);
-    const float ds = p * (dot32(doi, vj) - Dws[row_i * kHeads + h]) * scale;
+    const long row_i = seq_row(m, t.seq, i);
+    float qi[16], doi[16];
+    load16(qkv + row_i * kQKV + col, qi);
+    load16(d_o + row_i * kHD + col, doi);
+    const float p = __expf(dot_pair(qi, kj) * scale - lse[row_i * kHeads + t.h]);
+    const float ds = p * (dot_pair(doi, vj) - Dws[row_i * kHeads + t.h]) * scale;
 #pragma unroll
-    for (int e = 0; e < 32; ++e) {
+    for (int e = 0; e < 16; ++e) {
       dv[e] = fmaf(p, doi[e], dv[e]);
       dk[e] = fmaf(ds, qi[e], dk[e]);
     }
   }
-  store32(dqkv + row_j * kQKV + kHD + h * kDh, dk);
-  store32(dqkv + row_j * kQKV + 2 * kHD + h * kDh, dv);
+  if (t.valid) {
+    store16(dqkv + row_j * kQKV + kHD + col, dk);
+    store16(dqkv + row_j * kQKV + 2 * kHD + col, dv);
+  }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -338,7 +385,7 @@ __global__ void __launch_bounds__(256) sla_apply_kernel(const bf16* __restrict__
     softmax32(q);
 #pragma unroll
     for (int e = 0; e < 32; ++e) o[e] = 0.f;
-#pragma unroll 4
+#pragma unroll
     for (int d = 0; d < 32; ++d) {
       const float qd = q[d];
 #pragma unroll
@@ -442,7 +489,7 @@ __global__ void __launch_bounds__(256) sla_bwd_tokens_kernel(const bf16* __restr
     softmax32(a);                            // q~
     load32(dtok + row * kHD + h * kDh, g);   // d_tok
     float dotq = 0.f;
-#pragma unroll 4
+#pragma unroll
     for (int d = 0; d < 32; ++d) {
       float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
 #pragma unroll
@@ -463,7 +510,7 @@ __global__ void __launch_bounds__(256) sla_bwd_tokens_kernel(const bf16* __restr
     load32(qkv + row * kQKV + 2 * kHD + h * kDh, g);  // v
 #pragma unroll
     for (int d = 0; d < 32; ++d) a[d] = __expf(a[d] - sm_m[h * 32 + d]) * sm_is[h * 32 + d];  // k~
-#pragma unroll 4
+#pragma unroll
     for (int d = 0; d < 32; ++d) {
       float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
 #pragma unroll
@@ -478,7 +525,7 @@ __global__ void __launch_bounds__(256) sla_bwd_tokens_kernel(const bf16* __restr
     // ---- dv[e] = sum_d k~[d] dctx[d][e] ----
 #pragma unroll
     for (int e = 0; e < 32; ++e) r[e] = 0.f;
-#pragma unroll 4
+#pragma unroll
     for (int d = 0; d < 32; ++d) {
       const float kd = a[d];
 #pragma unroll
@@ -514,7 +561,7 @@ static SeqMap make_seqmap(int mode, int B, int F, int HW) {
 extern "C" int vdn_mha_core_fwd(const void* qkv, void* o, float* lse, int mode, int B, int F, int HW, void* stream) {
   VDN_REQUIRE(qkv && o && lse && B > 0 && F > 0 && HW > 0 && (mode == 0 || mode == 1), VDN_E_SHAPE, "mha_core_fwd: bad args");
   const SeqMap m = make_seqmap(mode, B, F, HW);
-  const long total = m.n_seq * m.S * kHeads;
+  const long total = m.n_seq * m.S * kHeads * 2;
   mha_core_fwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const bf16*>(qkv), reinterpret_cast<bf16*>(o), lse, m);
   return check_launch("mha_core_fwd");
@@ -524,7 +571,7 @@ extern "C" int vdn_mha_core_bwd(const void* qkv, const void* o, const void* d_o,
                                 void* dqkv, int mode, int B, int F, int HW, void* stream) {
   VDN_REQUIRE(qkv && o && d_o && lse && D_ws && dqkv && (mode == 0 || mode == 1), VDN_E_SHAPE, "mha_core_bwd: bad args");
   const SeqMap m = make_seqmap(mode, B, F, HW);
-  const long total = m.n_seq * m.S * kHeads;
+  const long total = m.n_seq * m.S * kHeads * 2;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const unsigned grid = (unsigned)((total + 255) / 256);
   mha_core_bwd_dq_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const bf16*>(qkv), reinterpret_cast<const bf16*>(o),

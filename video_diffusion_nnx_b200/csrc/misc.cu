@@ -733,7 +733,7 @@ extern "C" int vdn_p_sample(const float* x, const float* eps, const float* z, co
 extern "C" int vdn_colsum(const void* dy, float* db, long P, int C, void* stream) {
   VDN_REQUIRE(C % 8 == 0 && C / 8 <= 256, VDN_E_SHAPE, "colsum: C=%d unsupported", C);
   const int pl_n = 256 / (C / 8);
-  const int grid = (int)std::max<long>(1, std::min<long>((P + pl_n * 16 - 1) / (pl_n * 16), num_sms() * 4));
+  const int grid = (int)std::max<long>(1, std::min<long>((P + pl_n * 4 - 1) / (pl_n * 4), num_sms() * 8));
   colsum_kernel<<<grid, 256, 256 * 8 * sizeof(float), ST(stream)>>>(reinterpret_cast<const bf16*>(dy), db, P, C);
   return check_launch("colsum");
 }

@@ -491,7 +491,7 @@ extern "C" int vdn_gn_silu_bwd(const void* dy, const void* x_raw, const float* g
   cudaError_t e = cudaMemsetAsync(T_ws, 0, (size_t)B * C * 2 * sizeof(float), st);
   VDN_REQUIRE(e == cudaSuccess, VDN_E_CUDA, "gn_silu_bwd memset: %s", cudaGetErrorString(e));
   const int pl_n = kNormThreads / (C / 8);
-  dim3 grid(grid_x_for(rows_per_sample, pl_n * 16, B), B);
+  dim3 grid(grid_x_for(rows_per_sample, pl_n * 4, B), B);
   const size_t smem_r = (4 * C + kNormThreads * 16) * sizeof(float);
   gn_bwd_reduce_kernel<<<grid, kNormThreads, smem_r, st>>>(a, reinterpret_cast<const bf16*>(dy), T_ws);
   rc = check_launch("gn_bwd_reduce");
