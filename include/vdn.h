@@ -176,6 +176,15 @@ int vdn_sla_core_fwd(const void* qkv, void* tok_out, float* ctx, float* kstat, f
 int vdn_sla_core_bwd(const void* qkv, const void* d_tok, const float* ctx, const float* kstat, float* dctx,
                      void* dqkv, int n_img, int N, void* stream);
 
+/* Fused temporal attention forward (unet3d.py:86-96,118-120 + modules.py:285-323): the QKV projection on
+ * tensor cores and the F x F attention core in one kernel; qkv is not materialised unless asked for.
+ * x bf16 (B,F,H,W,C); w_hm bf16 [768][C], bias_hm fp32 [768]: head-major repack of the fused qkv
+ * projection (row h*96 + part*32 + d) produced by vdn_qkv_headmajor_pack from w fp32 [C][768] / bias [768];
+ * o bf16 [P][256]; optional qkv bf16 [P][768] (q|k|v) and lse fp32 [P][8] for the backward. */
+int vdn_qkv_headmajor_pack(const float* w, const float* bias, void* dst, float* bias_dst, int C, void* stream);
+int vdn_mha_temporal_fused_fwd(const void* x, const void* w_hm, const float* bias_hm, void* o, void* qkv, float* lse,
+                               int B, int F, int H, int W, int C, void* stream);
+
 /* ---------------------------------------------------------------------------------
  * Small layers. init conv: nnx.Conv(channels, dim, (1,k,k)) on x fp32 (B,Cin,F,H,W) (unet3d.py:110-115,
  * :280-282) -> bf16 (B*F,H,W,Cout); w fp32 [k*k][Cin][Cout]. final conv: nnx.Conv(dim, out, 1)

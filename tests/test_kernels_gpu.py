@@ -394,3 +394,40 @@ def test_diffusion_elementwise_colsum_adam():
     p_ref = p0 - 1e-3 * (m_ref / 0.1) / ((v_ref / 0.001).sqrt() + 1e-8)
     assert torch.allclose(p, p_ref, atol=1e-6)
     assert torch.allclose(ema, 0.995 * p0 + 0.005 * p_ref, atol=1e-6)
+
+
+@pytest.mark.parametrize("B,Fr,H,W,Cc", [(2, 10, 16, 16, 32), (1, 2, 64, 64, 64), (1, 16, 8, 8, 128), (2, 4, 8, 16, 256),
+                                          (1, 3, 4, 4, 32)])
+def test_mha_temporal_fused_fwd(B, Fr, H, W, Cc):
+    """Fused projection + temporal attention vs torch fp32 on the same bf16-rounded operands, and vs the
+    unfused GEMM + core kernels (identical rounding points: q, k, v rounded to bf16)."""
+    from video_diffusion_nnx_b200 import ops
+
+    _setup()
+    x = _bf(B, Fr, H, W, Cc)
+    w = torch.randn(Cc, 768, device=DEV) / Cc ** 0.5
+    bias = 0.1 * torch.randn(768, device=DEV)
+    w_hm = torch.empty(768, Cc, dtype=torch.bfloat16, device=DEV)
+    b_hm = torch.empty(768, device=DEV)
+    ops.qkv_headmajor_pack(w.contiguous(), bias, w_hm, b_hm, Cc)
+    P = B * Fr * H * W
+    o = torch.empty(P, 256, dtype=torch.bfloat16, device=DEV)
+    qkv = torch.empty(P, 768, dtype=torch.bfloat16, device=DEV)
+    lse = torch.empty(P, 8, device=DEV)
+    ops.mha_temporal_fused_fwd(x, w_hm, b_hm, o, qkv, lse, B, Fr, H, W, Cc)
+    torch.cuda.synchronize()
+    wq = w.to(torch.bfloat16).float()
+    qkv_ref = (x.float().reshape(P, Cc) @ wq + bias).to(torch.bfloat16)
+    assert _rel(qkv, qkv_ref) < 1e-2
+    t = qkv_ref.float().reshape(B, Fr, H * W, 3, 8, 32).permute(0, 2, 1, 3, 4, 5)
+    q, k, v = t[..., 0, :, :], t[..., 1, :, :], t[..., 2, :, :]
+    s = torch.einsum("...ihd,...jhd->...hij", q / math.sqrt(32), k)
+    att = s.softmax(-1)
+    o_ref = torch.einsum("...hij,...jhd->...ihd", att, v).permute(0, 2, 1, 3, 4).reshape(P, 256)
+    lse_ref = torch.logsumexp(s, -1).permute(0, 3, 1, 2).reshape(P, 8)   # (B,HW,h,i) -> (B,i,HW,h)
+    assert _rel(o, o_ref) < 1e-2
+    assert _rel(lse, lse_ref) < 3e-3  # q, k are rounded to bf16 from differently-ordered fp32 sums
+    # without the optional outputs
+    o2 = torch.empty_like(o)
+    ops.mha_temporal_fused_fwd(x, w_hm, b_hm, o2, None, None, B, Fr, H, W, Cc)
+    assert torch.equal(o, o2)

@@ -674,9 +674,12 @@ extern "C" int vdn_tapgemm(const vdn_tapgemm_desc* d, const void* src0, const vo
   const int a_bytes = kTileM * BK * 2;
   const int b_bytes = (a.BN * BK * 2 + 1023) & ~1023;
   const int stage_bytes = a_bytes + b_bytes;
-  // small tiles are latency bound: keep shared memory low so that many CTAs share an SM
-  const int budget = stage_bytes > 24 * 1024 ? 192 * 1024 : (stage_bytes > 12 * 1024 ? 64 * 1024 : 32 * 1024);
+  // Few CTAs per SM (small-M layers): the K loop is a latency chain, so pipeline as deep as shared
+  // memory allows. Many CTAs per SM (large-M layers): keep shared memory low so that they co-reside.
   const int n_steps = d->n_taps * d->n_src * a.chunks;
+  const int n_ctas = ceil_div(a.M, kTileM) * (d->n_out / a.BN);
+  const int ctas_per_sm = std::min(6, ceil_div(n_ctas, num_sms()));
+  const int budget = (200 * 1024) / ctas_per_sm;
   a.stages = std::max(2, std::min(std::min(kMaxStages, budget / stage_bytes), std::max(n_steps, 2)));
   if (const char* e = getenv("VDN_STAGES")) a.stages = std::max(1, std::min(kMaxStages, atoi(e)));
   int cols = 32;

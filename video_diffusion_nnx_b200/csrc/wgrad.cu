@@ -321,7 +321,9 @@ extern "C" int vdn_wgrad(int kind, const void* src0, const void* src1, const voi
   const int m_tiles = ceil_div(a.atoms_total, a.atoms_per_tile);
   const int n_tiles = Cn / a.BN;
   const int base_ctas = m_tiles * n_tiles;
-  int splits = std::max(1, std::min(a.n_pix_tiles, (2 * num_sms() + base_ctas - 1) / base_ctas));
+  // split K (pixels) over CTAs to fill the machine, but keep >= 8 K steps per split: every split adds a
+  // full set of fp32 atomics on the output tile, which dominates at the low-resolution levels.
+  int splits = std::max(1, std::min(std::max(1, a.n_pix_tiles / 8), (2 * num_sms() + base_ctas - 1) / base_ctas));
   a.tiles_per_split = ceil_div(a.n_pix_tiles, splits);
   splits = ceil_div(a.n_pix_tiles, a.tiles_per_split);
   const int a_bytes = a.atoms_per_tile * kKPix * a.cw * 2;

@@ -283,17 +283,34 @@ class MHABlock:
         self.eng, self.C, self.n_img, self.H, self.W, self.mode = eng, C, n_img, H, W, mode
         self.qkv_proj = GemmConv(eng, prefix + ".qkv.kernel", prefix + ".qkv.bias", TAPS_1x1, 1, C, 3 * HD)
         self.out_proj = GemmConv(eng, prefix + ".out.kernel", prefix + ".out.bias", TAPS_1x1, 1, HD, C)
-        self.qkv = eng.new((n_img, H, W, 3 * HD))
+        # temporal attention runs the fused projection + core kernel; qkv is only materialised when the
+        # (unfused) backward needs it, i.e. in training engines
+        self.fused = mode == 0
+        need_qkv = eng.training or not self.fused
+        self.qkv = eng.new((n_img, H, W, 3 * HD)) if need_qkv else None
         self.o = eng.new((n_img, H, W, HD))
-        self.lse = eng.new((n_img * H * W, HEADS), F32)
+        self.lse = eng.new((n_img * H * W, HEADS), F32) if need_qkv else None
         self.out = eng.new((n_img, H, W, C))
+        if self.fused:
+            self.w_hm = torch.empty(3 * HD, C, dtype=BF16, device=eng.device)
+            self.b_hm = torch.empty(3 * HD, dtype=F32, device=eng.device)
+            self._wq, self._bq = eng.store.view(prefix + ".qkv.kernel"), eng.store.view(prefix + ".qkv.bias")
+            eng.extra_packers.append(self._repack_hm)
         self.x = None
+
+    def _repack_hm(self):
+        ops.qkv_headmajor_pack(self._wq, self._bq, self.w_hm, self.b_hm, self.C)
 
     def forward(self, x):
         eng = self.eng
         self.x = x
-        self.qkv_proj.fwd([x], self.qkv)
-        ops.mha_core_fwd(self.qkv, self.o, self.lse, self.mode, eng.B, self.n_img // eng.B, self.H * self.W)
+        Fr = self.n_img // eng.B
+        if self.fused:
+            ops.mha_temporal_fused_fwd(x, self.w_hm, self.b_hm, self.o, self.qkv, self.lse, eng.B, Fr, self.H, self.W,
+                                       self.C)
+        else:
+            self.qkv_proj.fwd([x], self.qkv)
+            ops.mha_core_fwd(self.qkv, self.o, self.lse, self.mode, eng.B, Fr, self.H * self.W)
         self.out_proj.fwd([self.o], self.out, residual=x)
         return self.out
 
@@ -440,6 +457,7 @@ class UnetEngine:
         self.out_dim = channels if out_dim is None else out_dim
         self.ks = init_kernel_size
         self.pack_jobs = []
+        self.extra_packers = []
         self.pool = _Pool(self.device)
         self._gn_slots: List[torch.Tensor] = []
         self._gn_count = 0
@@ -541,6 +559,8 @@ class UnetEngine:
     def repack(self):
         """Refresh every packed bf16 GEMM operand from the fp32 master weights (one batched launch)."""
         ops.pack_batched(self.pack_table, self.n_pack_jobs, self.pack_total)
+        for f in self.extra_packers:
+            f()
 
     # -- forward -----------------------------------------------------------------------------
     def forward(self, x: torch.Tensor, time: torch.Tensor) -> torch.Tensor:

@@ -281,3 +281,13 @@ def make_pack_table(jobs, device):
 
 def pack_batched(table, n_jobs: int, total: int):
     check(lib.vdn_pack_batched(ptr(table), n_jobs, C.c_longlong(total), stream_ptr()), "vdn_pack_batched")
+
+
+def qkv_headmajor_pack(w, bias, dst, bias_dst, Cc):
+    check(lib.vdn_qkv_headmajor_pack(ptr(w), ptr(bias), ptr(dst), ptr(bias_dst), Cc, stream_ptr()),
+          "vdn_qkv_headmajor_pack")
+
+
+def mha_temporal_fused_fwd(x, w_hm, bias_hm, o, qkv, lse, B, F, H, W, Cc):
+    check(lib.vdn_mha_temporal_fused_fwd(ptr(x), ptr(w_hm), ptr(bias_hm), ptr(o), ptr(qkv), ptr(lse), B, F, H, W, Cc,
+                                         stream_ptr()), "vdn_mha_temporal_fused_fwd")
