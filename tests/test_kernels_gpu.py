@@ -205,6 +205,11 @@ def test_mha_core(mode, B, Fr, HW):
     Dws = torch.empty(P, 8, device=DEV)
     ops.mha_core_bwd(qkv, out, do, lse, Dws, dqkv, mode, B, Fr, HW)
     assert _rel(dqkv, qf.grad) < 2e-2
+    if mode == 0 and Fr <= 16:  # single-kernel temporal backward (smem exchange)
+        side = int(round(HW ** 0.5))
+        dq2 = torch.zeros_like(qkv)
+        ops.mha_temporal_bwd(qkv, out, do, lse, dq2, B, Fr, side, side)
+        assert _rel(dq2, qf.grad) < 2e-2
 
 
 @pytest.mark.parametrize("n_img,N", [(3, 64), (2, 256), (2, 1024), (1, 4096), (2, 100)])
@@ -430,4 +435,4 @@ def test_mha_temporal_fused_fwd(B, Fr, H, W, Cc):
     # without the optional outputs
     o2 = torch.empty_like(o)
     ops.mha_temporal_fused_fwd(x, w_hm, b_hm, o2, None, None, B, Fr, H, W, Cc)
-    assert torch.equal(o, o2)
+    assert _rel(o2, o_ref) < 1e-2  # inference mode keeps q, k, v in fp32 (no bf16 rounding)

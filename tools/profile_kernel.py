@@ -41,3 +41,17 @@ elif what == "wgrad_l0":
         ops.wgrad(ops.VDN_TAP_UNIT, [x], g, dw, ops.TAPS_3x3)
 torch.cuda.synchronize()
 print("done")
+if what == "mha_fused_l0":
+    C = 32
+    x = bf(B, F, 64, 64, C)
+    w = torch.randn(C, 768, device=dev) / C ** 0.5
+    bias = torch.zeros(768, device=dev)
+    w_hm = torch.empty(768, C, dtype=torch.bfloat16, device=dev)
+    b_hm = torch.empty(768, device=dev)
+    ops.qkv_headmajor_pack(w, bias, w_hm, b_hm, C)
+    P = B * F * 64 * 64
+    o = torch.empty(P, 256, dtype=torch.bfloat16, device=dev)
+    for _ in range(4):
+        ops.mha_temporal_fused_fwd(x, w_hm, b_hm, o, None, None, B, F, 64, 64, C)
+    torch.cuda.synchronize()
+    print("done")

@@ -233,21 +233,33 @@ __global__ void __launch_bounds__(256) mha_core_bwd_dkv_kernel(const bf16* __res
 constexpr int kSlaTile = 64;  // tokens per smem tile
 
 // Partial context over a token range with online softmax over tokens (per feature column d).
-// grid (n_split, heads, n_img), 256 threads; thread owns ctx[d][e4..e4+3], d = tid/8, e4 = (tid%8)*4.
+// grid (n_split, heads, n_img), 256 threads = 4 token sub-groups x 64 threads; a thread owns the 4x4
+// register tile ctx[d4..d4+3][e4..e4+3] for the tokens n = sub (mod 4) of each 64-token smem tile:
+// 2 LDS.128 feed 16 FMAs. The 4 sub-group partials are summed through smem at the end.
 __global__ void __launch_bounds__(256) sla_ctx_partial_kernel(const bf16* __restrict__ qkv, int N, int tokens_per_split,
                                                               float* __restrict__ ctx_part /*[img][h][split][32][32]*/,
                                                               float* __restrict__ ms_part /*[img][h][split][2][32]*/) {
-  __shared__ float kt[kSlaTile][33];
+  __shared__ __align__(16) float kt[kSlaTile][36];   // k, then p = exp(k - m); pitch 36 keeps LDS.128 aligned
   __shared__ __align__(16) float vt[kSlaTile][32];
   __shared__ float pm[8][32];
-  __shared__ float sm_m[32];
+  __shared__ float sm_m[32], sm_corr[32];
+  __shared__ __align__(16) float red[4][1024 + 32];
   const int split = blockIdx.x, h = blockIdx.y, img = blockIdx.z;
   const int n_split = gridDim.x;
   const int tid = threadIdx.x;
-  const int d = tid >> 3, e4 = (tid & 7) * 4;
+  const int sub = tid >> 6, t64 = tid & 63;
+  const int d4 = (t64 >> 3) * 4, e4 = (t64 & 7) * 4;
   const int n_begin = split * tokens_per_split;
   const int n_end = min(N, n_begin + tokens_per_split);
-  float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f, ssum = 0.f, m_run = -INFINITY;
+  float c[4][4];
+  float ss[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    ss[i] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) c[i][j] = 0.f;
+  }
+  if (tid < 32) sm_m[tid] = -INFINITY;
   const bf16* base = qkv + (long)img * N * kQKV;
   for (int n0 = n_begin; n0 < n_end; n0 += kSlaTile) {
     const int nt = min(kSlaTile, n_end - n0);
@@ -289,14 +301,15 @@ __global__ void __launch_bounds__(256) sla_ctx_partial_kernel(const bf16* __rest
       pm[seg][col] = mxv;
     }
     __syncthreads();
-    float tmax = pm[0][d];
+    if (tid < 32) {
+      float tmax = pm[0][tid];
 #pragma unroll
-    for (int sgm = 1; sgm < 8; ++sgm) tmax = fmaxf(tmax, pm[sgm][d]);
-    const float m_new = fmaxf(m_run, tmax);
-    const float corr = __expf(m_run - m_new);  // m_run = -inf on the first tile -> 0
-    c0 *= corr; c1 *= corr; c2 *= corr; c3 *= corr; ssum *= corr;
-    m_run = m_new;
-    if ((tid & 7) == 0) sm_m[d] = m_new;
+      for (int sgm = 1; sgm < 8; ++sgm) tmax = fmaxf(tmax, pm[sgm][tid]);
+      const float m_old = sm_m[tid];
+      const float m_new = fmaxf(m_old, tmax);
+      sm_corr[tid] = __expf(m_old - m_new);  // m_old = -inf on the first tile -> 0
+      sm_m[tid] = m_new;
+    }
     __syncthreads();
     {  // p = exp(k - m) in place; thread -> (column tid%32, tokens seg*8..)
       const int col = tid & 31, seg = tid >> 5;
@@ -304,22 +317,41 @@ __global__ void __launch_bounds__(256) sla_ctx_partial_kernel(const bf16* __rest
 #pragma unroll
       for (int r = 0; r < 8; ++r) kt[seg * 8 + r][col] = __expf(kt[seg * 8 + r][col] - mc);
     }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float cr = sm_corr[d4 + i];
+      ss[i] *= cr;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) c[i][j] *= cr;
+    }
     __syncthreads();
-#pragma unroll 8
-    for (int n = 0; n < kSlaTile; ++n) {
-      const float p = kt[n][d];
+#pragma unroll 4
+    for (int n = sub; n < kSlaTile; n += 4) {
+      const float4 p4 = *reinterpret_cast<const float4*>(&kt[n][d4]);
       const float4 v4 = *reinterpret_cast<const float4*>(&vt[n][e4]);
-      c0 = fmaf(p, v4.x, c0); c1 = fmaf(p, v4.y, c1); c2 = fmaf(p, v4.z, c2); c3 = fmaf(p, v4.w, c3);
-      ssum += p;
+      const float pp[4] = {p4.x, p4.y, p4.z, p4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        c[i][0] = fmaf(pp[i], v4.x, c[i][0]); c[i][1] = fmaf(pp[i], v4.y, c[i][1]);
+        c[i][2] = fmaf(pp[i], v4.z, c[i][2]); c[i][3] = fmaf(pp[i], v4.w, c[i][3]);
+        ss[i] += pp[i];
+      }
     }
     __syncthreads();
   }
+  // reduce the 4 token sub-groups
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    *reinterpret_cast<float4*>(&red[sub][(d4 + i) * 32 + e4]) = make_float4(c[i][0], c[i][1], c[i][2], c[i][3]);
+    if (e4 == 0) red[sub][1024 + d4 + i] = ss[i];
+  }
+  __syncthreads();
   const long blk = ((long)img * kHeads + h) * n_split + split;
-  float* cp = ctx_part + blk * 1024 + d * 32 + e4;
-  cp[0] = c0; cp[1] = c1; cp[2] = c2; cp[3] = c3;
-  if ((tid & 7) == 0) {
-    ms_part[blk * 64 + d] = m_run;
-    ms_part[blk * 64 + 32 + d] = ssum;
+  for (int i = tid; i < 1024; i += 256)
+    ctx_part[blk * 1024 + i] = red[0][i] + red[1][i] + red[2][i] + red[3][i];
+  if (tid < 32) {
+    ms_part[blk * 64 + tid] = sm_m[tid];
+    ms_part[blk * 64 + 32 + tid] = red[0][1024 + tid] + red[1][1024 + tid] + red[2][1024 + tid] + red[3][1024 + tid];
   }
 }
 
@@ -399,17 +431,24 @@ __global__ void __launch_bounds__(256) sla_apply_kernel(const bf16* __restrict__
   }
 }
 
-// dctx[h][d][e] += sum_n q~[n,d] * dtok[n,e] over a token range. grid (n_split, heads, n_img).
+// dctx[h][d][e] += sum_n q~[n,d] * dtok[n,e] over a token range. grid (n_split, heads, n_img); same
+// 4 sub-groups x (4x4 register tile) scheme as sla_ctx_partial_kernel.
 __global__ void __launch_bounds__(256) sla_dctx_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dtok,
                                                        int N, int tokens_per_split, float* __restrict__ dctx) {
-  __shared__ float qt[kSlaTile][33];
+  __shared__ __align__(16) float qt[kSlaTile][36];
   __shared__ __align__(16) float gt[kSlaTile][32];
+  __shared__ __align__(16) float red[4][1024];
   const int split = blockIdx.x, h = blockIdx.y, img = blockIdx.z;
   const int tid = threadIdx.x;
-  const int d = tid >> 3, e4 = (tid & 7) * 4;
+  const int sub = tid >> 6, t64 = tid & 63;
+  const int d4 = (t64 >> 3) * 4, e4 = (t64 & 7) * 4;
   const int n_begin = split * tokens_per_split;
   const int n_end = min(N, n_begin + tokens_per_split);
-  float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
+  float c[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) c[i][j] = 0.f;
   for (int n0 = n_begin; n0 < n_end; n0 += kSlaTile) {
     const int nt = min(kSlaTile, n_end - n0);
     // q~ rows: one thread per token computes the 32-wide softmax (tokens 0..63 -> threads 0..63)
@@ -423,7 +462,7 @@ __global__ void __launch_bounds__(256) sla_dctx_kernel(const bf16* __restrict__ 
         for (int e = 0; e < 32; ++e) q[e] = 0.f;
       }
 #pragma unroll
-      for (int e = 0; e < 32; ++e) qt[tid][e] = q[e];
+      for (int e = 0; e < 32; e += 4) *reinterpret_cast<float4*>(&qt[tid][e]) = make_float4(q[e], q[e + 1], q[e + 2], q[e + 3]);
     } else if (tid < 2 * kSlaTile) {
       const int t = tid - kSlaTile;
       float g[32];
@@ -434,19 +473,28 @@ __global__ void __launch_bounds__(256) sla_dctx_kernel(const bf16* __restrict__ 
         for (int e = 0; e < 32; ++e) g[e] = 0.f;
       }
 #pragma unroll
-      for (int e = 0; e < 32; ++e) gt[t][e] = g[e];
+      for (int e = 0; e < 32; e += 4) *reinterpret_cast<float4*>(&gt[t][e]) = make_float4(g[e], g[e + 1], g[e + 2], g[e + 3]);
     }
     __syncthreads();
-#pragma unroll 8
-    for (int n = 0; n < kSlaTile; ++n) {
-      const float p = qt[n][d];
+#pragma unroll 4
+    for (int n = sub; n < kSlaTile; n += 4) {
+      const float4 p4 = *reinterpret_cast<const float4*>(&qt[n][d4]);
       const float4 v4 = *reinterpret_cast<const float4*>(&gt[n][e4]);
-      c0 = fmaf(p, v4.x, c0); c1 = fmaf(p, v4.y, c1); c2 = fmaf(p, v4.z, c2); c3 = fmaf(p, v4.w, c3);
+      const float pp[4] = {p4.x, p4.y, p4.z, p4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        c[i][0] = fmaf(pp[i], v4.x, c[i][0]); c[i][1] = fmaf(pp[i], v4.y, c[i][1]);
+        c[i][2] = fmaf(pp[i], v4.z, c[i][2]); c[i][3] = fmaf(pp[i], v4.w, c[i][3]);
+      }
     }
     __syncthreads();
   }
-  float* op = dctx + ((long)img * kHeads + h) * 1024 + d * 32 + e4;
-  atomicAdd(op + 0, c0); atomicAdd(op + 1, c1); atomicAdd(op + 2, c2); atomicAdd(op + 3, c3);
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    *reinterpret_cast<float4*>(&red[sub][(d4 + i) * 32 + e4]) = make_float4(c[i][0], c[i][1], c[i][2], c[i][3]);
+  __syncthreads();
+  float* op = dctx + ((long)img * kHeads + h) * 1024;
+  for (int i = tid; i < 1024; i += 256) atomicAdd(op + i, red[0][i] + red[1][i] + red[2][i] + red[3][i]);
 }
 
 // Per-token backward: dq, dk, dv from ctx, dctx, k statistics. Same thread mapping as sla_apply.

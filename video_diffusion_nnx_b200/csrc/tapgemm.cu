@@ -119,7 +119,8 @@ __global__ void __launch_bounds__(kGemmThreads) tapgemm_kernel(const __grid_cons
   const int BN = args.BN;
   const int b_bytes = (BN * BK * 2 + 1023) & ~1023;
   const int stage_bytes = kABytes + b_bytes;
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte aligned view of the dynamic smem; offset arithmetic keeps the pointer in the shared space
+  uint8_t* smem = smem_raw + (((smem_u32(smem_raw) + 1023u) & ~1023u) - smem_u32(smem_raw));
 
   const int n_tile = blockIdx.x;
   const int m0 = blockIdx.y * kTileM;

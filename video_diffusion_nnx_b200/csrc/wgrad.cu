@@ -55,7 +55,8 @@ __global__ void __launch_bounds__(kWgThreads) wgrad_kernel(const __grid_constant
   __shared__ uint32_t tmem_base_smem;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte aligned view of the dynamic smem; offset arithmetic keeps the pointer in the shared space
+  uint8_t* smem = smem_raw + (((smem_u32(smem_raw) + 1023u) & ~1023u) - smem_u32(smem_raw));
   const int atom_bytes_m = kKPix * a.cw * 2;
   const int atom_bytes_n = kKPix * a.cwn * 2;
   const int a_bytes = a.atoms_per_tile * atom_bytes_m;  // 128 * 128 * 2 = 32 KB

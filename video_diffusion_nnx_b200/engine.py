@@ -285,7 +285,7 @@ class MHABlock:
         self.out_proj = GemmConv(eng, prefix + ".out.kernel", prefix + ".out.bias", TAPS_1x1, 1, HD, C)
         # temporal attention runs the fused projection + core kernel; qkv is only materialised when the
         # (unfused) backward needs it, i.e. in training engines
-        self.fused = mode == 0
+        self.fused = mode == 0 and (n_img // eng.B) <= 16
         need_qkv = eng.training or not self.fused
         self.qkv = eng.new((n_img, H, W, 3 * HD)) if need_qkv else None
         self.o = eng.new((n_img, H, W, HD))
@@ -320,10 +320,14 @@ class MHABlock:
         do = pool.get(self.o.shape)
         self.out_proj.dgrad(dout, [do])
         dqkv = pool.get(self.qkv.shape)
-        D = pool.get(self.lse.shape, F32)
-        ops.mha_core_bwd(self.qkv, self.o, do, self.lse, D, dqkv, self.mode, eng.B, self.n_img // eng.B, self.H * self.W)
+        if self.fused:
+            ops.mha_temporal_bwd(self.qkv, self.o, do, self.lse, dqkv, eng.B, self.n_img // eng.B, self.H, self.W)
+        else:
+            D = pool.get(self.lse.shape, F32)
+            ops.mha_core_bwd(self.qkv, self.o, do, self.lse, D, dqkv, self.mode, eng.B, self.n_img // eng.B,
+                             self.H * self.W)
+            pool.put(D)
         pool.put(do)
-        pool.put(D)
         self.qkv_proj.wgrad([self.x], dqkv)
         dx = pool.get(self.x.shape)
         self.qkv_proj.dgrad(dqkv, [dx], residuals=[dout])

@@ -291,3 +291,8 @@ def qkv_headmajor_pack(w, bias, dst, bias_dst, Cc):
 def mha_temporal_fused_fwd(x, w_hm, bias_hm, o, qkv, lse, B, F, H, W, Cc):
     check(lib.vdn_mha_temporal_fused_fwd(ptr(x), ptr(w_hm), ptr(bias_hm), ptr(o), ptr(qkv), ptr(lse), B, F, H, W, Cc,
                                          stream_ptr()), "vdn_mha_temporal_fused_fwd")
+
+
+def mha_temporal_bwd(qkv, o, d_o, lse, dqkv, B, F, H, W):
+    check(lib.vdn_mha_temporal_bwd(ptr(qkv), ptr(o), ptr(d_o), ptr(lse), ptr(dqkv), B, F, H, W, stream_ptr()),
+          "vdn_mha_temporal_bwd")
