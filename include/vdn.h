@@ -184,6 +184,12 @@ int vdn_sla_core_bwd(const void* qkv, const void* d_tok, const float* ctx, const
 int vdn_qkv_headmajor_pack(const float* w, const float* bias, void* dst, float* bias_dst, int C, void* stream);
 int vdn_mha_temporal_fused_fwd(const void* x, const void* w_hm, const float* bias_hm, void* o, void* qkv, float* lse,
                                int B, int F, int H, int W, int C, void* stream);
+/* Tensor-core version of vdn_mha_temporal_fused_fwd (same contract): S = Q K^T and O = P V also run on
+ * tcgen05 over the whole pixel tile (block-diagonal use of a 128x128 score tile). Instantiated for F in
+ * {10, 16} (config_v2_2 / v2_3x), C % 32 == 0; vdn_mha_temporal_tc_supported tells. */
+int vdn_mha_temporal_tc_supported(int F, int C);
+int vdn_mha_temporal_tc_fwd(const void* x, const void* w_hm, const float* bias_hm, void* o, void* qkv, float* lse,
+                            int B, int F, int H, int W, int C, void* stream);
 /* Temporal attention core backward in one kernel (smem exchange of k, v, q, dO; P and dS computed once):
  * qkv / lse / o from the forward, d_o bf16 [P][256] -> dqkv bf16 [P][768]. F <= 16. */
 int vdn_mha_temporal_bwd(const void* qkv, const void* o, const void* d_o, const float* lse, void* dqkv, int B, int F,

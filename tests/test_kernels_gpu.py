@@ -436,3 +436,35 @@ def test_mha_temporal_fused_fwd(B, Fr, H, W, Cc):
     o2 = torch.empty_like(o)
     ops.mha_temporal_fused_fwd(x, w_hm, b_hm, o2, None, None, B, Fr, H, W, Cc)
     assert _rel(o2, o_ref) < 1e-2  # inference mode keeps q, k, v in fp32 (no bf16 rounding)
+
+
+@pytest.mark.parametrize("B,Fr,H,W,Cc", [(2, 10, 16, 16, 32), (1, 10, 8, 8, 256), (1, 16, 8, 8, 128), (2, 16, 8, 16, 64),
+                                          (1, 10, 64, 64, 32)])
+def test_mha_temporal_tc_fwd(B, Fr, H, W, Cc):
+    """All-tensor-core temporal attention (projection, Q K^T and P V on tcgen05) vs torch fp32."""
+    from video_diffusion_nnx_b200 import ops
+
+    _setup()
+    assert ops.mha_tc_supported(Fr, Cc)
+    x = _bf(B, Fr, H, W, Cc)
+    w = torch.randn(Cc, 768, device=DEV) / Cc ** 0.5
+    bias = 0.1 * torch.randn(768, device=DEV)
+    w_hm = torch.empty(768, Cc, dtype=torch.bfloat16, device=DEV)
+    b_hm = torch.empty(768, device=DEV)
+    ops.qkv_headmajor_pack(w.contiguous(), bias, w_hm, b_hm, Cc)
+    P = B * Fr * H * W
+    o = torch.zeros(P, 256, dtype=torch.bfloat16, device=DEV)
+    qkv = torch.zeros(P, 768, dtype=torch.bfloat16, device=DEV)
+    lse = torch.zeros(P, 8, device=DEV)
+    ops.mha_temporal_tc_fwd(x, w_hm, b_hm, o, qkv, lse, B, Fr, H, W, Cc)
+    torch.cuda.synchronize()
+    wq = w.to(torch.bfloat16).float()
+    qkv_ref = (x.float().reshape(P, Cc) @ wq + bias).to(torch.bfloat16)
+    assert _rel(qkv, qkv_ref) < 1e-2
+    t = qkv_ref.float().reshape(B, Fr, H * W, 3, 8, 32).permute(0, 2, 1, 3, 4, 5)
+    q, k, v = t[..., 0, :, :], t[..., 1, :, :], t[..., 2, :, :]
+    s = torch.einsum("...ihd,...jhd->...hij", q / math.sqrt(32), k)
+    o_ref = torch.einsum("...hij,...jhd->...ihd", s.softmax(-1), v).permute(0, 2, 1, 3, 4).reshape(P, 256)
+    lse_ref = torch.logsumexp(s, -1).permute(0, 3, 1, 2).reshape(P, 8)
+    assert _rel(o, o_ref) < 2e-2   # P is rounded to bf16 before the P V product
+    assert _rel(lse, lse_ref) < 3e-3

@@ -306,8 +306,8 @@ class MHABlock:
         self.x = x
         Fr = self.n_img // eng.B
         if self.fused:
-            ops.mha_temporal_fused_fwd(x, self.w_hm, self.b_hm, self.o, self.qkv, self.lse, eng.B, Fr, self.H, self.W,
-                                       self.C)
+            fn = ops.mha_temporal_tc_fwd if ops.mha_tc_supported(Fr, self.C) else ops.mha_temporal_fused_fwd
+            fn(x, self.w_hm, self.b_hm, self.o, self.qkv, self.lse, eng.B, Fr, self.H, self.W, self.C)
         else:
             self.qkv_proj.fwd([x], self.qkv)
             ops.mha_core_fwd(self.qkv, self.o, self.lse, self.mode, eng.B, Fr, self.H * self.W)

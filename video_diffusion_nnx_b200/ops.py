@@ -296,3 +296,12 @@ def mha_temporal_fused_fwd(x, w_hm, bias_hm, o, qkv, lse, B, F, H, W, Cc):
 def mha_temporal_bwd(qkv, o, d_o, lse, dqkv, B, F, H, W):
     check(lib.vdn_mha_temporal_bwd(ptr(qkv), ptr(o), ptr(d_o), ptr(lse), ptr(dqkv), B, F, H, W, stream_ptr()),
           "vdn_mha_temporal_bwd")
+
+
+def mha_tc_supported(F: int, Cc: int) -> bool:
+    return bool(lib.vdn_mha_temporal_tc_supported(F, Cc))
+
+
+def mha_temporal_tc_fwd(x, w_hm, bias_hm, o, qkv, lse, B, F, H, W, Cc):
+    check(lib.vdn_mha_temporal_tc_fwd(ptr(x), ptr(w_hm), ptr(bias_hm), ptr(o), ptr(qkv), ptr(lse), B, F, H, W, Cc,
+                                      stream_ptr()), "vdn_mha_temporal_tc_fwd")
