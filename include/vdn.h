@@ -190,6 +190,9 @@ int vdn_mha_temporal_fused_fwd(const void* x, const void* w_hm, const float* bia
 int vdn_mha_temporal_tc_supported(int F, int C);
 int vdn_mha_temporal_tc_fwd(const void* x, const void* w_hm, const float* bias_hm, void* o, void* qkv, float* lse,
                             int B, int F, int H, int W, int C, void* stream);
+/* Tensor-core temporal attention core backward (S, dP, dQ, dK, dV as tcgen05 MMAs); F in {10, 16}. */
+int vdn_mha_temporal_tc_bwd(const void* qkv, const void* d_o, const float* lse, void* dqkv, int B, int F, int H, int W,
+                            void* stream);
 /* Temporal attention core backward in one kernel (smem exchange of k, v, q, dO; P and dS computed once):
  * qkv / lse / o from the forward, d_o bf16 [P][256] -> dqkv bf16 [P][768]. F <= 16. */
 int vdn_mha_temporal_bwd(const void* qkv, const void* o, const void* d_o, const float* lse, void* dqkv, int B, int F,

@@ -178,7 +178,8 @@ def test_resblock_tail_and_ln_bwd(B, R, Cc):
 # ------------------------------------------------------------------------------------------
 # attention cores
 # ------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("mode,B,Fr,HW", [(0, 2, 10, 64), (0, 1, 16, 256), (1, 2, 3, 64), (1, 1, 2, 256), (0, 2, 2, 4096)])
+@pytest.mark.parametrize("mode,B,Fr,HW", [(0, 2, 10, 64), (0, 1, 16, 256), (1, 2, 3, 64), (1, 1, 2, 256), (0, 2, 2, 4096),
+                                          (0, 1, 10, 4096)])
 def test_mha_core(mode, B, Fr, HW):
     from video_diffusion_nnx_b200 import ops
 
@@ -210,6 +211,13 @@ def test_mha_core(mode, B, Fr, HW):
         dq2 = torch.zeros_like(qkv)
         ops.mha_temporal_bwd(qkv, out, do, lse, dq2, B, Fr, side, side)
         assert _rel(dq2, qf.grad) < 2e-2
+        if Fr in (10, 16):  # tensor-core backward
+            dq3 = torch.zeros_like(qkv)
+            ops.mha_temporal_tc_bwd(qkv, do, lse, dq3, B, Fr, side, side)
+            torch.cuda.synchronize()
+            for part, name in enumerate("qkv"):
+                e = _rel(dq3[:, part * 256:(part + 1) * 256], qf.grad[:, part * 256:(part + 1) * 256])
+                assert e < 3e-2, (name, e)   # P and dS are rounded to bf16 before the MMAs
 
 
 @pytest.mark.parametrize("n_img,N", [(3, 64), (2, 256), (2, 1024), (1, 4096), (2, 100)])

@@ -191,12 +191,13 @@ __global__ void __launch_bounds__(kTcThreads) mha_tc_fwd_kernel(const __grid_con
     const int pxB = validB ? r / F : 0, fB = validB ? r % F : 0;
     const long growB = (((long)b * F + fB) * a.H + y) * a.W + x0 + pxB;
     const int px_lo = (quarter * 32) / F;    // first pixel of this warp's rows
-    const int c0 = px_lo * F;                // first S column this warp needs
+    constexpr int kSlots = (32 % F == 0) ? (32 / F) : ((31 / F) + 2);  // pixels intersecting a warp's 32 rows
+    constexpr int kWin = kSlots * F > 32 ? 48 : 32;
+    // first S column this warp needs (clamped for padding-only warps so the window stays inside the tile)
+    const int c0 = min(px_lo * F, 128 - kWin);
     const int sel = pxB - px_lo;             // which F-wide slot of the window is mine (0..3)
     const uint32_t lane_sel = (uint32_t)(quarter * 32) << 16;
     const float scale = rsqrtf(32.f);
-    constexpr int kSlots = (31 / F) + 2;     // max pixels intersecting 32 consecutive rows
-    constexpr int kWin = kSlots * F > 32 ? 48 : 32;
 
     for (int h = 0; h < 8; ++h) {
       const uint32_t par = (uint32_t)(h & 1);
@@ -363,4 +364,232 @@ extern "C" int vdn_mha_temporal_tc_fwd(const void* x, const void* w_hm, const fl
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (F == 10) return BK == 64 ? launch_tc<64, 10>(maps, a, n_tiles, st) : launch_tc<32, 10>(maps, a, n_tiles, st);
   return BK == 64 ? launch_tc<64, 16>(maps, a, n_tiles, st) : launch_tc<32, 16>(maps, a, n_tiles, st);
+}
+
+// ---------------------------------------------------------------------------------------
+// Temporal attention core backward on tensor cores. Per (pixel tile, head), rows pixel-major:
+//   S = Q K^T, dP = dO V^T                      (two 128x128x32 MMAs, block-diagonal use)
+//   P = exp(S/sqrt(d) - lse), D = sum_j P dP, dS = P (dP - D)/sqrt(d)      (worker threads, fp32)
+//   dQ = dS K, dK = dS^T Q, dV = P^T dO         (three 128x32x128 MMAs; the transposes are MN-major
+//                                                reads of the same shared-memory tiles)
+// TMEM: S [0,128) and dP [128,256); dQ|dK|dV reuse [0,96) once the workers hold their S/dP windows.
+// ---------------------------------------------------------------------------------------
+namespace vdn {
+
+template <int F>
+__global__ void __launch_bounds__(160) mha_tc_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ d_o,
+                                                         const float* __restrict__ lse, bf16* __restrict__ dqkv, int B,
+                                                         int H, int W, int PX) {
+  constexpr int kTile = 128 * 64;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t in_ready, sdp_full, pds_ready, grad_full;
+  __shared__ uint32_t tmem_base_smem;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* smem = smem_raw + (((smem_u32(smem_raw) + 1023u) & ~1023u) - smem_u32(smem_raw));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + kTile;
+  uint8_t* sV = sK + kTile;
+  uint8_t* sG = sV + kTile;
+  uint8_t* sP = sG + kTile;      // 32 KB
+  uint8_t* sS = sP + 32768;      // 32 KB
+  const int rows = PX * F;
+  const int tiles_x = W / PX;
+  const int tile = blockIdx.x;
+  const int x0 = (tile % tiles_x) * PX;
+  const int y = (tile / tiles_x) % H;
+  const int b = tile / (tiles_x * H);
+
+  for (int i = threadIdx.x; i < (4 * kTile + 65536) / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  if (threadIdx.x == 0) {
+    mbar_init(&in_ready, 4);
+    mbar_init(&sdp_full, 1);
+    mbar_init(&pds_ready, 4);
+    mbar_init(&grad_full, 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(&tmem_base_smem, 256);
+    tmem_relinquish();
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint32_t id_ss = umma_idesc_bf16(128, 128, 0, 0);
+      const uint32_t id_dq = umma_idesc_bf16(128, 32, 0, 1);   // A K-major (dS), B MN-major (K)
+      const uint32_t id_tt = umma_idesc_bf16(128, 32, 1, 1);   // A MN-major (dS^T / P^T), B MN-major
+      const uint32_t l64 = umma_layout_type(64), l128 = umma_layout_type(128);
+      for (int h = 0; h < 8; ++h) {
+        const uint32_t par = (uint32_t)(h & 1);
+        mbar_wait(&in_ready, par);
+        tc_fence_after();
+        {
+          const uint64_t dq = umma_smem_desc(smem_u32(sQ), 16, 512, l64), dk = umma_smem_desc(smem_u32(sK), 16, 512, l64);
+          const uint64_t dg = umma_smem_desc(smem_u32(sG), 16, 512, l64), dv = umma_smem_desc(smem_u32(sV), 16, 512, l64);
+          umma_bf16(tmem_base, dq, dk, id_ss, 0u);
+          umma_bf16(tmem_base, dq + 2, dk + 2, id_ss, 1u);
+          umma_bf16(tmem_base + 128, dg, dv, id_ss, 0u);
+          umma_bf16(tmem_base + 128, dg + 2, dv + 2, id_ss, 1u);
+          tc_commit(&sdp_full);
+        }
+        mbar_wait(&pds_ready, par);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint32_t a_km = (uint32_t)((k >> 2) * 16384 + (k & 3) * 32);  // K-major slice of a [128x128] tile
+          const uint32_t a_mn = (uint32_t)(k * 2048);                          // MN-major slice (16 rows)
+          const uint32_t b_mn = (uint32_t)(k * 1024);                          // 16 token rows of a [128x32] tile
+          const uint32_t acc = k != 0 ? 1u : 0u;
+          umma_bf16(tmem_base, umma_smem_desc(smem_u32(sS) + a_km, 16, 1024, l128),
+                    umma_smem_desc(smem_u32(sK) + b_mn, (uint32_t)kTile, 512, l64), id_dq, acc);
+          umma_bf16(tmem_base + 32, umma_smem_desc(smem_u32(sS) + a_mn, 16384, 1024, l128),
+                    umma_smem_desc(smem_u32(sQ) + b_mn, (uint32_t)kTile, 512, l64), id_tt, acc);
+          umma_bf16(tmem_base + 64, umma_smem_desc(smem_u32(sP) + a_mn, 16384, 1024, l128),
+                    umma_smem_desc(smem_u32(sG) + b_mn, (uint32_t)kTile, 512, l64), id_tt, acc);
+        }
+        tc_commit(&grad_full);
+      }
+    }
+    __syncwarp();
+  } else {
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const bool valid = r < rows;
+    const int px = valid ? r / F : 0, f = valid ? r % F : 0;
+    const long grow = (((long)b * F + f) * H + y) * W + x0 + px;
+    const int px_lo = (quarter * 32) / F;
+    constexpr int kSlots = (32 % F == 0) ? (32 / F) : ((31 / F) + 2);
+    constexpr int kWin = kSlots * F > 32 ? 48 : 32;
+    const int c0 = min(px_lo * F, 128 - kWin);   // clamped for padding-only warps
+    const int sel = px - px_lo;
+    const uint32_t lane_sel = (uint32_t)(quarter * 32) << 16;
+    const float scale = rsqrtf(32.f);
+    for (int h = 0; h < 8; ++h) {
+      const uint32_t par = (uint32_t)(h & 1);
+      float L = 0.f;
+      if (valid) {
+        const uint4* qp = reinterpret_cast<const uint4*>(qkv + grow * 768 + h * 32);
+        const uint4* gp = reinterpret_cast<const uint4*>(d_o + grow * 256 + h * 32);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          *reinterpret_cast<uint4*>(sQ + sw64_off(r, c)) = qp[c];
+          *reinterpret_cast<uint4*>(sK + sw64_off(r, c)) = qp[32 + c];   // +256 bf16 = 32 uint4
+          *reinterpret_cast<uint4*>(sV + sw64_off(r, c)) = qp[64 + c];
+          *reinterpret_cast<uint4*>(sG + sw64_off(r, c)) = gp[c];
+        }
+        L = lse[grow * 8 + h];
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&in_ready);
+      mbar_wait(&sdp_full, par);
+      tc_fence_after();
+      float sc[F], dp[F];
+      {
+        uint32_t win[kWin];
+        tmem_ld_32x32(tmem_base + lane_sel + (uint32_t)c0, *reinterpret_cast<uint32_t(*)[32]>(&win[0]));
+        if (kWin == 48) tmem_ld_32x16(tmem_base + lane_sel + (uint32_t)(c0 + 32), *reinterpret_cast<uint32_t(*)[16]>(&win[32]));
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < F; ++j) {
+          float v = __uint_as_float(win[j]);
+#pragma unroll
+          for (int s = 1; s < kSlots; ++s)
+            if (s * F + j < kWin) v = (sel == s) ? __uint_as_float(win[s * F + j]) : v;
+          sc[j] = v;
+        }
+        tmem_ld_32x32(tmem_base + 128 + lane_sel + (uint32_t)c0, *reinterpret_cast<uint32_t(*)[32]>(&win[0]));
+        if (kWin == 48) tmem_ld_32x16(tmem_base + 128 + lane_sel + (uint32_t)(c0 + 32), *reinterpret_cast<uint32_t(*)[16]>(&win[32]));
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < F; ++j) {
+          float v = __uint_as_float(win[j]);
+#pragma unroll
+          for (int s = 1; s < kSlots; ++s)
+            if (s * F + j < kWin) v = (sel == s) ? __uint_as_float(win[s * F + j]) : v;
+          dp[j] = v;
+        }
+      }
+      float D = 0.f;
+#pragma unroll
+      for (int j = 0; j < F; ++j) {
+        sc[j] = __expf(sc[j] * scale - L);   // P_ij
+        D = fmaf(sc[j], dp[j], D);
+      }
+      if (valid) {
+#pragma unroll
+        for (int j = 0; j < F; j += 2) {
+          const float ds0 = sc[j] * (dp[j] - D) * scale;
+          const float ds1 = (j + 1 < F) ? sc[j + 1] * (dp[j + 1] - D) * scale : 0.f;
+          const uint32_t off = sw128_off(r, px * F + j);
+          *reinterpret_cast<uint32_t*>(sP + off) = pack_bf16x2(sc[j], (j + 1 < F) ? sc[j + 1] : 0.f);
+          *reinterpret_cast<uint32_t*>(sS + off) = pack_bf16x2(ds0, ds1);
+        }
+      }
+      tc_fence_before();
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&pds_ready);
+      mbar_wait(&grad_full, par);
+      tc_fence_after();
+#pragma unroll
+      for (int part = 0; part < 3; ++part) {
+        uint32_t raw[32];
+        tmem_ld_32x32(tmem_base + lane_sel + (uint32_t)(part * 32), raw);
+        tmem_ld_wait();
+        if (valid) {
+          uint4* gp = reinterpret_cast<uint4*>(dqkv + grow * 768 + part * 256 + h * 32);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint4 u;
+            u.x = pack_bf16x2(__uint_as_float(raw[8 * c + 0]), __uint_as_float(raw[8 * c + 1]));
+            u.y = pack_bf16x2(__uint_as_float(raw[8 * c + 2]), __uint_as_float(raw[8 * c + 3]));
+            u.z = pack_bf16x2(__uint_as_float(raw[8 * c + 4]), __uint_as_float(raw[8 * c + 5]));
+            u.w = pack_bf16x2(__uint_as_float(raw[8 * c + 6]), __uint_as_float(raw[8 * c + 7]));
+            gp[c] = u;
+          }
+        }
+      }
+      tc_fence_before();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+template <int F>
+static int launch_tc_bwd(const bf16* qkv, const bf16* d_o, const float* lse, bf16* dqkv, int B, int H, int W, int PX,
+                         cudaStream_t st) {
+  const int smem = 4 * 8192 + 65536 + 1024;
+  static bool cfg = false;
+  if (!cfg) {
+    cudaError_t e = cudaFuncSetAttribute(mha_tc_bwd_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+    VDN_REQUIRE(e == cudaSuccess, VDN_E_CUDA, "mha_tc_bwd cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    cfg = true;
+  }
+  mha_tc_bwd_kernel<F><<<B * H * (W / PX), 160, smem, st>>>(qkv, d_o, lse, dqkv, B, H, W, PX);
+  return check_launch("mha_tc_bwd_kernel");
+}
+
+}  // namespace vdn
+
+// Same contract as vdn_mha_temporal_bwd (o is not needed: D_i = sum_j P_ij dP_ij). F in {10, 16}.
+extern "C" int vdn_mha_temporal_tc_bwd(const void* qkv, const void* d_o, const float* lse, void* dqkv, int B, int F,
+                                       int H, int W, void* stream) {
+  VDN_REQUIRE(qkv && d_o && lse && dqkv && (F == 10 || F == 16), VDN_E_SHAPE, "mha_tc_bwd: bad args (F in {10,16})");
+  int PX = 1;
+  while (PX * 2 * F <= 128 && PX * 2 <= W && W % (PX * 2) == 0) PX *= 2;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const vdn::bf16* q = reinterpret_cast<const vdn::bf16*>(qkv);
+  const vdn::bf16* g = reinterpret_cast<const vdn::bf16*>(d_o);
+  vdn::bf16* dq = reinterpret_cast<vdn::bf16*>(dqkv);
+  return F == 10 ? vdn::launch_tc_bwd<10>(q, g, lse, dq, B, H, W, PX, st) : vdn::launch_tc_bwd<16>(q, g, lse, dq, B, H, W, PX, st);
 }

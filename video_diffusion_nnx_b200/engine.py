@@ -320,8 +320,11 @@ class MHABlock:
         do = pool.get(self.o.shape)
         self.out_proj.dgrad(dout, [do])
         dqkv = pool.get(self.qkv.shape)
-        if self.fused:
-            ops.mha_temporal_bwd(self.qkv, self.o, do, self.lse, dqkv, eng.B, self.n_img // eng.B, self.H, self.W)
+        Fr = self.n_img // eng.B
+        if self.fused and ops.mha_tc_supported(Fr, self.C):
+            ops.mha_temporal_tc_bwd(self.qkv, do, self.lse, dqkv, eng.B, Fr, self.H, self.W)
+        elif self.fused:
+            ops.mha_temporal_bwd(self.qkv, self.o, do, self.lse, dqkv, eng.B, Fr, self.H, self.W)
         else:
             D = pool.get(self.lse.shape, F32)
             ops.mha_core_bwd(self.qkv, self.o, do, self.lse, D, dqkv, self.mode, eng.B, self.n_img // eng.B,

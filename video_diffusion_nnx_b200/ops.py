@@ -305,3 +305,8 @@ def mha_tc_supported(F: int, Cc: int) -> bool:
 def mha_temporal_tc_fwd(x, w_hm, bias_hm, o, qkv, lse, B, F, H, W, Cc):
     check(lib.vdn_mha_temporal_tc_fwd(ptr(x), ptr(w_hm), ptr(bias_hm), ptr(o), ptr(qkv), ptr(lse), B, F, H, W, Cc,
                                       stream_ptr()), "vdn_mha_temporal_tc_fwd")
+
+
+def mha_temporal_tc_bwd(qkv, d_o, lse, dqkv, B, F, H, W):
+    check(lib.vdn_mha_temporal_tc_bwd(ptr(qkv), ptr(d_o), ptr(lse), ptr(dqkv), B, F, H, W, stream_ptr()),
+          "vdn_mha_temporal_tc_bwd")
