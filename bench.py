@@ -194,8 +194,14 @@ def conv_roofline(torch, ops, pk):
     tf = flops / (ms * 1e-3) / 1e12
     gbs = bytes_alg / (ms * 1e-3) / 1e9
     # this layer is below the ridge (AI = flops/bytes ~ 144 FLOP/B < 212): HBM is the binding roofline
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tp):  # dram bytes per launch of this kernel from the committed `ncu --set full` capture
+        td = json.load(open(tp))
+        traffic = td["dram_bytes_read"] + td["dram_bytes_write"]
     return {"kernel": "tapgemm_kernel<32> conv(1,3,3) 32->32 @64x64 (M=163840,N=32,K=288)", "bound": "hbm",
-            "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"], "traffic": None,
+            "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"], "traffic": traffic,
+            "algorithmic_bytes": bytes_alg,
             "us_per_launch": ms * 1e3, "tensor_tflops": tf, "tensor_frac_of_burst": tf / pk["tf_burst"],
             "peak_source": pk["src"]}
 

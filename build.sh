@@ -1,10 +1,20 @@
 #!/bin/bash
-# Builds the in-tree CUDA library for sm_100a. Usage: ./build.sh [extra nvcc flags]
+# Builds the in-tree CUDA library for sm_100a (one object per source, compiled in parallel).
+# Usage: ./build.sh [extra nvcc flags]
 set -e
 cd "$(dirname "$0")"
 PKG=video_diffusion_nnx_b200
-SRC=$(ls $PKG/csrc/*.cu)
-nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 \
-  -Xcompiler -fPIC -shared -Iinclude "$@" \
-  -o $PKG/libvdn.so $SRC
+OBJ=$PKG/csrc/.obj
+mkdir -p $OBJ
+FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Iinclude $*"
+pids=()
+for f in $PKG/csrc/*.cu; do
+  o=$OBJ/$(basename ${f%.cu}).o
+  if [ ! -f $o ] || [ $f -nt $o ] || [ $PKG/csrc/vdn_common.cuh -nt $o ] || [ $PKG/csrc/vdn_host.h -nt $o ] || [ include/vdn.h -nt $o ]; then
+    nvcc $FLAGS -c -o $o $f &
+    pids+=($!)
+  fi
+done
+for p in "${pids[@]}"; do wait $p; done
+nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $PKG/libvdn.so $OBJ/*.o
 echo "built $PKG/libvdn.so"

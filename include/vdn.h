@@ -138,7 +138,8 @@ int vdn_wgrad_ref(int kind, const void* src0, const void* src1, const void* g, f
  * statistics over (F,H,W,C/G), eps 1e-6, var = max(0, E[x^2]-E[x]^2).
  *   gn_silu_fwd:        out = silu( GN(x_raw)*gamma+beta [ *(scale+1)+shift ] )     modules.py:171-179
  *   resblock_tail_fwd:  out = silu(GN(b_raw)*gamma+beta) + LayerNorm_C(s)           modules.py:241-242
- *   gn_silu_bwd:        dx_raw, dgamma+=, dbeta+=, dss = (dscale | dshift) [B][2C]; T_ws fp32 [B][C][2]
+ *   gn_silu_bwd:        dx_raw, dgamma+=, dbeta+=, dss = (dscale | dshift) [B][2C]; T_ws fp32 [B][C][2];
+ *                       dconv_bias (optional, +=) = column sums of dx_raw = gradient of the conv bias
  *   ln_bwd:             ds, dgamma+=, dbeta+= of the per-pixel LayerNorm (norm_2)
  * scale_shift: fp32 rows [B][ss_ld], scale = [0,C), shift = [C,2C); NULL when the block has no time
  * embedding. All activation tensors bf16 [B][rows_per_sample][C].
@@ -151,7 +152,7 @@ int vdn_resblock_tail_fwd(const void* b_raw, const float* gn_sums, const float* 
                           int rows_per_sample, int C, int G, void* stream);
 int vdn_gn_silu_bwd(const void* dy, const void* x_raw, const float* gn_sums, const float* gamma, const float* beta,
                     const float* scale_shift, int ss_ld, float* T_ws, void* dx_raw, float* dgamma, float* dbeta,
-                    float* dss, int dss_ld, int B, int rows_per_sample, int C, int G, void* stream);
+                    float* dss, int dss_ld, float* dconv_bias, int B, int rows_per_sample, int C, int G, void* stream);
 int vdn_ln_bwd(const void* s, const void* dy, const float* ln_gamma, void* ds, float* dgamma, float* dbeta, long P,
                int C, void* stream);
 

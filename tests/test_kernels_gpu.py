@@ -137,9 +137,11 @@ def test_gn_silu_fwd_bwd(B, R, Cc, with_ss):
     dx = torch.empty_like(x)
     dgam, dbet = torch.zeros(Cc, device=DEV), torch.zeros(Cc, device=DEV)
     dss = torch.zeros(B, 2 * Cc, device=DEV) if with_ss else None
+    dcb = torch.zeros(Cc, device=DEV)
     ops.gn_silu_bwd(dy, x, sums, gamma.detach(), beta.detach(), ss.detach() if with_ss else None, T, dx, dgam, dbet,
-                    dss, B, R, Cc)
+                    dss, B, R, Cc, dconv_bias=dcb)
     assert _rel(dx, xf.grad) < 2e-2
+    assert _rel(dcb, xf.grad.sum(dim=(0, 1))) < 2e-2 or dcb.abs().max() < 1e-2 * xf.grad.abs().sum(dim=(0, 1)).max()
     assert _rel(dgam, gamma.grad) < 1e-3
     assert _rel(dbet, beta.grad) < 1e-3
     if with_ss:

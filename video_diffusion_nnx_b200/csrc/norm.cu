@@ -262,9 +262,13 @@ __global__ void gn_bwd_finalize_kernel(const GnArgs a, const float* __restrict__
 }
 
 // dx = rstd_g * (gamma_c*(s+1)*dz - m1_g - xhat*m2_g),  m1_g = mean_g(dxhat), m2_g = mean_g(dxhat*xhat)
+// The x == 0 block of each sample also finalises dgamma / dbeta (atomics over samples) and (dscale | dshift);
+// every block accumulates the column sums of dx = the gradient of the producing conv's bias.
 __global__ void __launch_bounds__(kNormThreads) gn_bwd_apply_kernel(const GnArgs a, const bf16* __restrict__ dy,
                                                                     const float* __restrict__ T,
-                                                                    bf16* __restrict__ dx) {
+                                                                    bf16* __restrict__ dx, float* __restrict__ dgamma,
+                                                                    float* __restrict__ dbeta, float* __restrict__ dss,
+                                                                    int dss_ld, float* __restrict__ dconv_bias) {
   extern __shared__ float sm[];
   float* sA = sm;
   float* sB = sm + a.C;
@@ -298,11 +302,25 @@ __global__ void __launch_bounds__(kNormThreads) gn_bwd_apply_kernel(const GnArgs
     }
     sM1[c] = m1 * inv_n;
     sM2[c] = m2 * inv_n;
+    if (blockIdx.x == 0) {  // finalize (once per sample)
+      const float t1 = T[((long)b * a.C + c) * 2], t2 = T[((long)b * a.C + c) * 2 + 1];
+      const float sc = a.ss ? a.ss[(long)b * a.ss_ld + c] + 1.f : 1.f;
+      atomicAdd(&dgamma[c], sc * t2);
+      atomicAdd(&dbeta[c], sc * t1);
+      if (dss) {
+        dss[(long)b * dss_ld + c] = a.gamma[c] * t2 + a.beta[c] * t1;  // dscale = sum dz * (xhat*gamma + beta)
+        dss[(long)b * dss_ld + a.C + c] = t1;                          // dshift
+      }
+    }
   }
   __syncthreads();
   const int c8n = a.C / 8;
   const long nvec = (long)a.rows * c8n;
   const long boff = (long)b * a.rows * a.C;
+  float bs[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) bs[j] = 0.f;
+  // blockDim (256) is a multiple of c8n, so a thread always owns the same 8 channels
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long)gridDim.x * blockDim.x) {
     const int c0 = (int)(i % c8n) * 8;
     float xv[8], dv[8], o[8];
@@ -315,8 +333,21 @@ __global__ void __launch_bounds__(kNormThreads) gn_bwd_apply_kernel(const GnArgs
       const float dz = dv[j] * silu_grad_f(z);
       const float xh = (xv[j] - sMean[c]) * sRstd[c];
       o[j] = sRstd[c] * (sK[c] * dz - sM1[c] - xh * sM2[c]);
+      bs[j] += o[j];
     }
     store8(dx + boff + i * 8, o);
+  }
+  if (dconv_bias) {
+    float* red = sm + 7 * a.C;  // [blockDim][8]
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[threadIdx.x * 8 + j] = bs[j];
+    __syncthreads();
+    const int per = blockDim.x / c8n;  // threads sharing a channel vector
+    for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
+      float acc = 0.f;
+      for (int q = 0; q < per; ++q) acc += red[(q * c8n + c / 8) * 8 + (c & 7)];
+      atomicAdd(&dconv_bias[c], acc);
+    }
   }
 }
 
@@ -481,8 +512,8 @@ extern "C" int vdn_resblock_tail_fwd(const void* b_raw, const float* gn_sums, co
 
 extern "C" int vdn_gn_silu_bwd(const void* dy, const void* x_raw, const float* gn_sums, const float* gamma,
                                const float* beta, const float* scale_shift, int ss_ld, float* T_ws, void* dx_raw,
-                               float* dgamma, float* dbeta, float* dss, int dss_ld, int B, int rows_per_sample, int C,
-                               int G, void* stream) {
+                               float* dgamma, float* dbeta, float* dss, int dss_ld, float* dconv_bias, int B,
+                               int rows_per_sample, int C, int G, void* stream) {
   int rc = check_gn("gn_silu_bwd", B, rows_per_sample, C, G);
   if (rc) return rc;
   VDN_REQUIRE(pow2(C / 8) && C / 8 <= kNormThreads, VDN_E_SHAPE, "gn_silu_bwd: C=%d must be 8 * power of two <= 2048", C);
@@ -496,13 +527,10 @@ extern "C" int vdn_gn_silu_bwd(const void* dy, const void* x_raw, const float* g
   gn_bwd_reduce_kernel<<<grid, kNormThreads, smem_r, st>>>(a, reinterpret_cast<const bf16*>(dy), T_ws);
   rc = check_launch("gn_bwd_reduce");
   if (rc) return rc;
-  gn_bwd_finalize_kernel<<<ceil_div(C, 128), 128, 0, st>>>(a, T_ws, dgamma, dbeta, dss, dss_ld);
-  rc = check_launch("gn_bwd_finalize");
-  if (rc) return rc;
   const long nvec = (long)rows_per_sample * (C / 8);
   dim3 grid2(grid_x_for(nvec, kNormThreads * 4, B), B);
-  gn_bwd_apply_kernel<<<grid2, kNormThreads, 7 * C * sizeof(float), st>>>(a, reinterpret_cast<const bf16*>(dy), T_ws,
-                                                                          reinterpret_cast<bf16*>(dx_raw));
+  gn_bwd_apply_kernel<<<grid2, kNormThreads, (7 * C + kNormThreads * 8) * sizeof(float), st>>>(
+      a, reinterpret_cast<const bf16*>(dy), T_ws, reinterpret_cast<bf16*>(dx_raw), dgamma, dbeta, dss, dss_ld, dconv_bias);
   return check_launch("gn_bwd_apply");
 }
 

@@ -183,9 +183,9 @@ class GemmConv:
             ops.tapgemm(VDN_TAP_UNIT, [dy], self.wd, self.taps, residual=r[0], residual2=r[1], out=outs[0],
                         out2=outs[1], split_col=self.c_src)
 
-    def wgrad(self, srcs, dy):
+    def wgrad(self, srcs, dy, bias_done=False):
         ops.wgrad(VDN_TAP_UNIT, srcs, dy, self.dw, self.taps)
-        if self.dbias is not None:
+        if self.dbias is not None and not bias_done:
             ops.colsum(dy, self.dbias, dy.numel() // self.cout, self.cout)
 
 
@@ -247,8 +247,9 @@ class ResBlock:
         T = pool.get((B, C, 2), F32)
         db_raw = pool.get(shape)
         ops.gn_silu_bwd(dout, self.b_raw, self.sums2, self.p["block_2.norm.scale"], self.p["block_2.norm.bias"], None,
-                        T, db_raw, self.g["block_2.norm.scale"], self.g["block_2.norm.bias"], None, B, self.rows, C)
-        self.conv2.wgrad([self.a], db_raw)
+                        T, db_raw, self.g["block_2.norm.scale"], self.g["block_2.norm.bias"], None, B, self.rows, C,
+                        dconv_bias=self.conv2.dbias)
+        self.conv2.wgrad([self.a], db_raw, bias_done=True)
         da = pool.get(shape)
         self.conv2.dgrad(db_raw, [da])
         pool.put(db_raw)
@@ -256,10 +257,10 @@ class ResBlock:
         dss = eng.dss[:, self.ss_off:self.ss_off + 2 * C] if self.ss_off is not None else None
         ops.gn_silu_bwd(da, self.a_raw, self.sums1, self.p["block_1.norm.scale"], self.p["block_1.norm.bias"],
                         self._ss(), T, da_raw, self.g["block_1.norm.scale"], self.g["block_1.norm.bias"], dss, B,
-                        self.rows, C)
+                        self.rows, C, dconv_bias=self.conv1.dbias)
         pool.put(da)
         pool.put(T)
-        self.conv1.wgrad(self.srcs, da_raw)
+        self.conv1.wgrad(self.srcs, da_raw, bias_done=True)
         sshape = (self.n_img, self.H, self.W, self.c_src)
         dsrc = [pool.get(sshape) for _ in range(self.n_src)]
         if self.res is not None:

@@ -113,11 +113,11 @@ def resblock_tail_fwd(b_raw, sums, gamma, beta, s, ln_g, ln_b, out, B, rows, Cc,
                                     ptr(out), B, rows, Cc, G, stream_ptr()), "vdn_resblock_tail_fwd")
 
 
-def gn_silu_bwd(dy, x_raw, sums, gamma, beta, ss, T_ws, dx_raw, dgamma, dbeta, dss, B, rows, Cc, G=8):
+def gn_silu_bwd(dy, x_raw, sums, gamma, beta, ss, T_ws, dx_raw, dgamma, dbeta, dss, B, rows, Cc, G=8, dconv_bias=None):
     ss_ld = ss.stride(0) if ss is not None else 0
     dss_ld = dss.stride(0) if dss is not None else 0
     check(lib.vdn_gn_silu_bwd(ptr(dy), ptr(x_raw), ptr(sums), ptr(gamma), ptr(beta), ptr(ss), ss_ld, ptr(T_ws),
-                              ptr(dx_raw), ptr(dgamma), ptr(dbeta), ptr(dss), dss_ld, B, rows, Cc, G, stream_ptr()),
+                              ptr(dx_raw), ptr(dgamma), ptr(dbeta), ptr(dss), dss_ld, ptr(dconv_bias), B, rows, Cc, G, stream_ptr()),
           "vdn_gn_silu_bwd")
 
 
