@@ -100,6 +100,10 @@ int vdn_tapgemm(const vdn_tapgemm_desc* d, const void* src0, const void* src1, c
 
 /* Reference (non tensor-core) implementation of the same contract, used only by the GPU
  * tests to localise faults. Not on any product path. */
+/* Debug only: device buffer of 8*3*64 int64 that the row-ring (1,3,3) conv kernel stamps with clock64()
+ * for its first 8 CTAs (producer / MMA / epilogue timelines); NULL switches it off. */
+void vdn_debug_rowconv_trace(void* dev_buf);
+
 int vdn_tapgemm_ref(const vdn_tapgemm_desc* d, const void* src0, const void* src1, const void* wp,
                     const float* bias, const void* residual, const void* residual2, void* out, void* out2,
                     float* gn_sums, void* stream);

@@ -56,7 +56,8 @@ __global__ void __launch_bounds__(kFThreads, 2) mha_fused_fwd_kernel(const __gri
   __shared__ uint32_t tmem_base_smem;
   __shared__ __align__(16) float s_bias[768];
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // warp-uniform role index
+  const int lane = threadIdx.x & 31;
   // 1024-byte aligned view of the dynamic smem; offset arithmetic keeps the pointer in the shared space
   uint8_t* smem = smem_raw + (((smem_u32(smem_raw) + 1023u) & ~1023u) - smem_u32(smem_raw));
   for (int i = threadIdx.x; i < 768; i += blockDim.x) s_bias[i] = a.bias ? a.bias[i] : 0.f;
@@ -90,7 +91,7 @@ __global__ void __launch_bounds__(kFThreads, 2) mha_fused_fwd_kernel(const __gri
   const uint32_t tmem_base = tmem_base_smem;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       for (int it = 0; it < n_steps; ++it) {
         const int pass = it / a.chunks, c = it - pass * a.chunks;
         const int st = it % kFStages;
@@ -110,7 +111,7 @@ __global__ void __launch_bounds__(kFThreads, 2) mha_fused_fwd_kernel(const __gri
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t idesc = umma_idesc_bf16(128, kPassCols, 0, 0);
       int it = 0;
       for (int pass = 0; pass < 4; ++pass) {

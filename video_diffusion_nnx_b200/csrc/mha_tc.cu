@@ -61,7 +61,8 @@ __global__ void __launch_bounds__(kTcThreads) mha_tc_fwd_kernel(const __grid_con
   __shared__ uint32_t tmem_base_smem;
   __shared__ __align__(16) float s_bias[768];
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // warp-uniform role index
+  const int lane = threadIdx.x & 31;
   uint8_t* smem = smem_raw + (((smem_u32(smem_raw) + 1023u) & ~1023u) - smem_u32(smem_raw));
   uint8_t* sQ = smem + kTcStages * kStageBytes;
   uint8_t* sK = sQ + kTile;
@@ -106,10 +107,10 @@ __global__ void __launch_bounds__(kTcThreads) mha_tc_fwd_kernel(const __grid_con
   const uint32_t t_qkv = tmem_base, t_s = tmem_base + 96, t_o = tmem_base + 224;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {  // one elected lane (not `lane == 0`): keeps the issue loop on the uniform datapath
       const int n_steps = 8 * a.chunks;
+      int h = 0, c = 0;
       for (int it = 0; it < n_steps; ++it) {
-        const int h = it / a.chunks, c = it - h * a.chunks;
         const int st = it % kTcStages;
         const uint32_t ph = (uint32_t)(it / kTcStages) & 1u;
         mbar_wait(&empty_bar[st], ph ^ 1u);
@@ -122,11 +123,15 @@ __global__ void __launch_bounds__(kTcThreads) mha_tc_fwd_kernel(const __grid_con
             "r"(0), "r"(b)
             : "memory");
         tma_load_2d(sx + kXBytes, &maps.w, &full_bar[st], c * BK, h * 96);
+        if (++c == a.chunks) {
+          c = 0;
+          ++h;
+        }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t id_proj = umma_idesc_bf16(128, 96, 0, 0);
       const uint32_t id_s = umma_idesc_bf16(128, 128, 0, 0);
       const uint32_t id_o = umma_idesc_bf16(128, 32, 0, 1);  // B = V read MN-major
@@ -384,7 +389,8 @@ __global__ void __launch_bounds__(160) mha_tc_bwd_kernel(const bf16* __restrict_
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t in_ready, sdp_full, pds_ready, grad_full;
   __shared__ uint32_t tmem_base_smem;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // warp-uniform role index
+  const int lane = threadIdx.x & 31;
   uint8_t* smem = smem_raw + (((smem_u32(smem_raw) + 1023u) & ~1023u) - smem_u32(smem_raw));
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + kTile;
@@ -418,7 +424,7 @@ __global__ void __launch_bounds__(160) mha_tc_bwd_kernel(const bf16* __restrict_
   const uint32_t tmem_base = tmem_base_smem;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t id_ss = umma_idesc_bf16(128, 128, 0, 0);
       const uint32_t id_dq = umma_idesc_bf16(128, 32, 0, 1);   // A K-major (dS), B MN-major (K)
       const uint32_t id_tt = umma_idesc_bf16(128, 32, 1, 1);   // A MN-major (dS^T / P^T), B MN-major

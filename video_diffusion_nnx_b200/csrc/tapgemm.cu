@@ -114,7 +114,8 @@ __global__ void __launch_bounds__(kGemmThreads) tapgemm_kernel(const __grid_cons
   __shared__ uint32_t tmem_base_smem;
   __shared__ float s_gn[4][16];  // per epilogue warp: (sum, sumsq) of up to 8 groups of this N tile
 
-  const int warp = threadIdx.x >> 5;
+  // warp-uniform role index (shfl broadcast): keeps the producer / MMA loops on the uniform datapath
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const int BN = args.BN;
   const int b_bytes = (BN * BK * 2 + 1023) & ~1023;
@@ -148,27 +149,34 @@ __global__ void __launch_bounds__(kGemmThreads) tapgemm_kernel(const __grid_cons
 
   if (warp == 0) {
     // ================= TMA producer =================
-    if (lane == 0) {
+    // One elected lane issues; `elect_one` (not `lane == 0`) lets the compiler treat the region as a single
+    // thread, so descriptors / coordinates stay in uniform registers instead of per-instruction waterfall loops.
+    if (elect_one()) {
       const int hw = args.H * args.W;
       const int n0 = m0 / hw;
       const int rem = m0 - n0 * hw;
       const int y0 = rem / args.W;
       const int x0 = rem - y0 * args.W;
-      int it = 0;
+      const uint32_t tx_bytes = (uint32_t)(kABytes + BN * BK * 2);
+      int st = 0, kcol = 0;
+      uint32_t ph = 1u;  // parity to wait for on the empty barrier of the slot
       for (int t = 0; t < args.n_taps; ++t) {
         const int cx = x0 + args.tap_dx[t];
         const int cy = y0 + args.tap_dy[t];
         for (int s = 0; s < args.n_src; ++s) {
           const CUtensorMap* am = &maps.a[args.tap_map[t] + s];
-          for (int c = 0; c < args.chunks; ++c, ++it) {
-            const int st = it % S;
-            const uint32_t ph = (uint32_t)(it / S) & 1u;
-            mbar_wait(&empty_bar[st], ph ^ 1u);
+          for (int c = 0; c < args.chunks; ++c) {
+            mbar_wait(&empty_bar[st], ph);
             uint8_t* sa = smem + st * stage_bytes;
             uint8_t* sb = sa + kABytes;
-            mbar_expect_tx(&full_bar[st], (uint32_t)(kABytes + BN * BK * 2));
+            mbar_expect_tx(&full_bar[st], tx_bytes);
             tma_load_4d(sa, am, &full_bar[st], c * BK, cx, cy, n0);
-            tma_load_2d(sb, &maps.b, &full_bar[st], it * BK, n_tile * BN);
+            tma_load_2d(sb, &maps.b, &full_bar[st], kcol, n_tile * BN);
+            kcol += BK;
+            if (++st == S) {
+              st = 0;
+              ph ^= 1u;
+            }
           }
         }
       }
@@ -176,23 +184,32 @@ __global__ void __launch_bounds__(kGemmThreads) tapgemm_kernel(const __grid_cons
     __syncwarp();
   } else if (warp == 1) {
     // ================= MMA issuer =================
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t idesc = umma_idesc_bf16(kTileM, BN, 0, 0);
+      // descriptor halves: hi = SBO | version | swizzle mode; lo = (address >> 4) | LBO(16 B) << 16
+      const uint32_t desc_hi = (kSBO >> 4) | (1u << 14) | (kLayout << 29);
+      const uint32_t stage16 = (uint32_t)stage_bytes >> 4;
+      const uint32_t a_lo0 = (smem_u32(smem) >> 4) | (1u << 16);
+      int st = 0;
+      uint32_t ph = 0u;
+      uint32_t a_lo = a_lo0;
       for (int it = 0; it < n_steps; ++it) {
-        const int st = it % S;
-        const uint32_t ph = (uint32_t)(it / S) & 1u;
         mbar_wait(&full_bar[st], ph);
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem + st * stage_bytes);
-        const uint32_t sb = sa + kABytes;
-        const uint64_t da = umma_smem_desc(sa, 16, kSBO, kLayout);
-        const uint64_t db = umma_smem_desc(sb, 16, kSBO, kLayout);
+        const uint32_t b_lo = a_lo + (uint32_t)(kABytes >> 4);
 #pragma unroll
         for (int k = 0; k < BK / 16; ++k) {
           // advance 16 K-elements = 32 bytes inside the swizzle span (encoded >> 4)
-          umma_bf16(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (it | k) != 0 ? 1u : 0u);
+          umma_bf16(tmem_base, (static_cast<uint64_t>(desc_hi) << 32) | (a_lo + 2u * k),
+                    (static_cast<uint64_t>(desc_hi) << 32) | (b_lo + 2u * k), idesc, (it | k) != 0 ? 1u : 0u);
         }
         tc_commit(&empty_bar[st]);  // frees the smem slot when these MMAs retire
+        a_lo += stage16;
+        if (++st == S) {
+          st = 0;
+          ph ^= 1u;
+          a_lo = a_lo0;
+        }
       }
       tc_commit(&tmem_full_bar);
     }
@@ -579,6 +596,10 @@ extern "C" int vdn_tapgemm(const vdn_tapgemm_desc* d, const void* src0, const vo
   VDN_REQUIRE(src0 && wp && out, VDN_E_SHAPE, "tapgemm: null operand");
   VDN_REQUIRE(d->n_src == 1 || src1, VDN_E_SHAPE, "tapgemm: src1 missing");
   VDN_REQUIRE(d->split_col == 0 || out2, VDN_E_SHAPE, "tapgemm: out2 missing");
+  VDN_REQUIRE(!(gn_sums && residual), VDN_E_SHAPE, "tapgemm: gn_sums and residual are mutually exclusive");
+  if (rowconv_applicable(d, residual, gn_sums))
+    return rowconv_launch(d, src0, src1, wp, bias, residual, residual2, out, out2, gn_sums,
+                          reinterpret_cast<cudaStream_t>(stream));
 
   const int C = d->src_c;
   const int BK = (C % 64 == 0) ? 64 : (C % 32 == 0) ? 32 : 16;

@@ -53,8 +53,10 @@ __global__ void __launch_bounds__(kWgThreads) wgrad_kernel(const __grid_constant
   __shared__ __align__(8) uint64_t empty_bar[kWgMaxStages];
   __shared__ __align__(8) uint64_t tmem_full_bar;
   __shared__ uint32_t tmem_base_smem;
+  __shared__ int4 s_atom[8];  // per M atom: (tensor map, channel offset, dx, dy)
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // warp-uniform role index
+  const int lane = threadIdx.x & 31;
   // 1024-byte aligned view of the dynamic smem; offset arithmetic keeps the pointer in the shared space
   uint8_t* smem = smem_raw + (((smem_u32(smem_raw) + 1023u) & ~1023u) - smem_u32(smem_raw));
   const int atom_bytes_m = kKPix * a.cw * 2;
@@ -90,55 +92,81 @@ __global__ void __launch_bounds__(kWgThreads) wgrad_kernel(const __grid_constant
 
   if (n_steps > 0) {
     if (warp == 0) {
-      if (lane == 0) {
+      // per-atom TMA parameters (map, channel offset, shift) are computed once by the first lanes
+      if (lane < n_atoms) {
+        const int id = atom0 + lane;
+        const int chunk = id % a.chunks;
+        const int src = (id / a.chunks) % a.n_src;
+        const int tap = id / (a.chunks * a.n_src);
+        s_atom[lane] = make_int4(a.tap_map[tap] + src, chunk * a.cw, a.tap_dx[tap], a.tap_dy[tap]);
+      }
+      __syncwarp();
+      if (elect_one()) {  // single elected lane: keeps the loop on the uniform datapath (no waterfall loops)
         const int hw = a.H * a.W;
         const int tap_n = a.per_tap_n ? (atom0 / (a.n_src * a.chunks)) : 0;
+        const int ndx = a.ntap_dx[tap_n], ndy = a.ntap_dy[tap_n];
+        const uint32_t tx_bytes = (uint32_t)(n_atoms * atom_bytes_m + b_bytes);
+        const int p_begin = t_begin * kKPix;
+        int n0 = p_begin / hw;
+        int rem = p_begin - n0 * hw;
+        int st = 0;
+        uint32_t ph = 1u;
         for (int it = 0; it < n_steps; ++it) {
-          const int st = it % S;
-          const uint32_t ph = (uint32_t)(it / S) & 1u;
-          const int p0 = (t_begin + it) * kKPix;
-          const int n0 = p0 / hw;
-          const int rem = p0 - n0 * hw;
           const int y0 = rem / a.W, x0 = rem - y0 * a.W;
-          mbar_wait(&empty_bar[st], ph ^ 1u);
+          mbar_wait(&empty_bar[st], ph);
           uint8_t* sa = smem + st * stage_bytes;
           uint8_t* sb = sa + a_bytes;
-          mbar_expect_tx(&full_bar[st], (uint32_t)(n_atoms * atom_bytes_m + b_bytes));
+          mbar_expect_tx(&full_bar[st], tx_bytes);
           for (int i = 0; i < n_atoms; ++i) {
-            const int id = atom0 + i;
-            const int chunk = id % a.chunks;
-            const int src = (id / a.chunks) % a.n_src;
-            const int tap = id / (a.chunks * a.n_src);
-            tma_load_4d(sa + i * atom_bytes_m, &maps.m[a.tap_map[tap] + src], &full_bar[st], chunk * a.cw,
-                        x0 + a.tap_dx[tap], y0 + a.tap_dy[tap], n0);
+            const int4 ai = s_atom[i];
+            tma_load_4d(sa + i * atom_bytes_m, &maps.m[ai.x], &full_bar[st], ai.y, x0 + ai.z, y0 + ai.w, n0);
           }
-          for (int j = 0; j < a.n_atoms_n; ++j) {
-            tma_load_4d(sb + j * atom_bytes_n, &maps.n, &full_bar[st], n_tile * a.BN + j * a.cwn,
-                        x0 + a.ntap_dx[tap_n], y0 + a.ntap_dy[tap_n], n0);
+          for (int j = 0; j < a.n_atoms_n; ++j)
+            tma_load_4d(sb + j * atom_bytes_n, &maps.n, &full_bar[st], n_tile * a.BN + j * a.cwn, x0 + ndx, y0 + ndy, n0);
+          rem += kKPix;
+          while (rem >= hw) {
+            rem -= hw;
+            ++n0;
+          }
+          if (++st == S) {
+            st = 0;
+            ph ^= 1u;
           }
         }
       }
       __syncwarp();
     } else if (warp == 1) {
-      if (lane == 0) {
+      if (elect_one()) {
         const uint32_t idesc = umma_idesc_bf16(128, a.BN, 1, 1);  // both operands MN-major
         const uint32_t lay_m = umma_layout_type(a.cw * 2), lay_n = umma_layout_type(a.cwn * 2);
-        const uint32_t sbo_m = 8u * a.cw * 2u, sbo_n = 8u * a.cwn * 2u;  // stride between 8-row K groups
+        // descriptor halves: hi = SBO (stride between 8-row K groups) | version | swizzle; lo = addr | LBO (atom stride)
+        const uint32_t hi_m = ((8u * a.cw * 2u) >> 4) | (1u << 14) | (lay_m << 29);
+        const uint32_t hi_n = ((8u * a.cwn * 2u) >> 4) | (1u << 14) | (lay_n << 29);
+        const uint32_t lbo_m = (((uint32_t)atom_bytes_m >> 4) & 0x3FFFu) << 16;
+        const uint32_t lbo_n = (((uint32_t)atom_bytes_n >> 4) & 0x3FFFu) << 16;
+        const uint32_t kstep_m = (uint32_t)(16 * a.cw * 2) >> 4, kstep_n = (uint32_t)(16 * a.cwn * 2) >> 4;
+        const uint32_t s0 = smem_u32(smem) >> 4, stage16 = (uint32_t)stage_bytes >> 4, ab16 = (uint32_t)a_bytes >> 4;
+        int st = 0;
+        uint32_t ph = 0u, sa16 = s0;
         for (int it = 0; it < n_steps; ++it) {
-          const int st = it % S;
-          const uint32_t ph = (uint32_t)(it / S) & 1u;
           mbar_wait(&full_bar[st], ph);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + st * stage_bytes);
-          const uint32_t sb = sa + a_bytes;
+          uint32_t lo_m = sa16 | lbo_m, lo_n = (sa16 + ab16) | lbo_n;
 #pragma unroll
           for (int k = 0; k < kKPix / 16; ++k) {
             // 16 pixels (two 8-row groups) per MMA: advance both operands by 16 rows
-            const uint64_t da = umma_smem_desc(sa + k * 16 * a.cw * 2, (uint32_t)atom_bytes_m, sbo_m, lay_m);
-            const uint64_t db = umma_smem_desc(sb + k * 16 * a.cwn * 2, (uint32_t)atom_bytes_n, sbo_n, lay_n);
-            umma_bf16(tmem_base, da, db, idesc, (it | k) != 0 ? 1u : 0u);
+            umma_bf16(tmem_base, (static_cast<uint64_t>(hi_m) << 32) | lo_m, (static_cast<uint64_t>(hi_n) << 32) | lo_n,
+                      idesc, (it | k) != 0 ? 1u : 0u);
+            lo_m += kstep_m;
+            lo_n += kstep_n;
           }
           tc_commit(&empty_bar[st]);
+          sa16 += stage16;
+          if (++st == S) {
+            st = 0;
+            ph ^= 1u;
+            sa16 = s0;
+          }
         }
         tc_commit(&tmem_full_bar);
       }
