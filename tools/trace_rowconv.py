@@ -19,7 +19,7 @@ out = torch.empty(n_img, H, W, N, dtype=torch.bfloat16, device=dev)
 bias = torch.zeros(N, device=dev)
 sums = torch.zeros(ops.GN_REPLICAS, 4, 8, 2, device=dev)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-trace = torch.zeros(8 * 3 * 64, dtype=torch.int64, device=dev)
+trace = torch.zeros(8 * 3 * 64 + 4 * 1024, dtype=torch.int64, device=dev)
 for rep in range(3):
     flush.zero_()
     trace.zero_()
@@ -28,7 +28,14 @@ for rep in range(3):
                 rows_per_sample=10 * H * W)
     torch.cuda.synchronize()
     lib.vdn_debug_rowconv_trace(None)
-tr = trace.view(8, 3, 64).cpu()
+tr = trace[:8 * 3 * 64].view(8, 3, 64).cpu()
+cta = trace[8 * 3 * 64:].view(1024, 4).cpu()
+cta = cta[cta[:, 0] != 0]
+t0g = int(cta[:, 0].min())
+import numpy as np
+st = (cta[:, 0] - t0g).numpy(); en = (cta[:, 1] - t0g).numpy()
+print("ctas", len(cta), "start ns: min/med/max", st.min(), np.median(st), st.max(), " end ns: min/med/max", en.min(), np.median(en), en.max(), " dur med/max", np.median(en - st), (en - st).max())
+print("distinct SMs", len(set(cta[:, 2].tolist())))
 for cta in (0, 1, 5):
     t0 = int(tr[cta, 0, 0])
     for role, name in enumerate(("producer", "mma", "epilogue")):

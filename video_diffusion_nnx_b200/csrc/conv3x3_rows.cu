@@ -101,6 +101,16 @@ __global__ void __launch_bounds__(kRcThreads) conv3x3_rows_kernel(const __grid_c
   const int t0 = (int)((long)blockIdx.x * a.n_tiles / gridDim.x);
   const int t1 = (int)((long)(blockIdx.x + 1) * a.n_tiles / gridDim.x);
 
+  pdl_trigger();
+  if (a.trace && threadIdx.x == 0) {
+    unsigned long long gt;
+    unsigned smid;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    a.trace[8 * 3 * 64 + blockIdx.x * 4 + 0] = (long long)gt;
+    a.trace[8 * 3 * 64 + blockIdx.x * 4 + 2] = smid;
+    a.trace[8 * 3 * 64 + blockIdx.x * 4 + 3] = clock64();
+  }
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < NSRC; ++s) {
       tma_prefetch_desc(&maps.a[s]);
@@ -126,6 +136,7 @@ __global__ void __launch_bounds__(kRcThreads) conv3x3_rows_kernel(const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  pdl_wait();  // everything above overlapped the tail of the previous kernel; global memory is touched below
 
   if (warp == 0) {
     // ================= TMA producer =================
@@ -330,6 +341,11 @@ __global__ void __launch_bounds__(kRcThreads) conv3x3_rows_kernel(const __grid_c
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
   }
+  if (a.trace && threadIdx.x == 0) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    a.trace[8 * 3 * 64 + blockIdx.x * 4 + 1] = (long long)gt;
+  }
 }
 
 template <int N, int KC, int NSRC>
@@ -341,7 +357,8 @@ static int launch_rowconv(const RowConvMaps& maps, const RowConvArgs& a, int gri
     VDN_REQUIRE(e == cudaSuccess, VDN_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     configured = true;
   }
-  conv3x3_rows_kernel<N, KC, NSRC><<<grid, kRcThreads, smem_bytes, st>>>(maps, a);
+  cudaError_t le = launch_pdl(conv3x3_rows_kernel<N, KC, NSRC>, dim3(grid), dim3(kRcThreads), (size_t)smem_bytes, st, 1, maps, a);
+  VDN_REQUIRE(le == cudaSuccess, VDN_E_CUDA, "conv3x3_rows launch: %s", cudaGetErrorString(le));
   return check_launch("conv3x3_rows_kernel");
 }
 

@@ -28,7 +28,7 @@ struct TcMaps {
   CUtensorMap w;  // (C, 768) bf16, head-major rows (h*96 + part*32 + d)
 };
 struct TcArgs {
-  int B, H, W, C, PX, chunks;
+  int B, H, W, C, PX, chunks;  // a tile = PX consecutive pixels of the flattened H*W index (all F frames)
   const float* bias;  // [768] head-major
   bf16* o;            // [P][256]
   bf16* qkv;          // [P][768] or null
@@ -71,11 +71,11 @@ __global__ void __launch_bounds__(kTcThreads) mha_tc_fwd_kernel(const __grid_con
 
   const int PX = a.PX;
   const int rows = PX * F;
-  const int tiles_x = a.W / PX;
+  const int HW = a.H * a.W;
+  const int tiles_img = (HW + PX - 1) / PX;  // the last tile of a batch element may be partial (TMA zero fill)
   const int tile = blockIdx.x;
-  const int x0 = (tile % tiles_x) * PX;
-  const int y = (tile / tiles_x) % a.H;
-  const int b = tile / (tiles_x * a.H);
+  const int b = tile / tiles_img;
+  const int p0 = (tile - b * tiles_img) * PX;
 
   for (int i = threadIdx.x; i < 768; i += blockDim.x) s_bias[i] = a.bias ? a.bias[i] : 0.f;
   // zero V (rows >= PX*F must be finite zeros: they meet P's zero columns) and the block-diagonal P tile
@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(kTcThreads) mha_tc_fwd_kernel(const __grid_con
         asm volatile(
             "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes"
             " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(smem_u32(sx)),
-            "l"(reinterpret_cast<uint64_t>(&maps.x)), "r"(smem_u32(&full_bar[st])), "r"(c * BK), "r"(x0), "r"(y),
+            "l"(reinterpret_cast<uint64_t>(&maps.x)), "r"(smem_u32(&full_bar[st])), "r"(c * BK), "r"(p0), "r"(0),
             "r"(0), "r"(b)
             : "memory");
         tma_load_2d(sx + kXBytes, &maps.w, &full_bar[st], c * BK, h * 96);
@@ -187,20 +187,23 @@ __global__ void __launch_bounds__(kTcThreads) mha_tc_fwd_kernel(const __grid_con
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;       // TMEM lane of this thread
     // role A: projection row r is token (f, px) in frame-major order (the TMA box order)
-    const bool validA = r < rows;
-    const int fA = validA ? r / PX : 0, pxA = validA ? r % PX : 0;
+    const bool inA = r < rows;
+    const int fA = inA ? r / PX : 0, pxA = inA ? r % PX : 0;
+    const bool validA = inA && p0 + pxA < HW;
     const int rpA = pxA * F + fA;            // its row in the pixel-major attention tiles
-    const long growA = (((long)b * F + fA) * a.H + y) * a.W + x0 + pxA;
+    const long growA = ((long)b * F + fA) * HW + p0 + pxA;
     // role B: attention row r is token (px, f) in pixel-major order
-    const bool validB = r < rows;
-    const int pxB = validB ? r / F : 0, fB = validB ? r % F : 0;
-    const long growB = (((long)b * F + fB) * a.H + y) * a.W + x0 + pxB;
+    const bool inB = r < rows;
+    const int pxB = inB ? r / F : 0, fB = inB ? r % F : 0;
+    const bool validB = inB && p0 + pxB < HW;
+    const long growB = ((long)b * F + fB) * HW + p0 + pxB;
     const int px_lo = (quarter * 32) / F;    // first pixel of this warp's rows
     constexpr int kSlots = (32 % F == 0) ? (32 / F) : ((31 / F) + 2);  // pixels intersecting a warp's 32 rows
     constexpr int kWin = kSlots * F > 32 ? 48 : 32;
-    // first S column this warp needs (clamped for padding-only warps so the window stays inside the tile)
+    // first S column this warp needs, clamped so the window stays inside the 128-column tile; the clamp
+    // shifts the window by a whole number of F-wide slots (F = 10: 90 -> 80), which `sel` absorbs
     const int c0 = min(px_lo * F, 128 - kWin);
-    const int sel = pxB - px_lo;             // which F-wide slot of the window is mine (0..3)
+    const int sel = pxB - px_lo + (px_lo * F - c0) / F;  // which F-wide slot of the window is mine
     const uint32_t lane_sel = (uint32_t)(quarter * 32) << 16;
     const float scale = rsqrtf(32.f);
 
@@ -222,13 +225,13 @@ __global__ void __launch_bounds__(kTcThreads) mha_tc_fwd_kernel(const __grid_con
           packed[e >> 1] = pack_bf16x2(__uint_as_float(raw[e]) + b4.x, __uint_as_float(raw[e + 1]) + b4.y);
           packed[(e >> 1) + 1] = pack_bf16x2(__uint_as_float(raw[e + 2]) + b4.z, __uint_as_float(raw[e + 3]) + b4.w);
         }
-        if (validA) {
+        if (inA) {
           uint8_t* dst = part == 0 ? sQ : (part == 1 ? sK : sV);
 #pragma unroll
           for (int c = 0; c < 4; ++c)
             *reinterpret_cast<uint4*>(dst + sw64_off(rpA, c)) =
                 make_uint4(packed[4 * c], packed[4 * c + 1], packed[4 * c + 2], packed[4 * c + 3]);
-          if (a.qkv) {
+          if (a.qkv && validA) {
             uint4* gp = reinterpret_cast<uint4*>(a.qkv + growA * 768 + part * 256 + h * 32);
 #pragma unroll
             for (int c = 0; c < 4; ++c) gp[c] = make_uint4(packed[4 * c], packed[4 * c + 1], packed[4 * c + 2], packed[4 * c + 3]);
@@ -269,7 +272,7 @@ __global__ void __launch_bounds__(kTcThreads) mha_tc_fwd_kernel(const __grid_con
         sc[j] = __expf(sc[j] - mx);
         l += sc[j];
       }
-      if (validB) {
+      if (inB) {
 #pragma unroll
         for (int j = 0; j < F; j += 2) {
           // columns pxB*F + j, +1 of my P row (F is even for the instantiated kernels -> aligned bf16x2 stores)
@@ -340,8 +343,7 @@ extern "C" int vdn_mha_temporal_tc_fwd(const void* x, const void* w_hm, const fl
                                        float* lse, int B, int F, int H, int W, int C, void* stream) {
   VDN_REQUIRE(x && w_hm && o && B > 0 && H > 0 && W > 0, VDN_E_SHAPE, "mha_tc: bad args");
   VDN_REQUIRE(vdn_mha_temporal_tc_supported(F, C), VDN_E_SHAPE, "mha_tc: F=%d C=%d not instantiated", F, C);
-  int PX = 1;
-  while (PX * 2 * F <= 128 && PX * 2 <= W && W % (PX * 2) == 0) PX *= 2;
+  const int PX = std::min(128 / F, H * W);  // pixels per 128-row tile (12 for F = 10, 8 for F = 16)
   const int BK = (C % 64 == 0) ? 64 : 32;
   TcArgs a;
   a.B = B; a.H = H; a.W = W; a.C = C; a.PX = PX; a.chunks = C / BK;
@@ -352,8 +354,10 @@ extern "C" int vdn_mha_temporal_tc_fwd(const void* x, const void* w_hm, const fl
   TcMaps maps;
   memset(&maps, 0, sizeof(maps));
   {
-    const uint64_t dims[5] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)F, (uint64_t)B};
-    const uint64_t str[4] = {(uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2, (uint64_t)F * H * W * C * 2};
+    // pixels flattened: (C, H*W, 1, F, B); a box = BK channels x PX pixels x F frames
+    const uint64_t HWl = (uint64_t)H * W;
+    const uint64_t dims[5] = {(uint64_t)C, HWl, 1u, (uint64_t)F, (uint64_t)B};
+    const uint64_t str[4] = {(uint64_t)C * 2, HWl * C * 2, HWl * C * 2, (uint64_t)F * HWl * C * 2};
     const uint32_t box[5] = {(uint32_t)BK, (uint32_t)PX, 1u, (uint32_t)F, 1u};
     int rc = encode_tmap_bf16(&maps.x, x, 5, dims, str, box, BK * 2);
     if (rc) return rc;
@@ -365,7 +369,7 @@ extern "C" int vdn_mha_temporal_tc_fwd(const void* x, const void* w_hm, const fl
     int rc = encode_tmap_bf16(&maps.w, w_hm, 2, dims, str, box, BK * 2);
     if (rc) return rc;
   }
-  const int n_tiles = B * H * (W / PX);
+  const int n_tiles = B * ((H * W + PX - 1) / PX);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (F == 10) return BK == 64 ? launch_tc<64, 10>(maps, a, n_tiles, st) : launch_tc<32, 10>(maps, a, n_tiles, st);
   return BK == 64 ? launch_tc<64, 16>(maps, a, n_tiles, st) : launch_tc<32, 16>(maps, a, n_tiles, st);
@@ -399,11 +403,11 @@ __global__ void __launch_bounds__(160) mha_tc_bwd_kernel(const bf16* __restrict_
   uint8_t* sP = sG + kTile;      // 32 KB
   uint8_t* sS = sP + 32768;      // 32 KB
   const int rows = PX * F;
-  const int tiles_x = W / PX;
+  const int HW = H * W;
+  const int tiles_img = (HW + PX - 1) / PX;
   const int tile = blockIdx.x;
-  const int x0 = (tile % tiles_x) * PX;
-  const int y = (tile / tiles_x) % H;
-  const int b = tile / (tiles_x * H);
+  const int b = tile / tiles_img;
+  const int p0 = (tile - b * tiles_img) * PX;
 
   for (int i = threadIdx.x; i < (4 * kTile + 65536) / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
   if (threadIdx.x == 0) {
@@ -464,14 +468,15 @@ __global__ void __launch_bounds__(160) mha_tc_bwd_kernel(const bf16* __restrict_
   } else {
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;
-    const bool valid = r < rows;
-    const int px = valid ? r / F : 0, f = valid ? r % F : 0;
-    const long grow = (((long)b * F + f) * H + y) * W + x0 + px;
+    const bool in_tile = r < rows;
+    const int px = in_tile ? r / F : 0, f = in_tile ? r % F : 0;
+    const bool valid = in_tile && p0 + px < HW;  // rows of a partial last tile stay zero in every smem tile
+    const long grow = ((long)b * F + f) * HW + p0 + px;
     const int px_lo = (quarter * 32) / F;
     constexpr int kSlots = (32 % F == 0) ? (32 / F) : ((31 / F) + 2);
     constexpr int kWin = kSlots * F > 32 ? 48 : 32;
-    const int c0 = min(px_lo * F, 128 - kWin);   // clamped for padding-only warps
-    const int sel = px - px_lo;
+    const int c0 = min(px_lo * F, 128 - kWin);   // clamped to the tile; the shift is a whole number of slots
+    const int sel = px - px_lo + (px_lo * F - c0) / F;
     const uint32_t lane_sel = (uint32_t)(quarter * 32) << 16;
     const float scale = rsqrtf(32.f);
     for (int h = 0; h < 8; ++h) {
@@ -581,7 +586,7 @@ static int launch_tc_bwd(const bf16* qkv, const bf16* d_o, const float* lse, bf1
     VDN_REQUIRE(e == cudaSuccess, VDN_E_CUDA, "mha_tc_bwd cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     cfg = true;
   }
-  mha_tc_bwd_kernel<F><<<B * H * (W / PX), 160, smem, st>>>(qkv, d_o, lse, dqkv, B, H, W, PX);
+  mha_tc_bwd_kernel<F><<<B * ((H * W + PX - 1) / PX), 160, smem, st>>>(qkv, d_o, lse, dqkv, B, H, W, PX);
   return check_launch("mha_tc_bwd_kernel");
 }
 
@@ -591,8 +596,10 @@ static int launch_tc_bwd(const bf16* qkv, const bf16* d_o, const float* lse, bf1
 extern "C" int vdn_mha_temporal_tc_bwd(const void* qkv, const void* d_o, const float* lse, void* dqkv, int B, int F,
                                        int H, int W, void* stream) {
   VDN_REQUIRE(qkv && d_o && lse && dqkv && (F == 10 || F == 16), VDN_E_SHAPE, "mha_tc_bwd: bad args (F in {10,16})");
+  // The backward is bound by its per-row global loads / stores, not by the MMA chain: 120-row tiles (PX = 12)
+  // measured slower than 80-row tiles, so it keeps power-of-two pixel counts (8 for F = 10 and F = 16).
   int PX = 1;
-  while (PX * 2 * F <= 128 && PX * 2 <= W && W % (PX * 2) == 0) PX *= 2;
+  while (PX * 2 * F <= 128 && PX * 2 <= H * W) PX *= 2;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const vdn::bf16* q = reinterpret_cast<const vdn::bf16*>(qkv);
   const vdn::bf16* g = reinterpret_cast<const vdn::bf16*>(d_o);

@@ -77,37 +77,76 @@ __device__ __forceinline__ void store8(bf16* p, const float (&v)[8]) {
   *reinterpret_cast<uint4*>(p) = q;
 }
 
+__device__ __forceinline__ void unpack8(const uint4& q, float (&v)[8]) {
+  float2 f;
+  f = unpack_bf16x2(q.x); v[0] = f.x; v[1] = f.y;
+  f = unpack_bf16x2(q.y); v[2] = f.x; v[3] = f.y;
+  f = unpack_bf16x2(q.z); v[4] = f.x; v[5] = f.y;
+  f = unpack_bf16x2(q.w); v[6] = f.x; v[7] = f.y;
+}
+// 8 consecutive per-channel coefficients from shared memory (two LDS.128)
+__device__ __forceinline__ void load_coef8(const float* sp, int c0, float (&v)[8]) {
+  const float4 lo = *reinterpret_cast<const float4*>(sp + c0), hi = *reinterpret_cast<const float4*>(sp + c0 + 4);
+  v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w;
+  v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
+}
+__device__ __forceinline__ uint4 ldg16(const bf16* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+
+// All kernels below follow one latency plan: a thread first ISSUES the 16-byte loads of every vector it
+// will process (fully unrolled, addresses do not depend on the statistics), then builds the per-sample
+// affine coefficients in shared memory (a second, independent chain of global loads), synchronises, and
+// only then consumes the data. The two DRAM round trips overlap, and a launch is one wave of short CTAs.
+constexpr int kVecPerThread = 4;
+
 // ---------------------------------------------------------------------------------------
 // out = silu(GN(x) [* (scale+1) + shift])            (Block, modules.py:171-179)
-// grid (chunks, B); each thread streams 8-channel vectors of its sample.
+// grid (ceil(nvec / (256*4)), B); each thread owns 4 8-channel vectors of its sample.
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kNormThreads) gn_silu_fwd_kernel(const GnArgs a, bf16* __restrict__ out) {
   extern __shared__ float sm[];
   float* sA = sm;
   float* sB = sm + a.C;
   const int b = blockIdx.y;
-  gn_affine_to_smem(a, b, sA, sB);
-  __syncthreads();
   const int c8n = a.C / 8;
   const long nvec = (long)a.rows * c8n;
   const bf16* xb = a.x + (long)b * a.rows * a.C;
   bf16* ob = out + (long)b * a.rows * a.C;
-#pragma unroll 2
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long)gridDim.x * blockDim.x) {
-    const int c0 = (int)(i % c8n) * 8;
-    float v[8];
-    load8(xb + i * 8, v);
+  const long i0 = (long)blockIdx.x * (kNormThreads * kVecPerThread) + threadIdx.x;
+  uint4 raw[kVecPerThread];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = silu_f(fmaf(v[j], sA[c0 + j], sB[c0 + j]));
+  for (int k = 0; k < kVecPerThread; ++k) {
+    const long i = i0 + k * kNormThreads;
+    raw[k] = i < nvec ? ldg16(xb + i * 8) : make_uint4(0, 0, 0, 0);
+  }
+  gn_affine_to_smem(a, b, sA, sB);
+  __syncthreads();
+  // when the block size is a multiple of the vectors per pixel a thread always owns the same 8 channels:
+  // their coefficients are read from shared memory once
+  const bool fixed_c = (kNormThreads % c8n) == 0;
+  float cA[8], cB[8];
+  load_coef8(sA, (int)(i0 % c8n) * 8, cA);
+  load_coef8(sB, (int)(i0 % c8n) * 8, cB);
+#pragma unroll
+  for (int k = 0; k < kVecPerThread; ++k) {
+    const long i = i0 + k * kNormThreads;
+    if (i >= nvec) break;
+    if (!fixed_c) {
+      load_coef8(sA, (int)(i % c8n) * 8, cA);
+      load_coef8(sB, (int)(i % c8n) * 8, cB);
+    }
+    float v[8];
+    unpack8(raw[k], v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = silu_f(fmaf(v[j], cA[j], cB[j]));
     store8(ob + i * 8, v);
   }
 }
 
 // ---------------------------------------------------------------------------------------
 // ResnetBlock tail (modules.py:241-242): out = silu(GN(b_raw)) + LayerNorm_C(s)
-// One lane group of LG = min(32, C/8) lanes per pixel; each lane owns 8*(C/(8*LG)) channels.
+// One lane group of LG = min(32, C/8) lanes per pixel; each lane owns 8*VPL channels; R pixels per thread.
 // ---------------------------------------------------------------------------------------
-template <int VPL>  // 8-channel vectors per lane
+template <int VPL, int R>
 __global__ void __launch_bounds__(kNormThreads) resblock_tail_fwd_kernel(const GnArgs a, const bf16* __restrict__ s,
                                                                          const float* __restrict__ ln_g,
                                                                          const float* __restrict__ ln_b,
@@ -118,28 +157,38 @@ __global__ void __launch_bounds__(kNormThreads) resblock_tail_fwd_kernel(const G
   float* sG = sm + 2 * a.C;
   float* sBt = sm + 3 * a.C;
   const int b = blockIdx.y;
+  const int lg = a.C / (8 * VPL);  // lanes per pixel (power of two <= 32)
+  const int sub = threadIdx.x % lg;
+  const int ppb = blockDim.x / lg;  // pixels per block pass
+  const long base = (long)b * a.rows;
+  uint4 sraw[R][VPL], xraw[R][VPL];
+  long roff[R];
+  bool valid[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const long p_raw = ((long)blockIdx.x * R + r) * ppb + threadIdx.x / lg;
+    valid[r] = p_raw < a.rows;
+    roff[r] = (base + (valid[r] ? p_raw : (long)a.rows - 1)) * a.C;  // clamped: the shuffles need whole warps
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      sraw[r][k] = ldg16(s + roff[r] + (k * lg + sub) * 8);
+      xraw[r][k] = ldg16(a.x + roff[r] + (k * lg + sub) * 8);
+    }
+  }
   gn_affine_to_smem(a, b, sA, sB);
   for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
     sG[c] = ln_g[c];
     sBt[c] = ln_b[c];
   }
   __syncthreads();
-  const int lg = a.C / (8 * VPL);  // lanes per pixel (power of two <= 32)
-  const int sub = threadIdx.x % lg;
-  const int ppb = blockDim.x / lg;  // pixels per block iteration
   const float inv_c = 1.f / (float)a.C;
-  const long base = (long)b * a.rows;
-  const long n_it = (a.rows + (long)gridDim.x * ppb - 1) / ((long)gridDim.x * ppb);
-  for (long it = 0; it < n_it; ++it) {  // uniform trip count: the shuffles below need whole warps
-    const long p_raw = (it * gridDim.x + blockIdx.x) * ppb + threadIdx.x / lg;
-    const bool valid = p_raw < a.rows;
-    const long p = valid ? p_raw : (long)a.rows - 1;
-    const long roff = (base + p) * a.C;
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
     float sv[VPL][8];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int k = 0; k < VPL; ++k) {
-      load8(s + roff + (k * lg + sub) * 8, sv[k]);
+      unpack8(sraw[r][k], sv[k]);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         s1 += sv[k][j];
@@ -155,14 +204,19 @@ __global__ void __launch_bounds__(kNormThreads) resblock_tail_fwd_kernel(const G
 #pragma unroll
     for (int k = 0; k < VPL; ++k) {
       const int c0 = (k * lg + sub) * 8;
-      float xv[8], o8[8];
-      load8(a.x + roff + c0, xv);
+      float xv[8], o8[8], cA[8], cB[8], cG[8], cBt[8];
+      load_coef8(sA, c0, cA);
+      load_coef8(sB, c0, cB);
+      load_coef8(sG, c0, cG);
+      load_coef8(sBt, c0, cBt);
+      unpack8(xraw[r][k], xv);
+      const float nmr = -mean * rstd;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float y = silu_f(fmaf(xv[j], sA[c0 + j], sB[c0 + j]));
-        o8[j] = y + (sv[k][j] - mean) * rstd * sG[c0 + j] + sBt[c0 + j];
+        const float y = silu_f(fmaf(xv[j], cA[j], cB[j]));
+        o8[j] = y + fmaf(fmaf(sv[k][j], rstd, nmr), cG[j], cBt[j]);
       }
-      if (valid) store8(out + roff + c0, o8);
+      if (valid[r]) store8(out + roff[r] + c0, o8);
     }
   }
 }
@@ -171,6 +225,8 @@ __global__ void __launch_bounds__(kNormThreads) resblock_tail_fwd_kernel(const G
 // Backward.
 //   z = x*A + Bc ; y = silu(z) ; dz = dy * silu'(z)
 //   T1[b,c] = sum_pix dz ; T2[b,c] = sum_pix dz * xhat      (xhat = (x - mean_g) * rstd_g)
+// grid (ceil(rows / (pixel lanes * 4)), B) in clusters along x: 4 pixels per thread, block partials are summed
+// across the cluster through DSMEM before the atomics into T.
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kNormThreads) gn_bwd_reduce_kernel(const GnArgs a, const bf16* __restrict__ dy,
                                                                      float* __restrict__ T /*[B][C][2]*/) {
@@ -179,8 +235,27 @@ __global__ void __launch_bounds__(kNormThreads) gn_bwd_reduce_kernel(const GnArg
   float* sB = sm + a.C;
   float* sMean = sm + 2 * a.C;   // per channel (group value replicated)
   float* sRstd = sm + 3 * a.C;
-  float* red = sm + 4 * a.C;     // [blockDim][16]
+  float* vals = sm + 4 * a.C;    // [C][2] block totals
+  float* red = sm + 6 * a.C;     // [blockDim][16]
   const int b = blockIdx.y;
+  const int c8n = a.C / 8;              // vectors per pixel
+  const int pl_n = blockDim.x / c8n;    // pixel lanes (>= 1 when C <= 2048)
+  const int ci = threadIdx.x % c8n;
+  const int pl = threadIdx.x / c8n;
+  const int c0 = ci * 8;
+  const long base = (long)b * a.rows;
+  uint4 xraw[kVecPerThread], draw[kVecPerThread];
+  bool valid[kVecPerThread];
+#pragma unroll
+  for (int k = 0; k < kVecPerThread; ++k) {
+    const long p = ((long)blockIdx.x * kVecPerThread + k) * pl_n + pl;
+    valid[k] = pl < pl_n && p < a.rows;
+    if (valid[k]) {
+      const long off = (base + p) * a.C + c0;
+      xraw[k] = ldg16(a.x + off);
+      draw[k] = ldg16(dy + off);
+    }
+  }
   gn_affine_to_smem(a, b, sA, sB);
   {
     const int cpg = a.C / a.G;
@@ -191,38 +266,35 @@ __global__ void __launch_bounds__(kNormThreads) gn_bwd_reduce_kernel(const GnArg
       gn_read_sums(a, b, g, s1, s2);
       const float mean = s1 * inv_n;
       const float var = fmaxf(s2 * inv_n - mean * mean, 0.f);
-      sMean[c] = mean;
-      sRstd[c] = rsqrtf(var + kEps);
+      const float rstd = rsqrtf(var + kEps);
+      sRstd[c] = rstd;
+      sMean[c] = -mean * rstd;  // xhat = x * rstd + (-mean * rstd)
     }
   }
   __syncthreads();
-  const int c8n = a.C / 8;              // vectors per pixel
-  const int pl_n = blockDim.x / c8n;    // pixel lanes (>= 1 when C <= 2048)
-  const int ci = threadIdx.x % c8n;
-  const int pl = threadIdx.x / c8n;
-  const int c0 = ci * 8;
-  float t1[8], t2[8];
+  float t1[8], t2[8], cA[8], cB[8], cR[8], cM[8];
+  load_coef8(sA, c0, cA);
+  load_coef8(sB, c0, cB);
+  load_coef8(sRstd, c0, cR);
+  load_coef8(sMean, c0, cM);
 #pragma unroll
   for (int j = 0; j < 8; ++j) t1[j] = t2[j] = 0.f;
-  const long base = (long)b * a.rows;
-  if (pl < pl_n) {
-#pragma unroll 2
-    for (long p = (long)blockIdx.x * pl_n + pl; p < a.rows; p += (long)gridDim.x * pl_n) {
-      const long off = (base + p) * a.C + c0;
-      float xv[8], dv[8];
-      load8(a.x + off, xv);
-      load8(dy + off, dv);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float z = fmaf(xv[j], sA[c0 + j], sB[c0 + j]);
-        const float dz = dv[j] * silu_grad_f(z);
-        const float xh = (xv[j] - sMean[c0 + j]) * sRstd[c0 + j];
-        t1[j] += dz;
-        t2[j] += dz * xh;
-      }
+  for (int k = 0; k < kVecPerThread; ++k) {
+    if (!valid[k]) continue;
+    float xv[8], dv[8];
+    unpack8(xraw[k], xv);
+    unpack8(draw[k], dv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float z = fmaf(xv[j], cA[j], cB[j]);
+      const float dz = dv[j] * silu_grad_f(z);
+      const float xh = fmaf(xv[j], cR[j], cM[j]);
+      t1[j] += dz;
+      t2[j] = fmaf(dz, xh, t2[j]);
     }
   }
-  // reduce over pixel lanes through smem, then one atomic per (c, {T1,T2}) per block
+  // reduce over pixel lanes through smem, over the cluster through DSMEM, then one atomic per (c, {T1,T2})
   float* my = red + (long)threadIdx.x * 16;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -234,36 +306,14 @@ __global__ void __launch_bounds__(kNormThreads) gn_bwd_reduce_kernel(const GnArg
     const int cc = i / 16, j = i % 16;
     float acc = 0.f;
     for (int q = 0; q < pl_n; ++q) acc += red[(long)(q * c8n + cc) * 16 + j];
-    const int c = cc * 8 + (j & 7);
-    atomicAdd(&T[((long)b * a.C + c) * 2 + (j >> 3)], acc);
+    vals[(cc * 8 + (j & 7)) * 2 + (j >> 3)] = acc;
   }
-}
-
-// dgamma/dbeta (accumulated), dscale/dshift per (b,c) from T.  One block per launch is plenty.
-__global__ void gn_bwd_finalize_kernel(const GnArgs a, const float* __restrict__ T, float* __restrict__ dgamma,
-                                       float* __restrict__ dbeta, float* __restrict__ dss /*[B][dss_ld] or null*/,
-                                       int dss_ld) {
-  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < a.C; c += gridDim.x * blockDim.x) {
-    float dg = 0.f, db = 0.f;
-    const float gam = a.gamma[c], bet = a.beta[c];
-    for (int b = 0; b < a.B; ++b) {
-      const float t1 = T[((long)b * a.C + c) * 2], t2 = T[((long)b * a.C + c) * 2 + 1];
-      const float sc = a.ss ? a.ss[(long)b * a.ss_ld + c] + 1.f : 1.f;
-      dg += sc * t2;
-      db += sc * t1;
-      if (dss) {
-        dss[(long)b * dss_ld + c] = gam * t2 + bet * t1;  // dscale = sum dz * (xhat*gamma + beta)
-        dss[(long)b * dss_ld + a.C + c] = t1;             // dshift
-      }
-    }
-    dgamma[c] += dg;
-    dbeta[c] += db;
-  }
+  cluster_reduce_atomic_add(vals, 2 * a.C, T + (long)b * a.C * 2);
 }
 
 // dx = rstd_g * (gamma_c*(s+1)*dz - m1_g - xhat*m2_g),  m1_g = mean_g(dxhat), m2_g = mean_g(dxhat*xhat)
 // The x == 0 block of each sample also finalises dgamma / dbeta (atomics over samples) and (dscale | dshift);
-// every block accumulates the column sums of dx = the gradient of the producing conv's bias.
+// every block accumulates the column sums of dx = the gradient of the producing conv's bias (cluster-reduced).
 __global__ void __launch_bounds__(kNormThreads) gn_bwd_apply_kernel(const GnArgs a, const bf16* __restrict__ dy,
                                                                     const float* __restrict__ T,
                                                                     bf16* __restrict__ dx, float* __restrict__ dgamma,
@@ -277,8 +327,23 @@ __global__ void __launch_bounds__(kNormThreads) gn_bwd_apply_kernel(const GnArgs
   float* sK = sm + 4 * a.C;    // gamma*(s+1)
   float* sM1 = sm + 5 * a.C;   // per channel copy of m1_g
   float* sM2 = sm + 6 * a.C;
+  float* vals = sm + 7 * a.C;  // [C] block column sums of dx
+  float* red = sm + 8 * a.C;   // [blockDim][8]
   const int b = blockIdx.y;
   const int cpg = a.C / a.G;
+  const int c8n = a.C / 8;
+  const long nvec = (long)a.rows * c8n;
+  const long boff = (long)b * a.rows * a.C;
+  const long i0 = (long)blockIdx.x * (kNormThreads * kVecPerThread) + threadIdx.x;
+  uint4 xraw[kVecPerThread], draw[kVecPerThread];
+#pragma unroll
+  for (int k = 0; k < kVecPerThread; ++k) {
+    const long i = i0 + k * kNormThreads;
+    if (i < nvec) {
+      xraw[k] = ldg16(a.x + boff + i * 8);
+      draw[k] = ldg16(dy + boff + i * 8);
+    }
+  }
   gn_affine_to_smem(a, b, sA, sB);
   const float inv_n = 1.f / ((float)a.rows * (float)cpg);
   for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
@@ -287,8 +352,9 @@ __global__ void __launch_bounds__(kNormThreads) gn_bwd_apply_kernel(const GnArgs
     gn_read_sums(a, b, g, s1, s2);
     const float mean = s1 * inv_n;
     const float var = fmaxf(s2 * inv_n - mean * mean, 0.f);
-    sMean[c] = mean;
-    sRstd[c] = rsqrtf(var + kEps);
+    const float rstd = rsqrtf(var + kEps);
+    sRstd[c] = rstd;
+    sMean[c] = -mean * rstd;  // xhat = x * rstd + (-mean * rstd)
     const float sc = a.ss ? a.ss[(long)b * a.ss_ld + c] + 1.f : 1.f;
     sK[c] = a.gamma[c] * sc;
   }
@@ -300,8 +366,8 @@ __global__ void __launch_bounds__(kNormThreads) gn_bwd_apply_kernel(const GnArgs
       m1 += sK[g0 + k] * T[((long)b * a.C + g0 + k) * 2];
       m2 += sK[g0 + k] * T[((long)b * a.C + g0 + k) * 2 + 1];
     }
-    sM1[c] = m1 * inv_n;
-    sM2[c] = m2 * inv_n;
+    sM1[c] = -m1 * inv_n * sRstd[c];  // pre-multiplied by rstd (and negated) for the FMA chain below
+    sM2[c] = -m2 * inv_n * sRstd[c];
     if (blockIdx.x == 0) {  // finalize (once per sample)
       const float t1 = T[((long)b * a.C + c) * 2], t2 = T[((long)b * a.C + c) * 2 + 1];
       const float sc = a.ss ? a.ss[(long)b * a.ss_ld + c] + 1.f : 1.f;
@@ -314,31 +380,39 @@ __global__ void __launch_bounds__(kNormThreads) gn_bwd_apply_kernel(const GnArgs
     }
   }
   __syncthreads();
-  const int c8n = a.C / 8;
-  const long nvec = (long)a.rows * c8n;
-  const long boff = (long)b * a.rows * a.C;
   float bs[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) bs[j] = 0.f;
   // blockDim (256) is a multiple of c8n, so a thread always owns the same 8 channels
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long)gridDim.x * blockDim.x) {
-    const int c0 = (int)(i % c8n) * 8;
+  const int c0 = (int)(i0 % c8n) * 8;
+  float cA[8], cB[8], cR[8], cM[8], cK[8], cM1[8], cM2[8];
+  load_coef8(sA, c0, cA);
+  load_coef8(sB, c0, cB);
+  load_coef8(sRstd, c0, cR);
+  load_coef8(sMean, c0, cM);
+  load_coef8(sK, c0, cK);
+  load_coef8(sM1, c0, cM1);
+  load_coef8(sM2, c0, cM2);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) cK[j] *= cR[j];
+#pragma unroll
+  for (int k = 0; k < kVecPerThread; ++k) {
+    const long i = i0 + k * kNormThreads;
+    if (i >= nvec) break;
     float xv[8], dv[8], o[8];
-    load8(a.x + boff + i * 8, xv);
-    load8(dy + boff + i * 8, dv);
+    unpack8(xraw[k], xv);
+    unpack8(draw[k], dv);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int c = c0 + j;
-      const float z = fmaf(xv[j], sA[c], sB[c]);
+      const float z = fmaf(xv[j], cA[j], cB[j]);
       const float dz = dv[j] * silu_grad_f(z);
-      const float xh = (xv[j] - sMean[c]) * sRstd[c];
-      o[j] = sRstd[c] * (sK[c] * dz - sM1[c] - xh * sM2[c]);
+      const float xh = fmaf(xv[j], cR[j], cM[j]);
+      o[j] = fmaf(xh, cM2[j], fmaf(dz, cK[j], cM1[j]));  // rstd * (K dz - m1 - xhat m2)
       bs[j] += o[j];
     }
     store8(dx + boff + i * 8, o);
   }
   if (dconv_bias) {
-    float* red = sm + 7 * a.C;  // [blockDim][8]
 #pragma unroll
     for (int j = 0; j < 8; ++j) red[threadIdx.x * 8 + j] = bs[j];
     __syncthreads();
@@ -346,52 +420,63 @@ __global__ void __launch_bounds__(kNormThreads) gn_bwd_apply_kernel(const GnArgs
     for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
       float acc = 0.f;
       for (int q = 0; q < per; ++q) acc += red[(q * c8n + c / 8) * 8 + (c & 7)];
-      atomicAdd(&dconv_bias[c], acc);
+      vals[c] = acc;
     }
+    cluster_reduce_atomic_add(vals, a.C, dconv_bias);
   }
 }
 
 // LayerNorm over channels, backward (norm_2 of ResnetBlock, modules.py:223,242):
 //   y = shat*g + b ; ds = rstd * (g*dy - mean_c(g*dy) - shat*mean_c(g*dy*shat)) ; dg += dy*shat ; db += dy
-template <int VPL>
+// R pixels per thread; block column sums (dg | db) are cluster-reduced before the global atomics.
+template <int VPL, int R>
 __global__ void __launch_bounds__(kNormThreads) ln_bwd_kernel(const bf16* __restrict__ s, const bf16* __restrict__ dy,
                                                               const float* __restrict__ ln_g, bf16* __restrict__ ds,
                                                               float* __restrict__ dg, float* __restrict__ db, long P,
                                                               int C) {
   extern __shared__ float sm[];
   float* sG = sm;            // [C]
-  float* accG = sm + C;      // [C] block-level accumulators
-  float* accB = sm + 2 * C;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    sG[c] = ln_g[c];
-    accG[c] = 0.f;
-    accB[c] = 0.f;
-  }
-  __syncthreads();
+  float* acc = sm + C;       // [2C] block-level accumulators: dg | db
   const int lg = C / (8 * VPL);
   const int sub = threadIdx.x % lg;
   const int ppb = blockDim.x / lg;
+  uint4 sraw[R][VPL], draw[R][VPL];
+  long roff[R];
+  bool valid[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const long p_raw = ((long)blockIdx.x * R + r) * ppb + threadIdx.x / lg;
+    valid[r] = p_raw < P;
+    roff[r] = (valid[r] ? p_raw : P - 1) * C;
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      sraw[r][k] = ldg16(s + roff[r] + (k * lg + sub) * 8);
+      draw[r][k] = ldg16(dy + roff[r] + (k * lg + sub) * 8);
+    }
+  }
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    sG[c] = ln_g[c];
+    acc[c] = 0.f;
+    acc[C + c] = 0.f;
+  }
+  __syncthreads();
   const float inv_c = 1.f / (float)C;
   float pg[VPL][8], pb[VPL][8];
 #pragma unroll
   for (int k = 0; k < VPL; ++k)
 #pragma unroll
     for (int j = 0; j < 8; ++j) pg[k][j] = pb[k][j] = 0.f;
-  const long n_it = (P + (long)gridDim.x * ppb - 1) / ((long)gridDim.x * ppb);
-  for (long it = 0; it < n_it; ++it) {  // uniform trip count (warp shuffles inside)
-    const long p_raw = (it * gridDim.x + blockIdx.x) * ppb + threadIdx.x / lg;
-    const bool valid = p_raw < P;
-    const long p = valid ? p_raw : P - 1;
-    const long roff = p * C;
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
     float sv[VPL][8], dv[VPL][8];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int k = 0; k < VPL; ++k) {
-      load8(s + roff + (k * lg + sub) * 8, sv[k]);
-      load8(dy + roff + (k * lg + sub) * 8, dv[k]);
+      unpack8(sraw[r][k], sv[k]);
+      unpack8(draw[r][k], dv[k]);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        if (!valid) dv[k][j] = 0.f;
+        if (!valid[r]) dv[k][j] = 0.f;
         s1 += sv[k][j];
         s2 += sv[k][j] * sv[k][j];
       }
@@ -429,23 +514,63 @@ __global__ void __launch_bounds__(kNormThreads) ln_bwd_kernel(const bf16* __rest
       float o8[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) o8[j] = rstd * (sG[c0 + j] * dv[k][j] - a1 - sv[k][j] * a2);
-      if (valid) store8(ds + roff + c0, o8);
+      if (valid[r]) store8(ds + roff[r] + c0, o8);
     }
   }
+  // lanes that own the same channels (same `sub`, other pixels of the warp) are summed with shuffles first
 #pragma unroll
   for (int k = 0; k < VPL; ++k) {
     const int c0 = (k * lg + sub) * 8;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      atomicAdd(&accG[c0 + j], pg[k][j]);
-      atomicAdd(&accB[c0 + j], pb[k][j]);
+      float g = pg[k][j], bb = pb[k][j];
+      for (int o = 16; o >= lg; o >>= 1) {
+        g += __shfl_xor_sync(0xffffffffu, g, o);
+        bb += __shfl_xor_sync(0xffffffffu, bb, o);
+      }
+      if ((threadIdx.x & 31) < lg) {
+        atomicAdd(&acc[c0 + j], g);
+        atomicAdd(&acc[C + c0 + j], bb);
+      }
     }
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    atomicAdd(&dg[c], accG[c]);
-    atomicAdd(&db[c], accB[c]);
+  // acc = (dg | db): cluster-level sum, then one atomic per channel
+  const uint32_t nrank = cluster_nctarank();
+  if (nrank > 1) cluster_sync_all();
+  if (nrank == 1 || cluster_ctarank() == 0) {
+    for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) {
+      float v = acc[c];
+      for (uint32_t r = 1; r < nrank; ++r) v += dsmem_ld_f32(acc + c, r);
+      atomicAdd(c < C ? &dg[c] : &db[c - C], v);
+    }
   }
+  if (nrank > 1) cluster_sync_all();
+}
+
+// Launch with thread-block clusters along grid.x (the CTAs of a cluster work on the same sample).
+template <typename Kern, typename... Args>
+static cudaError_t launch_clustered(Kern kern, dim3 grid, int cluster_x, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(kNormThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = (unsigned)cluster_x;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+// cluster width for a grid.x of `want` CTAs (power of two <= 8) and the padded grid.x
+static int cluster_for(int want, int* grid_x) {
+  int c = 1;
+  while (c < 8 && c * 2 <= want) c *= 2;
+  *grid_x = (want + c - 1) / c * c;
+  return c;
 }
 
 static int vpl_for(int C) {
@@ -463,10 +588,8 @@ static int check_gn(const char* who, int B, int rows, int C, int G) {
   return VDN_OK;
 }
 
-static int grid_x_for(long work_items, int per_block, int B) {
-  long want = (work_items + per_block - 1) / per_block;
-  long cap = std::max<long>(1, (long)num_sms() * 8 / std::max(B, 1));
-  return (int)std::max<long>(1, std::min(want, cap));
+static int grid_x_for(long work_items, int per_block) {
+  return (int)std::max<long>(1, (work_items + per_block - 1) / per_block);
 }
 
 }  // namespace vdn
@@ -480,7 +603,7 @@ extern "C" int vdn_gn_silu_fwd(const void* x_raw, const float* gn_sums, const fl
   if (rc) return rc;
   GnArgs a{reinterpret_cast<const bf16*>(x_raw), gn_sums, gamma, beta, scale_shift, ss_ld, B, rows_per_sample, C, G};
   const long nvec = (long)rows_per_sample * (C / 8);
-  dim3 grid(grid_x_for(nvec, kNormThreads * 4, B), B);
+  dim3 grid(grid_x_for(nvec, kNormThreads * kVecPerThread), B);
   gn_silu_fwd_kernel<<<grid, kNormThreads, 2 * C * sizeof(float), reinterpret_cast<cudaStream_t>(stream)>>>(
       a, reinterpret_cast<bf16*>(out));
   return check_launch("gn_silu_fwd");
@@ -496,16 +619,15 @@ extern "C" int vdn_resblock_tail_fwd(const void* b_raw, const float* gn_sums, co
   GnArgs a{reinterpret_cast<const bf16*>(b_raw), gn_sums, gamma, beta, nullptr, 0, B, rows_per_sample, C, G};
   const int lg = C / (8 * vpl);
   const int ppb = kNormThreads / lg;
-  dim3 grid(grid_x_for(rows_per_sample, ppb * 4, B), B);
   const size_t smem = 4 * C * sizeof(float);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const bf16* sp = reinterpret_cast<const bf16*>(s);
   bf16* op = reinterpret_cast<bf16*>(out);
-  switch (vpl) {
-    case 1: resblock_tail_fwd_kernel<1><<<grid, kNormThreads, smem, st>>>(a, sp, ln_gamma, ln_beta, op); break;
-    case 2: resblock_tail_fwd_kernel<2><<<grid, kNormThreads, smem, st>>>(a, sp, ln_gamma, ln_beta, op); break;
-    case 4: resblock_tail_fwd_kernel<4><<<grid, kNormThreads, smem, st>>>(a, sp, ln_gamma, ln_beta, op); break;
-    default: resblock_tail_fwd_kernel<8><<<grid, kNormThreads, smem, st>>>(a, sp, ln_gamma, ln_beta, op); break;
+  switch (vpl) {  // R pixels per thread: 8 16-byte loads in flight per thread
+    case 1: resblock_tail_fwd_kernel<1, 4><<<dim3(grid_x_for(rows_per_sample, ppb * 4), B), kNormThreads, smem, st>>>(a, sp, ln_gamma, ln_beta, op); break;
+    case 2: resblock_tail_fwd_kernel<2, 2><<<dim3(grid_x_for(rows_per_sample, ppb * 2), B), kNormThreads, smem, st>>>(a, sp, ln_gamma, ln_beta, op); break;
+    case 4: resblock_tail_fwd_kernel<4, 1><<<dim3(grid_x_for(rows_per_sample, ppb), B), kNormThreads, smem, st>>>(a, sp, ln_gamma, ln_beta, op); break;
+    default: resblock_tail_fwd_kernel<8, 1><<<dim3(grid_x_for(rows_per_sample, ppb), B), kNormThreads, smem, st>>>(a, sp, ln_gamma, ln_beta, op); break;
   }
   return check_launch("resblock_tail_fwd");
 }
@@ -522,15 +644,19 @@ extern "C" int vdn_gn_silu_bwd(const void* dy, const void* x_raw, const float* g
   cudaError_t e = cudaMemsetAsync(T_ws, 0, (size_t)B * C * 2 * sizeof(float), st);
   VDN_REQUIRE(e == cudaSuccess, VDN_E_CUDA, "gn_silu_bwd memset: %s", cudaGetErrorString(e));
   const int pl_n = kNormThreads / (C / 8);
-  dim3 grid(grid_x_for(rows_per_sample, pl_n * 4, B), B);
-  const size_t smem_r = (4 * C + kNormThreads * 16) * sizeof(float);
-  gn_bwd_reduce_kernel<<<grid, kNormThreads, smem_r, st>>>(a, reinterpret_cast<const bf16*>(dy), T_ws);
+  int gx, cl;
+  cl = cluster_for(grid_x_for(rows_per_sample, pl_n * kVecPerThread), &gx);
+  const size_t smem_r = (6 * C + kNormThreads * 16) * sizeof(float);
+  cudaError_t le = launch_clustered(gn_bwd_reduce_kernel, dim3(gx, B), cl, smem_r, st, a, reinterpret_cast<const bf16*>(dy), T_ws);
+  VDN_REQUIRE(le == cudaSuccess, VDN_E_CUDA, "gn_bwd_reduce launch: %s", cudaGetErrorString(le));
   rc = check_launch("gn_bwd_reduce");
   if (rc) return rc;
   const long nvec = (long)rows_per_sample * (C / 8);
-  dim3 grid2(grid_x_for(nvec, kNormThreads * 4, B), B);
-  gn_bwd_apply_kernel<<<grid2, kNormThreads, (7 * C + kNormThreads * 8) * sizeof(float), st>>>(
-      a, reinterpret_cast<const bf16*>(dy), T_ws, reinterpret_cast<bf16*>(dx_raw), dgamma, dbeta, dss, dss_ld, dconv_bias);
+  cl = cluster_for(grid_x_for(nvec, kNormThreads * kVecPerThread), &gx);
+  le = launch_clustered(gn_bwd_apply_kernel, dim3(gx, B), cl, (8 * C + kNormThreads * 8) * sizeof(float), st, a,
+                        reinterpret_cast<const bf16*>(dy), (const float*)T_ws, reinterpret_cast<bf16*>(dx_raw), dgamma, dbeta,
+                        dss, dss_ld, dconv_bias);
+  VDN_REQUIRE(le == cudaSuccess, VDN_E_CUDA, "gn_bwd_apply launch: %s", cudaGetErrorString(le));
   return check_launch("gn_bwd_apply");
 }
 
@@ -541,17 +667,21 @@ extern "C" int vdn_ln_bwd(const void* s, const void* dy, const float* ln_gamma, 
   VDN_REQUIRE(pow2(C / (8 * vpl)), VDN_E_SHAPE, "ln_bwd: C=%d must be 8 * power of two", C);
   const int lg = C / (8 * vpl);
   const int ppb = kNormThreads / lg;
-  const int grid = (int)std::max<long>(1, std::min<long>((P + ppb * 8 - 1) / (ppb * 8), num_sms() * 4));
   const size_t smem = 3 * C * sizeof(float);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const bf16* sp = reinterpret_cast<const bf16*>(s);
   const bf16* dp = reinterpret_cast<const bf16*>(dy);
   bf16* op = reinterpret_cast<bf16*>(ds);
+  const int R = vpl == 1 ? 4 : vpl == 2 ? 2 : 1;
+  int gx;
+  const int cl = cluster_for(grid_x_for(P, ppb * R), &gx);
+  cudaError_t le;
   switch (vpl) {
-    case 1: ln_bwd_kernel<1><<<grid, kNormThreads, smem, st>>>(sp, dp, ln_gamma, op, dgamma, dbeta, P, C); break;
-    case 2: ln_bwd_kernel<2><<<grid, kNormThreads, smem, st>>>(sp, dp, ln_gamma, op, dgamma, dbeta, P, C); break;
-    case 4: ln_bwd_kernel<4><<<grid, kNormThreads, smem, st>>>(sp, dp, ln_gamma, op, dgamma, dbeta, P, C); break;
-    default: ln_bwd_kernel<8><<<grid, kNormThreads, smem, st>>>(sp, dp, ln_gamma, op, dgamma, dbeta, P, C); break;
+    case 1: le = launch_clustered(ln_bwd_kernel<1, 4>, dim3(gx), cl, smem, st, sp, dp, ln_gamma, op, dgamma, dbeta, P, C); break;
+    case 2: le = launch_clustered(ln_bwd_kernel<2, 2>, dim3(gx), cl, smem, st, sp, dp, ln_gamma, op, dgamma, dbeta, P, C); break;
+    case 4: le = launch_clustered(ln_bwd_kernel<4, 1>, dim3(gx), cl, smem, st, sp, dp, ln_gamma, op, dgamma, dbeta, P, C); break;
+    default: le = launch_clustered(ln_bwd_kernel<8, 1>, dim3(gx), cl, smem, st, sp, dp, ln_gamma, op, dgamma, dbeta, P, C); break;
   }
+  VDN_REQUIRE(le == cudaSuccess, VDN_E_CUDA, "ln_bwd launch: %s", cudaGetErrorString(le));
   return check_launch("ln_bwd");
 }

@@ -3,6 +3,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <mutex>
 
 #include "vdn_common.cuh"
@@ -20,6 +21,11 @@ void set_last_error(const char* fmt, ...) {
 }
 
 static std::atomic<unsigned long long> g_launches{0};
+
+bool pdl_enabled() {
+  static const bool on = getenv("VDN_NO_PDL") == nullptr;
+  return on;
+}
 
 int check_launch(const char* what) {
   g_launches.fetch_add(1, std::memory_order_relaxed);

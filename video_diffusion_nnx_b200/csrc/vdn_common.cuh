@@ -61,11 +61,19 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
-__device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x)); }
-// d/dx [x * sigmoid(x)]
+// sigmoid with two MUFU ops (ex2.approx, rcp.approx) and no IEEE division: the elementwise kernels are
+// instruction-issue bound, and outputs are rounded to bf16 anyway.
+__device__ __forceinline__ float sigmoid_f(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));
+  return r;
+}
+__device__ __forceinline__ float silu_f(float x) { return x * sigmoid_f(x); }
+// d/dx [x * sigmoid(x)] = s + x*s*(1-s)
 __device__ __forceinline__ float silu_grad_f(float x) {
-  float s = 1.f / (1.f + __expf(-x));
-  return s * (1.f + x * (1.f - s));
+  const float s = sigmoid_f(x);
+  return fmaf(x * s, 1.f - s, s);
 }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
@@ -75,6 +83,60 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
   __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
   return __bfloat1622float2(v);
+}
+
+// ----------------------------------------------------------------------------
+// programmatic dependent launch (PDL): a kernel launched with the programmatic-serialization attribute may
+// start while its predecessor in the stream is still running. pdl_trigger() lets the NEXT kernel start
+// launching; pdl_wait() blocks until the PREVIOUS kernel has completed and its writes are visible. Every
+// global-memory access of a PDL-launched kernel must come after pdl_wait(). Both are no-ops otherwise.
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// ----------------------------------------------------------------------------
+// thread-block clusters: barrier + distributed shared memory reads
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_nctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// fp32 load from the shared memory of CTA `rank` of this cluster at the same offset as local pointer `p`
+__device__ __forceinline__ float dsmem_ld_f32(const float* p, uint32_t rank) {
+  uint32_t remote;
+  float v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(p)), "r"(rank));
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(remote) : "memory");
+  return v;
+}
+// Column-sum epilogue shared by the norm kernels: every CTA of the cluster holds n partial sums in its shared
+// memory `vals`; CTA 0 of the cluster adds them up through DSMEM and issues ONE atomicAdd per value, which cuts
+// the same-address atomic traffic at L2 by the cluster size. All threads of all CTAs of the cluster must call it.
+__device__ __forceinline__ void cluster_reduce_atomic_add(const float* vals, int n, float* dst) {
+  const uint32_t nrank = cluster_nctarank();
+  if (nrank == 1) {
+    __syncthreads();
+    for (int c = threadIdx.x; c < n; c += blockDim.x) atomicAdd(dst + c, vals[c]);
+    return;
+  }
+  cluster_sync_all();
+  if (cluster_ctarank() == 0) {
+    for (int c = threadIdx.x; c < n; c += blockDim.x) {
+      float acc = vals[c];
+      for (uint32_t r = 1; r < nrank; ++r) acc += dsmem_ld_f32(vals + c, r);
+      atomicAdd(dst + c, acc);
+    }
+  }
+  cluster_sync_all();  // peers keep their shared memory alive until CTA 0 has read it
 }
 
 // ----------------------------------------------------------------------------

@@ -17,6 +17,35 @@ int rowconv_launch(const vdn_tapgemm_desc* d, const void* src0, const void* src1
                    const void* residual, const void* residual2, void* out, void* out2, float* gn_sums,
                    cudaStream_t st);
 
+// Kernel launch with programmatic dependent launch (and optionally a thread-block cluster along grid.x). The
+// kernel must call pdl_wait() before touching global memory. VDN_NO_PDL=1 falls back to plain stream order.
+bool pdl_enabled();
+template <typename Kern, typename... Args>
+inline cudaError_t launch_pdl(Kern kern, dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster_x, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[2];
+  int n = 0;
+  if (pdl_enabled()) {
+    at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  if (cluster_x > 1) {
+    at[n].id = cudaLaunchAttributeClusterDimension;
+    at[n].val.clusterDim.x = (unsigned)cluster_x;
+    at[n].val.clusterDim.y = 1;
+    at[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  cfg.attrs = at;
+  cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline int num_sms() { return 148; }
 
