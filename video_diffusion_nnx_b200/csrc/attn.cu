@@ -12,6 +12,8 @@
 // are ~10 % of the FLOPs and run on CUDA cores with fp32 accumulation.
 #include <algorithm>
 
+#include <cstdlib>
+
 #include "vdn_common.cuh"
 #include "vdn_host.h"
 
@@ -653,6 +655,8 @@ extern "C" int vdn_sla_core_fwd(const void* qkv, void* tok_out, float* ctx, floa
   sla_ctx_merge_kernel<<<n_img * kHeads, 256, 0, st>>>(ctx_part, ms_part, ns, ctx, kstat);
   rc = check_launch("sla_ctx_merge");
   if (rc) return rc;
+  static const bool scalar = getenv("VDN_SLA_SCALAR") != nullptr;  // CUDA-core kernels (A/B comparison only)
+  if (!scalar) return sla_apply_mma_launch(qkv, ctx, tok_out, n_img, N, st);
   static bool cfg = false;
   if (!cfg) {
     cudaFuncSetAttribute(sla_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 1024 * 4);
@@ -677,6 +681,8 @@ extern "C" int vdn_sla_core_bwd(const void* qkv, const void* d_tok, const float*
                                                            reinterpret_cast<const bf16*>(d_tok), N, per_al, dctx);
   int rc = check_launch("sla_dctx");
   if (rc) return rc;
+  static const bool scalar = getenv("VDN_SLA_SCALAR") != nullptr;
+  if (!scalar) return sla_bwd_tokens_mma_launch(qkv, d_tok, ctx, dctx, kstat, dqkv, n_img, N, st);
   const size_t smem = (16 * 1024 + 3 * 256) * sizeof(float);
   static bool cfg = false;
   if (!cfg) {

@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(kTcThreads) mha_tc_fwd_kernel(const __grid_con
   const int b = tile / tiles_img;
   const int p0 = (tile - b * tiles_img) * PX;
 
-  for (int i = threadIdx.x; i < 768; i += blockDim.x) s_bias[i] = a.bias ? a.bias[i] : 0.f;
+  pdl_trigger();
   // zero V (rows >= PX*F must be finite zeros: they meet P's zero columns) and the block-diagonal P tile
   for (int i = threadIdx.x; i < (kTile + 32768) / 16; i += blockDim.x) reinterpret_cast<uint4*>(sV)[i] = make_uint4(0, 0, 0, 0);
   if (warp == 0 && lane == 0) {
@@ -105,6 +105,9 @@ __global__ void __launch_bounds__(kTcThreads) mha_tc_fwd_kernel(const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
   const uint32_t t_qkv = tmem_base, t_s = tmem_base + 96, t_o = tmem_base + 224;
+  pdl_wait();  // smem zero fill / barrier init / TMEM alloc above overlapped the previous kernel
+  for (int i = threadIdx.x; i < 768; i += blockDim.x) s_bias[i] = a.bias ? a.bias[i] : 0.f;
+  __syncthreads();
 
   if (warp == 0) {
     if (elect_one()) {  // one elected lane (not `lane == 0`): keeps the issue loop on the uniform datapath
@@ -327,7 +330,8 @@ static int launch_tc(const TcMaps& maps, const TcArgs& a, int n_tiles, cudaStrea
     VDN_REQUIRE(e == cudaSuccess, VDN_E_CUDA, "mha_tc cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     cfg = true;
   }
-  mha_tc_fwd_kernel<BK, F><<<n_tiles, kTcThreads, smem, st>>>(maps, a);
+  cudaError_t le = launch_pdl(mha_tc_fwd_kernel<BK, F>, dim3(n_tiles), dim3(kTcThreads), (size_t)smem, st, 1, maps, a);
+  VDN_REQUIRE(le == cudaSuccess, VDN_E_CUDA, "mha_tc_fwd launch: %s", cudaGetErrorString(le));
   return check_launch("mha_tc_fwd_kernel");
 }
 
@@ -409,6 +413,7 @@ __global__ void __launch_bounds__(160) mha_tc_bwd_kernel(const bf16* __restrict_
   const int b = tile / tiles_img;
   const int p0 = (tile - b * tiles_img) * PX;
 
+  pdl_trigger();
   for (int i = threadIdx.x; i < (4 * kTile + 65536) / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
   if (threadIdx.x == 0) {
     mbar_init(&in_ready, 4);
@@ -426,6 +431,7 @@ __global__ void __launch_bounds__(160) mha_tc_bwd_kernel(const bf16* __restrict_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  pdl_wait();
 
   if (warp == 0) {
     if (elect_one()) {
@@ -586,7 +592,9 @@ static int launch_tc_bwd(const bf16* qkv, const bf16* d_o, const float* lse, bf1
     VDN_REQUIRE(e == cudaSuccess, VDN_E_CUDA, "mha_tc_bwd cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     cfg = true;
   }
-  mha_tc_bwd_kernel<F><<<B * ((H * W + PX - 1) / PX), 160, smem, st>>>(qkv, d_o, lse, dqkv, B, H, W, PX);
+  cudaError_t le = launch_pdl(mha_tc_bwd_kernel<F>, dim3(B * ((H * W + PX - 1) / PX)), dim3(160), (size_t)smem, st, 1, qkv, d_o,
+                              lse, dqkv, B, H, W, PX);
+  VDN_REQUIRE(le == cudaSuccess, VDN_E_CUDA, "mha_tc_bwd launch: %s", cudaGetErrorString(le));
   return check_launch("mha_tc_bwd_kernel");
 }
 

@@ -522,6 +522,8 @@ __global__ void p_sample_kernel(const float* __restrict__ x, const float* __rest
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ dy, float* __restrict__ db, long P, int C) {
   extern __shared__ float red[];  // [256][8]
+  pdl_trigger();
+  pdl_wait();
   const int c8n = C / 8, pl_n = blockDim.x / c8n;
   const int ci = threadIdx.x % c8n, pl = threadIdx.x / c8n;
   float a[8];
@@ -734,7 +736,9 @@ extern "C" int vdn_colsum(const void* dy, float* db, long P, int C, void* stream
   VDN_REQUIRE(C % 8 == 0 && C / 8 <= 256, VDN_E_SHAPE, "colsum: C=%d unsupported", C);
   const int pl_n = 256 / (C / 8);
   const int grid = (int)std::max<long>(1, std::min<long>((P + pl_n * 4 - 1) / (pl_n * 4), num_sms() * 8));
-  colsum_kernel<<<grid, 256, 256 * 8 * sizeof(float), ST(stream)>>>(reinterpret_cast<const bf16*>(dy), db, P, C);
+  cudaError_t le = launch_pdl(colsum_kernel, dim3(grid), dim3(256), 256 * 8 * sizeof(float), ST(stream), 1,
+                              reinterpret_cast<const bf16*>(dy), db, P, C);
+  VDN_REQUIRE(le == cudaSuccess, VDN_E_CUDA, "colsum launch: %s", cudaGetErrorString(le));
   return check_launch("colsum");
 }
 

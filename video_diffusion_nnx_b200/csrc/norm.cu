@@ -104,6 +104,8 @@ constexpr int kVecPerThread = 4;
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kNormThreads) gn_silu_fwd_kernel(const GnArgs a, bf16* __restrict__ out) {
   extern __shared__ float sm[];
+  pdl_trigger();
+  pdl_wait();
   float* sA = sm;
   float* sB = sm + a.C;
   const int b = blockIdx.y;
@@ -152,6 +154,8 @@ __global__ void __launch_bounds__(kNormThreads) resblock_tail_fwd_kernel(const G
                                                                          const float* __restrict__ ln_b,
                                                                          bf16* __restrict__ out) {
   extern __shared__ float sm[];
+  pdl_trigger();
+  pdl_wait();
   float* sA = sm;
   float* sB = sm + a.C;
   float* sG = sm + 2 * a.C;
@@ -231,6 +235,8 @@ __global__ void __launch_bounds__(kNormThreads) resblock_tail_fwd_kernel(const G
 __global__ void __launch_bounds__(kNormThreads) gn_bwd_reduce_kernel(const GnArgs a, const bf16* __restrict__ dy,
                                                                      float* __restrict__ T /*[B][C][2]*/) {
   extern __shared__ float sm[];
+  pdl_trigger();
+  pdl_wait();
   float* sA = sm;
   float* sB = sm + a.C;
   float* sMean = sm + 2 * a.C;   // per channel (group value replicated)
@@ -320,6 +326,8 @@ __global__ void __launch_bounds__(kNormThreads) gn_bwd_apply_kernel(const GnArgs
                                                                     float* __restrict__ dbeta, float* __restrict__ dss,
                                                                     int dss_ld, float* __restrict__ dconv_bias) {
   extern __shared__ float sm[];
+  pdl_trigger();
+  pdl_wait();
   float* sA = sm;
   float* sB = sm + a.C;
   float* sMean = sm + 2 * a.C;
@@ -435,6 +443,8 @@ __global__ void __launch_bounds__(kNormThreads) ln_bwd_kernel(const bf16* __rest
                                                               float* __restrict__ dg, float* __restrict__ db, long P,
                                                               int C) {
   extern __shared__ float sm[];
+  pdl_trigger();
+  pdl_wait();
   float* sG = sm;            // [C]
   float* acc = sm + C;       // [2C] block-level accumulators: dg | db
   const int lg = C / (8 * VPL);
@@ -548,23 +558,6 @@ __global__ void __launch_bounds__(kNormThreads) ln_bwd_kernel(const bf16* __rest
   if (nrank > 1) cluster_sync_all();
 }
 
-// Launch with thread-block clusters along grid.x (the CTAs of a cluster work on the same sample).
-template <typename Kern, typename... Args>
-static cudaError_t launch_clustered(Kern kern, dim3 grid, int cluster_x, size_t smem, cudaStream_t st, Args... args) {
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = grid;
-  cfg.blockDim = dim3(kNormThreads);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = (unsigned)cluster_x;
-  at[0].val.clusterDim.y = 1;
-  at[0].val.clusterDim.z = 1;
-  cfg.attrs = at;
-  cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, kern, args...);
-}
 // cluster width for a grid.x of `want` CTAs (power of two <= 8) and the padded grid.x
 static int cluster_for(int want, int* grid_x) {
   int c = 1;
@@ -604,8 +597,9 @@ extern "C" int vdn_gn_silu_fwd(const void* x_raw, const float* gn_sums, const fl
   GnArgs a{reinterpret_cast<const bf16*>(x_raw), gn_sums, gamma, beta, scale_shift, ss_ld, B, rows_per_sample, C, G};
   const long nvec = (long)rows_per_sample * (C / 8);
   dim3 grid(grid_x_for(nvec, kNormThreads * kVecPerThread), B);
-  gn_silu_fwd_kernel<<<grid, kNormThreads, 2 * C * sizeof(float), reinterpret_cast<cudaStream_t>(stream)>>>(
-      a, reinterpret_cast<bf16*>(out));
+  cudaError_t le = launch_pdl(gn_silu_fwd_kernel, grid, dim3(kNormThreads), 2 * C * sizeof(float),
+                              reinterpret_cast<cudaStream_t>(stream), 1, a, reinterpret_cast<bf16*>(out));
+  VDN_REQUIRE(le == cudaSuccess, VDN_E_CUDA, "gn_silu_fwd launch: %s", cudaGetErrorString(le));
   return check_launch("gn_silu_fwd");
 }
 
@@ -623,12 +617,14 @@ extern "C" int vdn_resblock_tail_fwd(const void* b_raw, const float* gn_sums, co
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const bf16* sp = reinterpret_cast<const bf16*>(s);
   bf16* op = reinterpret_cast<bf16*>(out);
+  cudaError_t le;
   switch (vpl) {  // R pixels per thread: 8 16-byte loads in flight per thread
-    case 1: resblock_tail_fwd_kernel<1, 4><<<dim3(grid_x_for(rows_per_sample, ppb * 4), B), kNormThreads, smem, st>>>(a, sp, ln_gamma, ln_beta, op); break;
-    case 2: resblock_tail_fwd_kernel<2, 2><<<dim3(grid_x_for(rows_per_sample, ppb * 2), B), kNormThreads, smem, st>>>(a, sp, ln_gamma, ln_beta, op); break;
-    case 4: resblock_tail_fwd_kernel<4, 1><<<dim3(grid_x_for(rows_per_sample, ppb), B), kNormThreads, smem, st>>>(a, sp, ln_gamma, ln_beta, op); break;
-    default: resblock_tail_fwd_kernel<8, 1><<<dim3(grid_x_for(rows_per_sample, ppb), B), kNormThreads, smem, st>>>(a, sp, ln_gamma, ln_beta, op); break;
+    case 1: le = launch_pdl(resblock_tail_fwd_kernel<1, 4>, dim3(grid_x_for(rows_per_sample, ppb * 4), B), dim3(kNormThreads), smem, st, 1, a, sp, ln_gamma, ln_beta, op); break;
+    case 2: le = launch_pdl(resblock_tail_fwd_kernel<2, 2>, dim3(grid_x_for(rows_per_sample, ppb * 2), B), dim3(kNormThreads), smem, st, 1, a, sp, ln_gamma, ln_beta, op); break;
+    case 4: le = launch_pdl(resblock_tail_fwd_kernel<4, 1>, dim3(grid_x_for(rows_per_sample, ppb), B), dim3(kNormThreads), smem, st, 1, a, sp, ln_gamma, ln_beta, op); break;
+    default: le = launch_pdl(resblock_tail_fwd_kernel<8, 1>, dim3(grid_x_for(rows_per_sample, ppb), B), dim3(kNormThreads), smem, st, 1, a, sp, ln_gamma, ln_beta, op); break;
   }
+  VDN_REQUIRE(le == cudaSuccess, VDN_E_CUDA, "resblock_tail_fwd launch: %s", cudaGetErrorString(le));
   return check_launch("resblock_tail_fwd");
 }
 
@@ -647,13 +643,13 @@ extern "C" int vdn_gn_silu_bwd(const void* dy, const void* x_raw, const float* g
   int gx, cl;
   cl = cluster_for(grid_x_for(rows_per_sample, pl_n * kVecPerThread), &gx);
   const size_t smem_r = (6 * C + kNormThreads * 16) * sizeof(float);
-  cudaError_t le = launch_clustered(gn_bwd_reduce_kernel, dim3(gx, B), cl, smem_r, st, a, reinterpret_cast<const bf16*>(dy), T_ws);
+  cudaError_t le = launch_pdl(gn_bwd_reduce_kernel, dim3(gx, B), dim3(kNormThreads), (size_t)(smem_r), st, cl, a, reinterpret_cast<const bf16*>(dy), T_ws);
   VDN_REQUIRE(le == cudaSuccess, VDN_E_CUDA, "gn_bwd_reduce launch: %s", cudaGetErrorString(le));
   rc = check_launch("gn_bwd_reduce");
   if (rc) return rc;
   const long nvec = (long)rows_per_sample * (C / 8);
   cl = cluster_for(grid_x_for(nvec, kNormThreads * kVecPerThread), &gx);
-  le = launch_clustered(gn_bwd_apply_kernel, dim3(gx, B), cl, (8 * C + kNormThreads * 8) * sizeof(float), st, a,
+  le = launch_pdl(gn_bwd_apply_kernel, dim3(gx, B), dim3(kNormThreads), (size_t)((8 * C + kNormThreads * 8) * sizeof(float)), st, cl, a,
                         reinterpret_cast<const bf16*>(dy), (const float*)T_ws, reinterpret_cast<bf16*>(dx_raw), dgamma, dbeta,
                         dss, dss_ld, dconv_bias);
   VDN_REQUIRE(le == cudaSuccess, VDN_E_CUDA, "gn_bwd_apply launch: %s", cudaGetErrorString(le));
@@ -677,10 +673,10 @@ extern "C" int vdn_ln_bwd(const void* s, const void* dy, const float* ln_gamma, 
   const int cl = cluster_for(grid_x_for(P, ppb * R), &gx);
   cudaError_t le;
   switch (vpl) {
-    case 1: le = launch_clustered(ln_bwd_kernel<1, 4>, dim3(gx), cl, smem, st, sp, dp, ln_gamma, op, dgamma, dbeta, P, C); break;
-    case 2: le = launch_clustered(ln_bwd_kernel<2, 2>, dim3(gx), cl, smem, st, sp, dp, ln_gamma, op, dgamma, dbeta, P, C); break;
-    case 4: le = launch_clustered(ln_bwd_kernel<4, 1>, dim3(gx), cl, smem, st, sp, dp, ln_gamma, op, dgamma, dbeta, P, C); break;
-    default: le = launch_clustered(ln_bwd_kernel<8, 1>, dim3(gx), cl, smem, st, sp, dp, ln_gamma, op, dgamma, dbeta, P, C); break;
+    case 1: le = launch_pdl(ln_bwd_kernel<1, 4>, dim3(gx), dim3(kNormThreads), smem, st, cl, sp, dp, ln_gamma, op, dgamma, dbeta, P, C); break;
+    case 2: le = launch_pdl(ln_bwd_kernel<2, 2>, dim3(gx), dim3(kNormThreads), smem, st, cl, sp, dp, ln_gamma, op, dgamma, dbeta, P, C); break;
+    case 4: le = launch_pdl(ln_bwd_kernel<4, 1>, dim3(gx), dim3(kNormThreads), smem, st, cl, sp, dp, ln_gamma, op, dgamma, dbeta, P, C); break;
+    default: le = launch_pdl(ln_bwd_kernel<8, 1>, dim3(gx), dim3(kNormThreads), smem, st, cl, sp, dp, ln_gamma, op, dgamma, dbeta, P, C); break;
   }
   VDN_REQUIRE(le == cudaSuccess, VDN_E_CUDA, "ln_bwd launch: %s", cudaGetErrorString(le));
   return check_launch("ln_bwd");

@@ -128,6 +128,7 @@ __global__ void __launch_bounds__(kGemmThreads) tapgemm_kernel(const __grid_cons
   const int S = args.stages;
   const int n_steps = args.n_taps * args.n_src * args.chunks;
 
+  pdl_trigger();
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < args.n_maps; ++i) tma_prefetch_desc(&maps.a[i]);
     tma_prefetch_desc(&maps.b);
@@ -146,6 +147,7 @@ __global__ void __launch_bounds__(kGemmThreads) tapgemm_kernel(const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  pdl_wait();  // the prologue above overlapped the previous kernel's tail; global memory is touched below
 
   if (warp == 0) {
     // ================= TMA producer =================
@@ -580,7 +582,8 @@ static int launch_tapgemm(const TapMaps& maps, const TapArgs& args, int smem_byt
     configured = true;
   }
   dim3 grid(args.N / args.BN, ceil_div(args.M, kTileM));
-  tapgemm_kernel<BK><<<grid, kGemmThreads, smem_bytes, st>>>(maps, args);
+  cudaError_t le = launch_pdl(tapgemm_kernel<BK>, grid, dim3(kGemmThreads), (size_t)smem_bytes, st, 1, maps, args);
+  VDN_REQUIRE(le == cudaSuccess, VDN_E_CUDA, "tapgemm launch: %s", cudaGetErrorString(le));
   return check_launch("tapgemm_kernel");
 }
 

@@ -17,6 +17,11 @@ int rowconv_launch(const vdn_tapgemm_desc* d, const void* src0, const void* src1
                    const void* residual, const void* residual2, void* out, void* out2, float* gn_sums,
                    cudaStream_t st);
 
+// sla_mma.cu: per-token SpatialLinearAttention products on warp-level tensor-core MMAs
+int sla_apply_mma_launch(const void* qkv, const float* ctx, void* tok_out, int n_img, int N, cudaStream_t st);
+int sla_bwd_tokens_mma_launch(const void* qkv, const void* d_tok, const float* ctx, const float* dctx,
+                              const float* kstat, void* dqkv, int n_img, int N, cudaStream_t st);
+
 // Kernel launch with programmatic dependent launch (and optionally a thread-block cluster along grid.x). The
 // kernel must call pdl_wait() before touching global memory. VDN_NO_PDL=1 falls back to plain stream order.
 bool pdl_enabled();

@@ -73,6 +73,7 @@ __global__ void __launch_bounds__(kWgThreads) wgrad_kernel(const __grid_constant
   const int t_end = min(a.n_pix_tiles, t_begin + a.tiles_per_split);
   const int n_steps = t_end - t_begin;
 
+  pdl_trigger();
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < S; ++s) {
       mbar_init(&full_bar[s], 1);
@@ -89,6 +90,7 @@ __global__ void __launch_bounds__(kWgThreads) wgrad_kernel(const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  pdl_wait();  // global memory (TMA loads, dW atomics) only below
 
   if (n_steps > 0) {
     if (warp == 0) {
@@ -369,7 +371,9 @@ extern "C" int vdn_wgrad(int kind, const void* src0, const void* src1, const voi
     VDN_REQUIRE(e == cudaSuccess, VDN_E_CUDA, "wgrad cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     cfg = true;
   }
-  wgrad_kernel<0><<<dim3(m_tiles, n_tiles, splits), kWgThreads, smem_bytes, reinterpret_cast<cudaStream_t>(stream)>>>(maps, a);
+  cudaError_t le = launch_pdl(wgrad_kernel<0>, dim3(m_tiles, n_tiles, splits), dim3(kWgThreads), (size_t)smem_bytes,
+                              reinterpret_cast<cudaStream_t>(stream), 1, maps, a);
+  VDN_REQUIRE(le == cudaSuccess, VDN_E_CUDA, "wgrad launch: %s", cudaGetErrorString(le));
   return check_launch("wgrad_kernel");
 }
 
