@@ -243,7 +243,8 @@ def test_sla_core(n_img, N):
     kstat = torch.empty(n_img, 8, 2, 32, device=DEV)
     ws = torch.empty(ops.sla_workspace_floats(n_img, N), device=DEV)
     ops.sla_core_fwd(qkv, out, ctx_b, kstat, ws, n_img, N)
-    assert _rel(ctx_b, ctx) < 1e-3
+    # exp(k - m) is rounded to bf16 before the tensor-core product: expected relative error ~2^-9 / sqrt(3) = 1.1e-3
+    assert _rel(ctx_b, ctx) < 3e-3
     assert _rel(out, o_ref) < 1e-2
     dctx = torch.empty(n_img, 8, 32, 32, device=DEV)
     dqkv = torch.empty_like(qkv)

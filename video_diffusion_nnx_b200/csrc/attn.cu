@@ -648,14 +648,19 @@ extern "C" int vdn_sla_core_fwd(const void* qkv, void* tok_out, float* ctx, floa
   const int per_al = (per + kSlaTile - 1) / kSlaTile * kSlaTile;
   float* ctx_part = ws;
   float* ms_part = ws + (size_t)n_img * kHeads * ns * 1024;
-  sla_ctx_partial_kernel<<<dim3(ns, kHeads, n_img), 256, 0, st>>>(reinterpret_cast<const bf16*>(qkv), N, per_al,
-                                                                  ctx_part, ms_part);
-  int rc = check_launch("sla_ctx_partial");
+  static const bool scalar = getenv("VDN_SLA_SCALAR") != nullptr;  // CUDA-core kernels (A/B comparison only)
+  int rc;
+  if (scalar) {
+    sla_ctx_partial_kernel<<<dim3(ns, kHeads, n_img), 256, 0, st>>>(reinterpret_cast<const bf16*>(qkv), N, per_al,
+                                                                    ctx_part, ms_part);
+    rc = check_launch("sla_ctx_partial");
+  } else {
+    rc = sla_ctx_partial_mma_launch(qkv, N, per_al, ns, ctx_part, ms_part, n_img, st);
+  }
   if (rc) return rc;
   sla_ctx_merge_kernel<<<n_img * kHeads, 256, 0, st>>>(ctx_part, ms_part, ns, ctx, kstat);
   rc = check_launch("sla_ctx_merge");
   if (rc) return rc;
-  static const bool scalar = getenv("VDN_SLA_SCALAR") != nullptr;  // CUDA-core kernels (A/B comparison only)
   if (!scalar) return sla_apply_mma_launch(qkv, ctx, tok_out, n_img, N, st);
   static bool cfg = false;
   if (!cfg) {
@@ -677,11 +682,16 @@ extern "C" int vdn_sla_core_bwd(const void* qkv, const void* d_tok, const float*
   const int ns = sla_splits(N);
   const int per = (N + ns - 1) / ns;
   const int per_al = (per + kSlaTile - 1) / kSlaTile * kSlaTile;
-  sla_dctx_kernel<<<dim3(ns, kHeads, n_img), 256, 0, st>>>(reinterpret_cast<const bf16*>(qkv),
-                                                           reinterpret_cast<const bf16*>(d_tok), N, per_al, dctx);
-  int rc = check_launch("sla_dctx");
-  if (rc) return rc;
   static const bool scalar = getenv("VDN_SLA_SCALAR") != nullptr;
+  int rc;
+  if (scalar) {
+    sla_dctx_kernel<<<dim3(ns, kHeads, n_img), 256, 0, st>>>(reinterpret_cast<const bf16*>(qkv),
+                                                             reinterpret_cast<const bf16*>(d_tok), N, per_al, dctx);
+    rc = check_launch("sla_dctx");
+  } else {
+    rc = sla_dctx_mma_launch(qkv, d_tok, N, per_al, ns, dctx, n_img, st);
+  }
+  if (rc) return rc;
   if (!scalar) return sla_bwd_tokens_mma_launch(qkv, d_tok, ctx, dctx, kstat, dqkv, n_img, N, st);
   const size_t smem = (16 * 1024 + 3 * 256) * sizeof(float);
   static bool cfg = false;

@@ -253,6 +253,196 @@ __global__ void __launch_bounds__(256) sla_bwd_tokens_mma_kernel(const bf16* __r
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// Token-contraction products:  C[d][e] = sum_n A[n][d] * B[n][e]   (ctx = p^T v, dctx = q~^T dtok)
+// MMA roles: M = d, N = e, K = tokens. Both operands need two consecutive TOKENS of one feature packed in a
+// register while memory packs two consecutive FEATURES of one token; the 16-bit transposition happens in
+// registers (cvt.bf16x2 for values that pass through fp32, prmt for raw bf16), again with permuted indices:
+//   lane (g, j) owns tokens 4j..4j+3 of a 16-token group (logical k = 2j,2j+1 | 2j+8,2j+9)
+//   m-tile u: row g <-> feature 16u+2g, row g+8 <-> feature 16u+2g+1   (one 32-bit word per token)
+//   n-tile t: column n <-> feature 2n (t=0), 2n+1 (t=1), 2n+16 (t=2), 2n+17 (t=3)   (words g and g+8)
+// The accumulators live in registers, so the online softmax over tokens (ctx) rescales them exactly.
+// ---------------------------------------------------------------------------------------
+struct TokAcc {
+  float c[2][4][4];  // [m-tile][n-tile][d0..d3]
+};
+__device__ __forceinline__ void tokacc_zero(TokAcc& a) {
+#pragma unroll
+  for (int u = 0; u < 2; ++u)
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a.c[u][t][i] = 0.f;
+}
+// af[u][i][c]: A value of feature 16u+2g+i at the lane's token c (fp32); bw0/bw1[c]: raw B words g / g+8 of token c
+__device__ __forceinline__ void tok_mma(TokAcc& acc, const float (&af)[2][2][4], const uint32_t (&bw0)[4],
+                                        const uint32_t (&bw1)[4]) {
+  uint32_t b[4][2];
+  b[0][0] = __byte_perm(bw0[0], bw0[1], 0x5410); b[0][1] = __byte_perm(bw0[2], bw0[3], 0x5410);
+  b[1][0] = __byte_perm(bw0[0], bw0[1], 0x7632); b[1][1] = __byte_perm(bw0[2], bw0[3], 0x7632);
+  b[2][0] = __byte_perm(bw1[0], bw1[1], 0x5410); b[2][1] = __byte_perm(bw1[2], bw1[3], 0x5410);
+  b[3][0] = __byte_perm(bw1[0], bw1[1], 0x7632); b[3][1] = __byte_perm(bw1[2], bw1[3], 0x7632);
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const uint32_t a0 = pack_bf16x2(af[u][0][0], af[u][0][1]), a1 = pack_bf16x2(af[u][1][0], af[u][1][1]);
+    const uint32_t a2 = pack_bf16x2(af[u][0][2], af[u][0][3]), a3 = pack_bf16x2(af[u][1][2], af[u][1][3]);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) mma_bf16_16816(acc.c[u][t], a0, a1, a2, a3, b[t][0], b[t][1]);
+  }
+}
+// scatter the accumulators to out[d*32 + e] (plain store or atomicAdd)
+template <bool kAtomic>
+__device__ __forceinline__ void tokacc_store(const TokAcc& acc, float* out, int g, int j) {
+#pragma unroll
+  for (int u = 0; u < 2; ++u)
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int d = 16 * u + 2 * g + (i >> 1);
+        const int n = 2 * j + (i & 1);
+        const int e = 2 * n + (t & 1) + 16 * (t >> 1);
+        if (kAtomic) atomicAdd(out + d * 32 + e, acc.c[u][t][i]);
+        else out[d * 32 + e] = acc.c[u][t][i];
+      }
+}
+
+// Partial context over a token range with exact online softmax over tokens (per feature d).
+// grid (n_split, n_img), 256 threads = 8 warps = 8 heads. Outputs the format sla_ctx_merge_kernel consumes.
+__global__ void __launch_bounds__(256) sla_ctx_partial_mma_kernel(const bf16* __restrict__ qkv, int N,
+                                                                  int tokens_per_split,
+                                                                  float* __restrict__ ctx_part /*[img][h][split][32][32]*/,
+                                                                  float* __restrict__ ms_part /*[img][h][split][2][32]*/) {
+  pdl_trigger();
+  pdl_wait();
+  const int split = blockIdx.x, img = blockIdx.y, n_split = gridDim.x;
+  const int h = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, j = lane & 3;
+  const int n_begin = split * tokens_per_split;
+  const int n_end = min(N, n_begin + tokens_per_split);
+  TokAcc acc;
+  tokacc_zero(acc);
+  float mrow[2][2], srow[2][2];
+#pragma unroll
+  for (int u = 0; u < 2; ++u)
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      mrow[u][i] = -INFINITY;
+      srow[u][i] = 0.f;
+    }
+  const uint32_t* base = reinterpret_cast<const uint32_t*>(qkv + (long)img * N * kSmQKV + h * kSmDh);
+  for (int n0 = n_begin; n0 < n_end; n0 += 16) {
+    uint32_t kw[2][4], vw0[4], vw1[4];
+    bool valid[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int n = n0 + 4 * j + c;
+      valid[c] = n < n_end;
+      const uint32_t* row = base + (long)(valid[c] ? n : n_end - 1) * (kSmQKV / 2);
+      kw[0][c] = __ldg(row + kSmHD / 2 + g);
+      kw[1][c] = __ldg(row + kSmHD / 2 + 8 + g);
+      vw0[c] = __ldg(row + kSmHD + g);
+      vw1[c] = __ldg(row + kSmHD + 8 + g);
+    }
+    float kf[2][2][4];
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float2 f = unpack_bf16x2(kw[u][c]);
+        kf[u][0][c] = valid[c] ? f.x : -INFINITY;  // padded tokens: exp() -> 0
+        kf[u][1][c] = valid[c] ? f.y : -INFINITY;
+      }
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        float gm = fmaxf(fmaxf(kf[u][i][0], kf[u][i][1]), fmaxf(kf[u][i][2], kf[u][i][3]));
+        gm = quad_max(gm);  // over the 16 tokens of the group
+        const float m_new = fmaxf(mrow[u][i], gm);
+        const float corr = __expf(mrow[u][i] - m_new);  // first group: exp(-inf) = 0 on zero accumulators
+        mrow[u][i] = m_new;
+        srow[u][i] *= corr;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          acc.c[u][t][2 * i] *= corr;
+          acc.c[u][t][2 * i + 1] *= corr;
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          kf[u][i][c] = __expf(kf[u][i][c] - m_new);
+          srow[u][i] += kf[u][i][c];
+        }
+      }
+    tok_mma(acc, kf, vw0, vw1);
+  }
+  const long blk = ((long)img * kSmHeads + h) * n_split + split;
+  tokacc_store<false>(acc, ctx_part + blk * 1024, g, j);
+#pragma unroll
+  for (int u = 0; u < 2; ++u)
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const float S = quad_sum(srow[u][i]);
+      if (j == 0) {
+        const int d = 16 * u + 2 * g + i;
+        ms_part[blk * 64 + d] = mrow[u][i];
+        ms_part[blk * 64 + 32 + d] = S;
+      }
+    }
+}
+
+// dctx[h][d][e] += sum_n q~[n,d] * dtok[n,e] over a token range (atomic across splits; dctx pre-zeroed).
+__global__ void __launch_bounds__(256) sla_dctx_mma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dtok,
+                                                           int N, int tokens_per_split, float* __restrict__ dctx) {
+  pdl_trigger();
+  pdl_wait();
+  const int split = blockIdx.x, img = blockIdx.y;
+  const int h = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, j = lane & 3;
+  const int n_begin = split * tokens_per_split;
+  const int n_end = min(N, n_begin + tokens_per_split);
+  TokAcc acc;
+  tokacc_zero(acc);
+  const uint32_t* qbase = reinterpret_cast<const uint32_t*>(qkv + (long)img * N * kSmQKV + h * kSmDh);
+  const uint32_t* gbase = reinterpret_cast<const uint32_t*>(dtok + (long)img * N * kSmHD + h * kSmDh);
+  for (int n0 = n_begin; n0 < n_end; n0 += 16) {
+    uint32_t qw[2][4], gw0[4], gw1[4];
+    bool valid[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int n = n0 + 4 * j + c;
+      valid[c] = n < n_end;
+      const long nn = valid[c] ? n : n_end - 1;
+      qw[0][c] = __ldg(qbase + nn * (kSmQKV / 2) + g);
+      qw[1][c] = __ldg(qbase + nn * (kSmQKV / 2) + 8 + g);
+      gw0[c] = __ldg(gbase + nn * (kSmHD / 2) + g);
+      gw1[c] = __ldg(gbase + nn * (kSmHD / 2) + 8 + g);
+    }
+    float qf[2][2][4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      // softmax over the 32 features of token c: the 8 lanes with this j hold 4 features each
+      const float2 f0 = unpack_bf16x2(qw[0][c]), f1 = unpack_bf16x2(qw[1][c]);
+      float mx = fmaxf(fmaxf(f0.x, f0.y), fmaxf(f1.x, f1.y));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
+      const float e00 = __expf(f0.x - mx), e01 = __expf(f0.y - mx), e10 = __expf(f1.x - mx), e11 = __expf(f1.y - mx);
+      float sm = (e00 + e01) + (e10 + e11);
+      sm += __shfl_xor_sync(0xffffffffu, sm, 4);
+      sm += __shfl_xor_sync(0xffffffffu, sm, 8);
+      sm += __shfl_xor_sync(0xffffffffu, sm, 16);
+      const float inv = valid[c] ? 1.f / sm : 0.f;  // padded tokens contribute nothing
+      qf[0][0][c] = e00 * inv;
+      qf[0][1][c] = e01 * inv;
+      qf[1][0][c] = e10 * inv;
+      qf[1][1][c] = e11 * inv;
+    }
+    tok_mma(acc, qf, gw0, gw1);
+  }
+  tokacc_store<true>(acc, dctx + ((long)img * kSmHeads + h) * 1024, g, j);
+}
+
 // Host launchers used by vdn_sla_core_fwd / vdn_sla_core_bwd (attn.cu).
 int sla_apply_mma_launch(const void* qkv, const float* ctx, void* tok_out, int n_img, int N, cudaStream_t st) {
   const int n_groups = (N + 15) / 16;
@@ -278,6 +468,23 @@ int sla_bwd_tokens_mma_launch(const void* qkv, const void* d_tok, const float* c
                               reinterpret_cast<bf16*>(dqkv), N);
   VDN_REQUIRE(le == cudaSuccess, VDN_E_CUDA, "sla_bwd_tokens launch: %s", cudaGetErrorString(le));
   return check_launch("sla_bwd_tokens_mma");
+}
+
+int sla_ctx_partial_mma_launch(const void* qkv, int N, int tokens_per_split, int n_split, float* ctx_part,
+                               float* ms_part, int n_img, cudaStream_t st) {
+  cudaError_t le = launch_pdl(sla_ctx_partial_mma_kernel, dim3(n_split, n_img), dim3(256), (size_t)0, st, 1,
+                              reinterpret_cast<const bf16*>(qkv), N, tokens_per_split, ctx_part, ms_part);
+  VDN_REQUIRE(le == cudaSuccess, VDN_E_CUDA, "sla_ctx_partial launch: %s", cudaGetErrorString(le));
+  return check_launch("sla_ctx_partial_mma");
+}
+
+int sla_dctx_mma_launch(const void* qkv, const void* d_tok, int N, int tokens_per_split, int n_split, float* dctx,
+                        int n_img, cudaStream_t st) {
+  cudaError_t le = launch_pdl(sla_dctx_mma_kernel, dim3(n_split, n_img), dim3(256), (size_t)0, st, 1,
+                              reinterpret_cast<const bf16*>(qkv), reinterpret_cast<const bf16*>(d_tok), N,
+                              tokens_per_split, dctx);
+  VDN_REQUIRE(le == cudaSuccess, VDN_E_CUDA, "sla_dctx launch: %s", cudaGetErrorString(le));
+  return check_launch("sla_dctx_mma");
 }
 
 }  // namespace vdn

@@ -22,6 +22,11 @@ int sla_apply_mma_launch(const void* qkv, const float* ctx, void* tok_out, int n
 int sla_bwd_tokens_mma_launch(const void* qkv, const void* d_tok, const float* ctx, const float* dctx,
                               const float* kstat, void* dqkv, int n_img, int N, cudaStream_t st);
 
+int sla_ctx_partial_mma_launch(const void* qkv, int N, int tokens_per_split, int n_split, float* ctx_part,
+                               float* ms_part, int n_img, cudaStream_t st);
+int sla_dctx_mma_launch(const void* qkv, const void* d_tok, int N, int tokens_per_split, int n_split, float* dctx,
+                        int n_img, cudaStream_t st);
+
 // Kernel launch with programmatic dependent launch (and optionally a thread-block cluster along grid.x). The
 // kernel must call pdl_wait() before touching global memory. VDN_NO_PDL=1 falls back to plain stream order.
 bool pdl_enabled();
