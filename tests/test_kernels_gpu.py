@@ -213,7 +213,7 @@ def test_mha_core(mode, B, Fr, HW):
         dq2 = torch.zeros_like(qkv)
         ops.mha_temporal_bwd(qkv, out, do, lse, dq2, B, Fr, side, side)
         assert _rel(dq2, qf.grad) < 2e-2
-        if Fr in (10, 16):  # tensor-core backward
+        if Fr <= 16:  # tensor-core backward (warp-level MMAs, any F <= 16)
             dq3 = torch.zeros_like(qkv)
             ops.mha_temporal_tc_bwd(qkv, do, lse, dq3, B, Fr, side, side)
             torch.cuda.synchronize()

@@ -13,6 +13,7 @@
 //   5. O = P V as a 128x32x128 MMA (V read MN-major from the same smem tile), 1/l applied on the way out
 // TMEM: [0,96) qkv, [96,224) S, [224,256) O -> 256 columns, two CTAs per SM.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "vdn_common.cuh"
@@ -603,7 +604,11 @@ static int launch_tc_bwd(const bf16* qkv, const bf16* d_o, const float* lse, bf1
 // Same contract as vdn_mha_temporal_bwd (o is not needed: D_i = sum_j P_ij dP_ij). F in {10, 16}.
 extern "C" int vdn_mha_temporal_tc_bwd(const void* qkv, const void* d_o, const float* lse, void* dqkv, int B, int F,
                                        int H, int W, void* stream) {
-  VDN_REQUIRE(qkv && d_o && lse && dqkv && (F == 10 || F == 16), VDN_E_SHAPE, "mha_tc_bwd: bad args (F in {10,16})");
+  VDN_REQUIRE(qkv && d_o && lse && dqkv && F >= 1 && F <= 16, VDN_E_SHAPE, "mha_tc_bwd: bad args (F <= 16)");
+  static const bool use_tcgen05 = getenv("VDN_MHA_TC_BWD") != nullptr;  // block-diagonal tcgen05 kernel (A/B only)
+  if (!use_tcgen05)
+    return vdn::mha_temporal_mma_bwd_launch(qkv, d_o, lse, dqkv, B, F, H, W, reinterpret_cast<cudaStream_t>(stream));
+  VDN_REQUIRE(F == 10 || F == 16, VDN_E_SHAPE, "mha_tc_bwd: the tcgen05 kernel is instantiated for F in {10,16}");
   // The backward is bound by its per-row global loads / stores, not by the MMA chain: 120-row tiles (PX = 12)
   // measured slower than 80-row tiles, so it keeps power-of-two pixel counts (8 for F = 10 and F = 16).
   int PX = 1;

@@ -27,6 +27,10 @@ int sla_ctx_partial_mma_launch(const void* qkv, int N, int tokens_per_split, int
 int sla_dctx_mma_launch(const void* qkv, const void* d_tok, int N, int tokens_per_split, int n_split, float* dctx,
                         int n_img, cudaStream_t st);
 
+// mha_mma.cu: temporal attention core backward, one warp per (pixel, head), register-resident
+int mha_temporal_mma_bwd_launch(const void* qkv, const void* d_o, const float* lse, void* dqkv, int B, int F, int H,
+                                int W, cudaStream_t st);
+
 // Kernel launch with programmatic dependent launch (and optionally a thread-block cluster along grid.x). The
 // kernel must call pdl_wait() before touching global memory. VDN_NO_PDL=1 falls back to plain stream order.
 bool pdl_enabled();
