@@ -450,7 +450,8 @@ def test_mha_temporal_fused_fwd(B, Fr, H, W, Cc):
 
 
 @pytest.mark.parametrize("B,Fr,H,W,Cc", [(2, 10, 16, 16, 32), (1, 10, 8, 8, 256), (1, 16, 8, 8, 128), (2, 16, 8, 16, 64),
-                                          (1, 10, 64, 64, 32)])
+                                          (1, 10, 64, 64, 32), (1, 2, 8, 8, 32), (2, 16, 8, 8, 32), (2, 3, 4, 4, 32),
+                                          (1, 9, 5, 7, 32)])
 def test_mha_temporal_tc_fwd(B, Fr, H, W, Cc):
     """All-tensor-core temporal attention (projection, Q K^T and P V on tcgen05) vs torch fp32."""
     from video_diffusion_nnx_b200 import ops
@@ -479,3 +480,7 @@ def test_mha_temporal_tc_fwd(B, Fr, H, W, Cc):
     lse_ref = torch.logsumexp(s, -1).permute(0, 3, 1, 2).reshape(P, 8)
     assert _rel(o, o_ref) < 2e-2   # P is rounded to bf16 before the P V product
     assert _rel(lse, lse_ref) < 3e-3
+    # inference mode (no qkv / lse outputs) must give the same o
+    o2 = torch.zeros_like(o)
+    ops.mha_temporal_tc_fwd(x, w_hm, b_hm, o2, None, None, B, Fr, H, W, Cc)
+    assert _rel(o2, o_ref) < 2e-2

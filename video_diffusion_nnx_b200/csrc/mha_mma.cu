@@ -194,6 +194,288 @@ __global__ void __launch_bounds__(256) mha_temporal_mma_bwd_kernel(const bf16* _
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// Fused forward for C = 32: QKV projection + attention core of one (pixel, head) per warp, all in registers
+// (reference: modules.py:285-323; same contract as vdn_mha_temporal_fused_fwd).
+//   q|k|v = x W_h + b_h     [F x 32] each  (x rows as 16-byte chunk operands, weights as B fragments)
+//   v^T   = W_v^T x^T       (recomputed transposed: the B operand of P V contracts over tokens)
+//   S = q k^T / sqrt(32), P = softmax(S), O = P V, lse = max + log(sum)
+// The output-feature order of each projection is permuted (by choosing which weight row feeds which
+// fragment column) so that a lane's accumulator registers ARE the 16-byte chunk j of token rows g / g+8:
+// q/k/v feed the next MMA without any data movement, and qkv (training) / o are written with 16-byte stores.
+// Weight fragments stay in registers across the pixel loop (48 registers for C = 32).
+// ---------------------------------------------------------------------------------------
+struct ProjW {
+  uint32_t b[4][2][2];  // [n-tile][k-step][2]  B fragments of x W (output feature psi(t, g))
+  float bias[4][2];     // bias of output features psi(t, 2j), psi(t, 2j+1)
+};
+// psi(t, c): feature held by fragment column c of n-tile t  ->  lane j ends up with features 8j .. 8j+7
+__device__ __forceinline__ int psi(int t, int c) { return 8 * (c >> 1) + 4 * (t >> 1) + 2 * (t & 1) + (c & 1); }
+__device__ __forceinline__ void load_projw(ProjW& w, const bf16* w_rows /*[32 feat][32 c]*/, const float* bias, int g,
+                                           int j) {
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const uint32_t* row = reinterpret_cast<const uint32_t*>(w_rows + psi(t, g) * 32);
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      w.b[t][s][0] = __ldg(row + 4 * j + 2 * s);      // channels 8j+4s, 8j+4s+1
+      w.b[t][s][1] = __ldg(row + 4 * j + 2 * s + 1);  // channels 8j+4s+2, 8j+4s+3
+    }
+    w.bias[t][0] = __ldg(bias + psi(t, 2 * j));
+    w.bias[t][1] = __ldg(bias + psi(t, 2 * j + 1));
+  }
+}
+// Fragment sets live in shared memory as [24 words][32 lanes] (lane innermost: conflict-free LDS), written once
+// per warp: keeping them in registers (68+ per thread) caps the kernel at 8 warps per SM, and its chains of
+// dependent MMAs need more resident warps than that to hide their latency.
+constexpr int kProjWords = 24;  // 16 fragment words + 8 bias floats
+__device__ __forceinline__ void store_projw(uint32_t* sm, const ProjW& w, int lane) {
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      sm[((t * 2 + s) * 2 + 0) * 32 + lane] = w.b[t][s][0];
+      sm[((t * 2 + s) * 2 + 1) * 32 + lane] = w.b[t][s][1];
+    }
+    sm[(16 + 2 * t) * 32 + lane] = __float_as_uint(w.bias[t][0]);
+    sm[(16 + 2 * t + 1) * 32 + lane] = __float_as_uint(w.bias[t][1]);
+  }
+}
+// lo/hi = bf16 chunk j of the projected rows g / g+8
+__device__ __forceinline__ void project_chunks(const uint4& x_lo, const uint4& x_hi, const uint32_t* sm, int lane,
+                                               uint4& lo, uint4& hi) {
+  uint32_t l[4], h[4];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const float b0 = __uint_as_float(sm[(16 + 2 * t) * 32 + lane]), b1 = __uint_as_float(sm[(16 + 2 * t + 1) * 32 + lane]);
+    float c[4] = {b0, b1, b0, b1};
+    mma16816(c, x_lo.x, x_hi.x, x_lo.y, x_hi.y, sm[((t * 2 + 0) * 2 + 0) * 32 + lane], sm[((t * 2 + 0) * 2 + 1) * 32 + lane]);
+    mma16816(c, x_lo.z, x_hi.z, x_lo.w, x_hi.w, sm[((t * 2 + 1) * 2 + 0) * 32 + lane], sm[((t * 2 + 1) * 2 + 1) * 32 + lane]);
+    l[t] = pack_bf16x2(c[0], c[1]);
+    h[t] = pack_bf16x2(c[2], c[3]);
+  }
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+}
+
+struct ProjWT {
+  uint32_t a[2][2][4];  // [m-tile][k-step][4]  A fragments of W^T x^T (row g + 8r of m-tile u = feature rho(u, r, g))
+  float bias[2][2];     // bias of rows g, g+8
+};
+// rho: feature held by row g + 8r of m-tile u  ->  P V lands in the chunk layout (lane j: features 8j .. 8j+7)
+__device__ __forceinline__ int rho(int u, int r, int g) { return 8 * (g >> 1) + 2 * (2 * u + r) + (g & 1); }
+__device__ __forceinline__ void load_projwt(ProjWT& w, const bf16* w_rows, const float* bias, int g, int j) {
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const uint32_t* r0 = reinterpret_cast<const uint32_t*>(w_rows + rho(u, 0, g) * 32);
+    const uint32_t* r1 = reinterpret_cast<const uint32_t*>(w_rows + rho(u, 1, g) * 32);
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      w.a[u][s][0] = __ldg(r0 + 4 * j + 2 * s);
+      w.a[u][s][1] = __ldg(r1 + 4 * j + 2 * s);
+      w.a[u][s][2] = __ldg(r0 + 4 * j + 2 * s + 1);
+      w.a[u][s][3] = __ldg(r1 + 4 * j + 2 * s + 1);
+    }
+    w.bias[u][0] = __ldg(bias + rho(u, 0, g));
+    w.bias[u][1] = __ldg(bias + rho(u, 1, g));
+  }
+}
+
+constexpr int kProjWTWords = 20;  // 16 fragment words + 4 bias floats
+__device__ __forceinline__ void store_projwt(uint32_t* sm, const ProjWT& w, int lane) {
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+#pragma unroll
+    for (int s = 0; s < 2; ++s)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) sm[((u * 2 + s) * 4 + q) * 32 + lane] = w.a[u][s][q];
+    sm[(16 + 2 * u) * 32 + lane] = __float_as_uint(w.bias[u][0]);
+    sm[(16 + 2 * u + 1) * 32 + lane] = __float_as_uint(w.bias[u][1]);
+  }
+}
+
+template <bool kWriteQkv>
+__global__ void __launch_bounds__(256, 2) mha_temporal_mma_fwd_kernel(const bf16* __restrict__ x,
+                                                                   const bf16* __restrict__ w_hm,
+                                                                   const float* __restrict__ bias_hm,
+                                                                   bf16* __restrict__ o, bf16* __restrict__ qkv,
+                                                                   float* __restrict__ lse, int B, int F, long HW) {
+  pdl_trigger();
+  pdl_wait();
+  const int h = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, j = lane & 3;
+  const float scale = rsqrtf(32.f);
+  const long n_pix = (long)B * HW;
+  const bool v_lo = g < F, v_hi = g + 8 < F;
+  extern __shared__ uint32_t sm_w[];  // per head: q | k | v^T (| v) fragment sets
+  constexpr int kHeadWords = (2 * kProjWords + kProjWTWords + (kWriteQkv ? kProjWords : 0)) * 32;
+  uint32_t* s_q = sm_w + h * kHeadWords;
+  uint32_t* s_k = s_q + kProjWords * 32;
+  uint32_t* s_vt = s_k + kProjWords * 32;
+  uint32_t* s_v = s_vt + kProjWTWords * 32;
+  {
+    ProjW w;
+    load_projw(w, w_hm + (h * 96) * 32, bias_hm + h * 96, g, j);
+    store_projw(s_q, w, lane);
+    load_projw(w, w_hm + (h * 96 + 32) * 32, bias_hm + h * 96 + 32, g, j);
+    store_projw(s_k, w, lane);
+    if (kWriteQkv) {
+      load_projw(w, w_hm + (h * 96 + 64) * 32, bias_hm + h * 96 + 64, g, j);
+      store_projw(s_v, w, lane);
+    }
+    ProjWT wt;
+    load_projwt(wt, w_hm + (h * 96 + 64) * 32, bias_hm + h * 96 + 64, g, j);
+    store_projwt(s_vt, wt, lane);
+  }
+  __syncwarp();
+  const uint4 zero4 = make_uint4(0, 0, 0, 0);
+  // the x chunks of the NEXT pixel are fetched while the current one is processed (register double buffer)
+  uint4 nx_lo = zero4, nx_hi = zero4;
+  if (blockIdx.x < n_pix) {
+    const long b = blockIdx.x / HW, p = blockIdx.x - b * HW;
+    const long row0 = b * F * HW + p;
+    if (v_lo) nx_lo = __ldg(reinterpret_cast<const uint4*>(x + (row0 + (long)g * HW) * 32) + j);
+    if (v_hi) nx_hi = __ldg(reinterpret_cast<const uint4*>(x + (row0 + (long)(g + 8) * HW) * 32) + j);
+  }
+  for (long pix = blockIdx.x; pix < n_pix; pix += gridDim.x) {
+    const long b = pix / HW, p = pix - b * HW;
+    const long row0 = b * F * HW + p;
+    const long r_lo = row0 + (long)g * HW, r_hi = row0 + (long)(g + 8) * HW;
+    const uint4 x_lo = nx_lo, x_hi = nx_hi;
+    {
+      const long np = pix + gridDim.x;
+      if (np < n_pix) {
+        const long nb = np / HW, pp = np - nb * HW;
+        const long nrow0 = nb * F * HW + pp;
+        if (v_lo) nx_lo = __ldg(reinterpret_cast<const uint4*>(x + (nrow0 + (long)g * HW) * 32) + j);
+        if (v_hi) nx_hi = __ldg(reinterpret_cast<const uint4*>(x + (nrow0 + (long)(g + 8) * HW) * 32) + j);
+      }
+    }
+    uint4 q_lo, q_hi, k_lo, k_hi;
+    project_chunks(x_lo, x_hi, s_q, lane, q_lo, q_hi);
+    project_chunks(x_lo, x_hi, s_k, lane, k_lo, k_hi);
+    if (kWriteQkv) {  // training: the backward reads q | k | v
+      uint4 vv_lo, vv_hi;
+      project_chunks(x_lo, x_hi, s_v, lane, vv_lo, vv_hi);
+      if (v_lo) {
+        uint4* pr = reinterpret_cast<uint4*>(qkv + r_lo * 768 + h * 32) + j;
+        pr[0] = q_lo;
+        pr[32] = k_lo;
+        pr[64] = vv_lo;
+      }
+      if (v_hi) {
+        uint4* pr = reinterpret_cast<uint4*>(qkv + r_hi * 768 + h * 32) + j;
+        pr[0] = q_hi;
+        pr[32] = k_hi;
+        pr[64] = vv_hi;
+      }
+    }
+    // v^T[feature][token]: A = W_v^T fragments, B = x^T = the x chunks of tokens 8t + g
+    float vt[2][2][4];
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        vt[u][t][0] = vt[u][t][1] = __uint_as_float(s_vt[(16 + 2 * u) * 32 + lane]);
+        vt[u][t][2] = vt[u][t][3] = __uint_as_float(s_vt[(16 + 2 * u + 1) * 32 + lane]);
+        const uint4& xb = t == 0 ? x_lo : x_hi;
+        mma16816(vt[u][t], s_vt[((u * 2 + 0) * 4 + 0) * 32 + lane], s_vt[((u * 2 + 0) * 4 + 1) * 32 + lane],
+                 s_vt[((u * 2 + 0) * 4 + 2) * 32 + lane], s_vt[((u * 2 + 0) * 4 + 3) * 32 + lane], xb.x, xb.y);
+        mma16816(vt[u][t], s_vt[((u * 2 + 1) * 4 + 0) * 32 + lane], s_vt[((u * 2 + 1) * 4 + 1) * 32 + lane],
+                 s_vt[((u * 2 + 1) * 4 + 2) * 32 + lane], s_vt[((u * 2 + 1) * 4 + 3) * 32 + lane], xb.z, xb.w);
+      }
+    // S = q k^T, softmax over the key tokens (columns 8t + 2j + i)
+    float S[2][4];
+    chunk_abt(q_lo, q_hi, k_lo, k_hi, S);
+    float m_lo = -INFINITY, m_hi = -INFINITY;
+#pragma unroll
+    for (int t = 0; t < 2; ++t)
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const bool cv = 8 * t + 2 * j + i < F;
+        S[t][i] = cv ? S[t][i] * scale : -INFINITY;
+        S[t][2 + i] = cv ? S[t][2 + i] * scale : -INFINITY;
+        m_lo = fmaxf(m_lo, S[t][i]);
+        m_hi = fmaxf(m_hi, S[t][2 + i]);
+      }
+    m_lo = fmaxf(m_lo, __shfl_xor_sync(0xffffffffu, m_lo, 1));
+    m_lo = fmaxf(m_lo, __shfl_xor_sync(0xffffffffu, m_lo, 2));
+    m_hi = fmaxf(m_hi, __shfl_xor_sync(0xffffffffu, m_hi, 1));
+    m_hi = fmaxf(m_hi, __shfl_xor_sync(0xffffffffu, m_hi, 2));
+    float l_lo = 0.f, l_hi = 0.f;
+#pragma unroll
+    for (int t = 0; t < 2; ++t)
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        S[t][i] = __expf(S[t][i] - m_lo);
+        S[t][2 + i] = __expf(S[t][2 + i] - m_hi);
+        l_lo += S[t][i];
+        l_hi += S[t][2 + i];
+      }
+    l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 1);
+    l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 2);
+    l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 1);
+    l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 2);
+    // O = P V: A = P fragments, B = v^T fragments (tokens 2j,2j+1 | 8+2j,9+2j of feature rho(u, r, g))
+    const uint32_t a0 = pack_bf16x2(S[0][0], S[0][1]), a1 = pack_bf16x2(S[0][2], S[0][3]);
+    const uint32_t a2 = pack_bf16x2(S[1][0], S[1][1]), a3 = pack_bf16x2(S[1][2], S[1][3]);
+    float o_lo[8], o_hi[8];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {  // n-tile t = (u, r) = (t / 2, t % 2)
+      const int u = t >> 1, r = t & 1;
+      float c[4] = {0.f, 0.f, 0.f, 0.f};
+      mma16816(c, a0, a1, a2, a3, pack_bf16x2(vt[u][0][2 * r], vt[u][0][2 * r + 1]),
+               pack_bf16x2(vt[u][1][2 * r], vt[u][1][2 * r + 1]));
+      o_lo[2 * t] = c[0];
+      o_lo[2 * t + 1] = c[1];
+      o_hi[2 * t] = c[2];
+      o_hi[2 * t + 1] = c[3];
+    }
+    const float inv_lo = 1.f / l_lo, inv_hi = 1.f / l_hi;
+    if (v_lo) {
+      uint4 u4;
+      u4.x = pack_bf16x2(o_lo[0] * inv_lo, o_lo[1] * inv_lo);
+      u4.y = pack_bf16x2(o_lo[2] * inv_lo, o_lo[3] * inv_lo);
+      u4.z = pack_bf16x2(o_lo[4] * inv_lo, o_lo[5] * inv_lo);
+      u4.w = pack_bf16x2(o_lo[6] * inv_lo, o_lo[7] * inv_lo);
+      reinterpret_cast<uint4*>(o + r_lo * 256 + h * 32)[j] = u4;
+      if (lse && j == 0) lse[r_lo * 8 + h] = m_lo + __logf(l_lo);
+    }
+    if (v_hi) {
+      uint4 u4;
+      u4.x = pack_bf16x2(o_hi[0] * inv_hi, o_hi[1] * inv_hi);
+      u4.y = pack_bf16x2(o_hi[2] * inv_hi, o_hi[3] * inv_hi);
+      u4.z = pack_bf16x2(o_hi[4] * inv_hi, o_hi[5] * inv_hi);
+      u4.w = pack_bf16x2(o_hi[6] * inv_hi, o_hi[7] * inv_hi);
+      reinterpret_cast<uint4*>(o + r_hi * 256 + h * 32)[j] = u4;
+      if (lse && j == 0) lse[r_hi * 8 + h] = m_hi + __logf(l_hi);
+    }
+  }
+}
+
+int mha_temporal_mma_fwd_launch(const void* x, const void* w_hm, const float* bias_hm, void* o, void* qkv, float* lse,
+                                int B, int F, int H, int W, cudaStream_t st) {
+  const long HW = (long)H * W;
+  const long n_pix = (long)B * HW;
+  const int grid = (int)std::min<long>(n_pix, 148L * 16);
+  const size_t smem_t = (size_t)8 * (3 * kProjWords + kProjWTWords) * 32 * 4, smem_i = (size_t)8 * (2 * kProjWords + kProjWTWords) * 32 * 4;
+  static bool cfg = false;
+  if (!cfg) {
+    cudaFuncSetAttribute(mha_temporal_mma_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t);
+    cudaFuncSetAttribute(mha_temporal_mma_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_i);
+    cfg = true;
+  }
+  cudaError_t le =
+      qkv ? launch_pdl(mha_temporal_mma_fwd_kernel<true>, dim3(grid), dim3(256), smem_t, st, 1,
+                       reinterpret_cast<const bf16*>(x), reinterpret_cast<const bf16*>(w_hm), bias_hm,
+                       reinterpret_cast<bf16*>(o), reinterpret_cast<bf16*>(qkv), lse, B, F, HW)
+          : launch_pdl(mha_temporal_mma_fwd_kernel<false>, dim3(grid), dim3(256), smem_i, st, 1,
+                       reinterpret_cast<const bf16*>(x), reinterpret_cast<const bf16*>(w_hm), bias_hm,
+                       reinterpret_cast<bf16*>(o), reinterpret_cast<bf16*>(qkv), lse, B, F, HW);
+  VDN_REQUIRE(le == cudaSuccess, VDN_E_CUDA, "mha_temporal_mma_fwd launch: %s", cudaGetErrorString(le));
+  return check_launch("mha_temporal_mma_fwd");
+}
+
 int mha_temporal_mma_bwd_launch(const void* qkv, const void* d_o, const float* lse, void* dqkv, int B, int F, int H,
                                 int W, cudaStream_t st) {
   const long HW = (long)H * W;

@@ -341,13 +341,19 @@ static int launch_tc(const TcMaps& maps, const TcArgs& a, int n_tiles, cudaStrea
 using namespace vdn;
 
 // Returns 1 if (F, C) is served by the tensor-core kernel (otherwise use vdn_mha_temporal_fused_fwd).
-extern "C" int vdn_mha_temporal_tc_supported(int F, int C) { return (F == 10 || F == 16) && (C % 32 == 0) ? 1 : 0; }
+extern "C" int vdn_mha_temporal_tc_supported(int F, int C) {
+  if (C == 32 && F >= 1 && F <= 16) return 1;  // register-resident warp-MMA kernel (mha_mma.cu)
+  return (F == 10 || F == 16) && (C % 32 == 0) ? 1 : 0;
+}
 
 // Same contract as vdn_mha_temporal_fused_fwd.
 extern "C" int vdn_mha_temporal_tc_fwd(const void* x, const void* w_hm, const float* bias_hm, void* o, void* qkv,
                                        float* lse, int B, int F, int H, int W, int C, void* stream) {
   VDN_REQUIRE(x && w_hm && o && B > 0 && H > 0 && W > 0, VDN_E_SHAPE, "mha_tc: bad args");
   VDN_REQUIRE(vdn_mha_temporal_tc_supported(F, C), VDN_E_SHAPE, "mha_tc: F=%d C=%d not instantiated", F, C);
+  static const bool force_tcgen05 = getenv("VDN_MHA_TC_FWD") != nullptr;  // A/B comparison only
+  if (C == 32 && !(force_tcgen05 && (F == 10 || F == 16)))
+    return vdn::mha_temporal_mma_fwd_launch(x, w_hm, bias_hm, o, qkv, lse, B, F, H, W, reinterpret_cast<cudaStream_t>(stream));
   const int PX = std::min(128 / F, H * W);  // pixels per 128-row tile (12 for F = 10, 8 for F = 16)
   const int BK = (C % 64 == 0) ? 64 : 32;
   TcArgs a;

@@ -31,6 +31,9 @@ int sla_dctx_mma_launch(const void* qkv, const void* d_tok, int N, int tokens_pe
 int mha_temporal_mma_bwd_launch(const void* qkv, const void* d_o, const float* lse, void* dqkv, int B, int F, int H,
                                 int W, cudaStream_t st);
 
+int mha_temporal_mma_fwd_launch(const void* x, const void* w_hm, const float* bias_hm, void* o, void* qkv, float* lse,
+                                int B, int F, int H, int W, cudaStream_t st);
+
 // Kernel launch with programmatic dependent launch (and optionally a thread-block cluster along grid.x). The
 // kernel must call pdl_wait() before touching global memory. VDN_NO_PDL=1 falls back to plain stream order.
 bool pdl_enabled();
