@@ -10,6 +10,7 @@
 // shifted boxes, zero-filled at the borders) are stacked along M of one 128-row MMA.
 // K (all pixels) is split across CTAs; partial tiles are reduced with fp32 atomics into dW.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "vdn_common.cuh"
@@ -192,8 +193,17 @@ __global__ void __launch_bounds__(kWgThreads) wgrad_kernel(const __grid_constant
         tmem_ld_32x16(taddr + (uint32_t)c0, raw);
         tmem_ld_wait();
         if (valid) {
+          if (a.col_stride == 1) {  // contiguous output row: 128-bit vector reductions (4x fewer L2 atomics)
 #pragma unroll
-          for (int j = 0; j < 16; ++j) atomicAdd(orow + (long)(c0 + j) * a.col_stride, __uint_as_float(raw[j]));
+            for (int j = 0; j < 16; j += 4)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(orow + c0 + j), "f"(__uint_as_float(raw[j])),
+                           "f"(__uint_as_float(raw[j + 1])), "f"(__uint_as_float(raw[j + 2])),
+                           "f"(__uint_as_float(raw[j + 3]))
+                           : "memory");
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) atomicAdd(orow + (long)(c0 + j) * a.col_stride, __uint_as_float(raw[j]));
+          }
         }
       }
     }
@@ -352,9 +362,11 @@ extern "C" int vdn_wgrad(int kind, const void* src0, const void* src1, const voi
   const int m_tiles = ceil_div(a.atoms_total, a.atoms_per_tile);
   const int n_tiles = Cn / a.BN;
   const int base_ctas = m_tiles * n_tiles;
-  // split K (pixels) over CTAs to fill the machine, but keep >= 8 K steps per split: every split adds a
-  // full set of fp32 atomics on the output tile, which dominates at the low-resolution levels.
-  int splits = std::max(1, std::min(std::max(1, a.n_pix_tiles / 8), (2 * num_sms() + base_ctas - 1) / base_ctas));
+  // split K (pixels) over CTAs to fill the machine, but keep >= 4 K steps per split: every split adds a
+  // full set of fp32 reductions on the output tile (128-bit red.v4.f32 where the output row is contiguous).
+  static const int min_k = getenv("VDN_WG_MINK") ? std::max(1, atoi(getenv("VDN_WG_MINK"))) : 4;
+  static const int fill = getenv("VDN_WG_FILL") ? std::max(1, atoi(getenv("VDN_WG_FILL"))) : 2;
+  int splits = std::max(1, std::min(std::max(1, a.n_pix_tiles / min_k), (fill * num_sms() + base_ctas - 1) / base_ctas));
   a.tiles_per_split = ceil_div(a.n_pix_tiles, splits);
   splits = ceil_div(a.n_pix_tiles, a.tiles_per_split);
   const int a_bytes = a.atoms_per_tile * kKPix * a.cw * 2;
