@@ -132,6 +132,11 @@ int vdn_pack_batched(const void* jobs_dev, int n_jobs, long long total, void* st
  * --------------------------------------------------------------------------------- */
 int vdn_wgrad(int kind, const void* src0, const void* src1, const void* g, float* dw, int n_img, int H, int W,
               int n_src, int C, int Cout, int n_taps, const int* tap_dy, const int* tap_dx, void* stream);
+/* Same, plus the bias gradient dbias[Cout] += sum_pixels g[p] (fp32, may be NULL): computed inside the GEMM through
+ * a spare "ones" M atom when there is one, otherwise by a vdn_colsum pass. */
+int vdn_wgrad_bias(int kind, const void* src0, const void* src1, const void* g, float* dw, float* dbias, int n_img,
+                   int H, int W, int n_src, int C, int Cout, int n_taps, const int* tap_dy, const int* tap_dx,
+                   void* stream);
 /* test-only CUDA-core reference of the same contract */
 int vdn_wgrad_ref(int kind, const void* src0, const void* src1, const void* g, float* dw, int n_img, int H, int W,
                   int n_src, int C, int Cout, int n_taps, const int* tap_dy, const int* tap_dx, void* stream);
@@ -191,13 +196,16 @@ int vdn_mha_temporal_fused_fwd(const void* x, const void* w_hm, const float* bia
                                int B, int F, int H, int W, int C, void* stream);
 /* Tensor-core version of vdn_mha_temporal_fused_fwd (same contract): S = Q K^T and O = P V also run on
  * tcgen05 over the whole pixel tile (block-diagonal use of a 128x128 score tile). Instantiated for F in
- * {10, 16} (config_v2_2 / v2_3x), C % 32 == 0; vdn_mha_temporal_tc_supported tells. */
+ * {10, 16} (config_v2_2 / v2_3x), C % 32 == 0; for C == 32 and any F <= 16 a register-resident warp-MMA kernel
+ * (csrc/mha_mma.cu) takes over. vdn_mha_temporal_tc_supported tells. */
 int vdn_mha_temporal_tc_supported(int F, int C);
 int vdn_mha_temporal_tc_fwd(const void* x, const void* w_hm, const float* bias_hm, void* o, void* qkv, float* lse,
                             int B, int F, int H, int W, int C, void* stream);
-/* Tensor-core temporal attention core backward (S, dP, dQ, dK, dV as tcgen05 MMAs); F in {10, 16}. */
-int vdn_mha_temporal_tc_bwd(const void* qkv, const void* d_o, const float* lse, void* dqkv, int B, int F, int H, int W,
-                            void* stream);
+/* Tensor-core temporal attention core backward (S, dP, dQ, dK, dV), F <= 16: one warp per (pixel, head) on
+ * register-resident bf16 MMAs (csrc/mha_mma.cu). dbias (optional, fp32 [768], +=) receives the column sums of
+ * dqkv = the gradient of the q|k|v projection bias (modules.py:261-270), which saves a pass over dqkv. */
+int vdn_mha_temporal_tc_bwd(const void* qkv, const void* d_o, const float* lse, void* dqkv, float* dbias, int B, int F,
+                            int H, int W, void* stream);
 /* Temporal attention core backward in one kernel (smem exchange of k, v, q, dO; P and dS computed once):
  * qkv / lse / o from the forward, d_o bf16 [P][256] -> dqkv bf16 [P][768]. F <= 16. */
 int vdn_mha_temporal_bwd(const void* qkv, const void* o, const void* d_o, const float* lse, void* dqkv, int B, int F,

@@ -62,6 +62,12 @@ def test_wgrad_unit(n_img, H, W, c, cout, n_src):
         ops.wgrad(ops.VDN_TAP_UNIT, srcs, g, dw, taps)
         torch.cuda.synchronize()
         assert _rel(dw, ref) < 1e-4, f"taps={len(taps)}"
+        # with the fused bias gradient (ones atom in a spare M slot, or the colsum fallback)
+        dw2, db = torch.zeros_like(ref), torch.full((cout,), 0.5, device=DEV)
+        ops.wgrad(ops.VDN_TAP_UNIT, srcs, g, dw2, taps, dbias=db)
+        torch.cuda.synchronize()
+        assert _rel(dw2, ref) < 1e-4
+        assert _rel(db - 0.5, g.float().sum(dim=(0, 1, 2))) < 1e-4, f"bias taps={len(taps)}"
 
 
 @pytest.mark.parametrize("n_img,H,W,c", [(2, 32, 32, 32), (2, 16, 16, 128)])
@@ -76,9 +82,10 @@ def test_wgrad_down_and_up(n_img, H, W, c):
     y = F.conv2d(x.float().permute(0, 3, 1, 2), w, stride=2, padding=1)
     y.backward(g.float().permute(0, 3, 1, 2))
     ref = w.grad.permute(2, 3, 1, 0).reshape(16, c, c).contiguous()
-    dw = torch.zeros_like(ref)
-    ops.wgrad(ops.VDN_TAP_DOWN, [x], g, dw, ops.TAPS_4x4)
+    dw, db = torch.zeros_like(ref), torch.zeros(c, device=DEV)
+    ops.wgrad(ops.VDN_TAP_DOWN, [x], g, dw, ops.TAPS_4x4, dbias=db)
     assert _rel(dw, ref) < 1e-4
+    assert _rel(db, g.float().sum(dim=(0, 1, 2))) < 1e-4
     # transposed conv (flax, unflipped kernel): x (H x W) -> y (2H x 2W)
     x2 = _bf(n_img, H, W, c)
     g2 = _bf(n_img, 2 * H, 2 * W, c)
@@ -87,9 +94,10 @@ def test_wgrad_down_and_up(n_img, H, W, c):
     y2 = F.conv_transpose2d(x2.float().permute(0, 3, 1, 2), wt, stride=2, padding=1)
     y2.backward(g2.float().permute(0, 3, 1, 2))
     ref2 = wk.grad.reshape(16, c, c).contiguous()
-    dw2 = torch.zeros_like(ref2)
-    ops.wgrad(ops.VDN_TAP_UP, [x2], g2, dw2, ops.TAPS_4x4)
+    dw2, db2 = torch.zeros_like(ref2), torch.zeros(c, device=DEV)
+    ops.wgrad(ops.VDN_TAP_UP, [x2], g2, dw2, ops.TAPS_4x4, dbias=db2)
     assert _rel(dw2, ref2) < 1e-4
+    assert _rel(db2, g2.float().sum(dim=(0, 1, 2))) < 1e-4
     dw2r = torch.zeros_like(ref2)
     ops.wgrad(ops.VDN_TAP_UP, [x2], g2, dw2r, ops.TAPS_4x4, ref=True)
     assert _rel(dw2r, ref2) < 1e-4
@@ -215,8 +223,10 @@ def test_mha_core(mode, B, Fr, HW):
         assert _rel(dq2, qf.grad) < 2e-2
         if Fr <= 16:  # tensor-core backward (warp-level MMAs, any F <= 16)
             dq3 = torch.zeros_like(qkv)
-            ops.mha_temporal_tc_bwd(qkv, do, lse, dq3, B, Fr, side, side)
+            dbias = torch.zeros(768, device=DEV)
+            ops.mha_temporal_tc_bwd(qkv, do, lse, dq3, B, Fr, side, side, dbias=dbias)
             torch.cuda.synchronize()
+            assert _rel(dbias, qf.grad.sum(0)) < 2e-2   # fused gradient of the q|k|v projection bias
             for part, name in enumerate("qkv"):
                 e = _rel(dq3[:, part * 256:(part + 1) * 256], qf.grad[:, part * 256:(part + 1) * 256])
                 assert e < 3e-2, (name, e)   # P and dS are rounded to bf16 before the MMAs

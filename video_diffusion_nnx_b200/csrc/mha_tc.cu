@@ -608,12 +608,20 @@ static int launch_tc_bwd(const bf16* qkv, const bf16* d_o, const float* lse, bf1
 }  // namespace vdn
 
 // Same contract as vdn_mha_temporal_bwd (o is not needed: D_i = sum_j P_ij dP_ij). F in {10, 16}.
-extern "C" int vdn_mha_temporal_tc_bwd(const void* qkv, const void* d_o, const float* lse, void* dqkv, int B, int F,
-                                       int H, int W, void* stream) {
+extern "C" int vdn_colsum(const void* dy, float* db, long P, int C, void* stream);
+
+extern "C" int vdn_mha_temporal_tc_bwd(const void* qkv, const void* d_o, const float* lse, void* dqkv, float* dbias,
+                                       int B, int F, int H, int W, void* stream) {
   VDN_REQUIRE(qkv && d_o && lse && dqkv && F >= 1 && F <= 16, VDN_E_SHAPE, "mha_tc_bwd: bad args (F <= 16)");
   static const bool use_tcgen05 = getenv("VDN_MHA_TC_BWD") != nullptr;  // block-diagonal tcgen05 kernel (A/B only)
   if (!use_tcgen05)
-    return vdn::mha_temporal_mma_bwd_launch(qkv, d_o, lse, dqkv, B, F, H, W, reinterpret_cast<cudaStream_t>(stream));
+  {
+    // (accumulating the bias column sums inside the MMA kernel costs more than the separate pass: measured
+    //  +90 us on the 64x64 level from the extra live registers, vs 40 us for vdn_colsum)
+    int rc = vdn::mha_temporal_mma_bwd_launch(qkv, d_o, lse, dqkv, B, F, H, W, reinterpret_cast<cudaStream_t>(stream));
+    if (rc == 0 && dbias) rc = vdn_colsum(dqkv, dbias, (long)B * F * H * W, 768, stream);
+    return rc;
+  }
   VDN_REQUIRE(F == 10 || F == 16, VDN_E_SHAPE, "mha_tc_bwd: the tcgen05 kernel is instantiated for F in {10,16}");
   // The backward is bound by its per-row global loads / stores, not by the MMA chain: 120-row tiles (PX = 12)
   // measured slower than 80-row tiles, so it keeps power-of-two pixel counts (8 for F = 10 and F = 16).
@@ -623,5 +631,7 @@ extern "C" int vdn_mha_temporal_tc_bwd(const void* qkv, const void* d_o, const f
   const vdn::bf16* q = reinterpret_cast<const vdn::bf16*>(qkv);
   const vdn::bf16* g = reinterpret_cast<const vdn::bf16*>(d_o);
   vdn::bf16* dq = reinterpret_cast<vdn::bf16*>(dqkv);
-  return F == 10 ? vdn::launch_tc_bwd<10>(q, g, lse, dq, B, H, W, PX, st) : vdn::launch_tc_bwd<16>(q, g, lse, dq, B, H, W, PX, st);
+  int rc = F == 10 ? vdn::launch_tc_bwd<10>(q, g, lse, dq, B, H, W, PX, st) : vdn::launch_tc_bwd<16>(q, g, lse, dq, B, H, W, PX, st);
+  if (rc == 0 && dbias) rc = vdn_colsum(dqkv, dbias, (long)B * F * H * W, 768, stream);
+  return rc;
 }

@@ -45,6 +45,10 @@ struct WgArgs {
   float* out;
   long tap_stride, row_stride, col_stride;
   int tap_perm[16];
+  // bias gradient (column sums of the N-side tensor) for free: a spare M atom of the last M tile is filled
+  // with ones, so one accumulator row of that tile is sum_pixels g[p][n]
+  float* dbias;
+  int ones_tile;  // M tile holding the ones atom (its slot = first unused atom), or -1
 };
 
 template <int dummy>
@@ -75,6 +79,14 @@ __global__ void __launch_bounds__(kWgThreads) wgrad_kernel(const __grid_constant
   const int n_steps = t_end - t_begin;
 
   pdl_trigger();
+  const bool ones_here = a.dbias != nullptr && m_tile == a.ones_tile;
+  if (ones_here) {  // bf16 1.0 in every K row of the spare atom, in every stage (TMA never writes this slot)
+    for (int st = 0; st < S; ++st) {
+      uint32_t* dst = reinterpret_cast<uint32_t*>(smem + st * stage_bytes + n_atoms * atom_bytes_m);
+      for (int i = threadIdx.x; i < atom_bytes_m / 4; i += blockDim.x) dst[i] = 0x3F803F80u;
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // visible to the tensor-core (async) proxy
+  }
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < S; ++s) {
       mbar_init(&full_bar[s], 1);
@@ -188,10 +200,19 @@ __global__ void __launch_bounds__(kWgThreads) wgrad_kernel(const __grid_constant
       const long row = (long)src * a.src_c + chunk * a.cw + (r % a.cw);
       float* orow = a.out + a.tap_perm[tap] * a.tap_stride + row * a.row_stride + (long)(n_tile * a.BN) * a.col_stride;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+      const bool bias_row = ones_here && r == n_atoms * a.cw;  // first row of the ones atom = column sums of g
       for (int c0 = 0; c0 < a.BN; c0 += 16) {
         uint32_t raw[16];
         tmem_ld_32x16(taddr + (uint32_t)c0, raw);
         tmem_ld_wait();
+        if (bias_row) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(a.dbias + n_tile * a.BN + c0 + j),
+                         "f"(__uint_as_float(raw[j])), "f"(__uint_as_float(raw[j + 1])), "f"(__uint_as_float(raw[j + 2])),
+                         "f"(__uint_as_float(raw[j + 3]))
+                         : "memory");
+        }
         if (valid) {
           if (a.col_stride == 1) {  // contiguous output row: 128-bit vector reductions (4x fewer L2 atomics)
 #pragma unroll
@@ -268,9 +289,20 @@ using namespace vdn;
 // kind VDN_TAP_DOWN: src (n_img,2H,2W,C),       g (n_img,H,W,Cout), taps = kernel indices (ky,kx) in 0..3
 // kind VDN_TAP_UP  : src (n_img,H,W,C),         g (n_img,2H,2W,Cout), taps = kernel indices (a,b) in 0..3
 // dw: fp32 [n_taps][n_src*C][Cout] (reference kernel layout), accumulated into (+=).
+extern "C" int vdn_colsum(const void* dy, float* db, long P, int C, void* stream);
+extern "C" int vdn_wgrad_bias(int kind, const void* src0, const void* src1, const void* g, float* dw, float* dbias,
+                              int n_img, int H, int W, int n_src, int C, int Cout, int n_taps, const int* tap_dy,
+                              const int* tap_dx, void* stream);
+
 extern "C" int vdn_wgrad(int kind, const void* src0, const void* src1, const void* g, float* dw, int n_img, int H,
                          int W, int n_src, int C, int Cout, int n_taps, const int* tap_dy, const int* tap_dx,
                          void* stream) {
+  return vdn_wgrad_bias(kind, src0, src1, g, dw, nullptr, n_img, H, W, n_src, C, Cout, n_taps, tap_dy, tap_dx, stream);
+}
+
+extern "C" int vdn_wgrad_bias(int kind, const void* src0, const void* src1, const void* g, float* dw, float* dbias,
+                              int n_img, int H, int W, int n_src, int C, int Cout, int n_taps, const int* tap_dy,
+                              const int* tap_dx, void* stream) {
   VDN_REQUIRE(kind >= 0 && kind <= 2 && src0 && g && dw, VDN_E_SHAPE, "wgrad: bad args");
   VDN_REQUIRE(n_taps >= 1 && n_taps <= 16 && (n_src == 1 || (n_src == 2 && src1 && kind == VDN_TAP_UNIT)), VDN_E_SHAPE,
               "wgrad: bad taps/sources");
@@ -361,6 +393,18 @@ extern "C" int vdn_wgrad(int kind, const void* src0, const void* src1, const voi
 
   const int m_tiles = ceil_div(a.atoms_total, a.atoms_per_tile);
   const int n_tiles = Cn / a.BN;
+  // bias gradient: through a ones atom when the last M tile has a spare slot and the gradient is the N side
+  a.dbias = nullptr;
+  a.ones_tile = -1;
+  bool bias_by_colsum = false;
+  if (dbias) {
+    if (!swap && a.atoms_total % a.atoms_per_tile != 0) {
+      a.dbias = dbias;
+      a.ones_tile = m_tiles - 1;
+    } else {
+      bias_by_colsum = true;
+    }
+  }
   const int base_ctas = m_tiles * n_tiles;
   // split K (pixels) over CTAs to fill the machine, but keep >= 4 K steps per split: every split adds a
   // full set of fp32 reductions on the output tile (128-bit red.v4.f32 where the output row is contiguous).
@@ -386,7 +430,12 @@ extern "C" int vdn_wgrad(int kind, const void* src0, const void* src1, const voi
   cudaError_t le = launch_pdl(wgrad_kernel<0>, dim3(m_tiles, n_tiles, splits), dim3(kWgThreads), (size_t)smem_bytes,
                               reinterpret_cast<cudaStream_t>(stream), 1, maps, a);
   VDN_REQUIRE(le == cudaSuccess, VDN_E_CUDA, "wgrad launch: %s", cudaGetErrorString(le));
-  return check_launch("wgrad_kernel");
+  rc = check_launch("wgrad_kernel");
+  if (rc == 0 && bias_by_colsum) {
+    const long Pg = kind == VDN_TAP_UP ? 4 * P : P;  // the gradient of the transposed conv lives on the 2H x 2W grid
+    rc = vdn_colsum(g, dbias, Pg, Cout, stream);
+  }
+  return rc;
 }
 
 extern "C" int vdn_wgrad_ref(int kind, const void* src0, const void* src1, const void* g, float* dw, int n_img, int H,

@@ -184,9 +184,9 @@ class GemmConv:
                         out2=outs[1], split_col=self.c_src)
 
     def wgrad(self, srcs, dy, bias_done=False):
-        ops.wgrad(VDN_TAP_UNIT, srcs, dy, self.dw, self.taps)
-        if self.dbias is not None and not bias_done:
-            ops.colsum(dy, self.dbias, dy.numel() // self.cout, self.cout)
+        # the bias gradient (column sums of dy) rides on the weight-gradient GEMM (spare "ones" M atom)
+        ops.wgrad(VDN_TAP_UNIT, srcs, dy, self.dw, self.taps,
+                  dbias=self.dbias if (self.dbias is not None and not bias_done) else None)
 
 
 class ResBlock:
@@ -409,8 +409,7 @@ class DownConv:
 
     def backward(self, dy, acc):
         """acc (same shape as x) += dgrad(dy); returns acc."""
-        ops.wgrad(VDN_TAP_DOWN, [self.x], dy, self.dw, TAPS_4x4)
-        ops.colsum(dy, self.dbias, dy.numel() // self.C, self.C)
+        ops.wgrad(VDN_TAP_DOWN, [self.x], dy, self.dw, TAPS_4x4, dbias=self.dbias)
         for py, px, shifts, _, wd in self.cls:
             ops.tapgemm(VDN_TAP_UP, [dy], wd, shifts, residual=acc, out=acc, py=py, px=px)
         return acc
@@ -447,8 +446,7 @@ class UpConv:
 
     def backward(self, dy):
         pool = self.eng.pool
-        ops.wgrad(VDN_TAP_UP, [self.x], dy, self.dw, TAPS_4x4)
-        ops.colsum(dy, self.dbias, dy.numel() // self.C, self.C)
+        ops.wgrad(VDN_TAP_UP, [self.x], dy, self.dw, TAPS_4x4, dbias=self.dbias)
         dx = pool.get(self.x.shape)
         ops.tapgemm(VDN_TAP_DOWN, [dy], self.wd, TAPS_4x4, out=dx)
         return dx

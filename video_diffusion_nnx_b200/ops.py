@@ -75,7 +75,8 @@ def tapgemm(kind: int, srcs: Sequence[torch.Tensor], wp: torch.Tensor, taps, *, 
 # ------------------------------------------------------------------------------------------
 # wgrad
 # ------------------------------------------------------------------------------------------
-def wgrad(kind: int, srcs: Sequence[torch.Tensor], g: torch.Tensor, dw: torch.Tensor, taps, ref: bool = False) -> None:
+def wgrad(kind: int, srcs: Sequence[torch.Tensor], g: torch.Tensor, dw: torch.Tensor, taps, ref: bool = False,
+          dbias: Optional[torch.Tensor] = None) -> None:
     """dw[tap][n_src*C][Cout] (fp32, reference kernel layout) += sum_pixels src[p + tap]^T g[p]."""
     x0 = srcs[0]
     assert x0.dtype == torch.bfloat16 and g.dtype == torch.bfloat16 and dw.dtype == torch.float32
@@ -94,6 +95,10 @@ def wgrad(kind: int, srcs: Sequence[torch.Tensor], g: torch.Tensor, dw: torch.Te
     assert dw.numel() == len(taps) * len(srcs) * Cs * cout
     dy = (C.c_int * len(taps))(*[t[0] for t in taps])
     dx = (C.c_int * len(taps))(*[t[1] for t in taps])
+    if dbias is not None and not ref:
+        check(lib.vdn_wgrad_bias(kind, ptr(x0), ptr(srcs[1]) if len(srcs) > 1 else None, ptr(g), ptr(dw), ptr(dbias),
+                                 n_img, H, W, len(srcs), Cs, cout, len(taps), dy, dx, stream_ptr()), "vdn_wgrad_bias")
+        return
     fn = lib.vdn_wgrad_ref if ref else lib.vdn_wgrad
     check(fn(kind, ptr(x0), ptr(srcs[1]) if len(srcs) > 1 else None, ptr(g), ptr(dw), n_img, H, W, len(srcs), Cs,
              cout, len(taps), dy, dx, stream_ptr()), "vdn_wgrad")
@@ -307,6 +312,6 @@ def mha_temporal_tc_fwd(x, w_hm, bias_hm, o, qkv, lse, B, F, H, W, Cc):
                                       stream_ptr()), "vdn_mha_temporal_tc_fwd")
 
 
-def mha_temporal_tc_bwd(qkv, d_o, lse, dqkv, B, F, H, W):
-    check(lib.vdn_mha_temporal_tc_bwd(ptr(qkv), ptr(d_o), ptr(lse), ptr(dqkv), B, F, H, W, stream_ptr()),
+def mha_temporal_tc_bwd(qkv, d_o, lse, dqkv, B, F, H, W, dbias=None):
+    check(lib.vdn_mha_temporal_tc_bwd(ptr(qkv), ptr(d_o), ptr(lse), ptr(dqkv), ptr(dbias), B, F, H, W, stream_ptr()),
           "vdn_mha_temporal_tc_bwd")
