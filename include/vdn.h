@@ -110,7 +110,8 @@ int vdn_tapgemm_ref(const vdn_tapgemm_desc* d, const void* src0, const void* src
 
 /* ---------------------------------------------------------------------------------
  * Batched repack: every packed operand of a model in one launch. jobs_dev points to a device
- * array of vdn_pack_job (begin = exclusive prefix sum of taps*cin*cout); total = sum of sizes.
+ * array of vdn_pack_job; the work unit is a 32 x 32 (cin x cout) tile of one tap: begin = exclusive prefix sum of
+ * taps*ceil(cin/32)*ceil(cout/32), total = the sum over all jobs.
  * --------------------------------------------------------------------------------- */
 typedef struct {
   const float* src; /* fp32 [taps][cin][cout] */
@@ -269,6 +270,12 @@ int vdn_p_sample(const float* x, const float* eps, const float* z, const int* t,
                  int C, long FHW, int clip, void* stream);
 int vdn_randn(float* out, long n, unsigned long long seed, unsigned long long subseq, unsigned long long elem_offset,
               void* stream);
+/* Device-resident sampling loop (p_sample_loop, gaussian_diffusion.py:311-316): the same draws as vdn_randn with
+ * (seed, subseq_add, elem_offset) = params_dev[0..2] and subseq = subseq_add + t_dev[0], all read on the device
+ * (elem_offset must be a multiple of 4), and t_dev[b] -= 1; both are captured in the per-timestep CUDA graph so
+ * that a timestep is one graph replay with no host-side argument update, for any key. */
+int vdn_randn_t(float* out, long n, const unsigned long long* params_dev, const int* t_dev, void* stream);
+int vdn_countdown(int* t_dev, int B, void* stream);
 
 /* ---------------------------------------------------------------------------------
  * Training glue: bias gradients (column sums of a bf16 [P][C] gradient, +=), bf16 add, and the fused

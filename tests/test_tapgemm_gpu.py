@@ -168,3 +168,27 @@ def test_up_conv_transpose_k4s2(n_img, H, W, c):
             ops.pack_weight(w, wp, 4, c, c, 0, kidx)
             ops.tapgemm(ops.VDN_TAP_UP, [x], wp, shifts, bias=bias, out=out, py=py, px=px, out_dtype=torch.float32)
     _check(out, ref.contiguous(), 1e-4)
+
+
+def test_pack_batched_matches_pack_weight():
+    """The one-launch tiled repack (fp32 [taps][cin][cout] -> bf16 K-major operands, both modes, ragged tiles,
+    tap permutation) against the single-job kernel."""
+    from video_diffusion_nnx_b200 import ops
+
+    _setup()
+    jobs, refs = [], []
+    for taps, cin, cout, mode, perm in [(9, 48, 80, 0, None), (9, 48, 80, 1, [8 - t for t in range(9)]),
+                                        (1, 32, 768, 0, None), (4, 64, 64, 1, [5, 7, 13, 15]), (16, 16, 16, 0, None)]:
+        n_src_taps = 16 if perm and max(perm) > taps - 1 else taps
+        w = torch.randn(n_src_taps, cin, cout, device="cuda")
+        rows, k = (cout, taps * cin) if mode == 0 else (cin, taps * cout)
+        dst = torch.zeros(rows, k, dtype=torch.bfloat16, device="cuda")
+        ref = torch.zeros_like(dst)
+        ops.pack_weight(w, ref, taps, cin, cout, mode, perm)
+        jobs.append((w, dst, taps, cin, cout, mode, perm))
+        refs.append(ref)
+    table, n, total = ops.make_pack_table(jobs, "cuda")
+    ops.pack_batched(table, n, total)
+    torch.cuda.synchronize()
+    for (_, dst, *_), ref in zip(jobs, refs):
+        assert torch.equal(dst, ref)

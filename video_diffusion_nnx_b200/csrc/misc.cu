@@ -603,6 +603,31 @@ __global__ void randn_kernel(float* __restrict__ out, long n, unsigned long long
   }
 }
 
+// Device-resident timestep variant for the captured sampling loop (gaussian_diffusion.py:311-316): the Philox
+// subsequence is subseq_mul * t + subseq_add with t read from device memory, so one CUDA graph serves every
+// timestep with no host-side argument changes.
+__global__ void randn_t_kernel(float* __restrict__ out, long n, const unsigned long long* __restrict__ prm,
+                               const int* __restrict__ t) {
+  const unsigned long long seed = prm[0], elem_offset = prm[2];
+  const unsigned long long subseq = prm[1] + (unsigned long long)t[0];
+  const long n4 = (n + 3) / 4;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
+    curandStatePhilox4_32_10_t st;
+    curand_init(seed, subseq, 4ull * (unsigned long long)(elem_offset / 4 + i), &st);
+    const float4 z = curand_normal4(&st);
+    const long b = i * 4;
+    if (b + 0 < n) out[b + 0] = z.x;
+    if (b + 1 < n) out[b + 1] = z.y;
+    if (b + 2 < n) out[b + 2] = z.z;
+    if (b + 3 < n) out[b + 3] = z.w;
+  }
+}
+// t[b] -= 1 for the next replay of the sampling graph (the reverse loop counts T-1 .. 0)
+__global__ void countdown_kernel(int* __restrict__ t, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B) t[b] -= 1;
+}
+
 static int ew_grid(long n, int threads = 256) {
   return (int)std::max<long>(1, std::min<long>((n + threads - 1) / threads, (long)num_sms() * 8));
 }
@@ -755,6 +780,18 @@ extern "C" int vdn_randn(float* out, long n, unsigned long long seed, unsigned l
   VDN_REQUIRE(out && n > 0 && elem_offset % 4 == 0, VDN_E_SHAPE, "randn: bad args (elem_offset must be a multiple of 4)");
   randn_kernel<<<ew_grid((n + 3) / 4), 256, 0, ST(stream)>>>(out, n, seed, subseq, elem_offset);
   return check_launch("randn");
+}
+
+extern "C" int vdn_randn_t(float* out, long n, const unsigned long long* params_dev, const int* t_dev, void* stream) {
+  VDN_REQUIRE(out && t_dev && params_dev && n > 0, VDN_E_SHAPE, "randn_t: bad args");
+  randn_t_kernel<<<ew_grid((n + 3) / 4), 256, 0, ST(stream)>>>(out, n, params_dev, t_dev);
+  return check_launch("randn_t");
+}
+
+extern "C" int vdn_countdown(int* t_dev, int B, void* stream) {
+  VDN_REQUIRE(t_dev && B > 0, VDN_E_SHAPE, "countdown: bad args");
+  countdown_kernel<<<(B + 127) / 128, 128, 0, ST(stream)>>>(t_dev, B);
+  return check_launch("countdown");
 }
 
 extern "C" int vdn_adam_ema(float* p, const float* g, float* m, float* v, float* ema, const float* hp_dev, long n,

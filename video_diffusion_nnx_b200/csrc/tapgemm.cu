@@ -507,27 +507,51 @@ __global__ void pack_weight_kernel(const float* __restrict__ src, bf16* __restri
 
 namespace vdn {
 
-// All weight repacks of a model in ONE launch: each 256-element chunk locates its job by binary search.
+// All weight repacks of a model in ONE launch. Work unit = one 32 x 32 (cin x cout) tile of one tap of one
+// job; a block locates its job by binary search over the tile prefix sums. The tile goes through shared
+// memory so that BOTH the fp32 reads (cout fastest in the reference layout) and the bf16 writes (K fastest in
+// the packed operand: cin for the forward operand, cout for the dgrad operand) are coalesced.
 __global__ void __launch_bounds__(256) pack_batched_kernel(const vdn_pack_job* __restrict__ jobs, int n_jobs,
-                                                           long long total) {
-  for (long long c0 = (long long)blockIdx.x * 256; c0 < total; c0 += (long long)gridDim.x * 256) {
-    const long long i = c0 + threadIdx.x;
-    if (i >= total) continue;
+                                                           long long total_tiles) {
+  __shared__ float tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (long long tid = blockIdx.x; tid < total_tiles; tid += gridDim.x) {
     int lo = 0, hi = n_jobs - 1;
     while (lo < hi) {
       const int mid = (lo + hi + 1) >> 1;
-      if (jobs[mid].begin <= i) lo = mid; else hi = mid - 1;
+      if (jobs[mid].begin <= tid) lo = mid; else hi = mid - 1;
     }
     const vdn_pack_job& a = jobs[lo];
-    const long long r = i - a.begin;
-    const int kin = a.mode == 0 ? a.cin : a.cout;
-    const int k = (int)(r % kin);
-    const int t = (int)((r / kin) % a.taps);
-    const int n = (int)(r / ((long long)kin * a.taps));
-    const int ci = a.mode == 0 ? k : n;
-    const int co = a.mode == 0 ? n : k;
-    const float v = a.src[((long)a.perm[t] * a.cin + ci) * a.cout + co];
-    reinterpret_cast<bf16*>(a.dst)[(long)(a.n_off + n) * a.ld + a.k_off + (long)t * kin + k] = __float2bfloat16(v);
+    const int tiles_ci = (a.cin + 31) >> 5, tiles_co = (a.cout + 31) >> 5;
+    int r = (int)(tid - a.begin);
+    const int co0 = (r % tiles_co) * 32;
+    r /= tiles_co;
+    const int ci0 = (r % tiles_ci) * 32;
+    const int t = r / tiles_ci;
+    const float* src = a.src + (long)a.perm[t] * a.cin * a.cout;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int ci = ci0 + ty + 8 * q, co = co0 + tx;
+      tile[ty + 8 * q][tx] = (ci < a.cin && co < a.cout) ? src[(long)ci * a.cout + co] : 0.f;
+    }
+    __syncthreads();
+    bf16* dst = reinterpret_cast<bf16*>(a.dst);
+    if (a.mode == 0) {  // dst[(n_off + co)*ld + k_off + t*cin + ci]: ci fastest
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int co = co0 + ty + 8 * q, ci = ci0 + tx;
+        if (ci < a.cin && co < a.cout)
+          dst[(long)(a.n_off + co) * a.ld + a.k_off + (long)t * a.cin + ci] = __float2bfloat16(tile[tx][ty + 8 * q]);
+      }
+    } else {            // dst[(n_off + ci)*ld + k_off + t*cout + co]: co fastest
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int ci = ci0 + ty + 8 * q, co = co0 + tx;
+        if (ci < a.cin && co < a.cout)
+          dst[(long)(a.n_off + ci) * a.ld + a.k_off + (long)t * a.cout + co] = __float2bfloat16(tile[ty + 8 * q][tx]);
+      }
+    }
+    __syncthreads();
   }
 }
 
@@ -769,7 +793,7 @@ extern "C" int vdn_tapgemm_ref(const vdn_tapgemm_desc* d, const void* src0, cons
 
 extern "C" int vdn_pack_batched(const void* jobs_dev, int n_jobs, long long total, void* stream) {
   VDN_REQUIRE(jobs_dev && n_jobs > 0 && total > 0, VDN_E_SHAPE, "pack_batched: bad args");
-  const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 16);
+  const int blocks = (int)std::min<long long>(total, 148 * 16);
   pack_batched_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const vdn_pack_job*>(jobs_dev), n_jobs, total);
   return check_launch("pack_batched_kernel");

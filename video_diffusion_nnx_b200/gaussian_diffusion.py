@@ -183,36 +183,58 @@ class GaussianDiffusion:
         per_sample = shape[1] * shape[2] * shape[3] * shape[4]
         assert per_sample % 4 == 0
         loop_key, init_key = key.split(2)
-        img = self._normal(shape, init_key, sample_offset * per_sample)
         T = self.num_timesteps if timesteps is None else timesteps
-        eng = self.denoise_fn.engine(B, self.num_frames, self.image_size, self.image_size, training=False)
-        t_dev = torch.empty(B, dtype=torch.int32, device=self.device)
-        z = torch.empty(shape, dtype=torch.float32, device=self.device)
-        nxt = torch.empty_like(img)
+        FHW = per_sample // shape[1]
+        # Per-batch-size sampler state: persistent buffers + ONE captured graph of a whole timestep
+        # (Philox z drawn from the device-resident t, Unet forward, posterior update, t -= 1). A timestep is a
+        # single graph replay with no host-side argument update; the graph is reused across calls.
+        st = self._samplers.get(B) if hasattr(self, "_samplers") else None
+        if not hasattr(self, "_samplers"):
+            self._samplers = {}
+        if st is None:
+            st = {"eng": self.denoise_fn.engine(B, self.num_frames, self.image_size, self.image_size, training=False),
+                  "img": torch.empty(shape, dtype=torch.float32, device=self.device),
+                  "t": torch.empty(B, dtype=torch.int32, device=self.device),
+                  "z": torch.empty(shape, dtype=torch.float32, device=self.device),
+                  "nxt": torch.empty(shape, dtype=torch.float32, device=self.device),
+                  "prm": torch.zeros(3, dtype=torch.int64, device=self.device), "graph": None}
+            self._samplers[B] = st
+        eng, img, t_dev, z, nxt = st["eng"], st["img"], st["t"], st["z"], st["nxt"]
+        img.copy_(self._normal(shape, init_key, sample_offset * per_sample))
         tabs = [self.table(n) for n in ("sqrt_recip_alphas_cumprod", "sqrt_recipm1_alphas_cumprod",
                                         "posterior_mean_coef1", "posterior_mean_coef2",
                                         "posterior_log_variance_clipped")]
-        FHW = per_sample // shape[1]
+        # z_i = Philox(seed, stream*4099 + i + 1, global element offset): the three values live in device memory
+        seed64 = loop_key.seed & (2 ** 64 - 1)
+        prm_host = torch.tensor([seed64 - 2 ** 64 if seed64 >= 2 ** 63 else seed64, loop_key.stream * 4099 + 1,
+                                 sample_offset * per_sample], dtype=torch.int64)
+        st["prm"].copy_(prm_host)
+        prm = st["prm"]
 
         def body():
+            ops.randn_t(z, prm, t_dev)
             eps = eng.forward(img, t_dev)
             ops.p_sample(img, eps, z, t_dev, *tabs, nxt, B, shape[1], FHW, True)
             img.copy_(nxt)
+            ops.countdown(t_dev)
 
-        graph = None
-        for n, i in enumerate(reversed(range(T))):
-            t_dev.fill_(i)
-            ops.randn(z, loop_key.seed, loop_key.stream * 4099 + i + 1, sample_offset * per_sample)
-            if use_graph and n == 1 and graph is None:
+        t_dev.fill_(T - 1)
+        if not use_graph:
+            for _ in range(T):
+                body()
+        else:
+            if st["graph"] is None:
+                body()  # one eager timestep (also warms every lazily-built operand)
                 torch.cuda.synchronize()
                 graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(graph):
                     body()
-                graph.replay()
-            elif graph is not None:
-                graph.replay()
-            else:
-                body()
+                st["graph"] = graph
+                # restart from the initial state: the eager + captured steps consumed two timesteps
+                img.copy_(self._normal(shape, init_key, sample_offset * per_sample))
+                t_dev.fill_(T - 1)
+            for _ in range(T):
+                st["graph"].replay()
         return (img + 1) * 0.5  # unnormalize_img, utils.py:259-268
 
     def sample(self, key, cond=None, cond_scale: float = 1.0, batch_size: int = 16, **kw):

@@ -261,6 +261,16 @@ def randn(out, seed: int, subseq: int = 0, elem_offset: int = 0):
                         C.c_ulonglong(elem_offset), stream_ptr()), "vdn_randn")
 
 
+def randn_t(out, params_dev, t_dev):
+    """As randn() with (seed, subseq_add, elem_offset) = params_dev[0..2] (int64 device tensor) and
+    subseq = subseq_add + t_dev[0], all read on the device (graph-capturable countdown)."""
+    check(lib.vdn_randn_t(ptr(out), C.c_long(out.numel()), ptr(params_dev), ptr(t_dev), stream_ptr()), "vdn_randn_t")
+
+
+def countdown(t_dev):
+    check(lib.vdn_countdown(ptr(t_dev), t_dev.numel(), stream_ptr()), "vdn_countdown")
+
+
 class PackJob(C.Structure):
     _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("taps", C.c_int), ("cin", C.c_int), ("cout", C.c_int),
                 ("mode", C.c_int), ("ld", C.c_int), ("n_off", C.c_int), ("k_off", C.c_int), ("perm", C.c_int * 16),
@@ -269,7 +279,7 @@ class PackJob(C.Structure):
 
 def make_pack_table(jobs, device):
     """jobs: list of (src fp32 tensor, dst bf16 2-D tensor, taps, cin, cout, mode, perm|None). Returns
-    (device table, n_jobs, total elements) for pack_batched()."""
+    (device table, n_jobs, total 32x32 tiles) for pack_batched()."""
     arr = (PackJob * len(jobs))()
     begin = 0
     for i, (src, dst, taps, cin, cout, mode, perm) in enumerate(jobs):
@@ -279,7 +289,7 @@ def make_pack_table(jobs, device):
         for t in range(16):
             a.perm[t] = perm[t] if (perm is not None and t < len(perm)) else t
         a.begin = begin
-        begin += taps * cin * cout
+        begin += taps * ((cin + 31) // 32) * ((cout + 31) // 32)
     host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
     return host.to(device), len(jobs), begin
 
