@@ -5,7 +5,7 @@
 // m16n8k16 fragments of a single warp, so everything between the global loads and the global stores lives
 // in registers - no shared memory, no TMEM, no barriers:
 //   S   = Q K^T          dP   = dO V^T         (rows = query tokens)
-//   S^T = K Q^T          dP^T = V dO^T         (rows = key tokens; recomputed instead of transposed)
+//   P^T, dS^T            8x8-tile transposes of the fragments (movmatrix), rows = key tokens
 //   P = exp(S/sqrt(d) - lse),  D = rowsum(P dP),  dS = P (dP - D)/sqrt(d)
 //   dQ = dS K            dK = dS^T Q           dV = P^T dO
 // Operand access uses the same permuted-fragment trick as sla_mma.cu: with the contraction index over the 32
@@ -62,11 +62,16 @@ __device__ __forceinline__ void load_tokwords(TokWords& w, const bf16* base, lon
     }
   }
 }
-// out[16 x 32] = A[16 x 16 tokens] * X[16 tokens x 32]: A as C-fragments of two 8-column tiles (rows g / g+8),
-// X as token words. o[t][i]: n-tile t (features 2n | 2n+1 | 2n+16 | 2n+17), fragment element i.
-__device__ __forceinline__ void frag_times_tokens(const float (&a)[2][4], const TokWords& x, float (&o)[4][4]) {
-  const uint32_t a0 = pack_bf16x2(a[0][0], a[0][1]), a1 = pack_bf16x2(a[0][2], a[0][3]);
-  const uint32_t a2 = pack_bf16x2(a[1][0], a[1][1]), a3 = pack_bf16x2(a[1][2], a[1][3]);
+// transpose of an 8x8 bf16 tile held one 32-bit register per lane (row = lane/4, columns 2*(lane%4), +1)
+__device__ __forceinline__ uint32_t movmatrix_trans(uint32_t a) {
+  uint32_t d;
+  asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(d) : "r"(a));
+  return d;
+}
+// out[16 x 32] = A[16 x 16 tokens] * X[16 tokens x 32]: A as packed A-fragment registers {a0,a1,a2,a3}, X as token
+// words. o[t][i]: n-tile t (features 2n | 2n+1 | 2n+16 | 2n+17), fragment element i.
+__device__ __forceinline__ void afrag_times_tokens(const uint32_t (&af)[4], const TokWords& x, float (&o)[4][4]) {
+  const uint32_t a0 = af[0], a1 = af[1], a2 = af[2], a3 = af[3];
   uint32_t b[4][2];
   b[0][0] = __byte_perm(x.w0[0], x.w0[1], 0x5410); b[0][1] = __byte_perm(x.w0[2], x.w0[3], 0x5410);
   b[1][0] = __byte_perm(x.w0[0], x.w0[1], 0x7632); b[1][1] = __byte_perm(x.w0[2], x.w0[3], 0x7632);
@@ -78,6 +83,12 @@ __device__ __forceinline__ void frag_times_tokens(const float (&a)[2][4], const 
     for (int i = 0; i < 4; ++i) o[t][i] = 0.f;
     mma16816(o[t], a0, a1, a2, a3, b[t][0], b[t][1]);
   }
+}
+// same with A given as C-fragments of two 8-column tiles (rows g / g+8)
+__device__ __forceinline__ void frag_times_tokens(const float (&a)[2][4], const TokWords& x, float (&o)[4][4]) {
+  const uint32_t af[4] = {pack_bf16x2(a[0][0], a[0][1]), pack_bf16x2(a[0][2], a[0][3]), pack_bf16x2(a[1][0], a[1][1]),
+                          pack_bf16x2(a[1][2], a[1][3])};
+  afrag_times_tokens(af, x, o);
 }
 // Stores the [16 x 32] result fragments of frag_times_tokens: per row two 8-byte pieces (features 4j..4j+3 and
 // 4j+16..4j+19).
@@ -168,28 +179,20 @@ __global__ void __launch_bounds__(256) mha_temporal_mma_bwd_kernel(const bf16* _
     frag_times_tokens(dS, wk, o);  // dQ = dS K
     store_rows(o, dqkv + r_lo * 768 + h * 32, dqkv + r_hi * 768 + h * 32, v_lo, v_hi, j);
 
-    // ---- key-major pass: P^T, dS^T (rows = key tokens g / g+8, columns = query tokens) ----
-    float ST[2][4], dPT[2][4];
-    chunk_abt(k_lo, k_hi, q_lo, q_hi, ST);
-    chunk_abt(vv_lo, vv_hi, g_lo, g_hi, dPT);
-#pragma unroll
-    for (int t = 0; t < 2; ++t)
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const int qc = 2 * j + i;  // query column within the tile; its L and D sit in the lanes of row qc
-        const float Lc = __shfl_sync(0xffffffffu, t == 0 ? L_lo : L_hi, 4 * qc);
-        const float Dc = __shfl_sync(0xffffffffu, t == 0 ? D_lo : D_hi, 4 * qc);
-        const bool cv = 8 * t + qc < F;
-        const float p_lo = (cv && v_lo) ? __expf(ST[t][i] * scale - Lc) : 0.f;
-        const float p_hi = (cv && v_hi) ? __expf(ST[t][2 + i] * scale - Lc) : 0.f;
-        ST[t][i] = p_lo;
-        ST[t][2 + i] = p_hi;
-        dPT[t][i] = p_lo * (dPT[t][i] - Dc) * scale;        // dS^T
-        dPT[t][2 + i] = p_hi * (dPT[t][2 + i] - Dc) * scale;
-      }
-    frag_times_tokens(dPT, wq, o);  // dK = dS^T Q
+    // ---- key-major operands: P^T and dS^T are the 8x8-tile transposes of the query-major fragments
+    //      (movmatrix), A fragment = {T(q0-7 x k0-7), T(q0-7 x k8-15), T(q8-15 x k0-7), T(q8-15 x k8-15)} ----
+    uint32_t pT[4], dsT[4];
+    pT[0] = movmatrix_trans(pack_bf16x2(S[0][0], S[0][1]));
+    pT[1] = movmatrix_trans(pack_bf16x2(S[1][0], S[1][1]));
+    pT[2] = movmatrix_trans(pack_bf16x2(S[0][2], S[0][3]));
+    pT[3] = movmatrix_trans(pack_bf16x2(S[1][2], S[1][3]));
+    dsT[0] = movmatrix_trans(pack_bf16x2(dS[0][0], dS[0][1]));
+    dsT[1] = movmatrix_trans(pack_bf16x2(dS[1][0], dS[1][1]));
+    dsT[2] = movmatrix_trans(pack_bf16x2(dS[0][2], dS[0][3]));
+    dsT[3] = movmatrix_trans(pack_bf16x2(dS[1][2], dS[1][3]));
+    afrag_times_tokens(dsT, wq, o);  // dK = dS^T Q
     store_rows(o, dqkv + r_lo * 768 + 256 + h * 32, dqkv + r_hi * 768 + 256 + h * 32, v_lo, v_hi, j);
-    frag_times_tokens(ST, wg, o);   // dV = P^T dO
+    afrag_times_tokens(pT, wg, o);   // dV = P^T dO
     store_rows(o, dqkv + r_lo * 768 + 512 + h * 32, dqkv + r_hi * 768 + 512 + h * 32, v_lo, v_hi, j);
   }
 }
@@ -198,7 +201,7 @@ __global__ void __launch_bounds__(256) mha_temporal_mma_bwd_kernel(const bf16* _
 // Fused forward for C = 32: QKV projection + attention core of one (pixel, head) per warp, all in registers
 // (reference: modules.py:285-323; same contract as vdn_mha_temporal_fused_fwd).
 //   q|k|v = x W_h + b_h     [F x 32] each  (x rows as 16-byte chunk operands, weights as B fragments)
-//   v^T   = W_v^T x^T       (recomputed transposed: the B operand of P V contracts over tokens)
+//   v^T                     8x8-tile transposes of the v registers (movmatrix): the B operand of P V
 //   S = q k^T / sqrt(32), P = softmax(S), O = P V, lse = max + log(sum)
 // The output-feature order of each projection is permuted (by choosing which weight row feeds which
 // fragment column) so that a lane's accumulator registers ARE the 16-byte chunk j of token rows g / g+8:
@@ -258,42 +261,6 @@ __device__ __forceinline__ void project_chunks(const uint4& x_lo, const uint4& x
   hi = make_uint4(h[0], h[1], h[2], h[3]);
 }
 
-struct ProjWT {
-  uint32_t a[2][2][4];  // [m-tile][k-step][4]  A fragments of W^T x^T (row g + 8r of m-tile u = feature rho(u, r, g))
-  float bias[2][2];     // bias of rows g, g+8
-};
-// rho: feature held by row g + 8r of m-tile u  ->  P V lands in the chunk layout (lane j: features 8j .. 8j+7)
-__device__ __forceinline__ int rho(int u, int r, int g) { return 8 * (g >> 1) + 2 * (2 * u + r) + (g & 1); }
-__device__ __forceinline__ void load_projwt(ProjWT& w, const bf16* w_rows, const float* bias, int g, int j) {
-#pragma unroll
-  for (int u = 0; u < 2; ++u) {
-    const uint32_t* r0 = reinterpret_cast<const uint32_t*>(w_rows + rho(u, 0, g) * 32);
-    const uint32_t* r1 = reinterpret_cast<const uint32_t*>(w_rows + rho(u, 1, g) * 32);
-#pragma unroll
-    for (int s = 0; s < 2; ++s) {
-      w.a[u][s][0] = __ldg(r0 + 4 * j + 2 * s);
-      w.a[u][s][1] = __ldg(r1 + 4 * j + 2 * s);
-      w.a[u][s][2] = __ldg(r0 + 4 * j + 2 * s + 1);
-      w.a[u][s][3] = __ldg(r1 + 4 * j + 2 * s + 1);
-    }
-    w.bias[u][0] = __ldg(bias + rho(u, 0, g));
-    w.bias[u][1] = __ldg(bias + rho(u, 1, g));
-  }
-}
-
-constexpr int kProjWTWords = 20;  // 16 fragment words + 4 bias floats
-__device__ __forceinline__ void store_projwt(uint32_t* sm, const ProjWT& w, int lane) {
-#pragma unroll
-  for (int u = 0; u < 2; ++u) {
-#pragma unroll
-    for (int s = 0; s < 2; ++s)
-#pragma unroll
-      for (int q = 0; q < 4; ++q) sm[((u * 2 + s) * 4 + q) * 32 + lane] = w.a[u][s][q];
-    sm[(16 + 2 * u) * 32 + lane] = __float_as_uint(w.bias[u][0]);
-    sm[(16 + 2 * u + 1) * 32 + lane] = __float_as_uint(w.bias[u][1]);
-  }
-}
-
 template <bool kWriteQkv>
 __global__ void __launch_bounds__(256, 2) mha_temporal_mma_fwd_kernel(const bf16* __restrict__ x,
                                                                    const bf16* __restrict__ w_hm,
@@ -308,24 +275,18 @@ __global__ void __launch_bounds__(256, 2) mha_temporal_mma_fwd_kernel(const bf16
   const long n_pix = (long)B * HW;
   const bool v_lo = g < F, v_hi = g + 8 < F;
   extern __shared__ uint32_t sm_w[];  // per head: q | k | v^T (| v) fragment sets
-  constexpr int kHeadWords = (2 * kProjWords + kProjWTWords + (kWriteQkv ? kProjWords : 0)) * 32;
+  constexpr int kHeadWords = 3 * kProjWords * 32;
   uint32_t* s_q = sm_w + h * kHeadWords;
   uint32_t* s_k = s_q + kProjWords * 32;
-  uint32_t* s_vt = s_k + kProjWords * 32;
-  uint32_t* s_v = s_vt + kProjWTWords * 32;
+  uint32_t* s_v = s_k + kProjWords * 32;
   {
     ProjW w;
     load_projw(w, w_hm + (h * 96) * 32, bias_hm + h * 96, g, j);
     store_projw(s_q, w, lane);
     load_projw(w, w_hm + (h * 96 + 32) * 32, bias_hm + h * 96 + 32, g, j);
     store_projw(s_k, w, lane);
-    if (kWriteQkv) {
-      load_projw(w, w_hm + (h * 96 + 64) * 32, bias_hm + h * 96 + 64, g, j);
-      store_projw(s_v, w, lane);
-    }
-    ProjWT wt;
-    load_projwt(wt, w_hm + (h * 96 + 64) * 32, bias_hm + h * 96 + 64, g, j);
-    store_projwt(s_vt, wt, lane);
+    load_projw(w, w_hm + (h * 96 + 64) * 32, bias_hm + h * 96 + 64, g, j);
+    store_projw(s_v, w, lane);
   }
   __syncwarp();
   const uint4 zero4 = make_uint4(0, 0, 0, 0);
@@ -354,9 +315,9 @@ __global__ void __launch_bounds__(256, 2) mha_temporal_mma_fwd_kernel(const bf16
     uint4 q_lo, q_hi, k_lo, k_hi;
     project_chunks(x_lo, x_hi, s_q, lane, q_lo, q_hi);
     project_chunks(x_lo, x_hi, s_k, lane, k_lo, k_hi);
+    uint4 vv_lo, vv_hi;
+    project_chunks(x_lo, x_hi, s_v, lane, vv_lo, vv_hi);
     if (kWriteQkv) {  // training: the backward reads q | k | v
-      uint4 vv_lo, vv_hi;
-      project_chunks(x_lo, x_hi, s_v, lane, vv_lo, vv_hi);
       if (v_lo) {
         uint4* pr = reinterpret_cast<uint4*>(qkv + r_lo * 768 + h * 32) + j;
         pr[0] = q_lo;
@@ -370,20 +331,13 @@ __global__ void __launch_bounds__(256, 2) mha_temporal_mma_fwd_kernel(const bf16
         pr[64] = vv_hi;
       }
     }
-    // v^T[feature][token]: A = W_v^T fragments, B = x^T = the x chunks of tokens 8t + g
-    float vt[2][2][4];
-#pragma unroll
-    for (int u = 0; u < 2; ++u)
-#pragma unroll
-      for (int t = 0; t < 2; ++t) {
-        vt[u][t][0] = vt[u][t][1] = __uint_as_float(s_vt[(16 + 2 * u) * 32 + lane]);
-        vt[u][t][2] = vt[u][t][3] = __uint_as_float(s_vt[(16 + 2 * u + 1) * 32 + lane]);
-        const uint4& xb = t == 0 ? x_lo : x_hi;
-        mma16816(vt[u][t], s_vt[((u * 2 + 0) * 4 + 0) * 32 + lane], s_vt[((u * 2 + 0) * 4 + 1) * 32 + lane],
-                 s_vt[((u * 2 + 0) * 4 + 2) * 32 + lane], s_vt[((u * 2 + 0) * 4 + 3) * 32 + lane], xb.x, xb.y);
-        mma16816(vt[u][t], s_vt[((u * 2 + 1) * 4 + 0) * 32 + lane], s_vt[((u * 2 + 1) * 4 + 1) * 32 + lane],
-                 s_vt[((u * 2 + 1) * 4 + 2) * 32 + lane], s_vt[((u * 2 + 1) * 4 + 3) * 32 + lane], xb.z, xb.w);
-      }
+    // B fragments of P V (contraction over tokens) = 8x8-tile transposes of the v chunk registers (movmatrix):
+    // n-tile t holds the features psi(t, .) of the chunk layout, so O lands in the chunk layout as well
+    uint32_t vb[4][2];
+    vb[0][0] = movmatrix_trans(vv_lo.x); vb[0][1] = movmatrix_trans(vv_hi.x);
+    vb[1][0] = movmatrix_trans(vv_lo.y); vb[1][1] = movmatrix_trans(vv_hi.y);
+    vb[2][0] = movmatrix_trans(vv_lo.z); vb[2][1] = movmatrix_trans(vv_hi.z);
+    vb[3][0] = movmatrix_trans(vv_lo.w); vb[3][1] = movmatrix_trans(vv_hi.w);
     // S = q k^T, softmax over the key tokens (columns 8t + 2j + i)
     float S[2][4];
     chunk_abt(q_lo, q_hi, k_lo, k_hi, S);
@@ -416,16 +370,14 @@ __global__ void __launch_bounds__(256, 2) mha_temporal_mma_fwd_kernel(const bf16
     l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 2);
     l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 1);
     l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 2);
-    // O = P V: A = P fragments, B = v^T fragments (tokens 2j,2j+1 | 8+2j,9+2j of feature rho(u, r, g))
+    // O = P V: A = P fragments (keys 2j,2j+1 | 8+2j,9+2j), B = transposed v tiles
     const uint32_t a0 = pack_bf16x2(S[0][0], S[0][1]), a1 = pack_bf16x2(S[0][2], S[0][3]);
     const uint32_t a2 = pack_bf16x2(S[1][0], S[1][1]), a3 = pack_bf16x2(S[1][2], S[1][3]);
     float o_lo[8], o_hi[8];
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {  // n-tile t = (u, r) = (t / 2, t % 2)
-      const int u = t >> 1, r = t & 1;
+    for (int t = 0; t < 4; ++t) {
       float c[4] = {0.f, 0.f, 0.f, 0.f};
-      mma16816(c, a0, a1, a2, a3, pack_bf16x2(vt[u][0][2 * r], vt[u][0][2 * r + 1]),
-               pack_bf16x2(vt[u][1][2 * r], vt[u][1][2 * r + 1]));
+      mma16816(c, a0, a1, a2, a3, vb[t][0], vb[t][1]);
       o_lo[2 * t] = c[0];
       o_lo[2 * t + 1] = c[1];
       o_hi[2 * t] = c[2];
@@ -458,7 +410,7 @@ int mha_temporal_mma_fwd_launch(const void* x, const void* w_hm, const float* bi
   const long HW = (long)H * W;
   const long n_pix = (long)B * HW;
   const int grid = (int)std::min<long>(n_pix, 148L * 16);
-  const size_t smem_t = (size_t)8 * (3 * kProjWords + kProjWTWords) * 32 * 4, smem_i = (size_t)8 * (2 * kProjWords + kProjWTWords) * 32 * 4;
+  const size_t smem_t = (size_t)8 * 3 * kProjWords * 32 * 4, smem_i = smem_t;
   static bool cfg = false;
   if (!cfg) {
     cudaFuncSetAttribute(mha_temporal_mma_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t);
