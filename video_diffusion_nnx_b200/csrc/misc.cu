@@ -121,9 +121,17 @@ __global__ void __launch_bounds__(256) init_conv_wgrad_kernel(const float* __res
         if (j < per_thr && tc < n_tc) {
           const int t = tc / Cin, ci = tc % Cin;
           const float* xr = sX + (ci * hs + t / ks) * hs + t % ks;
-          float a = 0.f;
-          for (int p = 0; p < 256; ++p) a = fmaf(xr[(p / kIT) * hs + p % kIT], sD[p * 33 + col], a);
-          acc[j] += a;
+          // four independent chains: the loop is bound by the smem load latency, not by the FMAs
+          float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 4
+          for (int p = 0; p < 256; p += 4) {
+            const float* xp = xr + (p / kIT) * hs + p % kIT;  // kIT is a multiple of 4: p..p+3 share a tile row
+            a0 = fmaf(xp[0], sD[p * 33 + col], a0);
+            a1 = fmaf(xp[1], sD[(p + 1) * 33 + col], a1);
+            a2 = fmaf(xp[2], sD[(p + 2) * 33 + col], a2);
+            a3 = fmaf(xp[3], sD[(p + 3) * 33 + col], a3);
+          }
+          acc[j] += (a0 + a1) + (a2 + a3);
         }
       }
     }
@@ -303,36 +311,55 @@ __global__ void __launch_bounds__(256) time_mlp_bwd_kernel(const float* __restri
                                                            float* __restrict__ dw2, float* __restrict__ db2,
                                                            float* __restrict__ dh1_ws /*[B][4dim]*/, int B, int dim) {
   const int td = 4 * dim;
-  // dw2[k][j] = sum_b gelu(h1[b][k]) dt[b][j] ; db2[j] = sum_b dt[b][j]
-  for (long i = threadIdx.x; i < (long)td * td; i += blockDim.x) {
-    const int k = (int)(i / td), j = (int)(i % td);
-    float a = 0.f;
-    for (int b = 0; b < B; ++b) a = fmaf(gelu_tanh_f(h1[(long)b * td + k]), dt[(long)b * td + j], a);
-    dw2[i] += a;
-  }
-  for (int j = threadIdx.x; j < td; j += blockDim.x) {
-    float a = 0.f;
-    for (int b = 0; b < B; ++b) a += dt[(long)b * td + j];
-    db2[j] += a;
-  }
-  // dh1[b][k] = gelu'(h1) * sum_j w2[k][j] dt[b][j]
+  // Every block first rebuilds dh1 (B x td, tiny) and gelu(h1), dt in shared memory, then owns a slice of the
+  // weight-gradient elements: the work is a few hundred kFLOP, so the kernel is pure latency and one block of
+  // 256 threads (the previous shape) took 120 us.
+  extern __shared__ float smt[];
+  float* s_dt = smt;                 // [B][td]
+  float* s_g = smt + B * td;         // gelu(h1) [B][td]
+  float* s_dh = smt + 2 * B * td;    // dh1 [B][td]
   for (int i = threadIdx.x; i < B * td; i += blockDim.x) {
-    const int b = i / td, k = i % td;
-    float a = 0.f;
-    for (int j = 0; j < td; ++j) a = fmaf(w2[(long)k * td + j], dt[(long)b * td + j], a);
-    dh1_ws[i] = a * gelu_tanh_grad_f(h1[i]);
+    s_dt[i] = dt[i];
+    s_g[i] = gelu_tanh_f(h1[i]);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < dim * td; i += blockDim.x) {
-    const int k = i / td, j = i % td;
+  // dh1[b][k] = gelu'(h1) * sum_j w2[k][j] dt[b][j]: one warp per (b, k), lanes over j
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
+  for (int i = warp; i < B * td; i += n_warps) {
+    const int b = i / td, k = i % td;
     float a = 0.f;
-    for (int b = 0; b < B; ++b) a = fmaf(emb[(long)b * dim + k], dh1_ws[(long)b * td + j], a);
+    for (int j = lane; j < td; j += 32) a = fmaf(w2[(long)k * td + j], s_dt[b * td + j], a);
+    a = warp_sum(a);
+    if (lane == 0) {
+      const float v = a * gelu_tanh_grad_f(h1[i]);
+      s_dh[i] = v;
+      if (blockIdx.x == 0) dh1_ws[i] = v;
+    }
+  }
+  __syncthreads();
+  const long gtid = (long)blockIdx.x * blockDim.x + threadIdx.x, gsz = (long)gridDim.x * blockDim.x;
+  // dw2[k][j] = sum_b gelu(h1[b][k]) dt[b][j] ; db2[j] = sum_b dt[b][j]
+  for (long i = gtid; i < (long)td * td; i += gsz) {
+    const int k = (int)(i / td), j = (int)(i % td);
+    float a = 0.f;
+    for (int b = 0; b < B; ++b) a = fmaf(s_g[b * td + k], s_dt[b * td + j], a);
+    dw2[i] += a;
+  }
+  // dw1[k][j] = sum_b emb[b][k] dh1[b][j] ; db1[j] = sum_b dh1[b][j]
+  for (long i = gtid; i < (long)dim * td; i += gsz) {
+    const int k = (int)(i / td), j = (int)(i % td);
+    float a = 0.f;
+    for (int b = 0; b < B; ++b) a = fmaf(emb[(long)b * dim + k], s_dh[b * td + j], a);
     dw1[i] += a;
   }
-  for (int j = threadIdx.x; j < td; j += blockDim.x) {
-    float a = 0.f;
-    for (int b = 0; b < B; ++b) a += dh1_ws[(long)b * td + j];
-    db1[j] += a;
+  for (long j = gtid; j < td; j += gsz) {
+    float a = 0.f, c = 0.f;
+    for (int b = 0; b < B; ++b) {
+      a += s_dt[b * td + j];
+      c += s_dh[b * td + j];
+    }
+    db2[j] += a;
+    db1[j] += c;
   }
 }
 
@@ -660,7 +687,7 @@ extern "C" int vdn_init_conv_wgrad(const float* x, const void* dy, float* dw, fl
   const int hs = kIT + ks - 1;
   const size_t smem = (size_t)(Cin * hs * hs + 256 * 33) * sizeof(float);
   const int n_tiles = (H / kIT) * (W / kIT);
-  const int tpb = std::max(1, std::min(4, n_tiles));
+  const int tpb = 1;  // one 16x16 tile per block: 640 blocks at v2_2 (the kernel is latency bound, not atomic bound)
   init_conv_wgrad_kernel<<<dim3(ceil_div(n_tiles, tpb), B * F), 256, smem, ST(stream)>>>(
       x, reinterpret_cast<const bf16*>(dy), dw, dbias, B, Cin, F, H, W, Cout, ks, tpb);
   return check_launch("init_conv_wgrad");
@@ -708,7 +735,11 @@ extern "C" int vdn_time_mlp_fwd(const int* time, const float* w1, const float* b
 
 extern "C" int vdn_time_mlp_bwd(const float* dt, const float* emb, const float* h1, const float* w2, float* dw1,
                                 float* db1, float* dw2, float* db2, float* dh1_ws, int B, int dim, void* stream) {
-  time_mlp_bwd_kernel<<<1, 256, 0, ST(stream)>>>(dt, emb, h1, w2, dw1, db1, dw2, db2, dh1_ws, B, dim);
+  const int td = 4 * dim;
+  const size_t smem = (size_t)3 * B * td * sizeof(float);
+  VDN_REQUIRE(smem <= 48 * 1024, VDN_E_SHAPE, "time_mlp_bwd: B=%d dim=%d does not fit shared memory", B, dim);
+  const int blocks = std::max(1, std::min(148, (td * td + 255) / 256));
+  time_mlp_bwd_kernel<<<blocks, 256, smem, ST(stream)>>>(dt, emb, h1, w2, dw1, db1, dw2, db2, dh1_ws, B, dim);
   return check_launch("time_mlp_bwd");
 }
 
