@@ -227,6 +227,8 @@ def main():
     ap.add_argument("--no-sampling", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sample-timesteps", type=int, default=CFG["timesteps"])
+    ap.add_argument("--sample-batch", type=int, default=16,
+                    help="samples per GPU in the sampling metric (16 = the reference default, gaussian_diffusion.py:323)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
@@ -346,7 +348,7 @@ def main():
     # ---------------- sampling metric (frames/s of the full T-step loop) ----------------
     if not args.no_sampling:
         net.train(False)
-        sb = B
+        sb = args.sample_batch
         T = args.sample_timesteps
         gd.p_sample_loop((sb,), 11, sample_offset=rank * sb, timesteps=4)  # warm-up + capture path
         barrier()

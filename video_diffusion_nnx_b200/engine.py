@@ -249,10 +249,11 @@ class ResBlock:
         ops.gn_silu_bwd(dout, self.b_raw, self.sums2, self.p["block_2.norm.scale"], self.p["block_2.norm.bias"], None,
                         T, db_raw, self.g["block_2.norm.scale"], self.g["block_2.norm.bias"], None, B, self.rows, C,
                         dconv_bias=self.conv2.dbias)
-        self.conv2.wgrad([self.a], db_raw, bias_done=True)
+        # weight gradients are off the critical path: they run on the side stream, overlapped with the
+        # data-gradient chain below, and are joined before their operands go back to the pool
+        h2 = eng.side(lambda: self.conv2.wgrad([self.a], db_raw, bias_done=True))
         da = pool.get(shape)
         self.conv2.dgrad(db_raw, [da])
-        pool.put(db_raw)
         da_raw = pool.get(shape)
         dss = eng.dss[:, self.ss_off:self.ss_off + 2 * C] if self.ss_off is not None else None
         ops.gn_silu_bwd(da, self.a_raw, self.sums1, self.p["block_1.norm.scale"], self.p["block_1.norm.bias"],
@@ -260,15 +261,18 @@ class ResBlock:
                         self.rows, C, dconv_bias=self.conv1.dbias)
         pool.put(da)
         pool.put(T)
-        self.conv1.wgrad(self.srcs, da_raw, bias_done=True)
+        h1 = eng.side(lambda: self.conv1.wgrad(self.srcs, da_raw, bias_done=True))
         sshape = (self.n_img, self.H, self.W, self.c_src)
         dsrc = [pool.get(sshape) for _ in range(self.n_src)]
+        hr = None
         if self.res is not None:
-            self.res.wgrad(self.srcs, ds)
+            hr = eng.side(lambda: self.res.wgrad(self.srcs, ds))
             self.conv1.dgrad(da_raw, dsrc)
             self.res.dgrad(ds, dsrc, residuals=dsrc)  # in-place accumulate
         else:
             self.conv1.dgrad(da_raw, dsrc, residuals=[ds])
+        eng.join(h2, h1, hr)
+        pool.put(db_raw)
         pool.put(ds)
         pool.put(da_raw)
         if extra is not None:
@@ -317,7 +321,7 @@ class MHABlock:
 
     def backward(self, dout):
         eng, pool = self.eng, self.eng.pool
-        self.out_proj.wgrad([self.o], dout)
+        ho = eng.side(lambda: self.out_proj.wgrad([self.o], dout))
         do = pool.get(self.o.shape)
         self.out_proj.dgrad(dout, [do])
         dqkv = pool.get(self.qkv.shape)
@@ -332,9 +336,10 @@ class MHABlock:
                              self.H * self.W)
             pool.put(D)
         pool.put(do)
-        self.qkv_proj.wgrad([self.x], dqkv)
+        hq = eng.side(lambda: self.qkv_proj.wgrad([self.x], dqkv))
         dx = pool.get(self.x.shape)
         self.qkv_proj.dgrad(dqkv, [dx], residuals=[dout])
+        eng.join(ho, hq)  # dout belongs to the caller, dqkv to the pool
         pool.put(dqkv)
         return dx
 
@@ -363,8 +368,8 @@ class SLABlock:
         return self.out
 
     def backward(self, dout):
-        pool = self.eng.pool
-        self.out_proj.wgrad([self.tok], dout)
+        eng, pool = self.eng, self.eng.pool
+        ho = eng.side(lambda: self.out_proj.wgrad([self.tok], dout))
         dtok = pool.get(self.tok.shape)
         self.out_proj.dgrad(dout, [dtok])
         dqkv = pool.get(self.qkv.shape)
@@ -372,9 +377,10 @@ class SLABlock:
         ops.sla_core_bwd(self.qkv, dtok, self.ctx, self.kstat, dctx, dqkv, self.n_img, self.H * self.W)
         pool.put(dtok)
         pool.put(dctx)
-        self.qkv_proj.wgrad([self.x], dqkv)
+        hq = eng.side(lambda: self.qkv_proj.wgrad([self.x], dqkv))
         dx = pool.get(self.x.shape)
         self.qkv_proj.dgrad(dqkv, [dx], residuals=[dout])
+        eng.join(ho, hq)
         pool.put(dqkv)
         return dx
 
@@ -409,9 +415,10 @@ class DownConv:
 
     def backward(self, dy, acc):
         """acc (same shape as x) += dgrad(dy); returns acc."""
-        ops.wgrad(VDN_TAP_DOWN, [self.x], dy, self.dw, TAPS_4x4, dbias=self.dbias)
+        hw = self.eng.side(lambda: ops.wgrad(VDN_TAP_DOWN, [self.x], dy, self.dw, TAPS_4x4, dbias=self.dbias))
         for py, px, shifts, _, wd in self.cls:
             ops.tapgemm(VDN_TAP_UP, [dy], wd, shifts, residual=acc, out=acc, py=py, px=px)
+        self.eng.join(hw)
         return acc
 
 
@@ -446,9 +453,10 @@ class UpConv:
 
     def backward(self, dy):
         pool = self.eng.pool
-        ops.wgrad(VDN_TAP_UP, [self.x], dy, self.dw, TAPS_4x4, dbias=self.dbias)
+        hw = self.eng.side(lambda: ops.wgrad(VDN_TAP_UP, [self.x], dy, self.dw, TAPS_4x4, dbias=self.dbias))
         dx = pool.get(self.x.shape)
         ops.tapgemm(VDN_TAP_DOWN, [dy], self.wd, TAPS_4x4, out=dx)
+        self.eng.join(hw)
         return dx
 
 
@@ -456,6 +464,28 @@ class UpConv:
 # the engine
 # ------------------------------------------------------------------------------------------
 class UnetEngine:
+    def side(self, fn):
+        """Runs fn() on the side stream, ordered after everything enqueued so far on the current stream; returns
+        an event to join(). Works eagerly and under CUDA-graph capture (fork / join edges of the graph)."""
+        if self.side_stream is None:
+            fn()
+            return None
+        main = torch.cuda.current_stream()
+        ev = torch.cuda.Event()
+        ev.record(main)
+        self.side_stream.wait_event(ev)
+        with torch.cuda.stream(self.side_stream):
+            fn()
+            done = torch.cuda.Event()
+            done.record(self.side_stream)
+        return done
+
+    def join(self, *handles):
+        main = torch.cuda.current_stream()
+        for h in handles:
+            if h is not None:
+                main.wait_event(h)
+
     def __init__(self, store: ParamStore, *, dim: int, channels: int, dim_mults=(1, 2, 4, 8), init_kernel_size=7,
                  B: int, F: int, H: int, W: int, training: bool, out_dim: Optional[int] = None):
         self.store, self.device, self.training = store, store.flat.device, training
@@ -465,6 +495,10 @@ class UnetEngine:
         self.pack_jobs = []
         self.extra_packers = []
         self.pool = _Pool(self.device)
+        # second stream for the weight-gradient GEMMs (see side() / join()); VDN_NO_OVERLAP=1 serialises them
+        import os
+        self.side_stream = (torch.cuda.Stream(device=self.device)
+                            if training and self.device.type == "cuda" and not os.environ.get("VDN_NO_OVERLAP") else None)
         self._gn_slots: List[torch.Tensor] = []
         self._gn_count = 0
         self._heads: List[dict] = []
