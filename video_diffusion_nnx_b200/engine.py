@@ -221,15 +221,17 @@ class ResBlock:
     def forward(self, srcs):
         eng, B = self.eng, self.eng.B
         self.srcs = list(srcs)
+        hres = None
+        if self.res is not None:  # the 1x1 residual projection is independent of the conv chain: side stream
+            hres = eng.side(lambda: self.res.fwd(srcs, self.s))
+            s = self.s
+        else:
+            s = srcs[0]
         self.conv1.fwd(srcs, self.a_raw, gn_sums=self.sums1, rows_per_sample=self.rows)
         ops.gn_silu_fwd(self.a_raw, self.sums1, self.p["block_1.norm.scale"], self.p["block_1.norm.bias"], self._ss(),
                         self.a, B, self.rows, self.cout)
         self.conv2.fwd([self.a], self.b_raw, gn_sums=self.sums2, rows_per_sample=self.rows)
-        if self.res is not None:
-            self.res.fwd(srcs, self.s)
-            s = self.s
-        else:
-            s = srcs[0]
+        eng.join(hres)
         ops.resblock_tail_fwd(self.b_raw, self.sums2, self.p["block_2.norm.scale"], self.p["block_2.norm.bias"], s,
                               self.p["norm_2.scale"], self.p["norm_2.bias"], self.out, B, self.rows, self.cout)
         return self.out
@@ -243,7 +245,9 @@ class ResBlock:
         P = self.n_img * self.H * self.W
         s = self.s if self.res is not None else self.srcs[0]
         ds = pool.get(shape)
-        ops.ln_bwd(s, dout, self.p["norm_2.scale"], ds, self.g["norm_2.scale"], self.g["norm_2.bias"], P, C)
+        # LayerNorm backward of the residual branch does not depend on the GroupNorm chain: side stream
+        hln = eng.side(lambda: ops.ln_bwd(s, dout, self.p["norm_2.scale"], ds, self.g["norm_2.scale"],
+                                          self.g["norm_2.bias"], P, C))
         T = pool.get((B, C, 2), F32)
         db_raw = pool.get(shape)
         ops.gn_silu_bwd(dout, self.b_raw, self.sums2, self.p["block_2.norm.scale"], self.p["block_2.norm.bias"], None,
@@ -266,10 +270,12 @@ class ResBlock:
         dsrc = [pool.get(sshape) for _ in range(self.n_src)]
         hr = None
         if self.res is not None:
-            hr = eng.side(lambda: self.res.wgrad(self.srcs, ds))
+            hr = eng.side(lambda: self.res.wgrad(self.srcs, ds))  # same stream as ln_bwd: ordered after it
             self.conv1.dgrad(da_raw, dsrc)
+            eng.join(hln)
             self.res.dgrad(ds, dsrc, residuals=dsrc)  # in-place accumulate
         else:
+            eng.join(hln)
             self.conv1.dgrad(da_raw, dsrc, residuals=[ds])
         eng.join(h2, h1, hr)
         pool.put(db_raw)
@@ -498,7 +504,7 @@ class UnetEngine:
         # second stream for the weight-gradient GEMMs (see side() / join()); VDN_NO_OVERLAP=1 serialises them
         import os
         self.side_stream = (torch.cuda.Stream(device=self.device)
-                            if training and self.device.type == "cuda" and not os.environ.get("VDN_NO_OVERLAP") else None)
+                            if self.device.type == "cuda" and not os.environ.get("VDN_NO_OVERLAP") else None)
         self._gn_slots: List[torch.Tensor] = []
         self._gn_count = 0
         self._heads: List[dict] = []
