@@ -72,6 +72,30 @@ __device__ __forceinline__ void chunk_matmul(const uint4& lo, const uint4& hi, c
   }
 }
 
+// the same with the fragment set in shared memory, laid out [(s*4 + t)*2 + r][32 lanes]
+__device__ __forceinline__ void store_bfrag(uint32_t* sb, const BFrag& f, int lane) {
+#pragma unroll
+  for (int s = 0; s < 2; ++s)
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      sb[((s * 4 + t) * 2 + 0) * 32 + lane] = f.r[s][t][0];
+      sb[((s * 4 + t) * 2 + 1) * 32 + lane] = f.r[s][t][1];
+    }
+}
+__device__ __forceinline__ void chunk_matmul_s(const uint4& lo, const uint4& hi, const uint32_t* sb, int lane,
+                                               float (&olo)[8], float (&ohi)[8]) {
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    float d[4] = {0.f, 0.f, 0.f, 0.f};
+    mma_bf16_16816(d, lo.x, hi.x, lo.y, hi.y, sb[((0 * 4 + t) * 2 + 0) * 32 + lane], sb[((0 * 4 + t) * 2 + 1) * 32 + lane]);
+    mma_bf16_16816(d, lo.z, hi.z, lo.w, hi.w, sb[((1 * 4 + t) * 2 + 0) * 32 + lane], sb[((1 * 4 + t) * 2 + 1) * 32 + lane]);
+    olo[2 * t] = d[0];
+    olo[2 * t + 1] = d[1];
+    ohi[2 * t] = d[2];
+    ohi[2 * t + 1] = d[3];
+  }
+}
+
 __device__ __forceinline__ void unpack_chunk(const uint4& q, float (&v)[8]) {
   float2 f;
   f = unpack_bf16x2(q.x); v[0] = f.x; v[1] = f.y;
@@ -151,48 +175,65 @@ __global__ void __launch_bounds__(256) sla_apply_mma_kernel(const bf16* __restri
 // ---------------------------------------------------------------------------------------
 // backward, per token: dq, dk, dv from ctx, dctx and the k statistics (m, S).
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) sla_bwd_tokens_mma_kernel(const bf16* __restrict__ qkv,
+__global__ void __launch_bounds__(256, 2) sla_bwd_tokens_mma_kernel(const bf16* __restrict__ qkv,
                                                                  const bf16* __restrict__ dtok,
                                                                  const float* __restrict__ ctx,
                                                                  const float* __restrict__ dctx,
                                                                  const float* __restrict__ kstat,
                                                                  bf16* __restrict__ dqkv, int N) {
-  extern __shared__ float smem[];
-  float* sctx = smem;                // [8][32][32]
-  float* sdctx = smem + 8 * 1024;    // [8][32][32]
-  float* sm_m = smem + 16 * 1024;    // [8][32]
-  float* sm_is = sm_m + 256;         // [8][32]  1/S
-  float* sm_r = sm_is + 256;         // [8][32]  r[d] = sum_e dctx[d][e]*ctx[d][e]
+  // The three B-fragment sets of the warp's head live in shared memory as [16 words][32 lanes] (lane innermost:
+  // conflict-free) - in registers they cost 48 per thread and cap the kernel at 8 warps per SM, too few to cover
+  // the global-load latency of a kernel that should run at HBM speed.
+  extern __shared__ uint32_t smem_b[];
   pdl_trigger();
   pdl_wait();
   const int img = blockIdx.y;
-  for (int i = threadIdx.x; i < 8 * 1024; i += blockDim.x) {
-    sctx[i] = ctx[(long)img * 8 * 1024 + i];
-    sdctx[i] = dctx[(long)img * 8 * 1024 + i];
-  }
-  __syncthreads();
-  {
-    const int hh = threadIdx.x >> 5, dd = threadIdx.x & 31;
-    sm_m[threadIdx.x] = kstat[((long)img * kSmHeads + hh) * 64 + dd];
-    sm_is[threadIdx.x] = 1.f / kstat[((long)img * kSmHeads + hh) * 64 + 32 + dd];
-    float r = 0.f;
-    for (int e = 0; e < 32; ++e) r += sdctx[hh * 1024 + dd * 32 + e] * sctx[hh * 1024 + dd * 32 + e];
-    sm_r[threadIdx.x] = r;
-  }
-  __syncthreads();
   const int h = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, j = lane & 3;
-  BFrag b_ctxT, b_dctxT, b_dctx;
-  load_bfrag(b_ctxT, sctx + h * 1024, 1, 32, g, j);    // B[k = e][n = d] = ctx[d][e]    (dq~ = dtok ctx^T)
-  load_bfrag(b_dctxT, sdctx + h * 1024, 1, 32, g, j);  // B[k = e][n = d] = dctx[d][e]   (dk~ = v dctx^T)
-  load_bfrag(b_dctx, sdctx + h * 1024, 32, 1, g, j);   // B[k = d][n = e] = dctx[d][e]   (dv = k~ dctx)
-  float km[8], kis[8], kr[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    km[i] = sm_m[h * 32 + 8 * j + i];
-    kis[i] = sm_is[h * 32 + 8 * j + i];
-    kr[i] = sm_r[h * 32 + 8 * j + i];
+  // stage ctx / dctx of the frame through the same shared memory (coalesced), build the fragments in registers,
+  // then overwrite the staging area with the lane-major fragment sets
+  float* stage = reinterpret_cast<float*>(smem_b);  // [2][8][32][32] fp32 = 64 KB
+  {
+    const float4* c4 = reinterpret_cast<const float4*>(ctx + (long)img * kSmHeads * 1024);
+    const float4* d4 = reinterpret_cast<const float4*>(dctx + (long)img * kSmHeads * 1024);
+    for (int i = threadIdx.x; i < 2048; i += blockDim.x) {
+      reinterpret_cast<float4*>(stage)[i] = __ldg(c4 + i);
+      reinterpret_cast<float4*>(stage + 8192)[i] = __ldg(d4 + i);
+    }
   }
+  __syncthreads();
+  const float* ch = stage + h * 1024;
+  const float* dch = stage + 8192 + h * 1024;
+  BFrag f_ctxT, f_dctxT, f_dctx;
+  load_bfrag(f_ctxT, ch, 1, 32, g, j);    // B[k = e][n = d] = ctx[d][e]    (dq~ = dtok ctx^T)
+  load_bfrag(f_dctxT, dch, 1, 32, g, j);  // B[k = e][n = d] = dctx[d][e]   (dk~ = v dctx^T)
+  load_bfrag(f_dctx, dch, 32, 1, g, j);   // B[k = d][n = e] = dctx[d][e]   (dv = k~ dctx)
+  float km[8], kis[8], kr[8];
+  {
+    // r[d] = sum_e dctx[d][e] * ctx[d][e]: lane = d, then broadcast the lane's 8 features through shuffles
+    float r = 0.f;
+    for (int e = 0; e < 32; ++e) {
+      const int ee = (e + lane) & 31;  // rotated: conflict-free shared-memory reads
+      r = fmaf(dch[lane * 32 + ee], ch[lane * 32 + ee], r);
+    }
+    const float m = kstat[((long)img * kSmHeads + h) * 64 + lane];
+    const float is = 1.f / kstat[((long)img * kSmHeads + h) * 64 + 32 + lane];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      km[i] = __shfl_sync(0xffffffffu, m, 8 * j + i);
+      kis[i] = __shfl_sync(0xffffffffu, is, 8 * j + i);
+      kr[i] = __shfl_sync(0xffffffffu, r, 8 * j + i);
+    }
+  }
+  __syncthreads();  // every warp is done reading the staging area
+  uint32_t* sb = smem_b + h * (3 * 16 * 32);
+  store_bfrag(sb, f_ctxT, lane);
+  store_bfrag(sb + 16 * 32, f_dctxT, lane);
+  store_bfrag(sb + 32 * 32, f_dctx, lane);
+  __syncwarp();
+  const uint32_t* b_ctxT = sb;
+  const uint32_t* b_dctxT = sb + 16 * 32;
+  const uint32_t* b_dctx = sb + 32 * 32;
   const int n_groups = (N + 15) / 16;
   for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
     const int n_lo = grp * 16 + g, n_hi = n_lo + 8;
@@ -214,7 +255,7 @@ __global__ void __launch_bounds__(256) sla_bwd_tokens_mma_kernel(const bf16* __r
     unpack_chunk(q_hi, a_hi);
     quad_softmax(a_lo);
     quad_softmax(a_hi);
-    chunk_matmul(g_lo, g_hi, b_ctxT, t_lo, t_hi);
+    chunk_matmul_s(g_lo, g_hi, b_ctxT, lane, t_lo, t_hi);
     float dot_lo = 0.f, dot_hi = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -238,7 +279,7 @@ __global__ void __launch_bounds__(256) sla_bwd_tokens_mma_kernel(const bf16* __r
       a_lo[i] = __expf(a_lo[i] - km[i]) * kis[i];
       a_hi[i] = __expf(a_hi[i] - km[i]) * kis[i];
     }
-    chunk_matmul(v_lo4, v_hi4, b_dctxT, t_lo, t_hi);
+    chunk_matmul_s(v_lo4, v_hi4, b_dctxT, lane, t_lo, t_hi);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       t_lo[i] = a_lo[i] * (t_lo[i] - kr[i]);
@@ -247,7 +288,7 @@ __global__ void __launch_bounds__(256) sla_bwd_tokens_mma_kernel(const bf16* __r
     if (v_lo) o_lo[32] = pack_chunk(t_lo);
     if (v_hi) o_hi[32] = pack_chunk(t_hi);
     // ---- dv = k~ dctx ----
-    chunk_matmul(pack_chunk(a_lo), pack_chunk(a_hi), b_dctx, t_lo, t_hi);
+    chunk_matmul_s(pack_chunk(a_lo), pack_chunk(a_hi), b_dctx, lane, t_lo, t_hi);
     if (v_lo) o_lo[64] = pack_chunk(t_lo);
     if (v_hi) o_hi[64] = pack_chunk(t_hi);
   }
@@ -455,14 +496,14 @@ int sla_apply_mma_launch(const void* qkv, const float* ctx, void* tok_out, int n
 
 int sla_bwd_tokens_mma_launch(const void* qkv, const void* d_tok, const float* ctx, const float* dctx,
                               const float* kstat, void* dqkv, int n_img, int N, cudaStream_t st) {
-  const size_t smem = (16 * 1024 + 3 * 256) * sizeof(float);
+  const size_t smem = (size_t)2 * 8 * 1024 * sizeof(float);  // 64 KB staging, reused for the 48 KB of B fragments
   static bool cfg = false;
   if (!cfg) {
     cudaFuncSetAttribute(sla_bwd_tokens_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cfg = true;
   }
   const int n_groups = (N + 15) / 16;
-  const int gx = std::max(1, std::min(n_groups, std::max(1, 148 * 3 / n_img)));
+  const int gx = std::max(1, std::min(n_groups, std::max(1, 148 * 4 / n_img)));
   cudaError_t le = launch_pdl(sla_bwd_tokens_mma_kernel, dim3(gx, n_img), dim3(256), smem, st, 1,
                               reinterpret_cast<const bf16*>(qkv), reinterpret_cast<const bf16*>(d_tok), ctx, dctx, kstat,
                               reinterpret_cast<bf16*>(dqkv), N);
