@@ -291,15 +291,27 @@ __global__ void __launch_bounds__(256) time_mlp_fwd_kernel(const int* __restrict
   __syncthreads();
   for (int i = threadIdx.x; i < dim; i += blockDim.x) emb_out[(long)b * dim + i] = emb[i];
   for (int j = threadIdx.x; j < td; j += blockDim.x) {
-    float a = b1[j];
-    for (int k = 0; k < dim; ++k) a = fmaf(emb[k], w1[(long)k * td + j], a);
+    float a = b1[j], a1 = 0.f;
+#pragma unroll 8
+    for (int k = 0; k < dim; k += 2) {
+      a = fmaf(emb[k], w1[(long)k * td + j], a);
+      a1 = fmaf(emb[k + 1], w1[(long)(k + 1) * td + j], a1);
+    }
+    a += a1;
     h1_out[(long)b * td + j] = a;
     g[j] = gelu_tanh_f(a);
   }
   __syncthreads();
   for (int j = threadIdx.x; j < td; j += blockDim.x) {
-    float a = b2[j];
-    for (int k = 0; k < td; ++k) a = fmaf(g[k], w2[(long)k * td + j], a);
+    float a = b2[j], a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 4
+    for (int k = 0; k < td; k += 4) {
+      a = fmaf(g[k], w2[(long)k * td + j], a);
+      a1 = fmaf(g[k + 1], w2[(long)(k + 1) * td + j], a1);
+      a2 = fmaf(g[k + 2], w2[(long)(k + 2) * td + j], a2);
+      a3 = fmaf(g[k + 3], w2[(long)(k + 3) * td + j], a3);
+    }
+    a = (a + a1) + (a2 + a3);
     t_out[(long)b * td + j] = a;
   }
 }
@@ -380,8 +392,16 @@ __global__ void __launch_bounds__(256) time_heads_fwd_kernel(const float* __rest
   __syncthreads();
   float s1 = 0.f, s2 = 0.f;
   for (int j = threadIdx.x; j < hd.n_out; j += blockDim.x) {
-    float a = hd.b[j];
-    for (int k = 0; k < td; ++k) a = fmaf(st[k], hd.w[(long)k * hd.n_out + j], a);
+    // four independent chains and unrolled loads: the loop is a chain of L2-latency loads otherwise
+    float a = hd.b[j], a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 4
+    for (int k = 0; k < td; k += 4) {
+      a = fmaf(st[k], hd.w[(long)k * hd.n_out + j], a);
+      a1 = fmaf(st[k + 1], hd.w[(long)(k + 1) * hd.n_out + j], a1);
+      a2 = fmaf(st[k + 2], hd.w[(long)(k + 2) * hd.n_out + j], a2);
+      a3 = fmaf(st[k + 3], hd.w[(long)(k + 3) * hd.n_out + j], a3);
+    }
+    a = (a + a1) + (a2 + a3);
     e_pre[(long)b * ss_ld + hd.off + j] = a;
     s1 += a;
     s2 += a * a;

@@ -583,10 +583,11 @@ static int validate_desc(const vdn_tapgemm_desc* d) {
   return VDN_OK;
 }
 
-// N tile: as wide as possible (fewer re-reads of the A tile) while still giving every SM a CTA.
+// N tile: as wide as possible (fewer re-reads of the A tile) while still giving every SM a CTA - but not below
+// 64 columns when N allows it: 32-column tiles re-read A eight times at the 8x8 level and measured slower.
 static int pick_bn(int N, int m_tiles) {
   int best = -1;
-  for (int bn = 256; bn >= 32; bn >>= 1) {
+  for (int bn = 256; bn >= (N >= 64 && N % 64 == 0 ? 64 : 32); bn >>= 1) {
     if (bn > N || N % bn != 0) continue;
     if (best < 0) best = bn;
     if (m_tiles * (N / bn) >= num_sms()) return bn;

@@ -615,13 +615,19 @@ class UnetEngine:
         B, Fr, H, W = self.B, self.F, self.H, self.W
         self.x_in = x
         self.gn_all.zero_()
+
+        def time_path():  # latency-bound tiny kernels: overlapped with the init conv / init attention
+            ops.time_mlp_fwd(time, st.view("time_mlp.1.kernel"), st.view("time_mlp.1.bias"),
+                             st.view("time_mlp.3.kernel"), st.view("time_mlp.3.bias"), self.emb, self.h1, self.t_emb,
+                             B, self.dim)
+            ops.time_heads_fwd(self.t_emb, self.head_table, self.n_heads, self.e_pre, self.ss, B, self.td)
+
+        ht = self.side(time_path)
         ops.init_conv_fwd(x, st.view("init_conv.kernel"), st.view("init_conv.bias"), self.h0, B, self.channels, Fr, H,
                           W, self.dim, self.ks)
         h = self.init_attn.forward(self.h0)
         r = h
-        ops.time_mlp_fwd(time, st.view("time_mlp.1.kernel"), st.view("time_mlp.1.bias"), st.view("time_mlp.3.kernel"),
-                         st.view("time_mlp.3.bias"), self.emb, self.h1, self.t_emb, B, self.dim)
-        ops.time_heads_fwd(self.t_emb, self.head_table, self.n_heads, self.e_pre, self.ss, B, self.td)
+        self.join(ht)
         skips = []
         for b1, b2, sla, mha, down in self.downs:
             h = b1.forward([h])
@@ -714,15 +720,21 @@ class UnetEngine:
 
         def st_late():
             pool.put(S["dr"])
+
+            def time_path_bwd():  # dss is complete once downs.0 has run: overlap with the init attention backward
+                ops.time_heads_bwd(self.t_emb, self.head_table, self.n_heads, self.e_pre, self.dss, self.de_ws,
+                                   self.dt, self.B, self.td)
+                ops.time_mlp_bwd(self.dt, self.emb, self.h1, st.view("time_mlp.3.kernel"),
+                                 st.gview("time_mlp.1.kernel"), st.gview("time_mlp.1.bias"),
+                                 st.gview("time_mlp.3.kernel"), st.gview("time_mlp.3.bias"), self.dh1_ws, self.B,
+                                 self.dim)
+
+            ht = self.side(time_path_bwd)
             step(self.init_attn.backward)
             ops.init_conv_wgrad(self.x_in, S["d"], st.gview("init_conv.kernel"), st.gview("init_conv.bias"), self.B,
                                 self.channels, self.F, self.H, self.W, self.dim, self.ks)
             pool.put(S["d"])
-            ops.time_heads_bwd(self.t_emb, self.head_table, self.n_heads, self.e_pre, self.dss, self.de_ws, self.dt,
-                               self.B, self.td)
-            ops.time_mlp_bwd(self.dt, self.emb, self.h1, st.view("time_mlp.3.kernel"), st.gview("time_mlp.1.kernel"),
-                             st.gview("time_mlp.1.bias"), st.gview("time_mlp.3.kernel"), st.gview("time_mlp.3.bias"),
-                             self.dh1_ws, self.B, self.dim)
+            self.join(ht)
 
         stages = [("final", st_final)]
         stages += [(f"ups.{i}", make_up(i)) for i in reversed(range(n))]
