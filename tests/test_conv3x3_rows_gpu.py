@@ -51,14 +51,16 @@ def rc_grid(request):
         os.environ["VDN_RC_GRID"] = old
 
 
-@pytest.mark.parametrize("B,Fr,H,W,n_src,cout", [(2, 2, 64, 64, 1, 32), (2, 3, 64, 64, 2, 32), (1, 5, 32, 32, 1, 64),
-                                                (3, 1, 32, 32, 2, 32), (1, 2, 8, 64, 1, 64)])
-def test_rows_forward_bias_gn(rc_grid, B, Fr, H, W, n_src, cout):
+@pytest.mark.parametrize("B,Fr,H,W,n_src,cout,c", [(2, 2, 64, 64, 1, 32, 32), (2, 3, 64, 64, 2, 32, 32),
+                                                  (1, 5, 32, 32, 1, 64, 32), (3, 1, 32, 32, 2, 32, 32),
+                                                  (1, 2, 8, 64, 1, 64, 32), (2, 3, 32, 32, 1, 64, 64),
+                                                  (1, 1, 8, 32, 1, 64, 64)])
+def test_rows_forward_bias_gn(rc_grid, B, Fr, H, W, n_src, cout, c):
     from video_diffusion_nnx_b200 import ops
 
     torch.backends.cudnn.allow_tf32 = False
     torch.manual_seed(1)
-    n_img, c = B * Fr, 32
+    n_img = B * Fr
     xs = [_bf(n_img, H, W, c) for _ in range(n_src)]
     w = _bf(9, n_src * c, cout, scale=(9 * n_src * c) ** -0.5).float()
     bias = torch.randn(cout, device="cuda")

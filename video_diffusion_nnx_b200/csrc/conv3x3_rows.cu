@@ -371,8 +371,9 @@ bool rowconv_applicable(const vdn_tapgemm_desc* d, const void* residual, const f
   if (d->W != 64 && d->W != 32) return false;
   const int TR = kRcTileM / d->W;
   if (d->H % TR != 0) return false;
-  if (d->src_c != 32) return false;
+  if (d->src_c != 32 && d->src_c != 64) return false;
   if (d->n_out != 32 && d->n_out != 64) return false;
+  if (d->src_c == 64 && (d->n_src != 1 || d->n_out != 64 || d->W != 32)) return false;  // 64 -> 64 at the 32-wide level
   if (d->split_col != 0 && (d->n_out != 64 || d->split_col != 32)) return false;
   unsigned seen = 0;  // the taps must be a permutation of the 3x3 neighbourhood
   for (int t = 0; t < 9; ++t) {
@@ -456,6 +457,7 @@ int rowconv_launch(const vdn_tapgemm_desc* d, const void* src0, const void* src1
   int grid = std::min(a.n_tiles, num_sms() * cps);
   if (const char* e = getenv("VDN_RC_GRID")) grid = std::max(1, std::min(a.n_tiles, atoi(e)));  // tests: long runs per CTA
   const int smem = smem_for(S);
+  if (KC == 64) return launch_rowconv<64, 64, 1>(maps, a, grid, smem, st);
   if (N == 32 && d->n_src == 1) return launch_rowconv<32, 32, 1>(maps, a, grid, smem, st);
   if (N == 32) return launch_rowconv<32, 32, 2>(maps, a, grid, smem, st);
   if (d->n_src == 1) return launch_rowconv<64, 32, 1>(maps, a, grid, smem, st);
