@@ -186,6 +186,12 @@ int vdn_sla_core_fwd(const void* qkv, void* tok_out, float* ctx, float* kstat, f
                      void* stream);
 int vdn_sla_core_bwd(const void* qkv, const void* d_tok, const float* ctx, const float* kstat, float* dctx,
                      void* dqkv, int n_img, int N, void* stream);
+/* Fused SpatialLinearAttention block forward for C == 32 (modules.py:99-129 incl. the to_q/k/v and to_out 1x1
+ * convs and the residual of unet3d.py:170-178): out = x + to_out(SLA(x)) with no q/k/v/tok tensor in HBM. x, out
+ * bf16 [P][32]; w_qkv packed bf16 [768][32] (vdn_pack_weight mode 0 of the fused q|k|v kernel), w_out packed bf16
+ * [32][256]; ctx / kstat / ws as in vdn_sla_core_fwd. Used by inference engines (the backward needs q/k/v). */
+int vdn_sla_fused_fwd(const void* x, const void* w_qkv, const void* w_out, void* out, float* ctx, float* kstat,
+                      float* ws, int n_img, int N, int C, void* stream);
 
 /* Fused temporal attention forward (unet3d.py:86-96,118-120 + modules.py:285-323): the QKV projection on
  * tensor cores and the F x F attention core in one kernel; qkv is not materialised unless asked for.

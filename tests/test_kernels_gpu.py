@@ -262,6 +262,39 @@ def test_sla_core(n_img, N):
     assert _rel(dqkv, qf.grad) < 2e-2
 
 
+@pytest.mark.parametrize("n_img,H,W", [(3, 8, 8), (2, 16, 16), (1, 64, 64), (2, 10, 10)])
+def test_sla_fused_fwd(n_img, H, W):
+    """Fused SpatialLinearAttention block forward (x -> out, C = 32) against torch fp32 on the same bf16 operands
+    and against the unfused path (projection GEMM + core + to_out GEMM)."""
+    from video_diffusion_nnx_b200 import ops
+
+    _setup()
+    Cc, N = 32, H * W
+    P = n_img * N
+    x = _bf(n_img, H, W, Cc)
+    wq = _bf(Cc, 768, scale=Cc ** -0.5)      # fused q|k|v kernel [C][768]
+    wo = _bf(256, Cc, scale=256 ** -0.5)     # to_out kernel [256][C]
+    w_qkv = torch.empty(768, Cc, dtype=torch.bfloat16, device=DEV)
+    w_out = torch.empty(Cc, 256, dtype=torch.bfloat16, device=DEV)
+    ops.pack_weight(wq.float().reshape(1, Cc, 768).contiguous(), w_qkv, 1, Cc, 768, 0)
+    ops.pack_weight(wo.float().reshape(1, 256, Cc).contiguous(), w_out, 1, 256, Cc, 0)
+    qkv = (x.float().reshape(P, Cc) @ wq.float()).to(torch.bfloat16).float()
+    t = qkv.reshape(n_img, N, 3, 8, 32)
+    q = t[:, :, 0].softmax(-1)
+    k = t[:, :, 1].softmax(1)
+    ctx_ref = torch.einsum("bnhd,bnhe->bhde", k, t[:, :, 2])
+    tok = torch.einsum("bhde,bnhd->bnhe", ctx_ref, q).reshape(P, 256)
+    ref = tok @ wo.float() + x.float().reshape(P, Cc)
+    out = torch.empty(n_img, H, W, Cc, dtype=torch.bfloat16, device=DEV)
+    ctx = torch.empty(n_img, 8, 32, 32, device=DEV)
+    kstat = torch.empty(n_img, 8, 2, 32, device=DEV)
+    ws = torch.empty(ops.sla_workspace_floats(n_img, N), device=DEV)
+    ops.sla_fused_fwd(x, w_qkv, w_out, out, ctx, kstat, ws, n_img, N, Cc)
+    torch.cuda.synchronize()
+    assert _rel(ctx, ctx_ref) < 3e-3
+    assert _rel(out.reshape(P, Cc), ref) < 1e-2
+
+
 # ------------------------------------------------------------------------------------------
 # small kernels
 # ------------------------------------------------------------------------------------------

@@ -673,6 +673,27 @@ extern "C" int vdn_sla_core_fwd(const void* qkv, void* tok_out, float* ctx, floa
   return check_launch("sla_apply");
 }
 
+// Fused SpatialLinearAttention forward, C = 32: out = x + to_out(SLA(to_qkv(x))) without materialising q/k/v/tok.
+// w_qkv: packed bf16 [768][32] (rows q | k | v, head-major), w_out: packed bf16 [32][256]; ctx / kstat are outputs
+// like vdn_sla_core_fwd, ws the same scratch.
+extern "C" int vdn_sla_fused_fwd(const void* x, const void* w_qkv, const void* w_out, void* out, float* ctx,
+                                 float* kstat, float* ws, int n_img, int N, int C, void* stream) {
+  VDN_REQUIRE(x && w_qkv && w_out && out && ctx && kstat && ws && n_img > 0 && N > 0, VDN_E_SHAPE, "sla_fused_fwd: bad args");
+  VDN_REQUIRE(C == 32, VDN_E_SHAPE, "sla_fused_fwd: C=%d (only the 32-channel level is fused)", C);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int ns = sla_splits(N);
+  const int per = (N + ns - 1) / ns;
+  const int per_al = (per + kSlaTile - 1) / kSlaTile * kSlaTile;
+  float* ctx_part = ws;
+  float* ms_part = ws + (size_t)n_img * kHeads * ns * 1024;
+  int rc = sla_ctx_fused_launch(x, w_qkv, N, per_al, ns, ctx_part, ms_part, n_img, st);
+  if (rc) return rc;
+  sla_ctx_merge_kernel<<<n_img * kHeads, 256, 0, st>>>(ctx_part, ms_part, ns, ctx, kstat);
+  rc = check_launch("sla_ctx_merge");
+  if (rc) return rc;
+  return sla_apply_fused_launch(x, w_qkv, w_out, ctx, out, n_img, N, st);
+}
+
 extern "C" int vdn_sla_core_bwd(const void* qkv, const void* d_tok, const float* ctx, const float* kstat, float* dctx,
                                 void* dqkv, int n_img, int N, void* stream) {
   VDN_REQUIRE(qkv && d_tok && ctx && kstat && dctx && dqkv && n_img > 0 && N > 0, VDN_E_SHAPE, "sla_core_bwd: bad args");

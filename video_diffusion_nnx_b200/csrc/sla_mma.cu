@@ -484,6 +484,227 @@ __global__ void __launch_bounds__(256) sla_dctx_mma_kernel(const bf16* __restric
   tokacc_store<true>(acc, dctx + ((long)img * kSmHeads + h) * 1024, g, j);
 }
 
+// ---------------------------------------------------------------------------------------
+// Fused SpatialLinearAttention forward for C = 32 (inference engines): x -> out with NO q/k/v or tok tensors in
+// HBM (modules.py:99-129: to_q/to_k/to_v 1x1 convs without bias, core, to_out 1x1 conv, + residual).
+//   pass 1 (sla_ctx_fused_kernel):   k^T = W_k^T x^T, v^T = W_v^T x^T per (16 tokens, head) as MMAs whose
+//       accumulator fragments ARE the A / B fragments of ctx += p v (features x tokens), online softmax as above
+//   pass 2 (sla_apply_fused_kernel): q = x W_q (chunk layout), q~ = softmax_D, tok = q~ ctx, out_h = tok W_o,h;
+//       the 8 heads (= 8 warps of the block) are summed through shared memory, + x, one bf16 store.
+// At the 64x64 level this replaces 252 MB of qkv writes + reads and 84 MB of tok traffic per call by 2 reads of x.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 2) sla_ctx_fused_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w_qkv /*[768][32]*/,
+                                                               int N, int tokens_per_split,
+                                                               float* __restrict__ ctx_part, float* __restrict__ ms_part) {
+  pdl_trigger();
+  pdl_wait();
+  const int split = blockIdx.x, img = blockIdx.y, n_split = gridDim.x;
+  const int h = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, j = lane & 3;
+  const int n_begin = split * tokens_per_split;
+  const int n_end = min(N, n_begin + tokens_per_split);
+  // A fragments of W^T (rows = features 16u+g | 16u+8+g, k = channels in chunk order 8j+4s+{0,1} | +2)
+  uint32_t wk[2][2][4], wv[2][2][4];
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const uint32_t* k0 = reinterpret_cast<const uint32_t*>(w_qkv + (256 + h * 32 + 16 * u + g) * 32);
+    const uint32_t* k1 = reinterpret_cast<const uint32_t*>(w_qkv + (256 + h * 32 + 16 * u + 8 + g) * 32);
+    const uint32_t* v0 = reinterpret_cast<const uint32_t*>(w_qkv + (512 + h * 32 + 16 * u + g) * 32);
+    const uint32_t* v1 = reinterpret_cast<const uint32_t*>(w_qkv + (512 + h * 32 + 16 * u + 8 + g) * 32);
+#pragma unroll
+    for (int sx = 0; sx < 2; ++sx) {
+      wk[u][sx][0] = __ldg(k0 + 4 * j + 2 * sx); wk[u][sx][1] = __ldg(k1 + 4 * j + 2 * sx);
+      wk[u][sx][2] = __ldg(k0 + 4 * j + 2 * sx + 1); wk[u][sx][3] = __ldg(k1 + 4 * j + 2 * sx + 1);
+      wv[u][sx][0] = __ldg(v0 + 4 * j + 2 * sx); wv[u][sx][1] = __ldg(v1 + 4 * j + 2 * sx);
+      wv[u][sx][2] = __ldg(v0 + 4 * j + 2 * sx + 1); wv[u][sx][3] = __ldg(v1 + 4 * j + 2 * sx + 1);
+    }
+  }
+  float acc[2][4][4];  // [m-tile u: d = 16u+g | 16u+8+g][n-tile (u', r): e = 16u'+8r + 2j+{0,1}][frag]
+#pragma unroll
+  for (int u = 0; u < 2; ++u)
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[u][t][i] = 0.f;
+  float mrow[2][2], srow[2][2];
+#pragma unroll
+  for (int u = 0; u < 2; ++u)
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      mrow[u][r] = -INFINITY;
+      srow[u][r] = 0.f;
+    }
+  const bf16* xb = x + (long)img * N * 32;
+  const uint4 zero4 = make_uint4(0, 0, 0, 0);
+  for (int n0 = n_begin; n0 < n_end; n0 += 16) {
+    // x^T operand: chunk j of token rows n0+g (n-tile 0) and n0+8+g (n-tile 1)
+    const int t_lo = n0 + g, t_hi = n0 + 8 + g;
+    const uint4 x_lo = t_lo < n_end ? __ldg(reinterpret_cast<const uint4*>(xb + (long)t_lo * 32) + j) : zero4;
+    const uint4 x_hi = t_hi < n_end ? __ldg(reinterpret_cast<const uint4*>(xb + (long)t_hi * 32) + j) : zero4;
+    float kt[2][2][4], vt[2][2][4];  // [u][token tile][frag]: rows = features, cols = tokens 8t+2j+{0,1}
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const uint4& xc = t == 0 ? x_lo : x_hi;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) kt[u][t][i] = vt[u][t][i] = 0.f;
+        mma_bf16_16816(kt[u][t], wk[u][0][0], wk[u][0][1], wk[u][0][2], wk[u][0][3], xc.x, xc.y);
+        mma_bf16_16816(kt[u][t], wk[u][1][0], wk[u][1][1], wk[u][1][2], wk[u][1][3], xc.z, xc.w);
+        mma_bf16_16816(vt[u][t], wv[u][0][0], wv[u][0][1], wv[u][0][2], wv[u][0][3], xc.x, xc.y);
+        mma_bf16_16816(vt[u][t], wv[u][1][0], wv[u][1][1], wv[u][1][2], wv[u][1][3], xc.z, xc.w);
+      }
+    // k, v are rounded to bf16 exactly like the materialised path (projection output dtype)
+    // online softmax over tokens, per feature row (u, r): the lane holds 4 of the group's 16 tokens
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        float kv[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int tok = n0 + 8 * (c >> 1) + 2 * j + (c & 1);
+          const float kq = __bfloat162float(__float2bfloat16(kt[u][c >> 1][2 * r + (c & 1)]));
+          kv[c] = tok < n_end ? kq : -INFINITY;  // padded tokens: exp() -> 0
+        }
+        float gm = fmaxf(fmaxf(kv[0], kv[1]), fmaxf(kv[2], kv[3]));
+        gm = quad_max(gm);
+        const float m_new = fmaxf(mrow[u][r], gm);
+        const float corr = __expf(mrow[u][r] - m_new);
+        mrow[u][r] = m_new;
+        srow[u][r] *= corr;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          acc[u][t][2 * r] *= corr;
+          acc[u][t][2 * r + 1] *= corr;
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float pv = __expf(kv[c] - m_new);
+          srow[u][r] += pv;
+          kt[u][c >> 1][2 * r + (c & 1)] = pv;
+        }
+      }
+    // ctx += p^T v: A = p fragments (rows = d), B = v^T fragments (k = tokens, n = e)
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const uint32_t a0 = pack_bf16x2(kt[u][0][0], kt[u][0][1]), a1 = pack_bf16x2(kt[u][0][2], kt[u][0][3]);
+      const uint32_t a2 = pack_bf16x2(kt[u][1][0], kt[u][1][1]), a3 = pack_bf16x2(kt[u][1][2], kt[u][1][3]);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {  // n-tile t = (u', r) = (t / 2, t % 2): e = 16u' + 8r + n
+        const int up = t >> 1, r = t & 1;
+        mma_bf16_16816(acc[u][t], a0, a1, a2, a3, pack_bf16x2(vt[up][0][2 * r], vt[up][0][2 * r + 1]),
+                       pack_bf16x2(vt[up][1][2 * r], vt[up][1][2 * r + 1]));
+      }
+    }
+  }
+  const long blk = ((long)img * kSmHeads + h) * n_split + split;
+  float* cp = ctx_part + blk * 1024;
+#pragma unroll
+  for (int u = 0; u < 2; ++u)
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int d = 16 * u + 8 * (i >> 1) + g;
+        const int e = 16 * (t >> 1) + 8 * (t & 1) + 2 * j + (i & 1);
+        cp[d * 32 + e] = acc[u][t][i];
+      }
+#pragma unroll
+  for (int u = 0; u < 2; ++u)
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const float S = quad_sum(srow[u][r]);
+      if (j == 0) {
+        const int d = 16 * u + 8 * r + g;
+        ms_part[blk * 64 + d] = mrow[u][r];
+        ms_part[blk * 64 + 32 + d] = S;
+      }
+    }
+}
+
+// B fragments of a bf16 K-major matrix Wt[n][k] (row stride ld elements): B[k][n] = Wt[n_of(col)][k0 + k], with the
+// chunk-order contraction index (8j+4s+{0..3}) and an arbitrary column -> row map given by the caller.
+__device__ __forceinline__ void load_bfrag_kmajor(BFrag& f, const bf16* Wt, int ld, int k0, int g, int j, bool psi_cols) {
+#pragma unroll
+  for (int s = 0; s < 2; ++s)
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      // psi_cols: projection whose OUTPUT should land in chunk layout (column c of tile t -> 8(c/2)+4(t/2)+2(t%2)+c%2);
+      // otherwise the sigma map of chunk_matmul (8(c/2) + 2t + c%2) - both give lane j the features 8j..8j+7
+      const int n = psi_cols ? 8 * (g >> 1) + 4 * (t >> 1) + 2 * (t & 1) + (g & 1) : 8 * (g >> 1) + 2 * t + (g & 1);
+      const uint32_t* row = reinterpret_cast<const uint32_t*>(Wt + (long)n * ld + k0);
+      f.r[s][t][0] = __ldg(row + 4 * j + 2 * s);
+      f.r[s][t][1] = __ldg(row + 4 * j + 2 * s + 1);
+    }
+}
+
+__global__ void __launch_bounds__(256, 2) sla_apply_fused_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w_qkv /*[768][32]*/,
+                                                                 const bf16* __restrict__ w_out /*[32][256]*/,
+                                                                 const float* __restrict__ ctx, bf16* __restrict__ out,
+                                                                 int N) {
+  __shared__ float s_part[8][16][33];  // per head: [16 tokens][32 channels] partial of the to_out projection
+  extern __shared__ uint32_t s_frag[];  // per head: q-projection | ctx | to_out fragment sets, [16 words][32 lanes] each
+  pdl_trigger();
+  pdl_wait();
+  const int img = blockIdx.y;
+  const int h = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, j = lane & 3;
+  uint32_t* sb = s_frag + h * (3 * 16 * 32);
+  {
+    BFrag f;
+    load_bfrag_kmajor(f, w_qkv + (long)(h * 32) * 32, 32, 0, g, j, false);  // q = x W_q,h (sigma columns: chunk layout)
+    store_bfrag(sb, f, lane);
+    load_bfrag(f, ctx + ((long)img * kSmHeads + h) * 1024, 32, 1, g, j);     // B[k = d][n = e] = ctx[d][e]
+    store_bfrag(sb + 16 * 32, f, lane);
+    load_bfrag_kmajor(f, w_out, 256, h * 32, g, j, false);                   // B[k = e][n = c] = W_o[h*32+e][c]
+    store_bfrag(sb + 32 * 32, f, lane);
+  }
+  __syncwarp();
+  const bf16* xb = x + (long)img * N * 32;
+  bf16* ob = out + (long)img * N * 32;
+  const uint4 zero4 = make_uint4(0, 0, 0, 0);
+  const int n_groups = (N + 15) / 16;
+  for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {  // same trip count for every warp of the block
+    const int n_lo = grp * 16 + g, n_hi = n_lo + 8;
+    const uint4 x_lo = n_lo < N ? __ldg(reinterpret_cast<const uint4*>(xb + (long)n_lo * 32) + j) : zero4;
+    const uint4 x_hi = n_hi < N ? __ldg(reinterpret_cast<const uint4*>(xb + (long)n_hi * 32) + j) : zero4;
+    float a_lo[8], a_hi[8], o_lo[8], o_hi[8];
+    chunk_matmul_s(x_lo, x_hi, sb, lane, a_lo, a_hi);                          // q (bf16-rounded like the GEMM output)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      a_lo[i] = __bfloat162float(__float2bfloat16(a_lo[i]));
+      a_hi[i] = __bfloat162float(__float2bfloat16(a_hi[i]));
+    }
+    quad_softmax(a_lo);
+    quad_softmax(a_hi);
+    chunk_matmul_s(pack_chunk(a_lo), pack_chunk(a_hi), sb + 16 * 32, lane, o_lo, o_hi);   // tok = q~ ctx
+    chunk_matmul_s(pack_chunk(o_lo), pack_chunk(o_hi), sb + 32 * 32, lane, a_lo, a_hi);   // out_h = tok W_o,h
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      s_part[h][g][8 * j + i] = a_lo[i];
+      s_part[h][g + 8][8 * j + i] = a_hi[i];
+    }
+    __syncthreads();
+    // sum the 8 heads, add the residual, store: thread -> (token r = tid / 16, channels 2*(tid % 16), +1)
+    {
+      const int r = threadIdx.x >> 4, c = (threadIdx.x & 15) * 2;
+      const int n = grp * 16 + r;
+      if (n < N) {
+        float v0 = 0.f, v1 = 0.f;
+#pragma unroll
+        for (int hh = 0; hh < 8; ++hh) {
+          v0 += s_part[hh][r][c];
+          v1 += s_part[hh][r][c + 1];
+        }
+        const float2 xr = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(xb + (long)n * 32 + c));
+        *reinterpret_cast<uint32_t*>(ob + (long)n * 32 + c) = pack_bf16x2(v0 + xr.x, v1 + xr.y);
+      }
+    }
+    __syncthreads();
+  }
+}
+
 // Host launchers used by vdn_sla_core_fwd / vdn_sla_core_bwd (attn.cu).
 int sla_apply_mma_launch(const void* qkv, const float* ctx, void* tok_out, int n_img, int N, cudaStream_t st) {
   const int n_groups = (N + 15) / 16;
@@ -526,6 +747,34 @@ int sla_dctx_mma_launch(const void* qkv, const void* d_tok, int N, int tokens_pe
                               tokens_per_split, dctx);
   VDN_REQUIRE(le == cudaSuccess, VDN_E_CUDA, "sla_dctx launch: %s", cudaGetErrorString(le));
   return check_launch("sla_dctx_mma");
+}
+
+// x -> out fused forward (C = 32). The merge of the split partials (sla_ctx_merge_kernel, attn.cu) is launched by the
+// caller between the two passes.
+int sla_ctx_fused_launch(const void* x, const void* w_qkv, int N, int tokens_per_split, int n_split, float* ctx_part,
+                         float* ms_part, int n_img, cudaStream_t st) {
+  cudaError_t le = launch_pdl(sla_ctx_fused_kernel, dim3(n_split, n_img), dim3(256), (size_t)0, st, 1,
+                              reinterpret_cast<const bf16*>(x), reinterpret_cast<const bf16*>(w_qkv), N,
+                              tokens_per_split, ctx_part, ms_part);
+  VDN_REQUIRE(le == cudaSuccess, VDN_E_CUDA, "sla_ctx_fused launch: %s", cudaGetErrorString(le));
+  return check_launch("sla_ctx_fused");
+}
+
+int sla_apply_fused_launch(const void* x, const void* w_qkv, const void* w_out, const float* ctx, void* out, int n_img,
+                           int N, cudaStream_t st) {
+  const size_t smem = (size_t)8 * 3 * 16 * 32 * sizeof(uint32_t);
+  static bool cfg = false;
+  if (!cfg) {
+    cudaFuncSetAttribute(sla_apply_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cfg = true;
+  }
+  const int n_groups = (N + 15) / 16;
+  const int gx = std::max(1, std::min(n_groups, std::max(1, 148 * 4 / n_img)));
+  cudaError_t le = launch_pdl(sla_apply_fused_kernel, dim3(gx, n_img), dim3(256), smem, st, 1,
+                              reinterpret_cast<const bf16*>(x), reinterpret_cast<const bf16*>(w_qkv),
+                              reinterpret_cast<const bf16*>(w_out), ctx, reinterpret_cast<bf16*>(out), N);
+  VDN_REQUIRE(le == cudaSuccess, VDN_E_CUDA, "sla_apply_fused launch: %s", cudaGetErrorString(le));
+  return check_launch("sla_apply_fused");
 }
 
 }  // namespace vdn

@@ -34,6 +34,11 @@ int mha_temporal_mma_bwd_launch(const void* qkv, const void* d_o, const float* l
 int mha_temporal_mma_fwd_launch(const void* x, const void* w_hm, const float* bias_hm, void* o, void* qkv, float* lse,
                                 int B, int F, int H, int W, cudaStream_t st);
 
+int sla_ctx_fused_launch(const void* x, const void* w_qkv, int N, int tokens_per_split, int n_split, float* ctx_part,
+                         float* ms_part, int n_img, cudaStream_t st);
+int sla_apply_fused_launch(const void* x, const void* w_qkv, const void* w_out, const float* ctx, void* out, int n_img,
+                           int N, cudaStream_t st);
+
 // Kernel launch with programmatic dependent launch (and optionally a thread-block cluster along grid.x). The
 // kernel must call pdl_wait() before touching global memory. VDN_NO_PDL=1 falls back to plain stream order.
 bool pdl_enabled();

@@ -358,8 +358,10 @@ class SLABlock:
         self.qkv_proj = GemmConv(eng, prefix + ".qkv.kernel", None, TAPS_1x1, 1, C, 3 * HD)
         self.out_proj = GemmConv(eng, prefix + ".to_out.kernel", None, TAPS_1x1, 1, HD, C)
         N = H * W
-        self.qkv = eng.new((n_img, H, W, 3 * HD))
-        self.tok = eng.new((n_img, H, W, HD))
+        # inference engines at C = 32 run the fused x -> out kernels: no q/k/v/tok tensors at all
+        self.fused = (not eng.training) and C == 32
+        self.qkv = None if self.fused else eng.new((n_img, H, W, 3 * HD))
+        self.tok = None if self.fused else eng.new((n_img, H, W, HD))
         self.ctx = eng.new((n_img, HEADS, 32, 32), F32)
         self.kstat = eng.new((n_img, HEADS, 2, 32), F32)
         self.ws = eng.shared_ws(ops.sla_workspace_floats(n_img, N))
@@ -368,6 +370,10 @@ class SLABlock:
 
     def forward(self, x):
         self.x = x
+        if self.fused:
+            ops.sla_fused_fwd(x, self.qkv_proj.wp, self.out_proj.wp, self.out, self.ctx, self.kstat, self.ws,
+                              self.n_img, self.H * self.W, self.C)
+            return self.out
         self.qkv_proj.fwd([x], self.qkv)
         ops.sla_core_fwd(self.qkv, self.tok, self.ctx, self.kstat, self.ws, self.n_img, self.H * self.W)
         self.out_proj.fwd([self.tok], self.out, residual=x)

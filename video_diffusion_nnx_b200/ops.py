@@ -158,6 +158,11 @@ def sla_core_fwd(qkv, tok_out, ctx, kstat, ws, n_img, N):
           "vdn_sla_core_fwd")
 
 
+def sla_fused_fwd(x, w_qkv, w_out, out, ctx, kstat, ws, n_img, N, Cc):
+    check(lib.vdn_sla_fused_fwd(ptr(x), ptr(w_qkv), ptr(w_out), ptr(out), ptr(ctx), ptr(kstat), ptr(ws), n_img, N, Cc,
+                                stream_ptr()), "vdn_sla_fused_fwd")
+
+
 def sla_core_bwd(qkv, d_tok, ctx, kstat, dctx, dqkv, n_img, N):
     check(lib.vdn_sla_core_bwd(ptr(qkv), ptr(d_tok), ptr(ctx), ptr(kstat), ptr(dctx), ptr(dqkv), n_img, N,
                                stream_ptr()), "vdn_sla_core_bwd")
