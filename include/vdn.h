@@ -208,6 +208,15 @@ int vdn_mha_temporal_fused_fwd(const void* x, const void* w_hm, const float* bia
 int vdn_mha_temporal_tc_supported(int F, int C);
 int vdn_mha_temporal_tc_fwd(const void* x, const void* w_hm, const float* bias_hm, void* o, void* qkv, float* lse,
                             int B, int F, int H, int W, int C, void* stream);
+/* Folded temporal attention BLOCK for inference engines, C == 32, F <= 16: out = x + out_proj(MHA(x)) in one kernel
+ * (modules.py:285-326 + the residual of unet3d.py:86-96). vdn_mha_fold_pack builds, from the fp32 master weights
+ * (fused q|k|v kernel [32][768] + bias [768], out kernel [256][32] + bias [32]), A_h = W_q,h W_k,h^T / sqrt(32),
+ * u_h = b_q,h W_k,h^T / sqrt(32), M_h = W_v,h W_o,h and b' = sum_h b_v,h W_o,h + b_o; softmax(q k^T) only depends on
+ * (x A_h + u_h) x^T, and out = sum_h (P_h x) M_h + b'. x, out bf16 [P][32]. */
+int vdn_mha_fold_pack(const float* w_qkv, const float* b_qkv, const float* w_out, const float* b_out, void* fa,
+                      float* fu, void* fm, float* fb, void* stream);
+int vdn_mha_temporal_folded_fwd(const void* x, const void* fa, const float* fu, const void* fm, const float* fb,
+                                void* out, int B, int F, int H, int W, int C, void* stream);
 /* Tensor-core temporal attention core backward (S, dP, dQ, dK, dV), F <= 16: one warp per (pixel, head) on
  * register-resident bf16 MMAs (csrc/mha_mma.cu). dbias (optional, fp32 [768], +=) receives the column sums of
  * dqkv = the gradient of the q|k|v projection bias (modules.py:261-270), which saves a pass over dqkv. */

@@ -295,6 +295,34 @@ def test_sla_fused_fwd(n_img, H, W):
     assert _rel(out.reshape(P, Cc), ref) < 1e-2
 
 
+@pytest.mark.parametrize("B,Fr,H,W", [(2, 10, 8, 8), (1, 16, 4, 8), (2, 2, 16, 16), (1, 7, 5, 3)])
+def test_mha_temporal_folded_fwd(B, Fr, H, W):
+    """Folded inference temporal-attention block (x -> x + out_proj(MHA(x)), C = 32) vs torch fp32."""
+    from video_diffusion_nnx_b200 import ops
+
+    _setup()
+    Cc = 32
+    P = B * Fr * H * W
+    x = _bf(B, Fr, H, W, Cc)
+    wqkv = torch.randn(Cc, 768, device=DEV) / Cc ** 0.5
+    bqkv = 0.1 * torch.randn(768, device=DEV)
+    wo = torch.randn(256, Cc, device=DEV) / 16.0
+    bo = 0.1 * torch.randn(Cc, device=DEV)
+    fa, fm = (torch.empty(8, 32, 32, dtype=torch.bfloat16, device=DEV) for _ in range(2))
+    fu, fb = torch.empty(8, 32, device=DEV), torch.empty(32, device=DEV)
+    ops.mha_fold_pack(wqkv, bqkv, wo, bo, fa, fu, fm, fb)
+    out = torch.empty(B, Fr, H, W, Cc, dtype=torch.bfloat16, device=DEV)
+    ops.mha_temporal_folded_fwd(x, fa, fu, fm, fb, out, B, Fr, H, W, Cc)
+    torch.cuda.synchronize()
+    xf = x.float().reshape(P, Cc)
+    t = (xf @ wqkv + bqkv).reshape(B, Fr, H * W, 3, 8, 32).permute(0, 2, 1, 3, 4, 5)
+    q, k, v = t[..., 0, :, :], t[..., 1, :, :], t[..., 2, :, :]
+    att = torch.einsum("...ihd,...jhd->...hij", q / math.sqrt(32), k).softmax(-1)
+    o = torch.einsum("...hij,...jhd->...ihd", att, v).permute(0, 2, 1, 3, 4).reshape(P, 256)
+    ref = o @ wo + bo + xf
+    assert _rel(out.reshape(P, Cc), ref) < 2e-2
+
+
 # ------------------------------------------------------------------------------------------
 # small kernels
 # ------------------------------------------------------------------------------------------

@@ -428,6 +428,191 @@ int mha_temporal_mma_fwd_launch(const void* x, const void* w_hm, const float* bi
   return check_launch("mha_temporal_mma_fwd");
 }
 
+// ---------------------------------------------------------------------------------------
+// Folded temporal attention block for inference engines, C = 32: out = x + out_proj(MHA(x)) in one kernel.
+// Without a backward pass nothing forces q, k, v, o into memory, and the algebra folds:
+//   S_ij = q_i k_j / sqrt(d) = (x_i A_h + u_h) . x_j + (terms constant in j: softmax drops them)
+//          A_h = W_q,h W_k,h^T / sqrt(d) [C x C],  u_h = b_q,h W_k,h^T / sqrt(d)
+//   out  = sum_h softmax(S_h) v_h W_o,h + b_o = sum_h (P_h x) M_h + b',  M_h = W_v,h W_o,h,  b' = sum_h b_v,h W_o,h + b_o
+// so a (pixel, head) costs 24 MMAs (y = xA+u: 8, S: 4, Z = P x: 4, Z M_h: 8) instead of 32 + a separate out-projection
+// GEMM, and neither o nor the out-projection input ever exist. The 8 heads of a pixel are the 8 warps of a block and
+// are summed through shared memory. The folded matrices are rebuilt by mha_fold_pack_kernel after every weight
+// update (a few hundred kFLOP).
+// ---------------------------------------------------------------------------------------
+__global__ void mha_fold_pack_kernel(const float* __restrict__ w_qkv /*[32][768]*/, const float* __restrict__ b_qkv,
+                                     const float* __restrict__ w_out /*[256][32]*/, const float* __restrict__ b_out,
+                                     bf16* __restrict__ fa /*[8][32 n][32 c]*/, float* __restrict__ fu /*[8][32]*/,
+                                     bf16* __restrict__ fm /*[8][32 c][32 c']*/, float* __restrict__ fb /*[32]*/) {
+  const int h = blockIdx.x;
+  const float scale = rsqrtf(32.f);
+  for (int i = threadIdx.x; i < 1024; i += blockDim.x) {
+    const int n = i >> 5, c = i & 31;
+    // fa[h][n][c] = scale * A[c][n] = scale * sum_d W_q[c][h,d] W_k[n][h,d]
+    float a = 0.f, m = 0.f;
+    for (int d = 0; d < 32; ++d) {
+      a = fmaf(w_qkv[c * 768 + h * 32 + d], w_qkv[n * 768 + 256 + h * 32 + d], a);
+      // fm[h][n][c] = M[c][n] = sum_d W_v[c][h,d] W_o[h*32+d][n]
+      m = fmaf(w_qkv[c * 768 + 512 + h * 32 + d], w_out[(h * 32 + d) * 32 + n], m);
+    }
+    fa[(h * 32 + n) * 32 + c] = __float2bfloat16(a * scale);
+    fm[(h * 32 + n) * 32 + c] = __float2bfloat16(m);
+  }
+  for (int n = threadIdx.x; n < 32; n += blockDim.x) {
+    float u = 0.f;
+    for (int d = 0; d < 32; ++d) u = fmaf(b_qkv ? b_qkv[h * 32 + d] : 0.f, w_qkv[n * 768 + 256 + h * 32 + d], u);
+    fu[h * 32 + n] = u * scale;
+    if (h == 0) {  // b'[n] = b_o[n] + sum_{h,d} b_v[h,d] W_o[h*32+d][n]
+      float bsum = b_out ? b_out[n] : 0.f;
+      for (int r = 0; r < 256; ++r) bsum = fmaf(b_qkv ? b_qkv[512 + r] : 0.f, w_out[r * 32 + n], bsum);
+      fb[n] = bsum;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256, 2) mha_temporal_folded_fwd_kernel(const bf16* __restrict__ x,
+                                                                       const bf16* __restrict__ fa,
+                                                                       const float* __restrict__ fu,
+                                                                       const bf16* __restrict__ fm,
+                                                                       const float* __restrict__ fb,
+                                                                       bf16* __restrict__ out, int B, int F, long HW) {
+  __shared__ float s_part[8][16][33];
+  extern __shared__ uint32_t sm_w[];  // per head: y-projection fragment set (24 words) | M_h fragment set (16 words)
+  pdl_trigger();
+  pdl_wait();
+  const int h = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, j = lane & 3;
+  const long n_pix = (long)B * HW;
+  const bool v_lo = g < F, v_hi = g + 8 < F;
+  uint32_t* s_y = sm_w + h * (kProjWords + 16) * 32;
+  uint32_t* s_m = s_y + kProjWords * 32;
+  {
+    ProjW w;
+    load_projw(w, fa + (h * 32) * 32, fu + h * 32, g, j);  // psi-permuted outputs: y lands in chunk layout
+    store_projw(s_y, w, lane);
+    // B[k = c'][n = c] = M_h[c'][c] = fm[h][c][c'], sigma columns (result in chunk layout), chunk-order k
+#pragma unroll
+    for (int sx = 0; sx < 2; ++sx)
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int n = 8 * (g >> 1) + 2 * t + (g & 1);
+        const uint32_t* row = reinterpret_cast<const uint32_t*>(fm + (h * 32 + n) * 32);
+        s_m[((sx * 4 + t) * 2 + 0) * 32 + lane] = __ldg(row + 4 * j + 2 * sx);
+        s_m[((sx * 4 + t) * 2 + 1) * 32 + lane] = __ldg(row + 4 * j + 2 * sx + 1);
+      }
+  }
+  __syncwarp();
+  const float bias0 = fb[2 * (threadIdx.x & 15)], bias1 = fb[2 * (threadIdx.x & 15) + 1];
+  const uint4 zero4 = make_uint4(0, 0, 0, 0);
+  for (long pix = blockIdx.x; pix < n_pix; pix += gridDim.x) {  // uniform trip count for the whole block
+    const long b = pix / HW, p = pix - b * HW;
+    const long row0 = b * F * HW + p;
+    const long r_lo = row0 + (long)g * HW, r_hi = row0 + (long)(g + 8) * HW;
+    const uint4 x_lo = v_lo ? __ldg(reinterpret_cast<const uint4*>(x + r_lo * 32) + j) : zero4;
+    const uint4 x_hi = v_hi ? __ldg(reinterpret_cast<const uint4*>(x + r_hi * 32) + j) : zero4;
+    uint4 y_lo, y_hi;
+    project_chunks(x_lo, x_hi, s_y, lane, y_lo, y_hi);  // y = x A_h + u_h (already scaled by 1/sqrt(d))
+    float S[2][4];
+    chunk_abt(y_lo, y_hi, x_lo, x_hi, S);               // S'_ij = y_i . x_j
+    float m_lo = -INFINITY, m_hi = -INFINITY;
+#pragma unroll
+    for (int t = 0; t < 2; ++t)
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const bool cv = 8 * t + 2 * j + i < F;
+        S[t][i] = cv ? S[t][i] : -INFINITY;
+        S[t][2 + i] = cv ? S[t][2 + i] : -INFINITY;
+        m_lo = fmaxf(m_lo, S[t][i]);
+        m_hi = fmaxf(m_hi, S[t][2 + i]);
+      }
+    m_lo = fmaxf(m_lo, __shfl_xor_sync(0xffffffffu, m_lo, 1));
+    m_lo = fmaxf(m_lo, __shfl_xor_sync(0xffffffffu, m_lo, 2));
+    m_hi = fmaxf(m_hi, __shfl_xor_sync(0xffffffffu, m_hi, 1));
+    m_hi = fmaxf(m_hi, __shfl_xor_sync(0xffffffffu, m_hi, 2));
+    float l_lo = 0.f, l_hi = 0.f;
+#pragma unroll
+    for (int t = 0; t < 2; ++t)
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        S[t][i] = __expf(S[t][i] - m_lo);
+        S[t][2 + i] = __expf(S[t][2 + i] - m_hi);
+        l_lo += S[t][i];
+        l_hi += S[t][2 + i];
+      }
+    l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 1);
+    l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 2);
+    l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 1);
+    l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 2);
+    // Z = P x: B fragments = transposed x tiles; Z lands in chunk layout (channels 8j..8j+7)
+    const uint32_t a0 = pack_bf16x2(S[0][0], S[0][1]), a1 = pack_bf16x2(S[0][2], S[0][3]);
+    const uint32_t a2 = pack_bf16x2(S[1][0], S[1][1]), a3 = pack_bf16x2(S[1][2], S[1][3]);
+    const uint32_t xb[4][2] = {{movmatrix_trans(x_lo.x), movmatrix_trans(x_hi.x)},
+                               {movmatrix_trans(x_lo.y), movmatrix_trans(x_hi.y)},
+                               {movmatrix_trans(x_lo.z), movmatrix_trans(x_hi.z)},
+                               {movmatrix_trans(x_lo.w), movmatrix_trans(x_hi.w)}};
+    const float inv_lo = 1.f / l_lo, inv_hi = 1.f / l_hi;
+    uint32_t z_lo[4], z_hi[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      float c[4] = {0.f, 0.f, 0.f, 0.f};
+      mma16816(c, a0, a1, a2, a3, xb[t][0], xb[t][1]);
+      z_lo[t] = pack_bf16x2(c[0] * inv_lo, c[1] * inv_lo);
+      z_hi[t] = pack_bf16x2(c[2] * inv_hi, c[3] * inv_hi);
+    }
+    // out_h = Z M_h (chunk layout), summed over the block's 8 heads through shared memory
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      float d[4] = {0.f, 0.f, 0.f, 0.f};
+      mma16816(d, z_lo[0], z_hi[0], z_lo[1], z_hi[1], s_m[((0 * 4 + t) * 2 + 0) * 32 + lane], s_m[((0 * 4 + t) * 2 + 1) * 32 + lane]);
+      mma16816(d, z_lo[2], z_hi[2], z_lo[3], z_hi[3], s_m[((1 * 4 + t) * 2 + 0) * 32 + lane], s_m[((1 * 4 + t) * 2 + 1) * 32 + lane]);
+      s_part[h][g][8 * j + 2 * t] = d[0];
+      s_part[h][g][8 * j + 2 * t + 1] = d[1];
+      s_part[h][g + 8][8 * j + 2 * t] = d[2];
+      s_part[h][g + 8][8 * j + 2 * t + 1] = d[3];
+    }
+    __syncthreads();
+    {
+      const int r = threadIdx.x >> 4, c = (threadIdx.x & 15) * 2;  // token r, channels c, c+1
+      if (r < F) {
+        float v0 = bias0, v1 = bias1;
+#pragma unroll
+        for (int hh = 0; hh < 8; ++hh) {
+          v0 += s_part[hh][r][c];
+          v1 += s_part[hh][r][c + 1];
+        }
+        const long row = row0 + (long)r * HW;
+        const float2 xr = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(x + row * 32 + c));
+        *reinterpret_cast<uint32_t*>(out + row * 32 + c) = pack_bf16x2(v0 + xr.x, v1 + xr.y);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+int mha_fold_pack_launch(const float* w_qkv, const float* b_qkv, const float* w_out, const float* b_out, void* fa,
+                         float* fu, void* fm, float* fb, cudaStream_t st) {
+  mha_fold_pack_kernel<<<8, 256, 0, st>>>(w_qkv, b_qkv, w_out, b_out, reinterpret_cast<bf16*>(fa), fu,
+                                          reinterpret_cast<bf16*>(fm), fb);
+  return check_launch("mha_fold_pack");
+}
+
+int mha_temporal_folded_fwd_launch(const void* x, const void* fa, const float* fu, const void* fm, const float* fb,
+                                   void* out, int B, int F, int H, int W, cudaStream_t st) {
+  const long HW = (long)H * W;
+  const long n_pix = (long)B * HW;
+  const int grid = (int)std::min<long>(n_pix, 148L * 16);
+  const size_t smem = (size_t)8 * (kProjWords + 16) * 32 * 4;
+  static bool cfg = false;
+  if (!cfg) {
+    cudaFuncSetAttribute(mha_temporal_folded_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cfg = true;
+  }
+  cudaError_t le = launch_pdl(mha_temporal_folded_fwd_kernel, dim3(grid), dim3(256), smem, st, 1,
+                              reinterpret_cast<const bf16*>(x), reinterpret_cast<const bf16*>(fa), fu,
+                              reinterpret_cast<const bf16*>(fm), fb, reinterpret_cast<bf16*>(out), B, F, HW);
+  VDN_REQUIRE(le == cudaSuccess, VDN_E_CUDA, "mha_temporal_folded_fwd launch: %s", cudaGetErrorString(le));
+  return check_launch("mha_temporal_folded_fwd");
+}
+
 int mha_temporal_mma_bwd_launch(const void* qkv, const void* d_o, const float* lse, void* dqkv, int B, int F, int H,
                                 int W, cudaStream_t st) {
   const long HW = (long)H * W;
@@ -441,3 +626,22 @@ int mha_temporal_mma_bwd_launch(const void* qkv, const void* d_o, const float* l
 }
 
 }  // namespace vdn
+
+using namespace vdn;
+
+// Folded inference-only temporal attention block (C = 32): see mha_temporal_folded_fwd_kernel.
+// fold_pack: w_qkv fp32 [32][768] (q|k|v), b_qkv fp32 [768] or NULL, w_out fp32 [256][32], b_out fp32 [32] or NULL ->
+//            fa bf16 [8][32][32], fu fp32 [8][32], fm bf16 [8][32][32], fb fp32 [32].
+extern "C" int vdn_mha_fold_pack(const float* w_qkv, const float* b_qkv, const float* w_out, const float* b_out,
+                                 void* fa, float* fu, void* fm, float* fb, void* stream) {
+  VDN_REQUIRE(w_qkv && w_out && fa && fu && fm && fb, VDN_E_SHAPE, "mha_fold_pack: bad args");
+  return mha_fold_pack_launch(w_qkv, b_qkv, w_out, b_out, fa, fu, fm, fb, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int vdn_mha_temporal_folded_fwd(const void* x, const void* fa, const float* fu, const void* fm,
+                                           const float* fb, void* out, int B, int F, int H, int W, int C,
+                                           void* stream) {
+  VDN_REQUIRE(x && fa && fu && fm && fb && out && B > 0 && H > 0 && W > 0, VDN_E_SHAPE, "mha_temporal_folded_fwd: bad args");
+  VDN_REQUIRE(C == 32 && F >= 1 && F <= 16, VDN_E_SHAPE, "mha_temporal_folded_fwd: C=%d F=%d unsupported (C == 32, F <= 16)", C, F);
+  return mha_temporal_folded_fwd_launch(x, fa, fu, fm, fb, out, B, F, H, W, reinterpret_cast<cudaStream_t>(stream));
+}

@@ -297,17 +297,30 @@ class MHABlock:
         # temporal attention runs the fused projection + core kernel; qkv is only materialised when the
         # (unfused) backward needs it, i.e. in training engines
         self.fused = mode == 0 and (n_img // eng.B) <= 16
+        # inference engines at C = 32: the whole block (projections, core, out projection, residual) is one
+        # kernel on folded weights (A_h = W_q W_k^T, M_h = W_v W_o): no q/k/v/o tensors
+        self.folded = self.fused and (not eng.training) and C == 32
         need_qkv = eng.training or not self.fused
         self.qkv = eng.new((n_img, H, W, 3 * HD)) if need_qkv else None
-        self.o = eng.new((n_img, H, W, HD))
+        self.o = None if self.folded else eng.new((n_img, H, W, HD))
         self.lse = eng.new((n_img * H * W, HEADS), F32) if need_qkv else None
         self.out = eng.new((n_img, H, W, C))
-        if self.fused:
+        if self.folded:
+            dev = eng.device
+            self.fa, self.fm = (torch.empty(HEADS, 32, 32, dtype=BF16, device=dev) for _ in range(2))
+            self.fu, self.fb = torch.empty(HEADS, 32, dtype=F32, device=dev), torch.empty(32, dtype=F32, device=dev)
+            self._wq, self._bq = eng.store.view(prefix + ".qkv.kernel"), eng.store.view(prefix + ".qkv.bias")
+            self._wo, self._bo = eng.store.view(prefix + ".out.kernel"), eng.store.view(prefix + ".out.bias")
+            eng.extra_packers.append(self._repack_folded)
+        elif self.fused:
             self.w_hm = torch.empty(3 * HD, C, dtype=BF16, device=eng.device)
             self.b_hm = torch.empty(3 * HD, dtype=F32, device=eng.device)
             self._wq, self._bq = eng.store.view(prefix + ".qkv.kernel"), eng.store.view(prefix + ".qkv.bias")
             eng.extra_packers.append(self._repack_hm)
         self.x = None
+
+    def _repack_folded(self):
+        ops.mha_fold_pack(self._wq, self._bq, self._wo, self._bo, self.fa, self.fu, self.fm, self.fb)
 
     def _repack_hm(self):
         ops.qkv_headmajor_pack(self._wq, self._bq, self.w_hm, self.b_hm, self.C)
@@ -316,6 +329,10 @@ class MHABlock:
         eng = self.eng
         self.x = x
         Fr = self.n_img // eng.B
+        if self.folded:
+            ops.mha_temporal_folded_fwd(x, self.fa, self.fu, self.fm, self.fb, self.out, eng.B, Fr, self.H, self.W,
+                                        self.C)
+            return self.out
         if self.fused:
             fn = ops.mha_temporal_tc_fwd if ops.mha_tc_supported(Fr, self.C) else ops.mha_temporal_fused_fwd
             fn(x, self.w_hm, self.b_hm, self.o, self.qkv, self.lse, eng.B, Fr, self.H, self.W, self.C)

@@ -318,6 +318,16 @@ def mha_temporal_bwd(qkv, o, d_o, lse, dqkv, B, F, H, W):
           "vdn_mha_temporal_bwd")
 
 
+def mha_fold_pack(w_qkv, b_qkv, w_out, b_out, fa, fu, fm, fb):
+    check(lib.vdn_mha_fold_pack(ptr(w_qkv), ptr(b_qkv), ptr(w_out), ptr(b_out), ptr(fa), ptr(fu), ptr(fm), ptr(fb),
+                                stream_ptr()), "vdn_mha_fold_pack")
+
+
+def mha_temporal_folded_fwd(x, fa, fu, fm, fb, out, B, F, H, W, Cc):
+    check(lib.vdn_mha_temporal_folded_fwd(ptr(x), ptr(fa), ptr(fu), ptr(fm), ptr(fb), ptr(out), B, F, H, W, Cc,
+                                          stream_ptr()), "vdn_mha_temporal_folded_fwd")
+
+
 def mha_tc_supported(F: int, Cc: int) -> bool:
     return bool(lib.vdn_mha_temporal_tc_supported(F, Cc))
 
