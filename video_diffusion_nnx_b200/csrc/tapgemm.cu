@@ -636,6 +636,14 @@ extern "C" int vdn_tapgemm(const vdn_tapgemm_desc* d, const void* src0, const vo
   a.M = d->n_img * d->H * d->W;
   a.N = d->n_out;
   a.BN = pick_bn(d->n_out, ceil_div(a.M, kTileM));
+  {
+    // Short-K GEMMs (e.g. the 32 -> 256 / 768 projections) are all epilogue: a 256-column tile holds 256 of the
+    // SM's 512 TMEM columns, so only two CTAs are resident and nothing hides their load -> MMA -> store chain.
+    // Narrower tiles cost a few extra reads of the (tiny) A tile and buy 4-8 resident CTAs.
+    static const int smallk_bn = getenv("VDN_BN_SMALLK") ? atoi(getenv("VDN_BN_SMALLK")) : 128;
+    const int ktot = d->n_taps * d->n_src * d->src_c;
+    if (ktot <= 64 && smallk_bn >= 32 && a.BN > smallk_bn && d->n_out % smallk_bn == 0) a.BN = smallk_bn;
+  }
   if (const char* e = getenv("VDN_BN")) {  // tuning override (experiments only)
     const int v = atoi(e);
     if (v >= 16 && v <= 256 && d->n_out % v == 0) a.BN = v;
