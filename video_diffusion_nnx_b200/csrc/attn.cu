@@ -589,9 +589,14 @@ __global__ void __launch_bounds__(256) sla_bwd_tokens_kernel(const bf16* __restr
   }
 }
 
-static int sla_splits(int N) {
+// Token splits per frame for the context / dcontext passes: at most 32, and no more than needed to give every SM
+// ~4 blocks (n_img frames x splits): every split writes a 32 KB partial per frame that the merge pass re-reads,
+// which at large batch (n_img = 160) was more traffic than the input itself.
+static int sla_splits(int N, int n_img) {
   int per = std::max(kSlaTile, ((N + 31) / 32 + kSlaTile - 1) / kSlaTile * kSlaTile);  // <= 32 splits
-  return std::max(1, (N + per - 1) / per);
+  const int max_splits = std::max(1, (N + per - 1) / per);
+  const int want = std::max(1, (148 * 4 + n_img - 1) / std::max(1, n_img));
+  return std::min(max_splits, want);
 }
 
 }  // namespace vdn
@@ -635,7 +640,7 @@ extern "C" int vdn_mha_core_bwd(const void* qkv, const void* o, const void* d_o,
 }
 
 extern "C" size_t vdn_sla_workspace_floats(int n_img, int N) {
-  const int ns = sla_splits(N);
+  const int ns = sla_splits(N, n_img);
   return (size_t)n_img * kHeads * ns * (1024 + 64);
 }
 
@@ -643,7 +648,7 @@ extern "C" int vdn_sla_core_fwd(const void* qkv, void* tok_out, float* ctx, floa
                                 void* stream) {
   VDN_REQUIRE(qkv && tok_out && ctx && kstat && ws && n_img > 0 && N > 0, VDN_E_SHAPE, "sla_core_fwd: bad args");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const int ns = sla_splits(N);
+  const int ns = sla_splits(N, n_img);
   const int per = (N + ns - 1) / ns;
   const int per_al = (per + kSlaTile - 1) / kSlaTile * kSlaTile;
   float* ctx_part = ws;
@@ -681,7 +686,7 @@ extern "C" int vdn_sla_fused_fwd(const void* x, const void* w_qkv, const void* w
   VDN_REQUIRE(x && w_qkv && w_out && out && ctx && kstat && ws && n_img > 0 && N > 0, VDN_E_SHAPE, "sla_fused_fwd: bad args");
   VDN_REQUIRE(C == 32, VDN_E_SHAPE, "sla_fused_fwd: C=%d (only the 32-channel level is fused)", C);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const int ns = sla_splits(N);
+  const int ns = sla_splits(N, n_img);
   const int per = (N + ns - 1) / ns;
   const int per_al = (per + kSlaTile - 1) / kSlaTile * kSlaTile;
   float* ctx_part = ws;
@@ -700,7 +705,7 @@ extern "C" int vdn_sla_core_bwd(const void* qkv, const void* d_tok, const float*
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   cudaError_t e = cudaMemsetAsync(dctx, 0, (size_t)n_img * kHeads * 1024 * sizeof(float), st);
   VDN_REQUIRE(e == cudaSuccess, VDN_E_CUDA, "sla_core_bwd memset: %s", cudaGetErrorString(e));
-  const int ns = sla_splits(N);
+  const int ns = sla_splits(N, n_img);
   const int per = (N + ns - 1) / ns;
   const int per_al = (per + kSlaTile - 1) / kSlaTile * kSlaTile;
   static const bool scalar = getenv("VDN_SLA_SCALAR") != nullptr;
