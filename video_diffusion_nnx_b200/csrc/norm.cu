@@ -102,6 +102,7 @@ constexpr int kVecPerThread = 4;
 // out = silu(GN(x) [* (scale+1) + shift])            (Block, modules.py:171-179)
 // grid (ceil(nvec / (256*4)), B); each thread owns 4 8-channel vectors of its sample.
 // ---------------------------------------------------------------------------------------
+template <int V>  // 8-channel vectors per thread
 __global__ void __launch_bounds__(kNormThreads) gn_silu_fwd_kernel(const GnArgs a, bf16* __restrict__ out) {
   extern __shared__ float sm[];
   pdl_trigger();
@@ -113,10 +114,10 @@ __global__ void __launch_bounds__(kNormThreads) gn_silu_fwd_kernel(const GnArgs 
   const long nvec = (long)a.rows * c8n;
   const bf16* xb = a.x + (long)b * a.rows * a.C;
   bf16* ob = out + (long)b * a.rows * a.C;
-  const long i0 = (long)blockIdx.x * (kNormThreads * kVecPerThread) + threadIdx.x;
-  uint4 raw[kVecPerThread];
+  const long i0 = (long)blockIdx.x * (kNormThreads * V) + threadIdx.x;
+  uint4 raw[V];
 #pragma unroll
-  for (int k = 0; k < kVecPerThread; ++k) {
+  for (int k = 0; k < V; ++k) {
     const long i = i0 + k * kNormThreads;
     raw[k] = i < nvec ? ldg16(xb + i * 8) : make_uint4(0, 0, 0, 0);
   }
@@ -129,7 +130,7 @@ __global__ void __launch_bounds__(kNormThreads) gn_silu_fwd_kernel(const GnArgs 
   load_coef8(sA, (int)(i0 % c8n) * 8, cA);
   load_coef8(sB, (int)(i0 % c8n) * 8, cB);
 #pragma unroll
-  for (int k = 0; k < kVecPerThread; ++k) {
+  for (int k = 0; k < V; ++k) {
     const long i = i0 + k * kNormThreads;
     if (i >= nvec) break;
     if (!fixed_c) {
@@ -596,9 +597,13 @@ extern "C" int vdn_gn_silu_fwd(const void* x_raw, const float* gn_sums, const fl
   if (rc) return rc;
   GnArgs a{reinterpret_cast<const bf16*>(x_raw), gn_sums, gamma, beta, scale_shift, ss_ld, B, rows_per_sample, C, G};
   const long nvec = (long)rows_per_sample * (C / 8);
-  dim3 grid(grid_x_for(nvec, kNormThreads * kVecPerThread), B);
-  cudaError_t le = launch_pdl(gn_silu_fwd_kernel, grid, dim3(kNormThreads), 2 * C * sizeof(float),
-                              reinterpret_cast<cudaStream_t>(stream), 1, a, reinterpret_cast<bf16*>(out));
+  // large samples: 8 vectors per thread (the per-block statistics prologue is amortised over twice the data)
+  const bool big = nvec >= 64 * 1024;
+  dim3 grid(grid_x_for(nvec, kNormThreads * (big ? 8 : kVecPerThread)), B);
+  cudaError_t le = big ? launch_pdl(gn_silu_fwd_kernel<8>, grid, dim3(kNormThreads), 2 * C * sizeof(float),
+                                    reinterpret_cast<cudaStream_t>(stream), 1, a, reinterpret_cast<bf16*>(out))
+                       : launch_pdl(gn_silu_fwd_kernel<kVecPerThread>, grid, dim3(kNormThreads), 2 * C * sizeof(float),
+                                    reinterpret_cast<cudaStream_t>(stream), 1, a, reinterpret_cast<bf16*>(out));
   VDN_REQUIRE(le == cudaSuccess, VDN_E_CUDA, "gn_silu_fwd launch: %s", cudaGetErrorString(le));
   return check_launch("gn_silu_fwd");
 }
