@@ -118,6 +118,17 @@ __device__ __forceinline__ float dsmem_ld_f32(const float* p, uint32_t rank) {
   asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(remote) : "memory");
   return v;
 }
+// 16-byte load from the shared memory of CTA `rank` of this cluster at the same offset as local pointer `p`
+__device__ __forceinline__ float4 dsmem_ld_f32x4(const void* p, uint32_t rank) {
+  uint32_t remote;
+  float4 v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(p)), "r"(rank));
+  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "r"(remote)
+               : "memory");
+  return v;
+}
 // Column-sum epilogue shared by the norm kernels: every CTA of the cluster holds n partial sums in its shared
 // memory `vals`; CTA 0 of the cluster adds them up through DSMEM and issues ONE atomicAdd per value, which cuts
 // the same-address atomic traffic at L2 by the cluster size. All threads of all CTAs of the cluster must call it.
