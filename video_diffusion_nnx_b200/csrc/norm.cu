@@ -6,6 +6,7 @@
 // fast variance) arrive as raw sums [B][G][2] = (sum x, sum x^2) accumulated by the producing
 // conv's epilogue (tapgemm.cu).
 #include <algorithm>
+#include <cstdlib>
 
 #include "vdn_common.cuh"
 #include "vdn_host.h"
@@ -561,8 +562,12 @@ __global__ void __launch_bounds__(kNormThreads) ln_bwd_kernel(const bf16* __rest
 
 // cluster width for a grid.x of `want` CTAs (power of two <= 8) and the padded grid.x
 static int cluster_for(int want, int* grid_x) {
+  // Measured on B200 (profiles/r1_microbench_sweep.txt): launching these short kernels as thread-block clusters costs
+  // more (co-scheduling of 8 CTAs per GPC) than the DSMEM pre-reduction saves in L2 atomics - gn_silu_bwd 38.8 us with
+  // clusters of 8, 30.5 us without. The cluster path stays selectable (VDN_NORM_CLUSTER=2|4|8) but is off by default.
+  static const int cmax = getenv("VDN_NORM_CLUSTER") ? atoi(getenv("VDN_NORM_CLUSTER")) : 1;
   int c = 1;
-  while (c < 8 && c * 2 <= want) c *= 2;
+  while (c < cmax && c * 2 <= want) c *= 2;
   *grid_x = (want + c - 1) / c * c;
   return c;
 }
