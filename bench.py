@@ -30,6 +30,17 @@ CFG = dict(dim=32, channels=1, frames=10, size=64, timesteps=1000, loss="l2", lr
            per_gpu_batch=4)
 TRAIN_GFLOP_PER_CLIP = 159.3   # 3 x 53.1 GFLOP forward (SURVEY.md 8d / BASELINE.md section 4)
 FWD_GFLOP_PER_CLIP = 53.1
+WORKLOAD_NAME = "configs/config_v2_2.yaml"
+
+
+def select_workload(name):
+    """v2_2 is the headline workload (BASELINE.json configs[1]); v2_3x is BASELINE.json configs[3]: config_v2_3
+    scaled up to 16 frames at 128x128, dim 128 (the conv- and temporal-attention-bound case)."""
+    global TRAIN_GFLOP_PER_CLIP, FWD_GFLOP_PER_CLIP, WORKLOAD_NAME
+    if name == "v2_3x":
+        CFG.update(dim=128, frames=16, size=128)
+        TRAIN_GFLOP_PER_CLIP, FWD_GFLOP_PER_CLIP = 9954.0, 3318.0  # SURVEY.md 8d / Appendix B.1
+        WORKLOAD_NAME = "configs/config_v2_3.yaml scaled up (16 frames, 128x128, dim 128)"
 
 
 def peaks():
@@ -212,17 +223,26 @@ def conv_roofline(torch, ops, pk):
     bytes_alg = 2.0 * M * C * 2 + 9 * C * C * 2
     tf = flops / (ms * 1e-3) / 1e12
     gbs = bytes_alg / (ms * 1e-3) / 1e9
-    # this layer is below the ridge (AI = flops/bytes ~ 144 FLOP/B < 212): HBM is the binding roofline
+    # the dim-32 layer is below the ridge (AI = flops/bytes ~ 144 FLOP/B < 212): HBM is the binding roofline there;
+    # the dim-128 layer of the v2_3x workload (AI 576) is bound by the tensor pipe
+    ridge = pk["tf_burst"] * 1e3 / pk["hbm"]
+    tensor_bound = flops / bytes_alg > ridge
     traffic = None
     tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-    if os.path.exists(tp):  # dram bytes per launch of this kernel from the committed `ncu --set full` capture
+    if os.path.exists(tp) and C == 32:  # dram bytes per launch of this kernel from the committed `ncu --set full` capture
         td = json.load(open(tp))
         traffic = td["dram_bytes_read"] + td["dram_bytes_write"]
-    return {"kernel": "conv3x3_rows_kernel<32,32,1> conv(1,3,3) 32->32 @64x64 (M=163840,N=32,K=288)", "bound": "hbm",
-            "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"], "traffic": traffic,
-            "algorithmic_bytes": bytes_alg,
-            "us_per_launch": ms * 1e3, "tensor_tflops": tf, "tensor_frac_of_burst": tf / pk["tf_burst"],
-            "peak_source": pk["src"]}
+    name = (f"conv(1,3,3) {C}->{C} @{H}x{W} (M={M},N={C},K={9 * C}) "
+            + ("conv3x3_rows_kernel<32,32,1>" if C == 32 else "tapgemm_kernel<64>"))
+    r = {"kernel": name, "bound": "tensor" if tensor_bound else "hbm"}
+    if tensor_bound:
+        r.update(achieved=tf, peak=pk["tf_burst"], unit="TFLOP/s", frac=tf / pk["tf_burst"], traffic=traffic,
+                 algorithmic_flops=flops, hbm_gbs=gbs)
+    else:
+        r.update(achieved=gbs, peak=pk["hbm"], unit="GB/s", frac=gbs / pk["hbm"], traffic=traffic,
+                 algorithmic_bytes=bytes_alg, tensor_tflops=tf, tensor_frac_of_burst=tf / pk["tf_burst"])
+    r.update(us_per_launch=ms * 1e3, peak_source=pk["src"])
+    return r
 
 
 def main():
@@ -237,7 +257,13 @@ def main():
     ap.add_argument("--sample-timesteps", type=int, default=CFG["timesteps"])
     ap.add_argument("--sample-batch", type=int, default=16,
                     help="samples per GPU in the sampling metric (16 = the reference default, gaussian_diffusion.py:323)")
+    ap.add_argument("--workload", default="v2_2", choices=["v2_2", "v2_3x"])
     args = ap.parse_args()
+    select_workload(args.workload)
+    if args.workload == "v2_3x":  # big model: short sampling run (extrapolated to T), small sample batch
+        args.sample_timesteps = min(args.sample_timesteps, 20)
+        args.sample_batch = min(args.sample_batch, 4)
+        args.no_cpu_baseline = True
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
         return run_reference(args)
@@ -334,12 +360,12 @@ def main():
     if rank == 0:
         act_mb = sum(t.numel() * t.element_size() for t in ts.eng.__dict__.values() if isinstance(t, torch.Tensor)) / 1e6
         line = {
-            "metric": "train clips/sec (Unet3D config_v2_2 p_losses fwd+bwd+allreduce+Adam/EMA, device-timed)",
+            "metric": f"train clips/sec (Unet3D config_{args.workload} p_losses fwd+bwd+allreduce+Adam/EMA, device-timed)",
             "value": value, "unit": "clips/s", "n_gpus": world, "steps": K, "warmup": Wm,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"configs/config_v2_2.yaml training step: Unet3D dim 32, 1 ch, 10 frames, 64x64, "
-                                   f"T=1000, L2, Adam+EMA; per-GPU batch {B}, global batch {B * world}",
+            "config": {"workload": f"{WORKLOAD_NAME} training step: Unet3D dim {CFG['dim']}, 1 ch, {CFG['frames']} frames, "
+                                   f"{CFG['size']}x{CFG['size']}, T=1000, L2, Adam+EMA; per-GPU batch {B}, global batch {B * world}",
                        "parallelism": f"dp{world}", "global_batch": B * world,
                        "l2": "no explicit flush: one step streams > 2 GB of activations / saved tensors, far beyond the 126 MB L2",
                        "timing": "CUDA events on the launch stream around K CUDA-graph-replayed steps, max over ranks"},
@@ -371,11 +397,12 @@ def main():
         if rank == 0:
             fps = world * sb * CFG["frames"] / (float(sms.item()) * 1e-3) * (CFG["timesteps"] / T) / (CFG["timesteps"] / T)
             fps_full = world * sb * CFG["frames"] / (float(sms.item()) * 1e-3 * CFG["timesteps"] / T)
-            line["sampling"] = {"metric": "sampling frames/sec (p_sample_loop, T=1000, config_v2_2)", "value": fps_full,
+            line["sampling"] = {"metric": f"sampling frames/sec (p_sample_loop, T=1000, config_{args.workload})", "value": fps_full,
                                 "unit": "frames/s", "timesteps_run": T, "ms_per_timestep": float(sms.item()) / T,
                                 "sample_batch_per_gpu": sb, "finite": bool(torch.isfinite(vid).all().item()),
-                                "sampling_tflops": fps_full * 5.31,
-                                "frac_of_sustained_bf16_peak": fps_full / world * 5.31 / pk["tf_sust"]}
+                                "sampling_tflops": fps_full * FWD_GFLOP_PER_CLIP / CFG["frames"] * CFG["timesteps"] / 1e3,
+                                "frac_of_sustained_bf16_peak": fps_full / world * FWD_GFLOP_PER_CLIP / CFG["frames"]
+                                * CFG["timesteps"] / 1e3 / pk["tf_sust"]}
             del fps
 
     if rank == 0:

@@ -247,7 +247,7 @@ class ResBlock:
         ds = pool.get(shape)
         # LayerNorm backward of the residual branch does not depend on the GroupNorm chain: side stream
         hln = eng.side(lambda: ops.ln_bwd(s, dout, self.p["norm_2.scale"], ds, self.g["norm_2.scale"],
-                                          self.g["norm_2.bias"], P, C))
+                                          self.g["norm_2.bias"], P, C), lane=1)
         T = pool.get((B, C, 2), F32)
         db_raw = pool.get(shape)
         ops.gn_silu_bwd(dout, self.b_raw, self.sums2, self.p["block_2.norm.scale"], self.p["block_2.norm.bias"], None,
@@ -270,7 +270,7 @@ class ResBlock:
         dsrc = [pool.get(sshape) for _ in range(self.n_src)]
         hr = None
         if self.res is not None:
-            hr = eng.side(lambda: self.res.wgrad(self.srcs, ds))  # same stream as ln_bwd: ordered after it
+            hr = eng.side(lambda: self.res.wgrad(self.srcs, ds), lane=1)  # same stream as ln_bwd: ordered after it
             self.conv1.dgrad(da_raw, dsrc)
             eng.join(hln)
             self.res.dgrad(ds, dsrc, residuals=dsrc)  # in-place accumulate
@@ -493,20 +493,21 @@ class UpConv:
 # the engine
 # ------------------------------------------------------------------------------------------
 class UnetEngine:
-    def side(self, fn):
-        """Runs fn() on the side stream, ordered after everything enqueued so far on the current stream; returns
+    def side(self, fn, lane: int = 0):
+        """Runs fn() on side stream `lane`, ordered after everything enqueued so far on the current stream; returns
         an event to join(). Works eagerly and under CUDA-graph capture (fork / join edges of the graph)."""
         if self.side_stream is None:
             fn()
             return None
+        stream = self.side_stream if lane == 0 else self.side_stream2
         main = torch.cuda.current_stream()
         ev = torch.cuda.Event()
         ev.record(main)
-        self.side_stream.wait_event(ev)
-        with torch.cuda.stream(self.side_stream):
+        stream.wait_event(ev)
+        with torch.cuda.stream(stream):
             fn()
             done = torch.cuda.Event()
-            done.record(self.side_stream)
+            done.record(stream)
         return done
 
     def join(self, *handles):
@@ -528,6 +529,7 @@ class UnetEngine:
         import os
         self.side_stream = (torch.cuda.Stream(device=self.device)
                             if self.device.type == "cuda" and not os.environ.get("VDN_NO_OVERLAP") else None)
+        self.side_stream2 = torch.cuda.Stream(device=self.device) if self.side_stream is not None else None
         self._gn_slots: List[torch.Tensor] = []
         self._gn_count = 0
         self._heads: List[dict] = []
