@@ -234,8 +234,10 @@ __global__ void __launch_bounds__(kNormThreads) resblock_tail_fwd_kernel(const G
 // grid (ceil(rows / (pixel lanes * 4)), B) in clusters along x: 4 pixels per thread, block partials are summed
 // across the cluster through DSMEM before the atomics into T.
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kNormThreads) gn_bwd_reduce_kernel(const GnArgs a, const bf16* __restrict__ dy,
-                                                                     float* __restrict__ T /*[B][C][2]*/) {
+template <bool kMulti>
+__global__ void __launch_bounds__(kNormThreads, 2) gn_bwd_reduce_kernel(const GnArgs a, const bf16* __restrict__ dy,
+                                                                        float* __restrict__ T /*[B][C][2]*/, int iters_arg) {
+  const int iters = kMulti ? iters_arg : 1;
   extern __shared__ float sm[];
   pdl_trigger();
   pdl_wait();
@@ -252,18 +254,24 @@ __global__ void __launch_bounds__(kNormThreads) gn_bwd_reduce_kernel(const GnArg
   const int pl = threadIdx.x / c8n;
   const int c0 = ci * 8;
   const long base = (long)b * a.rows;
+  // A block owns `iters` consecutive chunks of kVecPerThread * pl_n pixels (large samples: the statistics
+  // prologue and the block-level reduction + atomics are amortised over `iters` times the data); two resident
+  // blocks per SM overlap one block's loads with the other's arithmetic.
   uint4 xraw[kVecPerThread], draw[kVecPerThread];
   bool valid[kVecPerThread];
+  auto issue = [&](int it, uint4 (&xr)[kVecPerThread], uint4 (&dr)[kVecPerThread], bool (&vl)[kVecPerThread]) {
 #pragma unroll
-  for (int k = 0; k < kVecPerThread; ++k) {
-    const long p = ((long)blockIdx.x * kVecPerThread + k) * pl_n + pl;
-    valid[k] = pl < pl_n && p < a.rows;
-    if (valid[k]) {
-      const long off = (base + p) * a.C + c0;
-      xraw[k] = ldg16(a.x + off);
-      draw[k] = ldg16(dy + off);
+    for (int k = 0; k < kVecPerThread; ++k) {
+      const long p = (((long)blockIdx.x * iters + it) * kVecPerThread + k) * pl_n + pl;
+      vl[k] = pl < pl_n && p < a.rows;
+      if (vl[k]) {
+        const long off = (base + p) * a.C + c0;
+        xr[k] = ldg16(a.x + off);
+        dr[k] = ldg16(dy + off);
+      }
     }
-  }
+  };
+  issue(0, xraw, draw, valid);
   gn_affine_to_smem(a, b, sA, sB);
   {
     const int cpg = a.C / a.G;
@@ -287,20 +295,23 @@ __global__ void __launch_bounds__(kNormThreads) gn_bwd_reduce_kernel(const GnArg
   load_coef8(sMean, c0, cM);
 #pragma unroll
   for (int j = 0; j < 8; ++j) t1[j] = t2[j] = 0.f;
+  for (int it = 0; it < iters; ++it) {
 #pragma unroll
-  for (int k = 0; k < kVecPerThread; ++k) {
-    if (!valid[k]) continue;
-    float xv[8], dv[8];
-    unpack8(xraw[k], xv);
-    unpack8(draw[k], dv);
+    for (int k = 0; k < kVecPerThread; ++k) {
+      if (!valid[k]) continue;
+      float xv[8], dv[8];
+      unpack8(xraw[k], xv);
+      unpack8(draw[k], dv);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float z = fmaf(xv[j], cA[j], cB[j]);
-      const float dz = dv[j] * silu_grad_f(z);
-      const float xh = fmaf(xv[j], cR[j], cM[j]);
-      t1[j] += dz;
-      t2[j] = fmaf(dz, xh, t2[j]);
+      for (int j = 0; j < 8; ++j) {
+        const float z = fmaf(xv[j], cA[j], cB[j]);
+        const float dz = dv[j] * silu_grad_f(z);
+        const float xh = fmaf(xv[j], cR[j], cM[j]);
+        t1[j] += dz;
+        t2[j] = fmaf(dz, xh, t2[j]);
+      }
     }
+    if (kMulti && it + 1 < iters) issue(it + 1, xraw, draw, valid);
   }
   // reduce over pixel lanes through smem, over the cluster through DSMEM, then one atomic per (c, {T1,T2})
   float* my = red + (long)threadIdx.x * 16;
@@ -322,11 +333,14 @@ __global__ void __launch_bounds__(kNormThreads) gn_bwd_reduce_kernel(const GnArg
 // dx = rstd_g * (gamma_c*(s+1)*dz - m1_g - xhat*m2_g),  m1_g = mean_g(dxhat), m2_g = mean_g(dxhat*xhat)
 // The x == 0 block of each sample also finalises dgamma / dbeta (atomics over samples) and (dscale | dshift);
 // every block accumulates the column sums of dx = the gradient of the producing conv's bias (cluster-reduced).
-__global__ void __launch_bounds__(kNormThreads) gn_bwd_apply_kernel(const GnArgs a, const bf16* __restrict__ dy,
-                                                                    const float* __restrict__ T,
-                                                                    bf16* __restrict__ dx, float* __restrict__ dgamma,
-                                                                    float* __restrict__ dbeta, float* __restrict__ dss,
-                                                                    int dss_ld, float* __restrict__ dconv_bias) {
+template <bool kMulti>
+__global__ void __launch_bounds__(kNormThreads, 2) gn_bwd_apply_kernel(const GnArgs a, const bf16* __restrict__ dy,
+                                                                       const float* __restrict__ T,
+                                                                       bf16* __restrict__ dx, float* __restrict__ dgamma,
+                                                                       float* __restrict__ dbeta, float* __restrict__ dss,
+                                                                       int dss_ld, float* __restrict__ dconv_bias,
+                                                                       int iters_arg) {
+  const int iters = kMulti ? iters_arg : 1;
   extern __shared__ float sm[];
   pdl_trigger();
   pdl_wait();
@@ -344,16 +358,20 @@ __global__ void __launch_bounds__(kNormThreads) gn_bwd_apply_kernel(const GnArgs
   const int c8n = a.C / 8;
   const long nvec = (long)a.rows * c8n;
   const long boff = (long)b * a.rows * a.C;
-  const long i0 = (long)blockIdx.x * (kNormThreads * kVecPerThread) + threadIdx.x;
+  // a block owns `iters` consecutive chunks of kNormThreads * kVecPerThread vectors (see gn_bwd_reduce_kernel)
+  const long i0 = (long)blockIdx.x * iters * (kNormThreads * kVecPerThread) + threadIdx.x;
   uint4 xraw[kVecPerThread], draw[kVecPerThread];
+  auto issue = [&](int it, uint4 (&xr)[kVecPerThread], uint4 (&dr)[kVecPerThread]) {
 #pragma unroll
-  for (int k = 0; k < kVecPerThread; ++k) {
-    const long i = i0 + k * kNormThreads;
-    if (i < nvec) {
-      xraw[k] = ldg16(a.x + boff + i * 8);
-      draw[k] = ldg16(dy + boff + i * 8);
+    for (int k = 0; k < kVecPerThread; ++k) {
+      const long i = i0 + ((long)it * kVecPerThread + k) * kNormThreads;
+      if (i < nvec) {
+        xr[k] = ldg16(a.x + boff + i * 8);
+        dr[k] = ldg16(dy + boff + i * 8);
+      }
     }
-  }
+  };
+  issue(0, xraw, draw);
   gn_affine_to_smem(a, b, sA, sB);
   const float inv_n = 1.f / ((float)a.rows * (float)cpg);
   for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
@@ -405,22 +423,25 @@ __global__ void __launch_bounds__(kNormThreads) gn_bwd_apply_kernel(const GnArgs
   load_coef8(sM2, c0, cM2);
 #pragma unroll
   for (int j = 0; j < 8; ++j) cK[j] *= cR[j];
+  for (int it = 0; it < iters; ++it) {
 #pragma unroll
-  for (int k = 0; k < kVecPerThread; ++k) {
-    const long i = i0 + k * kNormThreads;
-    if (i >= nvec) break;
-    float xv[8], dv[8], o[8];
-    unpack8(xraw[k], xv);
-    unpack8(draw[k], dv);
+    for (int k = 0; k < kVecPerThread; ++k) {
+      const long i = i0 + ((long)it * kVecPerThread + k) * kNormThreads;
+      if (i >= nvec) break;
+      float xv[8], dv[8], o[8];
+      unpack8(xraw[k], xv);
+      unpack8(draw[k], dv);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float z = fmaf(xv[j], cA[j], cB[j]);
-      const float dz = dv[j] * silu_grad_f(z);
-      const float xh = fmaf(xv[j], cR[j], cM[j]);
-      o[j] = fmaf(xh, cM2[j], fmaf(dz, cK[j], cM1[j]));  // rstd * (K dz - m1 - xhat m2)
-      bs[j] += o[j];
+      for (int j = 0; j < 8; ++j) {
+        const float z = fmaf(xv[j], cA[j], cB[j]);
+        const float dz = dv[j] * silu_grad_f(z);
+        const float xh = fmaf(xv[j], cR[j], cM[j]);
+        o[j] = fmaf(xh, cM2[j], fmaf(dz, cK[j], cM1[j]));  // rstd * (K dz - m1 - xhat m2)
+        bs[j] += o[j];
+      }
+      store8(dx + boff + i * 8, o);
     }
-    store8(dx + boff + i * 8, o);
+    if (kMulti && it + 1 < iters) issue(it + 1, xraw, draw);
   }
   if (dconv_bias) {
 #pragma unroll
@@ -651,17 +672,25 @@ extern "C" int vdn_gn_silu_bwd(const void* dy, const void* x_raw, const float* g
   VDN_REQUIRE(e == cudaSuccess, VDN_E_CUDA, "gn_silu_bwd memset: %s", cudaGetErrorString(e));
   const int pl_n = kNormThreads / (C / 8);
   int gx, cl;
-  cl = cluster_for(grid_x_for(rows_per_sample, pl_n * kVecPerThread), &gx);
+  // chunks per block: 1 until the launch exceeds ~2 waves of 8 blocks per SM, then up to 8 (large samples)
+  const long blocks1 = (long)grid_x_for(rows_per_sample, pl_n * kVecPerThread) * B;
+  const int iters = (int)std::max<long>(1, std::min<long>(8, blocks1 / (2 * 8 * num_sms())));
+  cl = cluster_for(grid_x_for(rows_per_sample, pl_n * kVecPerThread * iters), &gx);
   const size_t smem_r = (6 * C + kNormThreads * 16) * sizeof(float);
-  cudaError_t le = launch_pdl(gn_bwd_reduce_kernel, dim3(gx, B), dim3(kNormThreads), (size_t)(smem_r), st, cl, a, reinterpret_cast<const bf16*>(dy), T_ws);
+  cudaError_t le = iters > 1 ? launch_pdl(gn_bwd_reduce_kernel<true>, dim3(gx, B), dim3(kNormThreads), (size_t)(smem_r), st, cl, a, reinterpret_cast<const bf16*>(dy), T_ws, iters)
+                             : launch_pdl(gn_bwd_reduce_kernel<false>, dim3(gx, B), dim3(kNormThreads), (size_t)(smem_r), st, cl, a, reinterpret_cast<const bf16*>(dy), T_ws, 1);
   VDN_REQUIRE(le == cudaSuccess, VDN_E_CUDA, "gn_bwd_reduce launch: %s", cudaGetErrorString(le));
   rc = check_launch("gn_bwd_reduce");
   if (rc) return rc;
   const long nvec = (long)rows_per_sample * (C / 8);
-  cl = cluster_for(grid_x_for(nvec, kNormThreads * kVecPerThread), &gx);
-  le = launch_pdl(gn_bwd_apply_kernel, dim3(gx, B), dim3(kNormThreads), (size_t)((8 * C + kNormThreads * 8) * sizeof(float)), st, cl, a,
-                        reinterpret_cast<const bf16*>(dy), (const float*)T_ws, reinterpret_cast<bf16*>(dx_raw), dgamma, dbeta,
-                        dss, dss_ld, dconv_bias);
+  cl = cluster_for(grid_x_for(nvec, kNormThreads * kVecPerThread * iters), &gx);
+  const size_t smem_a = (size_t)((8 * C + kNormThreads * 8) * sizeof(float));
+  le = iters > 1 ? launch_pdl(gn_bwd_apply_kernel<true>, dim3(gx, B), dim3(kNormThreads), smem_a, st, cl, a,
+                              reinterpret_cast<const bf16*>(dy), (const float*)T_ws, reinterpret_cast<bf16*>(dx_raw), dgamma,
+                              dbeta, dss, dss_ld, dconv_bias, iters)
+                 : launch_pdl(gn_bwd_apply_kernel<false>, dim3(gx, B), dim3(kNormThreads), smem_a, st, cl, a,
+                              reinterpret_cast<const bf16*>(dy), (const float*)T_ws, reinterpret_cast<bf16*>(dx_raw), dgamma,
+                              dbeta, dss, dss_ld, dconv_bias, 1);
   VDN_REQUIRE(le == cudaSuccess, VDN_E_CUDA, "gn_bwd_apply launch: %s", cudaGetErrorString(le));
   return check_launch("gn_bwd_apply");
 }

@@ -628,6 +628,9 @@ extern "C" int vdn_tapgemm(const vdn_tapgemm_desc* d, const void* src0, const vo
   if (rowconv_applicable(d, residual, gn_sums))
     return rowconv_launch(d, src0, src1, wp, bias, residual, residual2, out, out2, gn_sums,
                           reinterpret_cast<cudaStream_t>(stream));
+  if (slabconv_applicable(d, residual, gn_sums))
+    return slabconv_launch(d, src0, src1, wp, bias, residual, residual2, out, out2, gn_sums,
+                           reinterpret_cast<cudaStream_t>(stream));
 
   const int C = d->src_c;
   const int BK = (C % 64 == 0) ? 64 : (C % 32 == 0) ? 32 : 16;

@@ -17,6 +17,13 @@ int rowconv_launch(const vdn_tapgemm_desc* d, const void* src0, const void* src1
                    const void* residual, const void* residual2, void* out, void* out2, float* gn_sums,
                    cudaStream_t st);
 
+// conv3x3_slab.cu: (1,3,3) conv of the wide-channel levels with operand reuse in shared memory (R row-adjacent
+// tiles per CTA share every weight tile, the three dy taps share one pixel slab); same contract
+bool slabconv_applicable(const vdn_tapgemm_desc* d, const void* residual, const float* gn_sums);
+int slabconv_launch(const vdn_tapgemm_desc* d, const void* src0, const void* src1, const void* wp, const float* bias,
+                    const void* residual, const void* residual2, void* out, void* out2, float* gn_sums,
+                    cudaStream_t st);
+
 // sla_mma.cu: per-token SpatialLinearAttention products on warp-level tensor-core MMAs
 int sla_apply_mma_launch(const void* qkv, const float* ctx, void* tok_out, int n_img, int N, cudaStream_t st);
 int sla_bwd_tokens_mma_launch(const void* qkv, const void* d_tok, const float* ctx, const float* dctx,
