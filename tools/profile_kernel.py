@@ -18,9 +18,12 @@ def bf(*s):
     return torch.randn(*s, device=dev).to(torch.bfloat16)
 
 
-if what in ("conv_l0", "conv_l3", "qkv_l0"):
+if what in ("conv_l0", "conv_l3", "qkv_l0", "conv_v23x_l0", "conv_v23x_l1"):
+    if what.startswith("conv_v23x"):  # config_v2_3 scale-up: 16 frames, 128x128, dim 128 (slab kernel; VDN_NO_SLABCONV=1: generic)
+        F = 16
     H, C, N, taps = {"conv_l0": (64, 32, 32, ops.TAPS_3x3), "conv_l3": (8, 256, 256, ops.TAPS_3x3),
-                     "qkv_l0": (64, 32, 768, ops.TAPS_1x1)}[what]
+                     "qkv_l0": (64, 32, 768, ops.TAPS_1x1), "conv_v23x_l0": (128, 128, 128, ops.TAPS_3x3),
+                     "conv_v23x_l1": (64, 256, 256, ops.TAPS_3x3)}[what]
     x = bf(B * F, H, H, C)
     w = torch.randn(len(taps), C, N, device=dev) * (len(taps) * C) ** -0.5
     wp = torch.empty(N, len(taps) * C, dtype=torch.bfloat16, device=dev)

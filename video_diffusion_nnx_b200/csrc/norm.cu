@@ -26,39 +26,71 @@ struct GnArgs {
   int B, rows, C, G;
 };
 
-__device__ __forceinline__ void gn_read_sums(const GnArgs& a, int b, int g, float& s1, float& s2) {
-  s1 = 0.f;
-  s2 = 0.f;
-#pragma unroll
-  for (int r = 0; r < kGnReplicas; ++r) {
+constexpr int kMaxGroups = 16;
+
+// (mean, rstd) of every group of sample b into shared memory: thread (g, r) reads replica r of group g, the 16
+// replicas are added up with shuffles (one coalesced round trip instead of 16 dependent loads per CHANNEL - at
+// C = 1024 the per-block statistics prologue used to cost more than the block's payload). Ends with a barrier.
+// Must be called by every thread of the block (blockDim >= 16 * G).
+__device__ __forceinline__ const float2* gn_group_stats(const GnArgs& a, int b) {
+  __shared__ float2 s_stat[kMaxGroups];
+  static_assert(kGnReplicas == 16, "one 16-lane segment per group");
+  const int g = threadIdx.x >> 4, r = threadIdx.x & 15;
+  float s1 = 0.f, s2 = 0.f;
+  if (g < a.G) {
     const float2 v = *reinterpret_cast<const float2*>(a.sums + ((long)(r * a.B + b) * a.G + g) * 2);
-    s1 += v.x;
-    s2 += v.y;
+    s1 = v.x;
+    s2 = v.y;
   }
+  if (threadIdx.x < 16 * kMaxGroups) {  // whole warps: the shuffles below are convergent
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) {
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    if (r == 0 && g < a.G) {
+      const float inv_n = 1.f / ((float)a.rows * (float)(a.C / a.G));
+      const float mean = s1 * inv_n;
+      const float var = fmaxf(s2 * inv_n - mean * mean, 0.f);
+      s_stat[g] = make_float2(mean, rsqrtf(var + kEps));
+    }
+  }
+  __syncthreads();
+  return s_stat;
 }
 
-// Per-sample affine in smem: y = x * A[c] + Bc[c]  (GN * gamma + beta, then *(scale+1)+shift)
-__device__ __forceinline__ void gn_affine_to_smem(const GnArgs& a, int b, float* sA, float* sB) {
-  const int cpg = a.C / a.G;
-  const float inv_n = 1.f / ((float)a.rows * (float)cpg);
-  for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
-    const int g = c / cpg;
-    float s1, s2;
-    gn_read_sums(a, b, g, s1, s2);
-    const float mean = s1 * inv_n;
-    const float var = fmaxf(s2 * inv_n - mean * mean, 0.f);
-    const float rstd = rsqrtf(var + kEps);
-    float A = rstd * a.gamma[c];
-    float Bc = a.beta[c] - mean * A;
+// Per-sample affine in smem: y = x * A[c] + Bc[c]  (GN * gamma + beta, then *(scale+1)+shift). Returns the
+// per-group (mean, rstd) table (shared memory).
+__device__ __forceinline__ const float2* gn_affine_to_smem(const GnArgs& a, int b, float* sA, float* sB) {
+  // the parameters of this thread's first channel are requested BEFORE the statistics round trip (they overlap)
+  const int c_first = threadIdx.x;
+  float ga = 0.f, be = 0.f, sc = 1.f, sh = 0.f;
+  if (c_first < a.C) {
+    ga = a.gamma[c_first];
+    be = a.beta[c_first];
     if (a.ss) {
-      const float sc = a.ss[(long)b * a.ss_ld + c] + 1.f;
-      const float sh = a.ss[(long)b * a.ss_ld + a.C + c];
-      A *= sc;
-      Bc = Bc * sc + sh;
+      sc = a.ss[(long)b * a.ss_ld + c_first] + 1.f;
+      sh = a.ss[(long)b * a.ss_ld + a.C + c_first];
     }
-    sA[c] = A;
-    sB[c] = Bc;
   }
+  const float2* st = gn_group_stats(a, b);
+  const int cpg = a.C / a.G;
+  for (int c = c_first; c < a.C; c += blockDim.x) {
+    if (c != c_first) {
+      ga = a.gamma[c];
+      be = a.beta[c];
+      if (a.ss) {
+        sc = a.ss[(long)b * a.ss_ld + c] + 1.f;
+        sh = a.ss[(long)b * a.ss_ld + a.C + c];
+      }
+    }
+    const float2 mr = st[c / cpg];
+    const float A = mr.y * ga;
+    const float Bc = be - mr.x * A;
+    sA[c] = A * sc;
+    sB[c] = Bc * sc + sh;
+  }
+  return st;
 }
 
 __device__ __forceinline__ void load8(const bf16* p, float (&v)[8]) {
@@ -272,19 +304,13 @@ __global__ void __launch_bounds__(kNormThreads, 2) gn_bwd_reduce_kernel(const Gn
     }
   };
   issue(0, xraw, draw, valid);
-  gn_affine_to_smem(a, b, sA, sB);
   {
+    const float2* st = gn_affine_to_smem(a, b, sA, sB);
     const int cpg = a.C / a.G;
-    const float inv_n = 1.f / ((float)a.rows * (float)cpg);
     for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
-      const int g = c / cpg;
-      float s1, s2;
-      gn_read_sums(a, b, g, s1, s2);
-      const float mean = s1 * inv_n;
-      const float var = fmaxf(s2 * inv_n - mean * mean, 0.f);
-      const float rstd = rsqrtf(var + kEps);
-      sRstd[c] = rstd;
-      sMean[c] = -mean * rstd;  // xhat = x * rstd + (-mean * rstd)
+      const float2 mr = st[c / cpg];
+      sRstd[c] = mr.y;
+      sMean[c] = -mr.x * mr.y;  // xhat = x * rstd + (-mean * rstd)
     }
   }
   __syncthreads();
@@ -372,17 +398,13 @@ __global__ void __launch_bounds__(kNormThreads, 2) gn_bwd_apply_kernel(const GnA
     }
   };
   issue(0, xraw, draw);
-  gn_affine_to_smem(a, b, sA, sB);
+  const float2* st = gn_affine_to_smem(a, b, sA, sB);
   const float inv_n = 1.f / ((float)a.rows * (float)cpg);
   for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
-    const int g = c / cpg;
-    float s1, s2;
-    gn_read_sums(a, b, g, s1, s2);
-    const float mean = s1 * inv_n;
-    const float var = fmaxf(s2 * inv_n - mean * mean, 0.f);
-    const float rstd = rsqrtf(var + kEps);
+    const float2 mr = st[c / cpg];
+    const float rstd = mr.y;
     sRstd[c] = rstd;
-    sMean[c] = -mean * rstd;  // xhat = x * rstd + (-mean * rstd)
+    sMean[c] = -mr.x * rstd;  // xhat = x * rstd + (-mean * rstd)
     const float sc = a.ss ? a.ss[(long)b * a.ss_ld + c] + 1.f : 1.f;
     sK[c] = a.gamma[c] * sc;
   }
@@ -605,6 +627,7 @@ static int check_gn(const char* who, int B, int rows, int C, int G) {
   VDN_REQUIRE(B > 0 && rows > 0 && C >= 8 && C % 8 == 0 && G > 0 && C % G == 0, VDN_E_SHAPE,
               "%s: bad shape B=%d rows=%d C=%d G=%d", who, B, rows, C, G);
   VDN_REQUIRE(C <= 2048, VDN_E_SHAPE, "%s: C=%d > 2048 unsupported", who, C);
+  VDN_REQUIRE(G <= kMaxGroups, VDN_E_SHAPE, "%s: G=%d > %d groups unsupported", who, G, kMaxGroups);
   return VDN_OK;
 }
 
