@@ -208,6 +208,11 @@ int vdn_mha_temporal_fused_fwd(const void* x, const void* w_hm, const float* bia
 int vdn_mha_temporal_tc_supported(int F, int C);
 int vdn_mha_temporal_tc_fwd(const void* x, const void* w_hm, const float* bias_hm, void* o, void* qkv, float* lse,
                             int B, int F, int H, int W, int C, void* stream);
+/* Temporal attention core forward on a materialised q|k|v tensor (modules.py:296-323: q / sqrt(32), softmax over the
+ * F <= 16 frames of a pixel, P V), for levels whose QKV projection runs as a tap-GEMM (training engines at C >= 64):
+ * qkv bf16 [P][768] (q|k|v, head h at columns h*32) -> o bf16 [P][256], optional lse fp32 [P][8]. One warp per
+ * (pixel, head) on register-resident bf16 MMAs (csrc/mha_mma.cu). */
+int vdn_mha_temporal_core_fwd(const void* qkv, void* o, float* lse, int B, int F, int H, int W, void* stream);
 /* Folded temporal attention BLOCK for inference engines, C == 32, F <= 16: out = x + out_proj(MHA(x)) in one kernel
  * (modules.py:285-326 + the residual of unet3d.py:86-96). vdn_mha_fold_pack builds, from the fp32 master weights
  * (fused q|k|v kernel [32][768] + bias [768], out kernel [256][32] + bias [32]), A_h = W_q,h W_k,h^T / sqrt(32),

@@ -555,3 +555,28 @@ def test_mha_temporal_tc_fwd(B, Fr, H, W, Cc):
     o2 = torch.zeros_like(o)
     ops.mha_temporal_tc_fwd(x, w_hm, b_hm, o2, None, None, B, Fr, H, W, Cc)
     assert _rel(o2, o_ref) < 2e-2
+
+
+@pytest.mark.parametrize("B,Fr,H,W", [(2, 10, 16, 16), (1, 16, 8, 32), (3, 2, 8, 8), (1, 7, 4, 4)])
+def test_mha_temporal_core_fwd(B, Fr, H, W):
+    """Attention core on a materialised q|k|v tensor (training engines at C >= 64) vs torch fp32, any F <= 16;
+    lse must be the one the shared backward kernel expects (max + log sum of the scaled logits)."""
+    from video_diffusion_nnx_b200 import ops
+
+    _setup()
+    P = B * Fr * H * W
+    qkv = _bf(P, 768)
+    o = torch.zeros(P, 256, dtype=torch.bfloat16, device=DEV)
+    lse = torch.zeros(P, 8, device=DEV)
+    ops.mha_temporal_core_fwd(qkv, o, lse, B, Fr, H, W)
+    torch.cuda.synchronize()
+    t = qkv.float().reshape(B, Fr, H * W, 3, 8, 32).permute(0, 2, 1, 3, 4, 5)
+    q, k, v = t[..., 0, :, :], t[..., 1, :, :], t[..., 2, :, :]
+    s = torch.einsum("...ihd,...jhd->...hij", q / math.sqrt(32), k)
+    o_ref = torch.einsum("...hij,...jhd->...ihd", s.softmax(-1), v).permute(0, 2, 1, 3, 4).reshape(P, 256)
+    lse_ref = torch.logsumexp(s, -1).permute(0, 3, 1, 2).reshape(P, 8)
+    assert _rel(o, o_ref) < 2e-2   # P is rounded to bf16 before the P V product
+    assert _rel(lse, lse_ref) < 3e-3
+    o2 = torch.zeros_like(o)
+    ops.mha_temporal_core_fwd(qkv, o2, None, B, Fr, H, W)
+    assert torch.equal(o2, o)

@@ -613,6 +613,122 @@ int mha_temporal_folded_fwd_launch(const void* x, const void* fa, const float* f
   return check_launch("mha_temporal_folded_fwd");
 }
 
+// ---------------------------------------------------------------------------------------
+// Attention core forward on a materialised q|k|v tensor (any C: the projection ran as a tap-GEMM at full tensor-core
+// rate): one warp per (pixel, head), everything in registers, every byte moved once with 16-byte accesses.
+//   S = q k^T / sqrt(32), P = softmax(S), O = P V, lse = max + log(sum)     (modules.py:296-323)
+// Same fragment scheme as the fused C = 32 kernel above: q, k, v arrive as the lane's 16-byte chunk j of token rows
+// g / g+8; the B operand of P V is the movmatrix transpose of the v chunk registers.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 3) mha_temporal_mma_core_fwd_kernel(const bf16* __restrict__ qkv,
+                                                                           bf16* __restrict__ o,
+                                                                           float* __restrict__ lse, int B, int F,
+                                                                           long HW) {
+  pdl_trigger();
+  pdl_wait();
+  const int h = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, j = lane & 3;
+  const float scale = rsqrtf(32.f);
+  const long n_pix = (long)B * HW;
+  const bool v_lo = g < F, v_hi = g + 8 < F;
+  const uint4 zero4 = make_uint4(0, 0, 0, 0);
+  for (long pix = blockIdx.x; pix < n_pix; pix += gridDim.x) {
+    const long b = pix / HW, p = pix - b * HW;
+    const long row0 = b * F * HW + p;  // token f lives at row0 + f*HW
+    const long r_lo = row0 + (long)g * HW, r_hi = row0 + (long)(g + 8) * HW;
+    uint4 q_lo = zero4, q_hi = zero4, k_lo = zero4, k_hi = zero4, vv_lo = zero4, vv_hi = zero4;
+    if (v_lo) {
+      const uint4* pr = reinterpret_cast<const uint4*>(qkv + r_lo * 768 + h * 32) + j;
+      q_lo = __ldg(pr);
+      k_lo = __ldg(pr + 32);
+      vv_lo = __ldg(pr + 64);
+    }
+    if (v_hi) {
+      const uint4* pr = reinterpret_cast<const uint4*>(qkv + r_hi * 768 + h * 32) + j;
+      q_hi = __ldg(pr);
+      k_hi = __ldg(pr + 32);
+      vv_hi = __ldg(pr + 64);
+    }
+    uint32_t vb[4][2];
+    vb[0][0] = movmatrix_trans(vv_lo.x); vb[0][1] = movmatrix_trans(vv_hi.x);
+    vb[1][0] = movmatrix_trans(vv_lo.y); vb[1][1] = movmatrix_trans(vv_hi.y);
+    vb[2][0] = movmatrix_trans(vv_lo.z); vb[2][1] = movmatrix_trans(vv_hi.z);
+    vb[3][0] = movmatrix_trans(vv_lo.w); vb[3][1] = movmatrix_trans(vv_hi.w);
+    float S[2][4];
+    chunk_abt(q_lo, q_hi, k_lo, k_hi, S);
+    float m_lo = -INFINITY, m_hi = -INFINITY;
+#pragma unroll
+    for (int t = 0; t < 2; ++t)
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const bool cv = 8 * t + 2 * j + i < F;
+        S[t][i] = cv ? S[t][i] * scale : -INFINITY;
+        S[t][2 + i] = cv ? S[t][2 + i] * scale : -INFINITY;
+        m_lo = fmaxf(m_lo, S[t][i]);
+        m_hi = fmaxf(m_hi, S[t][2 + i]);
+      }
+    m_lo = fmaxf(m_lo, __shfl_xor_sync(0xffffffffu, m_lo, 1));
+    m_lo = fmaxf(m_lo, __shfl_xor_sync(0xffffffffu, m_lo, 2));
+    m_hi = fmaxf(m_hi, __shfl_xor_sync(0xffffffffu, m_hi, 1));
+    m_hi = fmaxf(m_hi, __shfl_xor_sync(0xffffffffu, m_hi, 2));
+    float l_lo = 0.f, l_hi = 0.f;
+#pragma unroll
+    for (int t = 0; t < 2; ++t)
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        S[t][i] = __expf(S[t][i] - m_lo);
+        S[t][2 + i] = __expf(S[t][2 + i] - m_hi);
+        l_lo += S[t][i];
+        l_hi += S[t][2 + i];
+      }
+    l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 1);
+    l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 2);
+    l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 1);
+    l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 2);
+    const uint32_t a0 = pack_bf16x2(S[0][0], S[0][1]), a1 = pack_bf16x2(S[0][2], S[0][3]);
+    const uint32_t a2 = pack_bf16x2(S[1][0], S[1][1]), a3 = pack_bf16x2(S[1][2], S[1][3]);
+    float o_lo[8], o_hi[8];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      float c[4] = {0.f, 0.f, 0.f, 0.f};
+      mma16816(c, a0, a1, a2, a3, vb[t][0], vb[t][1]);
+      o_lo[2 * t] = c[0];
+      o_lo[2 * t + 1] = c[1];
+      o_hi[2 * t] = c[2];
+      o_hi[2 * t + 1] = c[3];
+    }
+    const float inv_lo = 1.f / l_lo, inv_hi = 1.f / l_hi;
+    if (v_lo) {
+      uint4 u4;
+      u4.x = pack_bf16x2(o_lo[0] * inv_lo, o_lo[1] * inv_lo);
+      u4.y = pack_bf16x2(o_lo[2] * inv_lo, o_lo[3] * inv_lo);
+      u4.z = pack_bf16x2(o_lo[4] * inv_lo, o_lo[5] * inv_lo);
+      u4.w = pack_bf16x2(o_lo[6] * inv_lo, o_lo[7] * inv_lo);
+      reinterpret_cast<uint4*>(o + r_lo * 256 + h * 32)[j] = u4;
+      if (lse && j == 0) lse[r_lo * 8 + h] = m_lo + __logf(l_lo);
+    }
+    if (v_hi) {
+      uint4 u4;
+      u4.x = pack_bf16x2(o_hi[0] * inv_hi, o_hi[1] * inv_hi);
+      u4.y = pack_bf16x2(o_hi[2] * inv_hi, o_hi[3] * inv_hi);
+      u4.z = pack_bf16x2(o_hi[4] * inv_hi, o_hi[5] * inv_hi);
+      u4.w = pack_bf16x2(o_hi[6] * inv_hi, o_hi[7] * inv_hi);
+      reinterpret_cast<uint4*>(o + r_hi * 256 + h * 32)[j] = u4;
+      if (lse && j == 0) lse[r_hi * 8 + h] = m_hi + __logf(l_hi);
+    }
+  }
+}
+
+int mha_temporal_mma_core_fwd_launch(const void* qkv, void* o, float* lse, int B, int F, int H, int W, cudaStream_t st) {
+  const long HW = (long)H * W;
+  const long n_pix = (long)B * HW;
+  const int grid = (int)std::min<long>(n_pix, 148L * 24);
+  cudaError_t le = launch_pdl(mha_temporal_mma_core_fwd_kernel, dim3(grid), dim3(256), (size_t)0, st, 1,
+                              reinterpret_cast<const bf16*>(qkv), reinterpret_cast<bf16*>(o), lse, B, F, HW);
+  VDN_REQUIRE(le == cudaSuccess, VDN_E_CUDA, "mha_temporal_mma_core_fwd launch: %s", cudaGetErrorString(le));
+  return check_launch("mha_temporal_mma_core_fwd");
+}
+
 int mha_temporal_mma_bwd_launch(const void* qkv, const void* d_o, const float* lse, void* dqkv, int B, int F, int H,
                                 int W, cudaStream_t st) {
   const long HW = (long)H * W;
@@ -628,6 +744,12 @@ int mha_temporal_mma_bwd_launch(const void* qkv, const void* d_o, const float* l
 }  // namespace vdn
 
 using namespace vdn;
+
+extern "C" int vdn_mha_temporal_core_fwd(const void* qkv, void* o, float* lse, int B, int F, int H, int W, void* stream) {
+  VDN_REQUIRE(qkv && o && B > 0 && H > 0 && W > 0, VDN_E_SHAPE, "mha_temporal_core_fwd: bad args");
+  VDN_REQUIRE(F >= 1 && F <= 16, VDN_E_SHAPE, "mha_temporal_core_fwd: F=%d unsupported (F <= 16)", F);
+  return mha_temporal_mma_core_fwd_launch(qkv, o, lse, B, F, H, W, reinterpret_cast<cudaStream_t>(stream));
+}
 
 // Folded inference-only temporal attention block (C = 32): see mha_temporal_folded_fwd_kernel.
 // fold_pack: w_qkv fp32 [32][768] (q|k|v), b_qkv fp32 [768] or NULL, w_out fp32 [256][32], b_out fp32 [32] or NULL ->

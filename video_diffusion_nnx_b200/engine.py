@@ -300,6 +300,11 @@ class MHABlock:
         # inference engines at C = 32: the whole block (projections, core, out projection, residual) is one
         # kernel on folded weights (A_h = W_q W_k^T, M_h = W_v W_o): no q/k/v/o tensors
         self.folded = self.fused and (not eng.training) and C == 32
+        # training engines at C >= 64: the projection runs as a tap-GEMM (full tensor-core rate, qkv has to be
+        # materialised for the backward anyway) and the F x F core as a register-resident warp-MMA kernel
+        # (VDN_MHA_SPLIT_FWD=0: the single-kernel tcgen05 version, which is a latency chain per head)
+        import os
+        self.split_fwd = (self.fused and eng.training and C >= 64 and os.environ.get("VDN_MHA_SPLIT_FWD", "1") != "0")
         need_qkv = eng.training or not self.fused
         self.qkv = eng.new((n_img, H, W, 3 * HD)) if need_qkv else None
         self.o = None if self.folded else eng.new((n_img, H, W, HD))
@@ -312,7 +317,7 @@ class MHABlock:
             self._wq, self._bq = eng.store.view(prefix + ".qkv.kernel"), eng.store.view(prefix + ".qkv.bias")
             self._wo, self._bo = eng.store.view(prefix + ".out.kernel"), eng.store.view(prefix + ".out.bias")
             eng.extra_packers.append(self._repack_folded)
-        elif self.fused:
+        elif self.fused and not self.split_fwd:
             self.w_hm = torch.empty(3 * HD, C, dtype=BF16, device=eng.device)
             self.b_hm = torch.empty(3 * HD, dtype=F32, device=eng.device)
             self._wq, self._bq = eng.store.view(prefix + ".qkv.kernel"), eng.store.view(prefix + ".qkv.bias")
@@ -333,7 +338,10 @@ class MHABlock:
             ops.mha_temporal_folded_fwd(x, self.fa, self.fu, self.fm, self.fb, self.out, eng.B, Fr, self.H, self.W,
                                         self.C)
             return self.out
-        if self.fused:
+        if self.split_fwd:
+            self.qkv_proj.fwd([x], self.qkv)
+            ops.mha_temporal_core_fwd(self.qkv, self.o, self.lse, eng.B, Fr, self.H, self.W)
+        elif self.fused:
             fn = ops.mha_temporal_tc_fwd if ops.mha_tc_supported(Fr, self.C) else ops.mha_temporal_fused_fwd
             fn(x, self.w_hm, self.b_hm, self.o, self.qkv, self.lse, eng.B, Fr, self.H, self.W, self.C)
         else:

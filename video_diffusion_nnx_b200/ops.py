@@ -323,6 +323,10 @@ def mha_fold_pack(w_qkv, b_qkv, w_out, b_out, fa, fu, fm, fb):
                                 stream_ptr()), "vdn_mha_fold_pack")
 
 
+def mha_temporal_core_fwd(qkv, o, lse, B, F, H, W):
+    check(lib.vdn_mha_temporal_core_fwd(ptr(qkv), ptr(o), ptr(lse), B, F, H, W, stream_ptr()), "vdn_mha_temporal_core_fwd")
+
+
 def mha_temporal_folded_fwd(x, fa, fu, fm, fb, out, B, F, H, W, Cc):
     check(lib.vdn_mha_temporal_folded_fwd(ptr(x), ptr(fa), ptr(fu), ptr(fm), ptr(fb), ptr(out), B, F, H, W, Cc,
                                           stream_ptr()), "vdn_mha_temporal_folded_fwd")
