@@ -75,18 +75,6 @@ __device__ __forceinline__ void sl_gn_accumulate16(const float (&v)[16], float* 
   }
 }
 
-// TMA store plumbing (bulk async-group completion)
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
-                   reinterpret_cast<uint64_t>(m)),
-               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
-               : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
 template <int kSlBK>  // channels per stage (2*kSlBK bytes = swizzle span): 32 or 16
 __global__ void __launch_bounds__(kSlThreads) conv3x3_slab_kernel(const __grid_constant__ SlabMaps maps,
                                                                   const SlabArgs a) {

@@ -27,6 +27,7 @@ constexpr int kGemmThreads = 192;
 struct TapMaps {
   CUtensorMap a[4];
   CUtensorMap b;
+  CUtensorMap o[2];  // persistent kernel only: outputs [M][ld] (second: columns >= split_col), box (min(BN,64), 128)
 };
 
 struct TapArgs {
@@ -50,6 +51,7 @@ struct TapArgs {
   int scatter, py, px;  // VDN_TAP_UP parity scatter into a 2H x 2W grid
   float* gn_sums;
   int gn_groups, cpg, rows_per_sample, n_samples;
+  int n_ntiles, n_items, stg_bufs;  // persistent kernel: (M tile, N tile) items, staging buffers
 };
 
 // ---------------------------------------------------------------------------------------
@@ -411,6 +413,288 @@ __global__ void __launch_bounds__(kGemmThreads) tapgemm_kernel(const __grid_cons
   }
 }
 
+
+// ---------------------------------------------------------------------------------------
+// Persistent variant for launches with many tiles per SM and a short K loop (the q|k|v / out projections and
+// their dgrads, 1x1 residual convs): there the one-tile-per-CTA kernel above is a serial chain per CTA
+// (prologue -> TMA latency -> a handful of MMAs -> epilogue -> exit) that only co-resident CTAs overlap, and it
+// measured ~3x off the HBM-write bound (N = 768, K = 128 at 1M pixels: 743 us against 250 us of output traffic).
+// Here a CTA walks (M tile, N tile) items; the TMA producer runs ahead across items through the smem ring, the
+// accumulator is double buffered in TMEM (the MMAs of item j+1 overlap the epilogue of item j), and the epilogue
+// stages the bf16 tile in the swizzled layout of the output tensor map and hands it to the TMA store engine, so the
+// HBM write is asynchronous. With a residual operand the staged tile is added and stored by the threads instead.
+// No GroupNorm sums, no fp32 output, no parity scatter (those launches keep the kernel above).
+// ---------------------------------------------------------------------------------------
+template <int BK, bool kRes>
+__global__ void __launch_bounds__(kGemmThreads) tapgemm_persist_kernel(const __grid_constant__ TapMaps maps,
+                                                                       const TapArgs args) {
+  constexpr int kSwizzle = BK * 2;
+  constexpr int kABytes = kTileM * BK * 2;
+  constexpr uint32_t kLayout = umma_layout_type(kSwizzle);
+  constexpr uint32_t kSBO = 8 * kSwizzle;
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t tfull_bar[2];
+  __shared__ __align__(8) uint64_t tempty_bar[2];
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const int BN = args.BN;
+  const int b_bytes = (BN * BK * 2 + 1023) & ~1023;
+  const int stage_bytes = kABytes + b_bytes;
+  uint8_t* smem = smem_raw + (((smem_u32(smem_raw) + 1023u) & ~1023u) - smem_u32(smem_raw));
+  const int S = args.stages;
+  uint8_t* stg = smem + S * stage_bytes;
+  const int n_steps = args.n_taps * args.n_src * args.chunks;
+
+  pdl_trigger();
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < args.n_maps; ++i) tma_prefetch_desc(&maps.a[i]);
+    tma_prefetch_desc(&maps.b);
+    tma_prefetch_desc(&maps.o[0]);
+    for (int s = 0; s < S; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tfull_bar[b], 1);
+      mbar_init(&tempty_bar[b], 128);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(&tmem_base_smem, (uint32_t)args.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+  pdl_wait();
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (elect_one()) {
+      const int hw = args.H * args.W;
+      const uint32_t tx_bytes = (uint32_t)(kABytes + BN * BK * 2);
+      int st = 0;
+      uint32_t ph = 1u;
+      for (int item = blockIdx.x; item < args.n_items; item += gridDim.x) {
+        const int n_tile = item % args.n_ntiles;
+        const int m0 = (item / args.n_ntiles) * kTileM;
+        const int n0 = m0 / hw;
+        const int rem = m0 - n0 * hw;
+        const int y0 = rem / args.W;
+        const int x0 = rem - y0 * args.W;
+        int kcol = 0;
+        for (int t = 0; t < args.n_taps; ++t) {
+          const int cx = x0 + args.tap_dx[t];
+          const int cy = y0 + args.tap_dy[t];
+          for (int s = 0; s < args.n_src; ++s) {
+            const CUtensorMap* am = &maps.a[args.tap_map[t] + s];
+            for (int c = 0; c < args.chunks; ++c) {
+              mbar_wait(&empty_bar[st], ph);
+              uint8_t* sa = smem + st * stage_bytes;
+              mbar_expect_tx(&full_bar[st], tx_bytes);
+              tma_load_4d(sa, am, &full_bar[st], c * BK, cx, cy, n0);
+              tma_load_2d(sa + kABytes, &maps.b, &full_bar[st], kcol, n_tile * BN);
+              kcol += BK;
+              if (++st == S) {
+                st = 0;
+                ph ^= 1u;
+              }
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (elect_one()) {
+      const uint32_t idesc = umma_idesc_bf16(kTileM, BN, 0, 0);
+      const uint32_t desc_hi = (kSBO >> 4) | (1u << 14) | (kLayout << 29);
+      const uint32_t stage16 = (uint32_t)stage_bytes >> 4;
+      const uint32_t a_lo0 = (smem_u32(smem) >> 4) | (1u << 16);
+      int st = 0;
+      uint32_t ph = 0u;
+      uint32_t a_lo = a_lo0;
+      uint32_t tph0 = 1u, tph1 = 1u;  // tempty parity to wait for, per accumulator buffer
+      int j = 0;
+      for (int item = blockIdx.x; item < args.n_items; item += gridDim.x, ++j) {
+        const int buf = j & 1;
+        mbar_wait(&tempty_bar[buf], buf ? tph1 : tph0);
+        if (buf) tph1 ^= 1u; else tph0 ^= 1u;
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + (uint32_t)(buf * BN);
+        for (int it = 0; it < n_steps; ++it) {
+          mbar_wait(&full_bar[st], ph);
+          tc_fence_after();
+          const uint32_t b_lo = a_lo + (uint32_t)(kABytes >> 4);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            umma_bf16(tacc, (static_cast<uint64_t>(desc_hi) << 32) | (a_lo + 2u * k),
+                      (static_cast<uint64_t>(desc_hi) << 32) | (b_lo + 2u * k), idesc, (it | k) != 0 ? 1u : 0u);
+          tc_commit(&empty_bar[st]);
+          a_lo += stage16;
+          if (++st == S) {
+            st = 0;
+            ph ^= 1u;
+            a_lo = a_lo0;
+          }
+        }
+        tc_commit(&tfull_bar[buf]);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ================= epilogue (warps 2..5) =================
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const int et = threadIdx.x - 64;
+    const int subw = BN < 64 ? BN : 64;        // columns per staged sub-tile = one swizzle span
+    const int n_sub = BN / subw;
+    const int row_b = subw * 2;                // 64 or 128 bytes
+    const int sub_bytes = kTileM * row_b;
+    const int buf_bytes = n_sub * sub_bytes;
+    const int cpr = row_b >> 4;                // 16-byte chunks per staged row (4 or 8)
+    // chunk position of chunk c of row r: 128-byte rows XOR (r & 7), 64-byte rows XOR ((r >> 1) & 3)
+    const uint32_t swz = row_b == 128 ? (uint32_t)(r & 7) : (uint32_t)((r >> 1) & 3);
+    int j = 0;
+    for (int item = blockIdx.x; item < args.n_items; item += gridDim.x, ++j) {
+      const int n_tile = item % args.n_ntiles;
+      const int m0 = (item / args.n_ntiles) * kTileM;
+      const int col_base = n_tile * BN;
+      uint8_t* outp;
+      const uint8_t* resp;
+      const CUtensorMap* omap;
+      int ld, col_o;
+      if (args.split_col > 0 && col_base >= args.split_col) {
+        outp = reinterpret_cast<uint8_t*>(args.out2);
+        resp = kRes ? reinterpret_cast<const uint8_t*>(args.res2) : nullptr;
+        ld = args.ld_out2;
+        col_o = col_base - args.split_col;
+        omap = &maps.o[1];
+      } else {
+        outp = reinterpret_cast<uint8_t*>(args.out);
+        resp = kRes ? reinterpret_cast<const uint8_t*>(args.res) : nullptr;
+        ld = args.ld_out;
+        col_o = col_base;
+        omap = &maps.o[0];
+      }
+      const int buf = j & 1;
+      uint8_t* sbuf = stg + (args.stg_bufs > 1 ? buf * buf_bytes : 0);
+      // residual operand: this thread's (up to 16) 16-byte segments of the tile - in the coalesced order of the
+      // write-out below - are requested NOW, so that their latency overlaps the wait for the accumulator
+      const int spr_log = 31 - __clz(BN >> 3);  // log2(16-byte segments per output row)
+      const int nseg = BN >> 3;                 // segments per thread per tile (128 rows * spr / 128 threads)
+      uint4 rq[kRes ? 16 : 1];
+      if (kRes && resp) {
+#pragma unroll
+        for (int u = 0; u < (kRes ? 16 : 0); ++u) {
+          const int idx = et + u * 128;
+          const int rr = idx >> spr_log, sg = idx & ((1 << spr_log) - 1);
+          if (u < nseg && m0 + rr < args.M)
+            rq[u] = *reinterpret_cast<const uint4*>(resp + ((long)(m0 + rr) * ld + col_o) * 2 + sg * 16);
+        }
+      }
+      // the TMA store that last read this staging buffer must have finished reading it
+      if (et == 0) {
+        if (args.stg_bufs > 1) bulk_wait_read_1(); else bulk_wait_read_0();
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      mbar_wait(&tfull_bar[buf], (uint32_t)(j >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * BN);
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t raw[32];
+        tmem_ld_32x32(taddr + (uint32_t)c0, raw);
+        tmem_ld_wait();
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          float v[16];
+          const int cl = c0 + h * 16;
+#pragma unroll
+          for (int q = 0; q < 16; ++q) v[q] = __uint_as_float(raw[h * 16 + q]);
+          if (args.bias) {
+#pragma unroll
+            for (int q = 0; q < 16; q += 4) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(args.bias + col_base + cl + q));
+              v[q] += b4.x; v[q + 1] += b4.y; v[q + 2] += b4.z; v[q + 3] += b4.w;
+            }
+          }
+          const int sub = cl / subw;
+          uint8_t* rowp = sbuf + sub * sub_bytes + r * row_b;
+          const uint32_t c16 = (uint32_t)(cl - sub * subw) >> 3;  // first 16-byte chunk of these 16 columns
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            uint4 u;
+            u.x = pack_bf16x2(v[8 * q + 0], v[8 * q + 1]);
+            u.y = pack_bf16x2(v[8 * q + 2], v[8 * q + 3]);
+            u.z = pack_bf16x2(v[8 * q + 4], v[8 * q + 5]);
+            u.w = pack_bf16x2(v[8 * q + 6], v[8 * q + 7]);
+            *reinterpret_cast<uint4*>(rowp + (((c16 + q) ^ swz) << 4)) = u;
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty_bar[buf]);  // accumulator buffer is free for item j+2
+      if (!resp) fence_proxy_async_smem();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (!resp) {
+        if (et == 0) {
+          for (int sub = 0; sub < n_sub; ++sub) tma_store_2d(omap, sbuf + sub * sub_bytes, col_o + sub * subw, m0);
+          bulk_commit();
+        }
+      } else if constexpr (kRes) {
+        // residual add + store by the threads: consecutive threads take consecutive 16-byte segments of a row
+        auto finish = [&](int u0, const uint4 (&rv)[16]) {
+#pragma unroll
+          for (int u = 0; u < 16; ++u) {
+            const int idx = et + (u0 + u) * 128;
+            const int rr = idx >> spr_log, sg = idx & ((1 << spr_log) - 1);
+            if (u0 + u >= nseg || m0 + rr >= args.M) continue;
+            const int sub = sg / cpr, c16 = sg - sub * cpr;
+            const uint32_t rsw = row_b == 128 ? (uint32_t)(rr & 7) : (uint32_t)((rr >> 1) & 3);
+            uint4 q = *reinterpret_cast<const uint4*>(sbuf + sub * sub_bytes + rr * row_b + (((uint32_t)c16 ^ rsw) << 4));
+            float2 x, y;
+            x = unpack_bf16x2(q.x); y = unpack_bf16x2(rv[u].x); q.x = pack_bf16x2(x.x + y.x, x.y + y.y);
+            x = unpack_bf16x2(q.y); y = unpack_bf16x2(rv[u].y); q.y = pack_bf16x2(x.x + y.x, x.y + y.y);
+            x = unpack_bf16x2(q.z); y = unpack_bf16x2(rv[u].z); q.z = pack_bf16x2(x.x + y.x, x.y + y.y);
+            x = unpack_bf16x2(q.w); y = unpack_bf16x2(rv[u].w); q.w = pack_bf16x2(x.x + y.x, x.y + y.y);
+            *reinterpret_cast<uint4*>(outp + ((long)(m0 + rr) * ld + col_o) * 2 + sg * 16) = q;
+          }
+        };
+        if (nseg > 16) {  // 256-column tiles: the second half of the residual is requested before the first is consumed
+          uint4 rq2[16];
+#pragma unroll
+          for (int u = 0; u < 16; ++u) {
+            const int idx = et + (16 + u) * 128;
+            const int rr = idx >> spr_log, sg = idx & ((1 << spr_log) - 1);
+            if (m0 + rr < args.M)
+              rq2[u] = *reinterpret_cast<const uint4*>(resp + ((long)(m0 + rr) * ld + col_o) * 2 + sg * 16);
+          }
+          finish(0, rq);
+          finish(16, rq2);
+        } else {
+          finish(0, rq);
+        }
+      }
+    }
+    if (et == 0) bulk_wait_all();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)args.tmem_cols);
+  }
+}
+
 // ---------------------------------------------------------------------------------------
 // Reference kernel (CUDA cores, one thread per output element). Test-only.
 // ---------------------------------------------------------------------------------------
@@ -612,6 +896,26 @@ static int launch_tapgemm(const TapMaps& maps, const TapArgs& args, int smem_byt
   return check_launch("tapgemm_kernel");
 }
 
+constexpr int kPersistSmemMax = 226 * 1024;  // of the SM's 227 KB per block; the kernel's static shared memory is < 256 B
+
+template <int BK, bool kRes>
+static int launch_tapgemm_persist(const TapMaps& maps, const TapArgs& args, int smem_bytes, int grid, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(tapgemm_persist_kernel<BK, kRes>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPersistSmemMax);
+    VDN_REQUIRE(e == cudaSuccess, VDN_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  cudaError_t le = launch_pdl(tapgemm_persist_kernel<BK, kRes>, dim3(grid), dim3(kGemmThreads), (size_t)smem_bytes, st, 1, maps, args);
+  VDN_REQUIRE(le == cudaSuccess, VDN_E_CUDA, "tapgemm_persist launch: %s", cudaGetErrorString(le));
+  return check_launch("tapgemm_persist_kernel");
+}
+
+static int tg_env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
 }  // namespace vdn
 
 using namespace vdn;
@@ -755,6 +1059,57 @@ extern "C" int vdn_tapgemm(const vdn_tapgemm_desc* d, const void* src0, const vo
               VDN_E_ALIGN, "tapgemm: out/residual/bias must be 16B aligned");
 
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+
+  // ---- persistent variant: many tiles per SM and a short K loop (see tapgemm_persist_kernel) ----
+  {
+    const int m_tiles = ceil_div(a.M, kTileM);
+    const long items = (long)m_tiles * (d->n_out / a.BN);
+    // 32-column tiles with a residual measured slower than the one-tile-per-CTA kernel (27.6 vs 23.6 us at K = 256,
+    // 163840 pixels); tests lower VDN_PERSIST_MIN_ITEMS and still reach that combination
+    const bool narrow_res = a.BN < 64 && (residual || residual2) && tg_env_int("VDN_PERSIST_MIN_ITEMS", 3 * num_sms()) > 1;
+    const bool shape_ok = !gn_sums && !a.out_f32 && !a.scatter && a.BN >= 32 && (a.BN & (a.BN - 1)) == 0 && !narrow_res &&
+                          n_steps <= tg_env_int("VDN_PERSIST_MAX_STEPS", 16) &&
+                          items >= (long)tg_env_int("VDN_PERSIST_MIN_ITEMS", 3 * num_sms());
+    static const bool persist_off = getenv("VDN_NO_PERSIST") != nullptr;
+    if (shape_ok && !persist_off) {
+      TapArgs p = a;
+      p.n_ntiles = d->n_out / a.BN;
+      p.n_items = (int)items;
+      p.tmem_cols = 32;
+      while (p.tmem_cols < 2 * a.BN) p.tmem_cols *= 2;
+      const int subw = std::min(a.BN, 64);
+      const int buf_bytes = kTileM * a.BN * 2;
+      // staging: two buffers unless that leaves fewer than two K stages per accumulator in flight
+      p.stg_bufs = (1024 + 2 * buf_bytes + std::min(2 * n_steps, 4) * stage_bytes <= kPersistSmemMax) ? 2 : 1;
+      if (p.stg_bufs == 1 && 1024 + 2 * buf_bytes + 2 * stage_bytes <= kPersistSmemMax) p.stg_bufs = 2;
+      int S = std::min(kMaxStages, (kPersistSmemMax - 1024 - p.stg_bufs * buf_bytes) / stage_bytes);
+      S = std::min(S, std::max(2, 3 * n_steps));
+      if (S >= 2) {
+        p.stages = S;
+        const uint64_t Mrows = (uint64_t)a.M;
+        const uint32_t obox[2] = {(uint32_t)subw, (uint32_t)kTileM};
+        const uint64_t dims0[2] = {(uint64_t)a.ld_out, Mrows};
+        const uint64_t str0[1] = {(uint64_t)a.ld_out * 2};
+        rc = encode_tmap_bf16(&maps.o[0], out, 2, dims0, str0, obox, subw * 2);
+        if (rc) return rc;
+        if (d->split_col > 0) {
+          const uint64_t dims1[2] = {(uint64_t)a.ld_out2, Mrows};
+          const uint64_t str1[1] = {(uint64_t)a.ld_out2 * 2};
+          rc = encode_tmap_bf16(&maps.o[1], out2, 2, dims1, str1, obox, subw * 2);
+          if (rc) return rc;
+        }
+        const int psmem = 1024 + S * stage_bytes + p.stg_bufs * buf_bytes;
+        const int cps = std::max(1, std::min(512 / p.tmem_cols, (227 * 1024) / (psmem + 1024)));
+        int grid = (int)std::min<long>(items, (long)num_sms() * cps);
+        if (const char* e = getenv("VDN_PERSIST_GRID")) grid = std::max(1, std::min((int)items, atoi(e)));
+        const bool has_res = residual != nullptr || residual2 != nullptr;
+        if (BK == 64) return has_res ? launch_tapgemm_persist<64, true>(maps, p, psmem, grid, st) : launch_tapgemm_persist<64, false>(maps, p, psmem, grid, st);
+        if (BK == 32) return has_res ? launch_tapgemm_persist<32, true>(maps, p, psmem, grid, st) : launch_tapgemm_persist<32, false>(maps, p, psmem, grid, st);
+        return has_res ? launch_tapgemm_persist<16, true>(maps, p, psmem, grid, st) : launch_tapgemm_persist<16, false>(maps, p, psmem, grid, st);
+      }
+    }
+  }
+
   if (BK == 64) return launch_tapgemm<64>(maps, a, smem_bytes, st);
   if (BK == 32) return launch_tapgemm<32>(maps, a, smem_bytes, st);
   return launch_tapgemm<16>(maps, a, smem_bytes, st);
