@@ -245,6 +245,84 @@ def conv_roofline(torch, ops, pk):
     return r
 
 
+def _graph_time_us(torch, run, n=32, warm=4):
+    """us per call of run(i), replayed from a CUDA graph of n calls (host work per call exceeds these kernels)."""
+    for i in range(warm):
+        run(i)
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(graph, stream=side):
+            for i in range(n):
+                run(i)
+    torch.cuda.current_stream().wait_stream(side)
+    graph.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    graph.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n * 1e3
+
+
+def extra_rooflines(torch, ops, pk):
+    """Three more kernels of the step at the workload's full-resolution level, timed live like the conv above
+    (rotating over buffers larger than L2): the q|k|v projection (persistent tap-GEMM, bound by its output
+    write), the GroupNorm+SiLU backward pair and the temporal-attention core backward (HBM streams)."""
+    dev = "cuda"
+    B, Fr, S, C = CFG["per_gpu_batch"], CFG["frames"], CFG["size"], CFG["dim"]
+    n_img, P = B * Fr, B * Fr * S * S
+    bf = torch.bfloat16
+    out = []
+    nb = max(3, int(300e6 // (P * 768 * 2)) + 1)  # q|k|v tensors: > 2 x L2 in rotation
+
+    def entry(name, us, bytes_alg, flops=0.0):
+        gbs = bytes_alg / (us * 1e-6) / 1e9
+        return {"kernel": name, "bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"],
+                "algorithmic_bytes": bytes_alg, "us_per_launch": us, "tensor_tflops": flops / (us * 1e-6) / 1e12}
+
+    # q|k|v projection: x [P][C] -> [P][768]
+    x = torch.randn(n_img, S, S, C, device=dev).to(bf)
+    w = torch.randn(1, C, 768, device=dev) * C ** -0.5
+    wp = torch.empty(768, C, dtype=bf, device=dev)
+    ops.pack_weight(w, wp, 1, C, 768, 0)
+    qkvs = [torch.empty(n_img, S, S, 768, dtype=bf, device=dev) for _ in range(nb)]
+    us = _graph_time_us(torch, lambda i: ops.tapgemm(ops.VDN_TAP_UNIT, [x], wp, ops.TAPS_1x1, out=qkvs[i % nb]))
+    out.append(entry(f"q|k|v projection {C}->768 (tapgemm_persist_kernel, M={P})", us, 2.0 * P * (C + 768) + 2 * C * 768,
+                     2.0 * P * C * 768))
+    # temporal attention core backward: reads qkv + dO + lse, writes dqkv
+    for q in qkvs:
+        q.normal_()
+    d_o = torch.randn(P, 256, device=dev).to(bf)
+    lse = torch.zeros(P, 8, device=dev)
+    ops.mha_temporal_core_fwd(qkvs[0].view(P, 768), torch.empty(P, 256, dtype=bf, device=dev), lse, B, Fr, S, S)
+    dq = [torch.empty(P, 768, dtype=bf, device=dev) for _ in range(2)]
+    us = _graph_time_us(torch, lambda i: ops.mha_temporal_tc_bwd(qkvs[i % nb].view(P, 768), d_o, lse, dq[i % 2], B, Fr, S, S),
+                        n=16)
+    out.append(entry(f"temporal attention core backward (mha_temporal_mma_bwd_kernel, {B * S * S} pixels x {Fr} frames)", us,
+                     2.0 * P * (768 + 256 + 768) + 4.0 * P * 8, 2.0 * P * Fr * 32 * 8 * 5))
+    del qkvs, dq
+    # GroupNorm + SiLU backward (reduce + apply): reads dy, x twice, writes dx
+    nbn = max(3, int(300e6 // (P * C * 2 * 3)) + 1)
+    xr = [torch.randn(n_img, S, S, C, device=dev).to(bf) for _ in range(nbn)]
+    dy = [torch.randn(n_img, S, S, C, device=dev).to(bf) for _ in range(nbn)]
+    dx = [torch.empty(n_img, S, S, C, dtype=bf, device=dev) for _ in range(nbn)]
+    rows = Fr * S * S
+    sums = torch.zeros(ops.GN_REPLICAS, B, 8, 2, device=dev)
+    sums[0, :, :, 1] = rows * (C // 8)  # unit variance, zero mean
+    gamma, beta = torch.ones(C, device=dev), torch.zeros(C, device=dev)
+    T = torch.zeros(B, C, 2, device=dev)
+    dg, db, dcb = torch.zeros(C, device=dev), torch.zeros(C, device=dev), torch.zeros(C, device=dev)
+    us = _graph_time_us(torch, lambda i: ops.gn_silu_bwd(dy[i % nbn], xr[i % nbn], sums, gamma, beta, None, T, dx[i % nbn], dg, db,
+                                                         None, B, rows, C, dconv_bias=dcb))
+    out.append(entry(f"GroupNorm+SiLU backward, 2 passes (gn_bwd_reduce_kernel + gn_bwd_apply_kernel, {P} pixels x {C} ch)", us,
+                     2.0 * P * C * 5))
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -407,6 +485,7 @@ def main():
 
     if rank == 0:
         line["roofline"] = conv_roofline(torch, ops, pk)
+        line["roofline_kernels"] = extra_rooflines(torch, ops, pk)
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_sample()
         print(json.dumps(line), flush=True)

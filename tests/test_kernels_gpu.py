@@ -120,11 +120,31 @@ def _ln_ref(x, gamma, beta, eps=1e-6):
     return (x - mean) * torch.rsqrt(var + eps) * gamma + beta
 
 
+@pytest.fixture(params=["two-kernel", "fused", "large-sample"])
+def gn_bwd_mode(request):
+    """gn_silu_bwd variants: the default two-kernel version, the opt-in single-launch version with the per-sample
+    grid barrier (VDN_GN_FUSED=1), and - through a larger sample - the multi-chunk blocks of the two-kernel version."""
+    import os
+
+    old = os.environ.get("VDN_GN_FUSED")
+    if request.param == "fused":
+        os.environ["VDN_GN_FUSED"] = "1"
+    else:
+        os.environ.pop("VDN_GN_FUSED", None)
+    yield request.param
+    if old is None:
+        os.environ.pop("VDN_GN_FUSED", None)
+    else:
+        os.environ["VDN_GN_FUSED"] = old
+
+
 @pytest.mark.parametrize("B,R,Cc,with_ss", [(2, 512, 32, True), (3, 160, 64, False), (2, 96, 256, True), (1, 64, 1024, True)])
-def test_gn_silu_fwd_bwd(B, R, Cc, with_ss):
+def test_gn_silu_fwd_bwd(gn_bwd_mode, B, R, Cc, with_ss):
     from video_diffusion_nnx_b200 import ops
 
     _setup()
+    if gn_bwd_mode == "large-sample":
+        R *= 2048 if Cc <= 64 else 1024
     x = _bf(B, R, Cc, scale=2.0)
     gamma = (1 + 0.2 * torch.randn(Cc, device=DEV)).requires_grad_(True)
     beta = (0.2 * torch.randn(Cc, device=DEV)).requires_grad_(True)

@@ -479,6 +479,188 @@ __global__ void __launch_bounds__(kNormThreads, 2) gn_bwd_apply_kernel(const GnA
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// Single-launch GroupNorm+SiLU backward for samples whose (x, dy) slices fit in the shared memory of the GPU's SMs
+// (every level of config_v2_2): one CTA per SM, gridDim.x CTAs per sample. A CTA streams its slice of x and dy from
+// HBM ONCE into shared memory while accumulating T1/T2, the CTAs of a sample meet at a per-sample barrier (global
+// counters; all CTAs are co-resident by construction: grid <= number of SMs, one CTA per SM), then dx is computed from
+// the shared-memory copy. Against the two-kernel version: 3 instead of 5 tensor passes over HBM/L2, one launch, one
+// statistics prologue. pdl_trigger() is issued only AFTER the barrier: a dependent grid that started early could
+// otherwise take the SM a not-yet-scheduled CTA of this grid needs, and the barrier would never complete.
+// ---------------------------------------------------------------------------------------
+constexpr int kFusedThreads = 512;
+constexpr int kFusedSlots = 64;
+constexpr int kFusedMaxB = 148;
+__device__ unsigned g_gn_barrier[kFusedSlots][kFusedMaxB][2];  // [launch slot][sample][arrived, left]; self-resetting
+
+__global__ void __launch_bounds__(kFusedThreads, 1) gn_bwd_fused_kernel(const GnArgs a, const bf16* __restrict__ dy,
+                                                                       float* __restrict__ T, bf16* __restrict__ dx,
+                                                                       float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                                       float* __restrict__ dss, int dss_ld,
+                                                                       float* __restrict__ dconv_bias, int rows_per_cta,
+                                                                       int slot) {
+  extern __shared__ __align__(16) float sm[];
+  pdl_wait();
+  float* sA = sm;
+  float* sB = sm + a.C;
+  float* sMean = sm + 2 * a.C;
+  float* sRstd = sm + 3 * a.C;
+  float* sK = sm + 4 * a.C;
+  float* sM1 = sm + 5 * a.C;
+  float* sM2 = sm + 6 * a.C;
+  float* vals = sm + 7 * a.C;                 // [2C]
+  float* red = sm + 9 * a.C;                  // [blockDim][16]
+  uint4* sx = reinterpret_cast<uint4*>(red + kFusedThreads * 16);
+  const int b = blockIdx.y;
+  const int cpg = a.C / a.G;
+  const int c8n = a.C / 8;
+  const int row0 = blockIdx.x * rows_per_cta;
+  const int nrows = max(0, min(a.rows - row0, rows_per_cta));
+  const int nvec = nrows * c8n;
+  uint4* sd = sx + (long)rows_per_cta * c8n;
+  const long v0 = ((long)b * a.rows + row0) * c8n;  // first vector of the slice
+  const int tid = threadIdx.x;
+  const int c0 = (tid % c8n) * 8;               // blockDim is a multiple of c8n: a thread always owns the same 8 channels
+
+  const float2* st = gn_affine_to_smem(a, b, sA, sB);
+  for (int c = tid; c < a.C; c += blockDim.x) {
+    const float2 mr = st[c / cpg];
+    sRstd[c] = mr.y;
+    sMean[c] = -mr.x * mr.y;  // xhat = x * rstd + (-mean * rstd)
+    const float sc = a.ss ? a.ss[(long)b * a.ss_ld + c] + 1.f : 1.f;
+    sK[c] = a.gamma[c] * sc;
+  }
+  __syncthreads();
+  float cA[8], cB[8], cR[8], cM[8];
+  load_coef8(sA, c0, cA);
+  load_coef8(sB, c0, cB);
+  load_coef8(sRstd, c0, cR);
+  load_coef8(sMean, c0, cM);
+  // ---- phase 1: HBM -> shared memory, T1 / T2 partial sums ----
+  float t1[8], t2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) t1[j] = t2[j] = 0.f;
+  for (int i0 = tid; i0 < nvec; i0 += kFusedThreads * 4) {
+    uint4 xr[4], dr[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int i = i0 + k * kFusedThreads;
+      if (i < nvec) {
+        xr[k] = ldg16(a.x + (v0 + i) * 8);
+        dr[k] = ldg16(dy + (v0 + i) * 8);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int i = i0 + k * kFusedThreads;
+      if (i >= nvec) break;
+      sx[i] = xr[k];
+      sd[i] = dr[k];
+      float xv[8], dv[8];
+      unpack8(xr[k], xv);
+      unpack8(dr[k], dv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float z = fmaf(xv[j], cA[j], cB[j]);
+        const float dz = dv[j] * silu_grad_f(z);
+        const float xh = fmaf(xv[j], cR[j], cM[j]);
+        t1[j] += dz;
+        t2[j] = fmaf(dz, xh, t2[j]);
+      }
+    }
+  }
+  {
+    float* my = red + (long)tid * 16;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      my[j] = t1[j];
+      my[8 + j] = t2[j];
+    }
+  }
+  __syncthreads();
+  const int per = blockDim.x / c8n;  // threads sharing a channel vector
+  for (int i = tid; i < c8n * 16; i += blockDim.x) {
+    const int cc = i / 16, j = i % 16;
+    float acc = 0.f;
+    for (int q = 0; q < per; ++q) acc += red[(long)(q * c8n + cc) * 16 + j];
+    atomicAdd(T + ((long)b * a.C + cc * 8 + (j & 7)) * 2 + (j >> 3), acc);
+  }
+  // ---- barrier over the CTAs of this sample ----
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    unsigned* bar = g_gn_barrier[slot][b];
+    atomicAdd(&bar[0], 1u);
+    while (*reinterpret_cast<volatile unsigned*>(&bar[0]) < gridDim.x) {
+    }
+    __threadfence();
+    if (atomicAdd(&bar[1], 1u) == gridDim.x - 1) {  // last one out resets the counters for the slot's next use
+      bar[0] = 0u;
+      bar[1] = 0u;
+      __threadfence();
+    }
+  }
+  __syncthreads();
+  pdl_trigger();
+  // ---- phase 2: dx from the shared-memory copy ----
+  const float inv_n = 1.f / ((float)a.rows * (float)cpg);
+  for (int c = tid; c < a.C; c += blockDim.x) {
+    const int g0 = (c / cpg) * cpg;
+    float m1 = 0.f, m2 = 0.f;
+    for (int k = 0; k < cpg; ++k) {
+      m1 += sK[g0 + k] * __ldcg(T + ((long)b * a.C + g0 + k) * 2);
+      m2 += sK[g0 + k] * __ldcg(T + ((long)b * a.C + g0 + k) * 2 + 1);
+    }
+    sM1[c] = -m1 * inv_n * sRstd[c];
+    sM2[c] = -m2 * inv_n * sRstd[c];
+    if (blockIdx.x == 0) {  // finalize (once per sample)
+      const float tt1 = __ldcg(T + ((long)b * a.C + c) * 2), tt2 = __ldcg(T + ((long)b * a.C + c) * 2 + 1);
+      const float sc = a.ss ? a.ss[(long)b * a.ss_ld + c] + 1.f : 1.f;
+      atomicAdd(&dgamma[c], sc * tt2);
+      atomicAdd(&dbeta[c], sc * tt1);
+      if (dss) {
+        dss[(long)b * dss_ld + c] = a.gamma[c] * tt2 + a.beta[c] * tt1;
+        dss[(long)b * dss_ld + a.C + c] = tt1;
+      }
+    }
+  }
+  __syncthreads();
+  float cK[8], cM1[8], cM2[8], bs[8];
+  load_coef8(sK, c0, cK);
+  load_coef8(sM1, c0, cM1);
+  load_coef8(sM2, c0, cM2);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    cK[j] *= cR[j];
+    bs[j] = 0.f;
+  }
+#pragma unroll 2
+  for (int i = tid; i < nvec; i += kFusedThreads) {
+    float xv[8], dv[8], o[8];
+    unpack8(sx[i], xv);
+    unpack8(sd[i], dv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float z = fmaf(xv[j], cA[j], cB[j]);
+      const float dz = dv[j] * silu_grad_f(z);
+      const float xh = fmaf(xv[j], cR[j], cM[j]);
+      o[j] = fmaf(xh, cM2[j], fmaf(dz, cK[j], cM1[j]));  // rstd * (K dz - m1 - xhat m2)
+      bs[j] += o[j];
+    }
+    store8(dx + (v0 + i) * 8, o);
+  }
+  if (dconv_bias) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[tid * 8 + j] = bs[j];
+    __syncthreads();
+    for (int c = tid; c < a.C; c += blockDim.x) {
+      float acc = 0.f;
+      for (int q = 0; q < per; ++q) acc += red[(q * c8n + c / 8) * 8 + (c & 7)];
+      atomicAdd(dconv_bias + c, acc);
+    }
+  }
+}
+
 // LayerNorm over channels, backward (norm_2 of ResnetBlock, modules.py:223,242):
 //   y = shat*g + b ; ds = rstd * (g*dy - mean_c(g*dy) - shat*mean_c(g*dy*shat)) ; dg += dy*shat ; db += dy
 // R pixels per thread; block column sums (dg | db) are cluster-reduced before the global atomics.
@@ -693,6 +875,36 @@ extern "C" int vdn_gn_silu_bwd(const void* dy, const void* x_raw, const float* g
   GnArgs a{reinterpret_cast<const bf16*>(x_raw), gn_sums, gamma, beta, scale_shift, ss_ld, B, rows_per_sample, C, G};
   cudaError_t e = cudaMemsetAsync(T_ws, 0, (size_t)B * C * 2 * sizeof(float), st);
   VDN_REQUIRE(e == cudaSuccess, VDN_E_CUDA, "gn_silu_bwd memset: %s", cudaGetErrorString(e));
+  {
+    // single-launch version when the (x, dy) slices of all samples fit in the SMs' shared memory. Opt-in
+    // (VDN_GN_FUSED=1): measured 23.7 us against 32.9 us for the two kernels at the 64x64 level of config_v2_2 in
+    // isolation, but no gain on the training step (6.87 vs 6.89 ms) - a grid that needs every SM cannot overlap with
+    // the weight-gradient GEMMs of the side streams, which is where the two-kernel version hides its latency.
+    const char* fe = getenv("VDN_GN_FUSED");
+    const bool fused_off = !(fe && fe[0] == '1');
+    const int cps = B <= kFusedMaxB ? num_sms() / B : 0;  // CTAs per sample; cps * B <= number of SMs
+    if (!fused_off && cps >= 1 && kFusedThreads % (C / 8) == 0) {
+      const int rpc = (rows_per_sample + cps - 1) / cps;
+      const size_t smem_f = (size_t)(9 * C + kFusedThreads * 16) * sizeof(float) + (size_t)rpc * C * 2 * 2;
+      if (smem_f <= 220 * 1024) {
+        static bool cfg = false;
+        if (!cfg) {
+          e = cudaFuncSetAttribute(gn_bwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+          VDN_REQUIRE(e == cudaSuccess, VDN_E_CUDA, "gn_bwd_fused cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+          cfg = true;
+        }
+        static int next_slot = 0;
+        const int slot = next_slot;
+        next_slot = (next_slot + 1) % kFusedSlots;
+        const int gx_f = (rows_per_sample + rpc - 1) / rpc;
+        cudaError_t lf = launch_pdl(gn_bwd_fused_kernel, dim3(gx_f, B), dim3(kFusedThreads), smem_f, st, 1, a,
+                                    reinterpret_cast<const bf16*>(dy), T_ws, reinterpret_cast<bf16*>(dx_raw), dgamma, dbeta, dss,
+                                    dss_ld, dconv_bias, rpc, slot);
+        VDN_REQUIRE(lf == cudaSuccess, VDN_E_CUDA, "gn_bwd_fused launch: %s", cudaGetErrorString(lf));
+        return check_launch("gn_bwd_fused");
+      }
+    }
+  }
   const int pl_n = kNormThreads / (C / 8);
   int gx, cl;
   // chunks per block: 1 until the launch exceeds ~2 waves of 8 blocks per SM, then up to 8 (large samples)
