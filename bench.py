@@ -233,7 +233,7 @@ def conv_roofline(torch, ops, pk):
         td = json.load(open(tp))
         traffic = td["dram_bytes_read"] + td["dram_bytes_write"]
     name = (f"conv(1,3,3) {C}->{C} @{H}x{W} (M={M},N={C},K={9 * C}) "
-            + ("conv3x3_rows_kernel<32,32,1>" if C == 32 else "tapgemm_kernel<64>"))
+            + ("conv3x3_rows_kernel<32,32,1>" if C == 32 else "conv3x3_slab_kernel<32>"))
     r = {"kernel": name, "bound": "tensor" if tensor_bound else "hbm"}
     if tensor_bound:
         r.update(achieved=tf, peak=pk["tf_burst"], unit="TFLOP/s", frac=tf / pk["tf_burst"], traffic=traffic,
