@@ -52,28 +52,66 @@ def peaks():
 
 
 class ClockSampler:
-    """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs."""
+    """Samples SM clocks / throttle reasons while the timed region runs: NVML polled every 5 ms (nvidia_ml_py), or
+    nvidia-smi every 0.2 s when NVML cannot be loaded."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    BITS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, gpu_index=0):
         self.idx, self.rows, self._stop, self._th = gpu_index, [], threading.Event(), None
+        self.sm, self.mx, self.reasons, self.how = [], None, set(), "nvidia-smi"
+        self._nvml = None
+        try:
+            import pynvml
 
-    def _run(self):
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[gpu_index]) if vis and vis.split(",")[gpu_index].strip().isdigit() else gpu_index
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+            self._nvml, self.how = pynvml, "nvml"
+        except Exception:
+            self._nvml = None
+
+    def _run_nvml(self):
+        nv = self._nvml
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                for n, bit in self.BITS.items():
+                    if mask & bit:
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            self._stop.wait(0.005)
+
+    def _run_smi(self):
         while not self._stop.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                       "-i", str(self.idx)], capture_output=True, text=True, timeout=5).stdout.strip()
                 if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                    r = [c.strip() for c in out.split(",")]
+                    if r[0].replace(".", "").isdigit():
+                        self.sm.append(float(r[0]))
+                    if len(r) > 1 and r[1].replace(".", "").isdigit():
+                        self.mx = float(r[1])
+                    for n, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[3:7]):
+                        if v.lower().startswith("active"):
+                            self.reasons.add(n)
             except Exception:
                 pass
             self._stop.wait(0.2)
 
     def __enter__(self):
-        self._th = threading.Thread(target=self._run, daemon=True)
+        self._th = threading.Thread(target=self._run_nvml if self._nvml else self._run_smi, daemon=True)
         self._th.start()
         return self
 
@@ -82,16 +120,9 @@ class ClockSampler:
         self._th.join(timeout=6)
 
     def summary(self):
-        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
-        reasons = set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            for n, v in zip(names, r[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        mx = max((float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()), default=None)
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(self.rows)}
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_min_mhz": sm[0] if sm else None, "sm_max_mhz": self.mx,
+                "reasons": sorted(self.reasons), "samples": len(sm), "how": self.how}
 
 
 def run_reference(args):
@@ -326,7 +357,7 @@ def extra_rooflines(torch, ops, pk):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=CFG["per_gpu_batch"], help="per-GPU batch")
