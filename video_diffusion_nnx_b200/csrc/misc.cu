@@ -5,6 +5,7 @@
 //   (gaussian_diffusion.py:401-470,120-261), bias-gradient column sums, fused Adam + EMA
 //   (trainer.py:367-382).
 #include <algorithm>
+#include <cstdlib>
 
 #include <curand_kernel.h>
 
@@ -142,6 +143,182 @@ __global__ void __launch_bounds__(256) init_conv_wgrad_kernel(const float* __res
     }
     if (grp == 0) atomicAdd(&dbias[co0 + col], bsum);
   }
+}
+
+// ---------------------------------------------------------------------------------------
+// init conv, 7x7 specialisation (the reference default init_kernel_size, unet3d.py:64): register-blocked and with the
+// tap loops resolved at compile time. The generic kernels above spend most of their issue slots on index arithmetic
+// (t / ks, t % ks with a runtime ks) and shared-memory loads (9 LDS per 32 FMA forward, 2 LDS per FMA in the wgrad).
+//   forward: 16 x 32 pixel tile per block, a thread owns 2 pixels x 32 output channels (10 LDS per 64 FMA).
+//   wgrad:   a thread owns one kernel ROW (7 taps) x 4 output channels = 28 accumulators and slides a 7-wide window of
+//            x along the tile row (1 LDS + 1 LDS.64 per 28 FMA); blocks are persistent over tiles, partial sums are
+//            combined in shared memory and leave with ONE atomic per (tap, ci, co) per block.
+// ---------------------------------------------------------------------------------------
+constexpr int kI7 = 7, kI7TH = 16, kI7TW = 32;  // kernel size, forward tile
+__global__ void __launch_bounds__(256) init_conv7_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                             const float* __restrict__ bias, bf16* __restrict__ out,
+                                                             int B, int Cin, int F, int H, int W, int Cout) {
+  extern __shared__ float sm[];
+  constexpr int hh = kI7TH + kI7 - 1, hwv = kI7TW + kI7 - 1;  // 22 x 38 halo tile
+  constexpr int hw = 48;  // row pitch: the two pixel rows of a warp fall into disjoint bank halves
+  float* sW = sm;                              // [49*Cin][Cout]
+  float* sX = sm + kI7 * kI7 * Cin * Cout;     // [Cin][hh][hw]
+  const int tiles_x = W / kI7TW;
+  const int ty = blockIdx.x / tiles_x, tx = blockIdx.x % tiles_x;
+  const int img = blockIdx.y, b = img / F, f = img % F;
+  for (int i = threadIdx.x; i < kI7 * kI7 * Cin * Cout; i += blockDim.x) sW[i] = w[i];
+  for (int i = threadIdx.x; i < Cin * hh * hwv; i += blockDim.x) {
+    const int ci = i / (hh * hwv), r = i % (hh * hwv);
+    const int ry = r / hwv, rx = r % hwv;
+    const int yy = ty * kI7TH + ry - 3, xx = tx * kI7TW + rx - 3;
+    float v = 0.f;
+    if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = x[((((long)b * Cin + ci) * F + f) * H + yy) * W + xx];
+    sX[(ci * hh + ry) * hw + rx] = v;
+  }
+  __syncthreads();
+  const int py = threadIdx.x >> 4, px = threadIdx.x & 15;  // pixels (py, px) and (py, px + 16)
+  const long opix = ((long)img * H + ty * kI7TH + py) * W + tx * kI7TW + px;
+  for (int co0 = 0; co0 < Cout; co0 += 32) {
+    float a0[32], a1[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) a0[j] = a1[j] = __ldg(bias + co0 + j);
+    for (int ci = 0; ci < Cin; ++ci) {
+      const float* xb = sX + (ci * hh + py) * hw + px;
+#pragma unroll
+      for (int dy = 0; dy < kI7; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < kI7; ++dx) {
+          const float x0 = xb[dy * hw + dx], x1 = xb[dy * hw + dx + 16];
+          const float4* wp = reinterpret_cast<const float4*>(sW + ((dy * kI7 + dx) * Cin + ci) * Cout + co0);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 wv = wp[q];
+            a0[4 * q + 0] = fmaf(x0, wv.x, a0[4 * q + 0]); a1[4 * q + 0] = fmaf(x1, wv.x, a1[4 * q + 0]);
+            a0[4 * q + 1] = fmaf(x0, wv.y, a0[4 * q + 1]); a1[4 * q + 1] = fmaf(x1, wv.y, a1[4 * q + 1]);
+            a0[4 * q + 2] = fmaf(x0, wv.z, a0[4 * q + 2]); a1[4 * q + 2] = fmaf(x1, wv.z, a1[4 * q + 2]);
+            a0[4 * q + 3] = fmaf(x0, wv.w, a0[4 * q + 3]); a1[4 * q + 3] = fmaf(x1, wv.w, a1[4 * q + 3]);
+          }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint4 u, v;
+      u.x = pack_bf16x2(a0[8 * q + 0], a0[8 * q + 1]); v.x = pack_bf16x2(a1[8 * q + 0], a1[8 * q + 1]);
+      u.y = pack_bf16x2(a0[8 * q + 2], a0[8 * q + 3]); v.y = pack_bf16x2(a1[8 * q + 2], a1[8 * q + 3]);
+      u.z = pack_bf16x2(a0[8 * q + 4], a0[8 * q + 5]); v.z = pack_bf16x2(a1[8 * q + 4], a1[8 * q + 5]);
+      u.w = pack_bf16x2(a0[8 * q + 6], a0[8 * q + 7]); v.w = pack_bf16x2(a1[8 * q + 6], a1[8 * q + 7]);
+      reinterpret_cast<uint4*>(out + opix * Cout + co0)[q] = u;
+      reinterpret_cast<uint4*>(out + (opix + 16) * Cout + co0)[q] = v;
+    }
+  }
+}
+
+// block = 7 kernel rows x 32 lanes = 224 threads; lane -> (pixel range, group of 4 output channels):
+// cg_n = min(Cout, 128) / 4 channel groups, 32 / cg_n pixel ranges (each a band of rows of the 16 x 16 tile).
+constexpr int kW7Threads = 224;
+__global__ void __launch_bounds__(kW7Threads) init_conv7_wgrad_kernel(const float* __restrict__ x, const bf16* __restrict__ dy,
+                                                                      float* __restrict__ dw, float* __restrict__ dbias,
+                                                                      int B, int Cin, int F, int H, int W, int Cout,
+                                                                      int n_tiles_total) {
+  extern __shared__ float sm[];
+  constexpr int hs = kIT + kI7 - 1;  // 22
+  const int cb = min(Cout, 128);     // output channels per pass
+  constexpr int xp = hs + 3;         // odd row pitch: the pixel ranges of a warp read different banks
+  float* sX = sm;                                                      // [hs][xp] (one input channel at a time)
+  bf16* sD = reinterpret_cast<bf16*>(sm + 552);                        // [256 px][cb]   (552 >= hs * xp, 16-byte aligned)
+  float* sR = reinterpret_cast<float*>(sD + 256 * cb);                 // [7 rows][7 taps][cb] cross-range reduction
+  const int krow = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cg_n = cb >> 2, n_rng = 32 / cg_n, rows_per_rng = kIT / n_rng;
+  const int cg = lane % cg_n, rng = lane / cg_n;
+  const int tiles_x = W / kIT, tiles_img = tiles_x * (H / kIT);
+  for (int co0 = 0; co0 < Cout; co0 += cb)
+    for (int ci = 0; ci < Cin; ++ci) {
+      float acc[kI7][4];
+      float bsum[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int t = 0; t < kI7; ++t)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[t][c] = 0.f;
+      for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
+        const int img = tile / tiles_img, tr = tile % tiles_img;
+        const int ty = tr / tiles_x, tx = tr % tiles_x;
+        const int b = img / F, f = img % F;
+        __syncthreads();
+        for (int i = threadIdx.x; i < hs * hs; i += blockDim.x) {
+          const int ry = i / hs, rx = i % hs;
+          const int yy = ty * kIT + ry - 3, xx = tx * kIT + rx - 3;
+          float v = 0.f;
+          if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = x[((((long)b * Cin + ci) * F + f) * H + yy) * W + xx];
+          sX[ry * xp + rx] = v;
+        }
+        {
+          const int segs = cb >> 3;  // 16-byte segments per pixel
+          for (int i = threadIdx.x; i < 256 * segs; i += blockDim.x) {
+            const int p = i / segs, sg = i % segs;
+            const long opix = ((long)img * H + ty * kIT + p / kIT) * W + tx * kIT + p % kIT;
+            reinterpret_cast<uint4*>(sD)[i] = __ldg(reinterpret_cast<const uint4*>(dy + opix * Cout + co0) + sg);
+          }
+        }
+        __syncthreads();
+        for (int r = 0; r < rows_per_rng; ++r) {
+          const int py = rng * rows_per_rng + r;
+          const float* xr = sX + (py + krow) * xp;
+          float win[kI7];
+#pragma unroll
+          for (int t = 0; t < kI7 - 1; ++t) win[t + 1] = xr[t];
+#pragma unroll
+          for (int px = 0; px < kIT; ++px) {
+#pragma unroll
+            for (int t = 0; t < kI7 - 1; ++t) win[t] = win[t + 1];
+            win[kI7 - 1] = xr[px + kI7 - 1];
+            const uint2 d2 = *reinterpret_cast<const uint2*>(sD + (py * kIT + px) * cb + cg * 4);
+            const float2 d01 = unpack_bf16x2(d2.x), d23 = unpack_bf16x2(d2.y);
+#pragma unroll
+            for (int t = 0; t < kI7; ++t) {
+              acc[t][0] = fmaf(win[t], d01.x, acc[t][0]);
+              acc[t][1] = fmaf(win[t], d01.y, acc[t][1]);
+              acc[t][2] = fmaf(win[t], d23.x, acc[t][2]);
+              acc[t][3] = fmaf(win[t], d23.y, acc[t][3]);
+            }
+            if (krow == 0 && ci == 0) {
+              bsum[0] += d01.x; bsum[1] += d01.y; bsum[2] += d23.x; bsum[3] += d23.y;
+            }
+          }
+        }
+      }
+      // combine the pixel ranges of the block, then one atomic per (tap, ci, co)
+      for (int q = 0; q < n_rng; ++q) {
+        __syncthreads();
+        if (rng == q) {
+#pragma unroll
+          for (int t = 0; t < kI7; ++t)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              float* dst = sR + (krow * kI7 + t) * cb + cg * 4 + c;
+              *dst = (q == 0 ? 0.f : *dst) + acc[t][c];
+            }
+        }
+      }
+      __syncthreads();
+      for (int i = threadIdx.x; i < kI7 * kI7 * cb; i += blockDim.x) {
+        const int tap = i / cb, c = i % cb;
+        atomicAdd(&dw[((long)tap * Cin + ci) * Cout + co0 + c], sR[i]);
+      }
+      if (ci == 0) {
+        for (int q = 0; q < n_rng; ++q) {
+          __syncthreads();
+          if (krow == 0 && rng == q) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              float* dst = sR + cg * 4 + c;
+              *dst = (q == 0 ? 0.f : *dst) + bsum[c];
+            }
+          }
+        }
+        __syncthreads();
+        for (int c = threadIdx.x; c < cb; c += blockDim.x) atomicAdd(&dbias[co0 + c], sR[c]);
+      }
+    }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -688,6 +865,18 @@ extern "C" int vdn_init_conv_fwd(const float* x, const float* w, const float* bi
                                  int H, int W, int Cout, int ks, void* stream) {
   VDN_REQUIRE(H % kIT == 0 && W % kIT == 0 && Cout % 32 == 0 && (ks & 1) && ks <= 7 && Cin >= 1 && Cin <= 4, VDN_E_SHAPE,
               "init_conv_fwd: unsupported shape H=%d W=%d Cout=%d ks=%d Cin=%d", H, W, Cout, ks, Cin);
+  static const bool generic_only = getenv("VDN_INIT_CONV_GENERIC") != nullptr;
+  if (ks == kI7 && H % kI7TH == 0 && W % kI7TW == 0 && !generic_only) {
+    const size_t smem7 = (size_t)(kI7 * kI7 * Cin * Cout + Cin * (kI7TH + kI7 - 1) * 48) * sizeof(float);
+    static bool cfg7 = false;
+    if (!cfg7) {
+      cudaFuncSetAttribute(init_conv7_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+      cfg7 = true;
+    }
+    init_conv7_fwd_kernel<<<dim3((H / kI7TH) * (W / kI7TW), B * F), 256, smem7, ST(stream)>>>(
+        x, w, bias, reinterpret_cast<bf16*>(out), B, Cin, F, H, W, Cout);
+    return check_launch("init_conv7_fwd");
+  }
   const int hs = kIT + ks - 1;
   const size_t smem = (size_t)(ks * ks * Cin * Cout + Cin * hs * hs) * sizeof(float);
   static bool cfg = false;
@@ -704,6 +893,25 @@ extern "C" int vdn_init_conv_wgrad(const float* x, const void* dy, float* dw, fl
                                    int H, int W, int Cout, int ks, void* stream) {
   VDN_REQUIRE(H % kIT == 0 && W % kIT == 0 && Cout % 32 == 0 && (ks & 1) && ks <= 7 && Cin >= 1 && Cin <= 3, VDN_E_SHAPE,
               "init_conv_wgrad: unsupported shape");
+  static const bool generic_only = getenv("VDN_INIT_CONV_GENERIC") != nullptr;
+  if (ks == kI7 && !generic_only && (Cout <= 128 ? (Cout == 32 || Cout == 64 || Cout == 128) : Cout % 128 == 0)) {
+    const int cb = std::min(Cout, 128);
+    const int hs7 = kIT + kI7 - 1;
+    (void)hs7;
+    const size_t smem7 = (size_t)552 * sizeof(float) + (size_t)256 * cb * 2 + (size_t)kI7 * kI7 * cb * sizeof(float);
+    static bool cfg7 = false;
+    if (!cfg7) {
+      cudaFuncSetAttribute(init_conv7_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+      cfg7 = true;
+    }
+    const int n_total = (H / kIT) * (W / kIT) * B * F;
+    // persistent blocks: an equal number of tiles each, about two blocks per SM
+    const int per_block = std::max(1, ceil_div(n_total, 2 * num_sms()));
+    const int grid = ceil_div(n_total, per_block);
+    init_conv7_wgrad_kernel<<<grid, kW7Threads, smem7, ST(stream)>>>(x, reinterpret_cast<const bf16*>(dy), dw, dbias, B, Cin,
+                                                                     F, H, W, Cout, n_total);
+    return check_launch("init_conv7_wgrad");
+  }
   const int hs = kIT + ks - 1;
   const size_t smem = (size_t)(Cin * hs * hs + 256 * 33) * sizeof(float);
   const int n_tiles = (H / kIT) * (W / kIT);
