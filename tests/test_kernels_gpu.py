@@ -176,7 +176,8 @@ def test_gn_silu_fwd_bwd(gn_bwd_mode, B, R, Cc, with_ss):
         assert _rel(dss, ss.grad) < 1e-3
 
 
-@pytest.mark.parametrize("B,R,Cc", [(2, 256, 32), (2, 100, 128), (1, 40, 512), (1, 24, 1024)])
+@pytest.mark.parametrize("B,R,Cc", [(2, 256, 32), (2, 100, 128), (1, 40, 512), (1, 24, 1024),
+                                    (2, 655360, 32), (1, 320000, 128)])  # large: several chunks per block in ln_bwd
 def test_resblock_tail_and_ln_bwd(B, R, Cc):
     from video_diffusion_nnx_b200 import ops
 
@@ -201,8 +202,9 @@ def test_resblock_tail_and_ln_bwd(B, R, Cc):
     dg, db = torch.zeros(Cc, device=DEV), torch.zeros(Cc, device=DEV)
     ops.ln_bwd(s, dy, lg.detach(), ds, dg, db, B * R, Cc)
     assert _rel(ds, sf.grad) < 2e-2
-    assert _rel(dg, lg.grad) < 1e-3
-    assert _rel(db, lb.grad) < 1e-3
+    big = B * R > 100000  # fp32 atomics over ~1e6 pixels against torch's own fp32 reduction order
+    assert _rel(dg, lg.grad) < (3e-3 if big else 1e-3)
+    assert _rel(db, lb.grad) < (3e-3 if big else 1e-3)
 
 
 # ------------------------------------------------------------------------------------------

@@ -668,7 +668,7 @@ template <int VPL, int R>
 __global__ void __launch_bounds__(kNormThreads) ln_bwd_kernel(const bf16* __restrict__ s, const bf16* __restrict__ dy,
                                                               const float* __restrict__ ln_g, bf16* __restrict__ ds,
                                                               float* __restrict__ dg, float* __restrict__ db, long P,
-                                                              int C) {
+                                                              int C, int iters) {
   extern __shared__ float sm[];
   pdl_trigger();
   pdl_wait();
@@ -680,17 +680,22 @@ __global__ void __launch_bounds__(kNormThreads) ln_bwd_kernel(const bf16* __rest
   uint4 sraw[R][VPL], draw[R][VPL];
   long roff[R];
   bool valid[R];
+  // a block owns `iters` consecutive chunks of R * ppb pixels (large tensors: the column-sum reduction and its atomics
+  // are amortised over `iters` times the data)
+  auto issue = [&](int it) {
 #pragma unroll
-  for (int r = 0; r < R; ++r) {
-    const long p_raw = ((long)blockIdx.x * R + r) * ppb + threadIdx.x / lg;
-    valid[r] = p_raw < P;
-    roff[r] = (valid[r] ? p_raw : P - 1) * C;
+    for (int r = 0; r < R; ++r) {
+      const long p_raw = (((long)blockIdx.x * iters + it) * R + r) * ppb + threadIdx.x / lg;
+      valid[r] = p_raw < P;
+      roff[r] = (valid[r] ? p_raw : P - 1) * C;
 #pragma unroll
-    for (int k = 0; k < VPL; ++k) {
-      sraw[r][k] = ldg16(s + roff[r] + (k * lg + sub) * 8);
-      draw[r][k] = ldg16(dy + roff[r] + (k * lg + sub) * 8);
+      for (int k = 0; k < VPL; ++k) {
+        sraw[r][k] = ldg16(s + roff[r] + (k * lg + sub) * 8);
+        draw[r][k] = ldg16(dy + roff[r] + (k * lg + sub) * 8);
+      }
     }
-  }
+  };
+  issue(0);
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     sG[c] = ln_g[c];
     acc[c] = 0.f;
@@ -703,6 +708,7 @@ __global__ void __launch_bounds__(kNormThreads) ln_bwd_kernel(const bf16* __rest
   for (int k = 0; k < VPL; ++k)
 #pragma unroll
     for (int j = 0; j < 8; ++j) pg[k][j] = pb[k][j] = 0.f;
+  for (int it = 0; it < iters; ++it) {
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     float sv[VPL][8], dv[VPL][8];
@@ -753,6 +759,8 @@ __global__ void __launch_bounds__(kNormThreads) ln_bwd_kernel(const bf16* __rest
       for (int j = 0; j < 8; ++j) o8[j] = rstd * (sG[c0 + j] * dv[k][j] - a1 - sv[k][j] * a2);
       if (valid[r]) store8(ds + roff[r] + c0, o8);
     }
+  }
+    if (it + 1 < iters) issue(it + 1);
   }
   // lanes that own the same channels (same `sub`, other pixels of the warp) are summed with shuffles first
 #pragma unroll
@@ -944,13 +952,14 @@ extern "C" int vdn_ln_bwd(const void* s, const void* dy, const float* ln_gamma, 
   bf16* op = reinterpret_cast<bf16*>(ds);
   const int R = vpl == 1 ? 4 : vpl == 2 ? 2 : 1;
   int gx;
-  const int cl = cluster_for(grid_x_for(P, ppb * R), &gx);
+  const int iters = (int)std::max<long>(1, std::min<long>(8, (long)grid_x_for(P, ppb * R) / (2 * 8 * num_sms())));
+  const int cl = cluster_for(grid_x_for(P, ppb * R * iters), &gx);
   cudaError_t le;
   switch (vpl) {
-    case 1: le = launch_pdl(ln_bwd_kernel<1, 4>, dim3(gx), dim3(kNormThreads), smem, st, cl, sp, dp, ln_gamma, op, dgamma, dbeta, P, C); break;
-    case 2: le = launch_pdl(ln_bwd_kernel<2, 2>, dim3(gx), dim3(kNormThreads), smem, st, cl, sp, dp, ln_gamma, op, dgamma, dbeta, P, C); break;
-    case 4: le = launch_pdl(ln_bwd_kernel<4, 1>, dim3(gx), dim3(kNormThreads), smem, st, cl, sp, dp, ln_gamma, op, dgamma, dbeta, P, C); break;
-    default: le = launch_pdl(ln_bwd_kernel<8, 1>, dim3(gx), dim3(kNormThreads), smem, st, cl, sp, dp, ln_gamma, op, dgamma, dbeta, P, C); break;
+    case 1: le = launch_pdl(ln_bwd_kernel<1, 4>, dim3(gx), dim3(kNormThreads), smem, st, cl, sp, dp, ln_gamma, op, dgamma, dbeta, P, C, iters); break;
+    case 2: le = launch_pdl(ln_bwd_kernel<2, 2>, dim3(gx), dim3(kNormThreads), smem, st, cl, sp, dp, ln_gamma, op, dgamma, dbeta, P, C, iters); break;
+    case 4: le = launch_pdl(ln_bwd_kernel<4, 1>, dim3(gx), dim3(kNormThreads), smem, st, cl, sp, dp, ln_gamma, op, dgamma, dbeta, P, C, iters); break;
+    default: le = launch_pdl(ln_bwd_kernel<8, 1>, dim3(gx), dim3(kNormThreads), smem, st, cl, sp, dp, ln_gamma, op, dgamma, dbeta, P, C, iters); break;
   }
   VDN_REQUIRE(le == cudaSuccess, VDN_E_CUDA, "ln_bwd launch: %s", cudaGetErrorString(le));
   return check_launch("ln_bwd");
