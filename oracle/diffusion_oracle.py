@@ -91,8 +91,10 @@ class GaussianDiffusionOracle:
     return (b,f,h,w,c) like Unet3D (unet3d.py:387)."""
 
     def __init__(self, denoise_fn: Callable, *, image_size: int, num_frames: int, channels: int = 3,
-                 timesteps: int = 1000, loss_type: str = "l1", dtype=torch.float32):
+                 timesteps: int = 1000, loss_type: str = "l1", dtype=torch.float32, use_dynamic_thres: bool = False,
+                 dynamic_thres_percentile: float = 0.9):
         self.denoise_fn = denoise_fn
+        self.use_dynamic_thres, self.dynamic_thres_percentile = use_dynamic_thres, dynamic_thres_percentile  # :61-62
         self.image_size, self.num_frames, self.channels = image_size, num_frames, channels
         self.num_timesteps = int(timesteps)
         self.loss_type = loss_type
@@ -120,11 +122,18 @@ class GaussianDiffusionOracle:
         return (mean, extract(self.posterior_variance, t, x_t.shape),
                 extract(self.posterior_log_variance_clipped, t, x_t.shape))
 
-    def p_mean_variance(self, x, t, clip_denoised: bool = True):  # :162-228 (cond_scale 1, no dyn. thres.)
+    def p_mean_variance(self, x, t, clip_denoised: bool = True):  # :162-228 (cond_scale 1)
         eps = self.denoise_fn(x, t).permute(0, 4, 1, 2, 3)  # 'b f h w c -> b c f h w' :197
         x_recon = self.predict_start_from_noise(x, t, eps)
         if clip_denoised:
-            x_recon = x_recon.clamp(-1.0, 1.0) / 1.0
+            s = 1.0
+            if getattr(self, "use_dynamic_thres", False):  # :205-217 (Imagen): per-sample quantile of |x0|, >= 1
+                flat = x_recon.abs().reshape(x_recon.shape[0], -1)
+                s = torch.quantile(flat, self.dynamic_thres_percentile, dim=-1)  # jnp.quantile default: linear
+                s = torch.clamp(s, min=1.0).reshape(-1, 1, 1, 1, 1)
+                x_recon = torch.maximum(torch.minimum(x_recon, s), -s) / s
+            else:
+                x_recon = x_recon.clamp(-s, s) / s
         return self.q_posterior(x_recon, x, t)
 
     def p_sample(self, x, t, z, clip_denoised: bool = True):  # :231-261, z = the N(0,1) draw of :254

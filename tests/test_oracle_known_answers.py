@@ -108,3 +108,37 @@ def test_product_schedule_is_bit_identical_to_oracle():
         a, b = make_schedule(T), D.make_schedule(T)
         for k in D.SCHEDULE_NAMES:
             assert np.array_equal(a[k], b[k]), (T, k)
+
+
+def test_dynamic_thresholding_matches_definition():
+    """gaussian_diffusion.py:205-217 (Imagen dynamic thresholding, off by default): s = max(quantile(|x0|, p), 1) per
+    sample with linear interpolation, x0 <- clip(x0, -s, s) / s; equals static clipping whenever the quantile <= 1."""
+    import numpy as np
+
+    from oracle import diffusion_oracle as D
+
+    rng = np.random.default_rng(5)
+    B, C, Fr, S, T = 3, 1, 2, 8, 50
+    eps = torch.from_numpy(rng.standard_normal((B, Fr, S, S, C)).astype(np.float32))
+    mk = lambda dyn: D.GaussianDiffusionOracle(lambda x, t: eps, image_size=S, num_frames=Fr, channels=C, timesteps=T,  # noqa: E731
+                                               use_dynamic_thres=dyn, dynamic_thres_percentile=0.9)
+    scale = torch.tensor([0.2, 1.0, 4.0]).view(B, 1, 1, 1, 1)  # sample 0: everything inside [-1, 1]
+    x = torch.from_numpy(rng.standard_normal((B, C, Fr, S, S)).astype(np.float32)) * scale
+    t = torch.tensor([3, 3, 3], dtype=torch.int32)
+    gd_dyn, gd_st = mk(True), mk(False)
+    x0 = gd_dyn.predict_start_from_noise(x, t, eps.permute(0, 4, 1, 2, 3)) * torch.tensor([0.1, 1.0, 1.0]).view(B, 1, 1, 1, 1)
+    # feed x0 straight through q_posterior's inverse: compare the clipped x0 implied by the posterior mean
+    m_dyn, _, _ = gd_dyn.p_mean_variance(x, t, clip_denoised=True)
+    m_st, _, _ = gd_st.p_mean_variance(x, t, clip_denoised=True)
+    c1 = D.extract(gd_dyn.posterior_mean_coef1, t, x.shape)
+    c2 = D.extract(gd_dyn.posterior_mean_coef2, t, x.shape)
+    x0_dyn = (m_dyn - c2 * x) / c1
+    raw = gd_dyn.predict_start_from_noise(x, t, eps.permute(0, 4, 1, 2, 3))
+    for b in range(B):
+        s = max(float(np.quantile(np.abs(raw[b].numpy()).ravel(), 0.9)), 1.0)
+        want = np.clip(raw[b].numpy(), -s, s) / s
+        assert np.allclose(x0_dyn[b].numpy(), want, atol=2e-4)
+        if s == 1.0:
+            assert torch.allclose(m_dyn[b], m_st[b], atol=1e-6)
+    assert float(x0_dyn.abs().max()) <= 1.0 + 1e-4
+    del x0

@@ -71,8 +71,6 @@ class GaussianDiffusion:
     def __init__(self, denoise_fn, *, image_size: int, num_frames: int, text_use_bert_cls: bool = False,
                  channels: int = 3, timesteps: int = 1000, loss_type: str = "l1", use_dynamic_thres: bool = False,
                  dynamic_thres_percentile: float = 0.9):
-        if use_dynamic_thres:
-            raise NotImplementedError("dynamic thresholding (off in every reference config) is out of scope")
         if loss_type not in ("l1", "l2"):
             raise ValueError(f"Unsupported loss type: {loss_type}")
         self.denoise_fn = denoise_fn
@@ -150,7 +148,44 @@ class GaussianDiffusion:
         t = torch.randint(0, self.num_timesteps, (B,), generator=g, dtype=torch.int32)
         return self.p_losses(x, t, loss_key, *args, _normalize=True, **kwargs)
 
+    def _extract(self, name: str, t) -> torch.Tensor:
+        """utils.py:225-238: table[t] broadcast to (b, 1, 1, 1, 1)."""
+        return self.table(name)[self._i32(t).long()].view(-1, 1, 1, 1, 1)
+
+    def q_mean_variance(self, x_start, t):
+        """gaussian_diffusion.py:101-117 (host-visible helper, not on the hot path)."""
+        mean = self._extract("sqrt_alphas_cumprod", t) * self._f32(x_start)
+        variance = 1.0 - self._extract("alphas_cumprod", t)
+        return mean, variance, self._extract("log_one_minus_alphas_cumprod", t)
+
     # ---- reverse process --------------------------------------------------------------
+    def q_posterior(self, x_start, x_t, t):
+        """gaussian_diffusion.py:139-159 (host-visible helper; the sampling loop uses the fused kernel)."""
+        mean = (self._extract("posterior_mean_coef1", t) * self._f32(x_start)
+                + self._extract("posterior_mean_coef2", t) * self._f32(x_t))
+        return mean, self._extract("posterior_variance", t), self._extract("posterior_log_variance_clipped", t)
+
+    def _x0_from_eps(self, x, t, eps, clip_denoised: bool):
+        """x0 estimate of p_mean_variance (gaussian_diffusion.py:197-220) from the Unet output (b f h w c)."""
+        B = x.shape[0]
+        eps = eps.reshape(B, self.num_frames, self.image_size, self.image_size, self.channels).permute(0, 4, 1, 2, 3)
+        x_recon = self.predict_start_from_noise(x, t, eps.float())
+        if clip_denoised:
+            if self.use_dynamic_thres:  # :205-217: per-sample quantile of |x0| (linear interpolation), at least 1
+                s = torch.quantile(x_recon.abs().reshape(B, -1), self.dynamic_thres_percentile, dim=-1)
+                s = torch.clamp(s, min=1.0).view(-1, 1, 1, 1, 1)
+                x_recon = torch.maximum(torch.minimum(x_recon, s), -s) / s
+            else:
+                x_recon = x_recon.clamp(-1.0, 1.0)
+        return x_recon
+
+    def p_mean_variance(self, x, t, clip_denoised: bool, cond=None, cond_scale: float = 1.0):
+        """gaussian_diffusion.py:162-228 (host-visible helper: Unet forward on the CUDA engine, then the posterior
+        of the x0 estimate; p_sample / p_sample_loop fuse the same arithmetic into one kernel)."""
+        x, t = self._f32(x), self._i32(t)
+        eps = self.denoise_fn.forward_with_cond_scale(x, t, cond=cond, cond_scale=cond_scale)
+        return self.q_posterior(self._x0_from_eps(x, t, eps, clip_denoised), x, t)
+
     def predict_start_from_noise(self, x_t, t, noise):
         """gaussian_diffusion.py:120-136 (host-visible helper; the fused kernel is p_sample)."""
         rc = self.table("sqrt_recip_alphas_cumprod")[self._i32(t).long()].view(-1, 1, 1, 1, 1)
@@ -164,6 +199,12 @@ class GaussianDiffusion:
         eps = self.denoise_fn.forward_with_cond_scale(x, t, cond=cond, cond_scale=cond_scale)
         if z is None:
             z = self._normal(x.shape, as_key(key))
+        if self.use_dynamic_thres and clip_denoised:
+            # dynamic thresholding (off in every reference config) needs a per-sample quantile between the Unet and
+            # the posterior update: composed from the host-visible helpers instead of the fused kernel
+            mean, _, log_var = self.q_posterior(self._x0_from_eps(x, t, eps, True), x, t)
+            nonzero = (t != 0).to(torch.float32).view(-1, 1, 1, 1, 1)
+            return mean + nonzero * torch.exp(0.5 * log_var) * self._f32(z)
         out = torch.empty_like(x)
         B, C = x.shape[0], x.shape[1]
         ops.p_sample(x, eps, self._f32(z), t, self.table("sqrt_recip_alphas_cumprod"),
@@ -181,6 +222,15 @@ class GaussianDiffusion:
         B = shape[0]
         shape = (B, self.channels, self.num_frames, self.image_size, self.image_size)
         per_sample = shape[1] * shape[2] * shape[3] * shape[4]
+        if self.use_dynamic_thres:  # eager loop over p_sample (quantile between the Unet and the update); same draws
+            loop_key, init_key = key.split(2)
+            T = self.num_timesteps if timesteps is None else timesteps
+            img = self._normal(shape, init_key, sample_offset * per_sample)
+            z = torch.empty(shape, dtype=torch.float32, device=self.device)
+            for i in reversed(range(T)):
+                ops.randn(z, loop_key.seed, loop_key.stream * 4099 + i + 1, sample_offset * per_sample)
+                img = self.p_sample(img, torch.full((B,), i, dtype=torch.int32, device=self.device), z=z)
+            return (img + 1) * 0.5
         assert per_sample % 4 == 0
         loop_key, init_key = key.split(2)
         T = self.num_timesteps if timesteps is None else timesteps
