@@ -159,7 +159,10 @@ def norm_case(B, Fr, H, C):
 print(f"# peaks: HBM {HBM} GB/s, bf16 {TF} TFLOP/s (MEASURED_PEAKS.json); CUDA-graph timing, us per launch")
 print("# --- (1,3,3) convolutions (fwd + bias + GroupNorm partial sums) ---")
 for B_, Fr_, H_, C_, N_, ns_ in [(4, 10, 64, 32, 32, 1), (16, 10, 64, 32, 32, 1), (4, 10, 64, 32, 32, 2), (4, 10, 32, 64, 64, 1),
-                                 (4, 10, 16, 128, 128, 1), (4, 10, 8, 256, 256, 1), (4, 16, 32, 128, 128, 1), (2, 16, 128, 32, 32, 1)]:
+                                 (4, 10, 16, 128, 128, 1), (4, 10, 8, 256, 256, 1), (4, 16, 32, 128, 128, 1), (2, 16, 128, 32, 32, 1),
+                                 # the four levels of the v2_3x workload (slab kernel at widths >= 32) and its concat conv
+                                 (4, 16, 128, 128, 128, 1), (4, 16, 64, 256, 256, 1), (4, 16, 32, 512, 512, 1),
+                                 (4, 16, 16, 1024, 1024, 1), (4, 16, 128, 128, 128, 2)]:
     conv_case(B_, Fr_, H_, C_, N_, ns_)
 print("# --- SpatialLinearAttention ---")
 for B_, Fr_, H_, C_ in [(4, 10, 64, 32), (16, 10, 64, 32), (4, 10, 32, 64), (4, 10, 16, 128), (4, 16, 32, 128)]:
