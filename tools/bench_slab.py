@@ -9,16 +9,21 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from video_diffusion_nnx_b200 import ops  # noqa: E402
 
 
-def time_conv(n_img, H, W, C, N, nbuf=8, n=32):
+def time_conv(n_img, H, W, C, N, nbuf=8, n=32, gn=False):
     xs = [torch.randn(n_img, H, W, C, device="cuda").to(torch.bfloat16) for _ in range(nbuf)]
     outs = [torch.empty(n_img, H, W, N, device="cuda", dtype=torch.bfloat16) for _ in range(nbuf)]
     w = torch.randn(9, C, N, device="cuda") * (9 * C) ** -0.5
     wp = torch.empty(N, 9 * C, dtype=torch.bfloat16, device="cuda")
     ops.pack_weight(w, wp, 9, C, N, 0)
     bias = torch.zeros(N, device="cuda")
+    sums = torch.zeros(ops.GN_REPLICAS, 4, 8, 2, device="cuda")
 
     def run(i):
-        ops.tapgemm(ops.VDN_TAP_UNIT, [xs[i % nbuf]], wp, ops.TAPS_3x3, bias=bias, out=outs[i % nbuf])
+        if gn:
+            ops.tapgemm(ops.VDN_TAP_UNIT, [xs[i % nbuf]], wp, ops.TAPS_3x3, bias=bias, out=outs[i % nbuf], gn_sums=sums,
+                        gn_groups=8, rows_per_sample=n_img // 4 * H * W)
+        else:
+            ops.tapgemm(ops.VDN_TAP_UNIT, [xs[i % nbuf]], wp, ops.TAPS_3x3, bias=bias, out=outs[i % nbuf])
 
     for i in range(4):
         run(i)
@@ -44,6 +49,12 @@ def time_conv(n_img, H, W, C, N, nbuf=8, n=32):
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "gn":
+        for gn, dbg in ((False, "0"), (True, "0"), (True, "16"), (True, "32"), (True, "48")):
+            os.environ["VDN_SLAB_DBG"] = dbg
+            us, tf = time_conv(64, 128, 128, 128, 128, gn=gn)
+            print(f"gn={gn} dbg={dbg} (16: no atomics, 32: no accumulation): {us:8.1f} us {tf:7.1f} TF/s", flush=True)
+        sys.exit(0)
     shapes = [(64, 128, 128, 128, 128), (64, 64, 64, 256, 256), (64, 32, 32, 512, 512), (64, 16, 16, 1024, 1024)]
     if len(sys.argv) > 1:
         shapes = shapes[: int(sys.argv[1])]

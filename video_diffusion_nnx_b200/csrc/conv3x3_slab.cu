@@ -24,7 +24,9 @@
 
 namespace vdn {
 
-constexpr int kSlThreads = 192;
+constexpr int kSlEpiWarps = 8;  // two epilogue warps per TMEM lane quarter, each takes half of the tile's columns
+constexpr int kSlEpiThreads = 32 * kSlEpiWarps;
+constexpr int kSlThreads = 64 + kSlEpiThreads;
 constexpr int kSlMaxStages = 6;
 constexpr int kSlTileM = 128;
 
@@ -87,7 +89,7 @@ __global__ void __launch_bounds__(kSlThreads) conv3x3_slab_kernel(const __grid_c
   __shared__ __align__(8) uint64_t tfull_bar;
   __shared__ __align__(8) uint64_t tempty_bar[4];  // per accumulator: drained by the epilogue
   __shared__ uint32_t tmem_base_smem;
-  __shared__ float s_gn[2][4][16];  // [staging parity][epilogue warp][(sum, sumsq) x groups of the N tile]
+  __shared__ float s_gn[2][kSlEpiWarps][16];  // [staging parity][epilogue warp][(sum, sumsq) x groups of the N tile]
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // warp-uniform role index
   const int lane = threadIdx.x & 31;
@@ -107,7 +109,7 @@ __global__ void __launch_bounds__(kSlThreads) conv3x3_slab_kernel(const __grid_c
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(&tfull_bar, 1);
-    for (int i = 0; i < 4; ++i) mbar_init(&tempty_bar[i], 128);
+    for (int i = 0; i < 4; ++i) mbar_init(&tempty_bar[i], kSlEpiThreads);
     mbar_fence_init();
   }
   if (warp == 1) {
@@ -208,7 +210,8 @@ __global__ void __launch_bounds__(kSlThreads) conv3x3_slab_kernel(const __grid_c
     // the epilogue's critical path. With a residual operand the tile is added and stored by the threads instead.
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
     const int r = quarter * 32 + lane;
-    const int et = threadIdx.x - 64;  // epilogue thread id 0..127
+    const int et = threadIdx.x - 64;  // epilogue thread id 0..255
+    const int chalf = (warp - 2) >> 2;  // which half of the tile's columns this warp drains
     const bool gn_on = a.gn_sums != nullptr;
     const int cpg = a.cpg;
     const uint32_t swz = (uint32_t)(r & 7);
@@ -242,13 +245,19 @@ __global__ void __launch_bounds__(kSlThreads) conv3x3_slab_kernel(const __grid_c
         const int buf = tcount & 1;
         uint8_t* sbuf = stg + buf * (n_sub * 16384);
         if (et == 0) bulk_wait_read_1();  // the TMA store that read this staging buffer two tiles ago is done
-        if (et < 64) s_gn[buf][et >> 4][et & 15] = 0.f;
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (et < 16 * kSlEpiWarps) s_gn[buf][et >> 4][et & 15] = 0.f;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(i * BN);
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-          uint32_t raw[32];
-          tmem_ld_32x32(taddr + (uint32_t)c0, raw);
-          tmem_ld_wait();
+        // GroupNorm partial sums: groups of >= 16 channels are accumulated per thread over the whole tile
+        // (ga[2g] = sum, ga[2g+1] = sum of squares of group g of this N tile) and reduced over the warp ONCE per tile
+        // with 16 shuffles; a shuffle reduction per 16-column chunk (80 per tile) sat on the epilogue's serial
+        // path and cost 48 % of the kernel (378 vs 255 us at 128 -> 128 @128x128). Narrower groups keep the old path.
+        float ga[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) ga[q] = 0.f;
+        const bool gn_wide = gn_on && cpg >= 16 && (cpg & (cpg - 1)) == 0 && !(a.dbg & 32);
+        const int cpg_log = 31 - __clz(cpg);
+        auto process = [&](const uint32_t (&raw)[32], int c0) {
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             float v[16];
@@ -263,10 +272,31 @@ __global__ void __launch_bounds__(kSlThreads) conv3x3_slab_kernel(const __grid_c
                 v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
               }
             }
-            if (gn_on) {
+            if (gn_wide) {
+              // four independent partial chains (a single in-order warp per scheduler: a 16-deep dependent
+              // chain costs 16 x the FADD latency)
+              float p1[4], p2[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                p1[q] = v[q];
+                p2[q] = v[q] * v[q];
+              }
+#pragma unroll
+              for (int j = 4; j < 16; ++j) {
+                p1[j & 3] += v[j];
+                p2[j & 3] = fmaf(v[j], v[j], p2[j & 3]);
+              }
+              const float s1 = (p1[0] + p1[1]) + (p1[2] + p1[3]), s2 = (p2[0] + p2[1]) + (p2[2] + p2[3]);
+              const int g = cl >> cpg_log;  // group within this N tile (cpg is a power of two >= 16; warp-uniform)
+#pragma unroll
+              for (int gi = 0; gi < 8; ++gi)
+                if (gi == g) {
+                  ga[2 * gi] += s1;
+                  ga[2 * gi + 1] += s2;
+                }
+            } else if (gn_on && !(a.dbg & 32)) {
               float* slot = &s_gn[buf][warp - 2][2 * (cg / cpg - g_tile0)];
-              if (cpg >= 16) sl_gn_accumulate16<16>(v, slot, lane);
-              else if (cpg == 8) sl_gn_accumulate16<8>(v, slot, lane);
+              if (cpg == 8) sl_gn_accumulate16<8>(v, slot, lane);
               else if (cpg == 4) sl_gn_accumulate16<4>(v, slot, lane);
               else sl_gn_accumulate16<2>(v, slot, lane);
             }
@@ -283,11 +313,30 @@ __global__ void __launch_bounds__(kSlThreads) conv3x3_slab_kernel(const __grid_c
               *reinterpret_cast<uint4*>(rowp + (((j0 + j) ^ swz) << 4)) = q;
             }
           }
+        };
+        // the TMEM load of the next 32 columns is in flight while the current 32 are processed
+        uint32_t raw_a[32], raw_b[32];
+        const int cb = chalf * (BN >> 1), ce = cb + (BN >> 1);  // BN / 2 = 32 or 64 columns per warp
+        tmem_ld_32x32(taddr + (uint32_t)cb, raw_a);
+        for (int c0 = cb; c0 < ce; c0 += 64) {
+          tmem_ld_wait();
+          const bool two = c0 + 32 < ce;
+          if (two) tmem_ld_32x32(taddr + (uint32_t)(c0 + 32), raw_b);
+          process(raw_a, c0);
+          if (two) {
+            tmem_ld_wait();
+            if (c0 + 64 < ce) tmem_ld_32x32(taddr + (uint32_t)(c0 + 64), raw_a);
+            process(raw_b, c0 + 32);
+          }
+        }
+        if (gn_wide) {
+          const float tot = warp_sum16(ga, lane);
+          if ((lane & 1) == 0) s_gn[buf][warp - 2][lane >> 1] = tot;
         }
         tc_fence_before();
         mbar_arrive(&tempty_bar[i]);  // accumulator i has been read: the MMA warp may reuse it for the next item
         if (!resp) fence_proxy_async_smem();
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
         if (!resp) {
           if (et == 0) {
             for (int sub = 0; sub < n_sub; ++sub) tma_store_2d(omap, sbuf + sub * 16384, col_o + sub * 64, (int)m0);
@@ -297,7 +346,7 @@ __global__ void __launch_bounds__(kSlThreads) conv3x3_slab_kernel(const __grid_c
           // residual add: consecutive threads handle consecutive 16-byte segments of a row (coalesced)
           const int spr = BN >> 3;  // 16B segments per row
           const int total = kSlTileM * spr;
-          for (int idx = et; idx < total; idx += 128) {
+          for (int idx = et; idx < total; idx += kSlEpiThreads) {
             const int rr = idx / spr, sg = idx - rr * spr;
             uint4 q = *reinterpret_cast<const uint4*>(sbuf + (sg >> 3) * 16384 + rr * 128 + (((sg & 7) ^ (rr & 7)) << 4));
             const long goff = ((m0 + rr) * ld + col_o) * 2 + sg * 16;
@@ -310,10 +359,13 @@ __global__ void __launch_bounds__(kSlThreads) conv3x3_slab_kernel(const __grid_c
             *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(outp) + goff) = q;
           }
         }
-        if (gn_on && et < 2 * (BN / cpg)) {
+        if (gn_on && et < 2 * (BN / cpg) && !(a.dbg & 16)) {
           const int sample = (int)(m0 / a.rows_per_sample);
           float* gdst = a.gn_sums + ((long)((tile % kGnReplicas) * a.n_samples + sample) * a.gn_groups) * 2;
-          atomicAdd(gdst + 2 * g_tile0 + et, s_gn[buf][0][et] + s_gn[buf][1][et] + s_gn[buf][2][et] + s_gn[buf][3][et]);
+          float tot = 0.f;
+#pragma unroll
+          for (int w = 0; w < kSlEpiWarps; ++w) tot += s_gn[buf][w][et];
+          atomicAdd(gdst + 2 * g_tile0 + et, tot);
         }
       }
     }

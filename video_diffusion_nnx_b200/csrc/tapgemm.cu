@@ -267,6 +267,12 @@ __global__ void __launch_bounds__(kGemmThreads) tapgemm_kernel(const __grid_cons
       gdst = args.gn_sums + ((long)(rep * args.n_samples + sample) * args.gn_groups) * 2;
     }
     const int g_tile0 = col_base / args.cpg;  // first group covered by this N tile
+    // groups of a power-of-two >= 16 channels that tile BN evenly (every ResnetBlock conv with >= 128 channels)
+    const bool gn_wide = gn_cta && args.cpg >= 16 && (args.cpg & (args.cpg - 1)) == 0 && BN % args.cpg == 0;
+    const int cpg_log = 31 - __clz(args.cpg);
+    float ga[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) ga[q] = 0.f;
     const int pitch = BN * esz + 16;          // smem row pitch of the staged tile (bytes)
     uint8_t* srow = smem + (size_t)r * pitch;
     const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
@@ -297,7 +303,31 @@ __global__ void __launch_bounds__(kGemmThreads) tapgemm_kernel(const __grid_cons
         }
         if (gn_on) {
           const int cpg = args.cpg;
-          if (gn_cta) {
+          if (gn_wide) {
+            // per-thread partial sums over the whole tile (four independent chains per 16 columns), ONE 16-shuffle
+            // warp reduction after the column loop: a shuffle reduction per chunk sits on the serial path of the epilogue
+            float p1[4], p2[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float x = valid ? v[q] : 0.f;
+              p1[q] = x;
+              p2[q] = x * x;
+            }
+#pragma unroll
+            for (int j = 4; j < 16; ++j) {
+              const float x = valid ? v[j] : 0.f;
+              p1[j & 3] += x;
+              p2[j & 3] = fmaf(x, x, p2[j & 3]);
+            }
+            const float s1 = (p1[0] + p1[1]) + (p1[2] + p1[3]), s2 = (p2[0] + p2[1]) + (p2[2] + p2[3]);
+            const int g = cl >> cpg_log;  // group within this N tile (warp-uniform)
+#pragma unroll
+            for (int gi = 0; gi < 8; ++gi)
+              if (gi == g) {
+                ga[2 * gi] += s1;
+                ga[2 * gi + 1] += s2;
+              }
+          } else if (gn_cta) {
             float* slot = &s_gn[warp - 2][2 * (cg / cpg - g_tile0)];
             if (cpg >= 16) gn_accumulate16_warp<16>(v, valid, slot, lane);
             else if (cpg == 8) gn_accumulate16_warp<8>(v, valid, slot, lane);
@@ -371,6 +401,10 @@ __global__ void __launch_bounds__(kGemmThreads) tapgemm_kernel(const __grid_cons
           }
         }
       }
+    }
+    if (gn_wide) {
+      const float tot = warp_sum16(ga, lane);
+      if ((lane & 1) == 0) s_gn[warp - 2][lane >> 1] = tot;
     }
     if (staged) {
       asm volatile("bar.sync 1, 128;" ::: "memory");
