@@ -459,8 +459,11 @@ __global__ void __launch_bounds__(kGemmThreads) tapgemm_kernel(const __grid_cons
 // HBM write is asynchronous. With a residual operand the staged tile is added and stored by the threads instead.
 // No GroupNorm sums, no fp32 output, no parity scatter (those launches keep the kernel above).
 // ---------------------------------------------------------------------------------------
+constexpr int kPersistEpiThreads = 256;  // 8 epilogue warps
+constexpr int kPersistThreads = 64 + kPersistEpiThreads;
+
 template <int BK, bool kRes>
-__global__ void __launch_bounds__(kGemmThreads) tapgemm_persist_kernel(const __grid_constant__ TapMaps maps,
+__global__ void __launch_bounds__(kPersistThreads) tapgemm_persist_kernel(const __grid_constant__ TapMaps maps,
                                                                        const TapArgs args) {
   constexpr int kSwizzle = BK * 2;
   constexpr int kABytes = kTileM * BK * 2;
@@ -495,7 +498,7 @@ __global__ void __launch_bounds__(kGemmThreads) tapgemm_persist_kernel(const __g
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tfull_bar[b], 1);
-      mbar_init(&tempty_bar[b], 128);
+      mbar_init(&tempty_bar[b], kPersistEpiThreads);
     }
     mbar_fence_init();
   }
@@ -585,10 +588,14 @@ __global__ void __launch_bounds__(kGemmThreads) tapgemm_persist_kernel(const __g
     }
     __syncwarp();
   } else {
-    // ================= epilogue (warps 2..5) =================
+    // ================= epilogue (warps 2..9) =================
+    // Two warps per TMEM lane quarter, each draining half of the tile's columns: four epilogue warps are one in-order
+    // warp per scheduler, and every tcgen05.wait::ld / conversion chain is then paid in full. The TMEM load of the
+    // next 32 columns is in flight while the current 32 are converted and staged.
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;
-    const int et = threadIdx.x - 64;
+    const int et = threadIdx.x - 64;           // 0..255
+    const int chalf = (warp - 2) >> 2;
     const int subw = BN < 64 ? BN : 64;        // columns per staged sub-tile = one swizzle span
     const int n_sub = BN / subw;
     const int row_b = subw * 2;                // 64 or 128 bytes
@@ -597,6 +604,9 @@ __global__ void __launch_bounds__(kGemmThreads) tapgemm_persist_kernel(const __g
     const int cpr = row_b >> 4;                // 16-byte chunks per staged row (4 or 8)
     // chunk position of chunk c of row r: 128-byte rows XOR (r & 7), 64-byte rows XOR ((r >> 1) & 3)
     const uint32_t swz = row_b == 128 ? (uint32_t)(r & 7) : (uint32_t)((r >> 1) & 3);
+    // columns of this warp: half of the tile (32-column tiles are drained by the first warp of the quarter alone)
+    const int cb = BN >= 64 ? chalf * (BN >> 1) : 0;
+    const int ce = BN >= 64 ? cb + (BN >> 1) : (chalf == 0 ? BN : 0);
     int j = 0;
     for (int item = blockIdx.x; item < args.n_items; item += gridDim.x, ++j) {
       const int n_tile = item % args.n_ntiles;
@@ -624,12 +634,12 @@ __global__ void __launch_bounds__(kGemmThreads) tapgemm_persist_kernel(const __g
       // residual operand: this thread's (up to 16) 16-byte segments of the tile - in the coalesced order of the
       // write-out below - are requested NOW, so that their latency overlaps the wait for the accumulator
       const int spr_log = 31 - __clz(BN >> 3);  // log2(16-byte segments per output row)
-      const int nseg = BN >> 3;                 // segments per thread per tile (128 rows * spr / 128 threads)
+      const int nseg = BN >> 4;                 // segments per thread per tile (128 rows * BN/8 segments / 256 threads)
       uint4 rq[kRes ? 16 : 1];
       if (kRes && resp) {
 #pragma unroll
         for (int u = 0; u < (kRes ? 16 : 0); ++u) {
-          const int idx = et + u * 128;
+          const int idx = et + u * kPersistEpiThreads;
           const int rr = idx >> spr_log, sg = idx & ((1 << spr_log) - 1);
           if (u < nseg && m0 + rr < args.M)
             rq[u] = *reinterpret_cast<const uint4*>(resp + ((long)(m0 + rr) * ld + col_o) * 2 + sg * 16);
@@ -639,14 +649,11 @@ __global__ void __launch_bounds__(kGemmThreads) tapgemm_persist_kernel(const __g
       if (et == 0) {
         if (args.stg_bufs > 1) bulk_wait_read_1(); else bulk_wait_read_0();
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       mbar_wait(&tfull_bar[buf], (uint32_t)(j >> 1) & 1u);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * BN);
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t raw[32];
-        tmem_ld_32x32(taddr + (uint32_t)c0, raw);
-        tmem_ld_wait();
+      auto process = [&](const uint32_t (&raw)[32], int c0) {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           float v[16];
@@ -673,11 +680,26 @@ __global__ void __launch_bounds__(kGemmThreads) tapgemm_persist_kernel(const __g
             *reinterpret_cast<uint4*>(rowp + (((c16 + q) ^ swz) << 4)) = u;
           }
         }
+      };
+      if (cb < ce) {
+        uint32_t raw_a[32], raw_b[32];
+        tmem_ld_32x32(taddr + (uint32_t)cb, raw_a);
+        for (int c0 = cb; c0 < ce; c0 += 64) {
+          tmem_ld_wait();
+          const bool two = c0 + 32 < ce;
+          if (two) tmem_ld_32x32(taddr + (uint32_t)(c0 + 32), raw_b);
+          process(raw_a, c0);
+          if (two) {
+            tmem_ld_wait();
+            if (c0 + 64 < ce) tmem_ld_32x32(taddr + (uint32_t)(c0 + 64), raw_a);
+            process(raw_b, c0 + 32);
+          }
+        }
       }
       tc_fence_before();
       mbar_arrive(&tempty_bar[buf]);  // accumulator buffer is free for item j+2
       if (!resp) fence_proxy_async_smem();
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       if (!resp) {
         if (et == 0) {
           for (int sub = 0; sub < n_sub; ++sub) tma_store_2d(omap, sbuf + sub * sub_bytes, col_o + sub * subw, m0);
@@ -685,36 +707,20 @@ __global__ void __launch_bounds__(kGemmThreads) tapgemm_persist_kernel(const __g
         }
       } else if constexpr (kRes) {
         // residual add + store by the threads: consecutive threads take consecutive 16-byte segments of a row
-        auto finish = [&](int u0, const uint4 (&rv)[16]) {
 #pragma unroll
-          for (int u = 0; u < 16; ++u) {
-            const int idx = et + (u0 + u) * 128;
-            const int rr = idx >> spr_log, sg = idx & ((1 << spr_log) - 1);
-            if (u0 + u >= nseg || m0 + rr >= args.M) continue;
-            const int sub = sg / cpr, c16 = sg - sub * cpr;
-            const uint32_t rsw = row_b == 128 ? (uint32_t)(rr & 7) : (uint32_t)((rr >> 1) & 3);
-            uint4 q = *reinterpret_cast<const uint4*>(sbuf + sub * sub_bytes + rr * row_b + (((uint32_t)c16 ^ rsw) << 4));
-            float2 x, y;
-            x = unpack_bf16x2(q.x); y = unpack_bf16x2(rv[u].x); q.x = pack_bf16x2(x.x + y.x, x.y + y.y);
-            x = unpack_bf16x2(q.y); y = unpack_bf16x2(rv[u].y); q.y = pack_bf16x2(x.x + y.x, x.y + y.y);
-            x = unpack_bf16x2(q.z); y = unpack_bf16x2(rv[u].z); q.z = pack_bf16x2(x.x + y.x, x.y + y.y);
-            x = unpack_bf16x2(q.w); y = unpack_bf16x2(rv[u].w); q.w = pack_bf16x2(x.x + y.x, x.y + y.y);
-            *reinterpret_cast<uint4*>(outp + ((long)(m0 + rr) * ld + col_o) * 2 + sg * 16) = q;
-          }
-        };
-        if (nseg > 16) {  // 256-column tiles: the second half of the residual is requested before the first is consumed
-          uint4 rq2[16];
-#pragma unroll
-          for (int u = 0; u < 16; ++u) {
-            const int idx = et + (16 + u) * 128;
-            const int rr = idx >> spr_log, sg = idx & ((1 << spr_log) - 1);
-            if (m0 + rr < args.M)
-              rq2[u] = *reinterpret_cast<const uint4*>(resp + ((long)(m0 + rr) * ld + col_o) * 2 + sg * 16);
-          }
-          finish(0, rq);
-          finish(16, rq2);
-        } else {
-          finish(0, rq);
+        for (int u = 0; u < 16; ++u) {
+          const int idx = et + u * kPersistEpiThreads;
+          const int rr = idx >> spr_log, sg = idx & ((1 << spr_log) - 1);
+          if (u >= nseg || m0 + rr >= args.M) continue;
+          const int sub = sg / cpr, c16 = sg - sub * cpr;
+          const uint32_t rsw = row_b == 128 ? (uint32_t)(rr & 7) : (uint32_t)((rr >> 1) & 3);
+          uint4 q = *reinterpret_cast<const uint4*>(sbuf + sub * sub_bytes + rr * row_b + (((uint32_t)c16 ^ rsw) << 4));
+          float2 x, y;
+          x = unpack_bf16x2(q.x); y = unpack_bf16x2(rq[u].x); q.x = pack_bf16x2(x.x + y.x, x.y + y.y);
+          x = unpack_bf16x2(q.y); y = unpack_bf16x2(rq[u].y); q.y = pack_bf16x2(x.x + y.x, x.y + y.y);
+          x = unpack_bf16x2(q.z); y = unpack_bf16x2(rq[u].z); q.z = pack_bf16x2(x.x + y.x, x.y + y.y);
+          x = unpack_bf16x2(q.w); y = unpack_bf16x2(rq[u].w); q.w = pack_bf16x2(x.x + y.x, x.y + y.y);
+          *reinterpret_cast<uint4*>(outp + ((long)(m0 + rr) * ld + col_o) * 2 + sg * 16) = q;
         }
       }
     }
@@ -940,7 +946,7 @@ static int launch_tapgemm_persist(const TapMaps& maps, const TapArgs& args, int 
     VDN_REQUIRE(e == cudaSuccess, VDN_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     configured = true;
   }
-  cudaError_t le = launch_pdl(tapgemm_persist_kernel<BK, kRes>, dim3(grid), dim3(kGemmThreads), (size_t)smem_bytes, st, 1, maps, args);
+  cudaError_t le = launch_pdl(tapgemm_persist_kernel<BK, kRes>, dim3(grid), dim3(kPersistThreads), (size_t)smem_bytes, st, 1, maps, args);
   VDN_REQUIRE(le == cudaSuccess, VDN_E_CUDA, "tapgemm_persist launch: %s", cudaGetErrorString(le));
   return check_launch("tapgemm_persist_kernel");
 }
