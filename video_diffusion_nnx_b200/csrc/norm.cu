@@ -889,7 +889,9 @@ extern "C" int vdn_gn_silu_bwd(const void* dy, const void* x_raw, const float* g
     // isolation, but no gain on the training step (6.87 vs 6.89 ms) - a grid that needs every SM cannot overlap with
     // the weight-gradient GEMMs of the side streams, which is where the two-kernel version hides its latency.
     const char* fe = getenv("VDN_GN_FUSED");
-    const bool fused_off = !(fe && fe[0] == '1');
+    // VDN_GN_FUSED=1: every sample that fits; VDN_GN_FUSED_MAX=<elements per sample>: only samples up to that size
+    static const long fused_max = getenv("VDN_GN_FUSED_MAX") ? atol(getenv("VDN_GN_FUSED_MAX")) : 0;
+    const bool fused_off = !(fe && fe[0] == '1') && !((long)rows_per_sample * C <= fused_max);
     const int cps = B <= kFusedMaxB ? num_sms() / B : 0;  // CTAs per sample; cps * B <= number of SMs
     if (!fused_off && cps >= 1 && kFusedThreads % (C / 8) == 0) {
       const int rpc = (rows_per_sample + cps - 1) / cps;
