@@ -1106,7 +1106,8 @@ extern "C" int vdn_tapgemm(const vdn_tapgemm_desc* d, const void* src0, const vo
     const long items = (long)m_tiles * (d->n_out / a.BN);
     // 32-column tiles with a residual measured slower than the one-tile-per-CTA kernel (27.6 vs 23.6 us at K = 256,
     // 163840 pixels); tests lower VDN_PERSIST_MIN_ITEMS and still reach that combination
-    const bool narrow_res = a.BN < 64 && (residual || residual2) && tg_env_int("VDN_PERSIST_MIN_ITEMS", 3 * num_sms()) > 1;
+    const bool narrow_res = a.BN < 64 && (residual || residual2) && tg_env_int("VDN_PERSIST_MIN_ITEMS", 3 * num_sms()) > 1 &&
+                            !tg_env_int("VDN_PERSIST_NARROW_RES", 0);
     const bool shape_ok = !gn_sums && !a.out_f32 && !a.scatter && a.BN >= 32 && (a.BN & (a.BN - 1)) == 0 && !narrow_res &&
                           n_steps <= tg_env_int("VDN_PERSIST_MAX_STEPS", 16) &&
                           items >= (long)tg_env_int("VDN_PERSIST_MIN_ITEMS", 3 * num_sms());
