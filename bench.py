@@ -417,13 +417,12 @@ def main():
     x_dev = torch.rand(shape, generator=g).to(dev)
     t_all = torch.randint(0, CFG["timesteps"], (K + Wm + 2, B), generator=g, dtype=torch.int32).to(dev)
     ts.x.copy_(x_dev)
-    l0 = _lib.lib.vdn_launch_count()
     ts.t.copy_(t_all[0])
     ops.randn(ts.noise, 7 + rank, 0)
-    ts.step_device(0)  # eager warm-up step + graph capture + one replayed step
-    launches_capture = _lib.lib.vdn_launch_count() - l0
-    # the first call ran the step eagerly once and captured it once: launches per step is half of that (+2 randn)
-    launches_per_step = (launches_capture - 1) // 2 + 1
+    ts.step_device(0)  # eager warm-up pass (state restored) + graph capture + one replayed step
+    # kernels of libvdn in one replayed step (counted by the library while the step's graphs were captured) + the
+    # noise kernel launched per step below
+    launches_per_step = ts.launches_per_step + 1
     for i in range(Wm):
         ts.t.copy_(t_all[1 + i])
         ops.randn(ts.noise, 7 + rank, 1 + i)

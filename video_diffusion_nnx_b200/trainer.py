@@ -169,6 +169,8 @@ class TrainStep:
         """Capture [q_sample + fwd + loss + bwd segment 0], [bwd segment k]..., [adam + repack] as CUDA
         graphs; NCCL reductions are launched between the graph launches."""
         torch.cuda.synchronize()
+        from ._lib import lib as _vdn
+        n0 = _vdn.vdn_launch_count()
         graphs = []
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
@@ -187,6 +189,7 @@ class TrainStep:
             self._optimizer()
         graphs.append(g)
         self._graphs = graphs
+        self.launches_per_step = int(_vdn.vdn_launch_count() - n0)  # kernels of this library in one replayed step
 
     def _run_graphs(self):
         for g, (_, (lo, hi)) in zip(self._graphs[:-1], self._segments):
@@ -223,9 +226,16 @@ class TrainStep:
         self.set_hyper(step)
         if self.use_graph:
             if self._graphs is None:
-                self._run_eager()   # warm-up: allocates every pooled buffer, sets kernel attributes
-                self.count += 1
-                self.set_hyper(step)
+                # warm-up pass (allocates every pooled buffer, sets kernel attributes) on a snapshot of the training
+                # state: the first call must apply ONE optimizer update, like every other call
+                st = self.net.store
+                state = (st.flat, self.m, self.v, self.ema)
+                snap = [t.clone() for t in state]
+                self._run_eager()
+                torch.cuda.synchronize()
+                for dst, src in zip(state, snap):
+                    dst.copy_(src)
+                self.eng.repack()
                 self._capture()
             self._run_graphs()
         else:
