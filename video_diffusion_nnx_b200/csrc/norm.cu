@@ -919,7 +919,8 @@ extern "C" int vdn_gn_silu_bwd(const void* dy, const void* x_raw, const float* g
   int gx, cl;
   // chunks per block: 1 until the launch exceeds ~2 waves of 8 blocks per SM, then up to 8 (large samples)
   const long blocks1 = (long)grid_x_for(rows_per_sample, pl_n * kVecPerThread) * B;
-  const int iters = (int)std::max<long>(1, std::min<long>(8, blocks1 / (2 * 8 * num_sms())));
+  int iters = (int)std::max<long>(1, std::min<long>(8, blocks1 / (2 * 8 * num_sms())));
+  if (const char* ie = getenv("VDN_GN_ITERS")) iters = std::max(1, std::min(16, atoi(ie)));  // experiments
   cl = cluster_for(grid_x_for(rows_per_sample, pl_n * kVecPerThread * iters), &gx);
   const size_t smem_r = (6 * C + kNormThreads * 16) * sizeof(float);
   cudaError_t le = iters > 1 ? launch_pdl(gn_bwd_reduce_kernel<true>, dim3(gx, B), dim3(kNormThreads), (size_t)(smem_r), st, cl, a, reinterpret_cast<const bf16*>(dy), T_ws, iters)

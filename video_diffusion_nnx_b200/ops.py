@@ -3,6 +3,7 @@ purely as device-memory handles; all arithmetic happens in libvdn.so kernels."""
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional, Sequence
 
 import torch
@@ -42,6 +43,11 @@ def pack_weight(src: torch.Tensor, dst: torch.Tensor, taps: int, cin: int, cout:
           "vdn_pack_weight")
 
 
+# timing experiments only (tools/whatif.sh): VDN_SKIP="gn_bwd,wgrad,..." turns the named wrappers into no-ops so
+# that the step-time contribution of a kernel family can be read off (results are wrong, of course)
+_SKIP = set(filter(None, os.environ.get("VDN_SKIP", "").split(",")))
+
+
 def tapgemm(kind: int, srcs: Sequence[torch.Tensor], wp: torch.Tensor, taps, *, bias=None, residual=None,
             residual2=None, out=None, out2=None, split_col: int = 0, gn_sums=None, gn_groups: int = 0, rows_per_sample: int = 0,
             py: int = 0, px: int = 0, out_dtype=torch.bfloat16, ref: bool = False) -> torch.Tensor:
@@ -78,6 +84,8 @@ def tapgemm(kind: int, srcs: Sequence[torch.Tensor], wp: torch.Tensor, taps, *, 
 def wgrad(kind: int, srcs: Sequence[torch.Tensor], g: torch.Tensor, dw: torch.Tensor, taps, ref: bool = False,
           dbias: Optional[torch.Tensor] = None) -> None:
     """dw[tap][n_src*C][Cout] (fp32, reference kernel layout) += sum_pixels src[p + tap]^T g[p]."""
+    if "wgrad" in _SKIP:
+        return
     x0 = srcs[0]
     assert x0.dtype == torch.bfloat16 and g.dtype == torch.bfloat16 and dw.dtype == torch.float32
     assert x0.is_contiguous() and g.is_contiguous() and dw.is_contiguous()
@@ -108,17 +116,23 @@ def wgrad(kind: int, srcs: Sequence[torch.Tensor], g: torch.Tensor, dw: torch.Te
 # norms
 # ------------------------------------------------------------------------------------------
 def gn_silu_fwd(x_raw, sums, gamma, beta, ss, out, B, rows, Cc, G=8):
+    if "gn_fwd" in _SKIP:
+        return
     ss_ld = ss.stride(0) if ss is not None else 0
     check(lib.vdn_gn_silu_fwd(ptr(x_raw), ptr(sums), ptr(gamma), ptr(beta), ptr(ss), ss_ld, ptr(out), B, rows, Cc, G,
                               stream_ptr()), "vdn_gn_silu_fwd")
 
 
 def resblock_tail_fwd(b_raw, sums, gamma, beta, s, ln_g, ln_b, out, B, rows, Cc, G=8):
+    if "tail_fwd" in _SKIP:
+        return
     check(lib.vdn_resblock_tail_fwd(ptr(b_raw), ptr(sums), ptr(gamma), ptr(beta), ptr(s), ptr(ln_g), ptr(ln_b),
                                     ptr(out), B, rows, Cc, G, stream_ptr()), "vdn_resblock_tail_fwd")
 
 
 def gn_silu_bwd(dy, x_raw, sums, gamma, beta, ss, T_ws, dx_raw, dgamma, dbeta, dss, B, rows, Cc, G=8, dconv_bias=None):
+    if "gn_bwd" in _SKIP:
+        return
     ss_ld = ss.stride(0) if ss is not None else 0
     dss_ld = dss.stride(0) if dss is not None else 0
     check(lib.vdn_gn_silu_bwd(ptr(dy), ptr(x_raw), ptr(sums), ptr(gamma), ptr(beta), ptr(ss), ss_ld, ptr(T_ws),
@@ -127,6 +141,8 @@ def gn_silu_bwd(dy, x_raw, sums, gamma, beta, ss, T_ws, dx_raw, dgamma, dbeta, d
 
 
 def ln_bwd(s, dy, ln_g, ds, dg, db, P, Cc):
+    if "ln_bwd" in _SKIP:
+        return
     check(lib.vdn_ln_bwd(ptr(s), ptr(dy), ptr(ln_g), ptr(ds), ptr(dg), ptr(db), C.c_long(P), Cc, stream_ptr()),
           "vdn_ln_bwd")
 
@@ -154,6 +170,8 @@ def sla_workspace_floats(n_img, N) -> int:
 
 
 def sla_core_fwd(qkv, tok_out, ctx, kstat, ws, n_img, N):
+    if "sla_fwd" in _SKIP:
+        return
     check(lib.vdn_sla_core_fwd(ptr(qkv), ptr(tok_out), ptr(ctx), ptr(kstat), ptr(ws), n_img, N, stream_ptr()),
           "vdn_sla_core_fwd")
 
@@ -164,6 +182,8 @@ def sla_fused_fwd(x, w_qkv, w_out, out, ctx, kstat, ws, n_img, N, Cc):
 
 
 def sla_core_bwd(qkv, d_tok, ctx, kstat, dctx, dqkv, n_img, N):
+    if "sla_bwd" in _SKIP:
+        return
     check(lib.vdn_sla_core_bwd(ptr(qkv), ptr(d_tok), ptr(ctx), ptr(kstat), ptr(dctx), ptr(dqkv), n_img, N,
                                stream_ptr()), "vdn_sla_core_bwd")
 
@@ -309,6 +329,8 @@ def qkv_headmajor_pack(w, bias, dst, bias_dst, Cc):
 
 
 def mha_temporal_fused_fwd(x, w_hm, bias_hm, o, qkv, lse, B, F, H, W, Cc):
+    if "mha_fwd" in _SKIP:
+        return
     check(lib.vdn_mha_temporal_fused_fwd(ptr(x), ptr(w_hm), ptr(bias_hm), ptr(o), ptr(qkv), ptr(lse), B, F, H, W, Cc,
                                          stream_ptr()), "vdn_mha_temporal_fused_fwd")
 
@@ -337,10 +359,14 @@ def mha_tc_supported(F: int, Cc: int) -> bool:
 
 
 def mha_temporal_tc_fwd(x, w_hm, bias_hm, o, qkv, lse, B, F, H, W, Cc):
+    if "mha_fwd" in _SKIP:
+        return
     check(lib.vdn_mha_temporal_tc_fwd(ptr(x), ptr(w_hm), ptr(bias_hm), ptr(o), ptr(qkv), ptr(lse), B, F, H, W, Cc,
                                       stream_ptr()), "vdn_mha_temporal_tc_fwd")
 
 
 def mha_temporal_tc_bwd(qkv, d_o, lse, dqkv, B, F, H, W, dbias=None):
+    if "mha_bwd" in _SKIP:
+        return
     check(lib.vdn_mha_temporal_tc_bwd(ptr(qkv), ptr(d_o), ptr(lse), ptr(dqkv), ptr(dbias), B, F, H, W, stream_ptr()),
           "vdn_mha_temporal_tc_bwd")
