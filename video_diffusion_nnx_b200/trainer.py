@@ -172,20 +172,26 @@ class TrainStep:
         from ._lib import lib as _vdn
         n0 = _vdn.vdn_launch_count()
         graphs = []
+        # The critical path is captured on a HIGH-priority stream (kernel nodes inherit the priority of the stream
+        # they were captured on), the engine's side streams keep the default (lowest) priority: when both have
+        # blocks ready, the dependency chain goes first and the weight-gradient GEMMs fill what is left.
+        import os
+        cap = torch.cuda.Stream(priority=-1) if os.environ.get("VDN_NO_PRIORITY") is None else None
+        kw = {"stream": cap} if cap is not None else {}
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
+        with torch.cuda.graph(g, **kw):
             self._fwd_loss()
             for f in self._segments[0][0]:
                 f()
         graphs.append(g)
         for fns, _ in self._segments[1:]:
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            with torch.cuda.graph(g, **kw):
                 for f in fns:
                     f()
             graphs.append(g)
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
+        with torch.cuda.graph(g, **kw):
             self._optimizer()
         graphs.append(g)
         self._graphs = graphs
