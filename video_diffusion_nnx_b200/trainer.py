@@ -111,7 +111,7 @@ class TrainStep:
         self.count = 0
         self._graphs = None
         self._segments = self._plan_segments(bucket_bytes)
-        self.comm_stream = torch.cuda.Stream() if self.world > 1 else None
+        self.comm_stream = torch.cuda.Stream(priority=-1) if self.world > 1 else None  # reductions start as soon as issued
         self.launches_per_step = None
 
     # -- plan: group backward stages into segments, one gradient bucket per segment ----------
