@@ -105,3 +105,26 @@ def test_keys_are_deterministic_and_distinct():
     assert (a.seed, a.stream) != (b.seed, b.stream) != (c.seed, c.stream)
     a2, _, _ = Key(5).split(3)
     assert (a.seed, a.stream) == (a2.seed, a2.stream)
+
+
+def test_checkpoint_bridge_round_trip(tmp_path):
+    """{'model', 'ema_params'} tree (utils.py:445-455) <-> flat .npz <-> Unet3D.load_state_dict, on the host."""
+    from video_diffusion_nnx_b200 import checkpoint as ck
+    from video_diffusion_nnx_b200.unet3d import Unet3D
+
+    net = Unet3D(dim=32, channels=1, rngs=1)
+    model = net.state_dict()
+    ema = {k: v + 1.0 for k, v in model.items()}
+    path = str(tmp_path / "ckpt_7.npz")
+    ck.save_checkpoint(path, model, ema, step=7)
+    got, step = ck.load_checkpoint(path)
+    got_ema, _ = ck.load_checkpoint(path, load_ema_params=True)
+    assert step == 7 and set(got) == set(model)
+    assert all(np.array_equal(got[k], model[k]) for k in model)
+    assert all(np.array_equal(got_ema[k], ema[k]) for k in model)
+    # nested (orbax / nnx.State.to_pure_dict) form and back
+    nested = ck.nest(model)
+    assert "proj" in nested["downs"]["0"]["0"]["block_1"] and ck.unnest(nested).keys() == model.keys()
+    other = Unet3D(dim=32, channels=1, rngs=2)
+    other.load_state_dict(got_ema)
+    assert np.array_equal(other.state_dict()["init_conv.bias"], ema["init_conv.bias"])
