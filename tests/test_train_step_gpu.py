@@ -83,3 +83,14 @@ def test_three_adam_ema_steps_match_the_oracle():
         # Adam normalises each gradient element, so elements whose gradient is bf16 noise move in a random direction:
         # the bound is on the whole update vector
         assert rel < 0.25 and erel < 0.25
+
+
+def test_device_prefetcher_keeps_order_and_values():
+    from video_diffusion_nnx_b200.data import DevicePrefetcher
+
+    g = torch.Generator().manual_seed(3)
+    host = [torch.rand(2, 1, 2, 64, 64, generator=g) for _ in range(7)]
+    got = [b.clone() for b in DevicePrefetcher(iter(host), depth=3)]
+    torch.cuda.synchronize()
+    assert len(got) == 7 and all(b.is_cuda for b in got)
+    assert all(torch.equal(b.cpu(), h) for b, h in zip(got, host))
