@@ -838,16 +838,35 @@ namespace vdn {
 __global__ void __launch_bounds__(256) pack_batched_kernel(const vdn_pack_job* __restrict__ jobs, int n_jobs,
                                                            long long total_tiles) {
   __shared__ float tile[32][33];
+  // the tile prefix sums of all jobs live in shared memory: the per-tile binary search used to be ~10 dependent
+  // global loads (3 us of latency per 4 KB tile: 73 us for the 10 M parameters of config_v2_2)
+  constexpr int kMaxCached = 768;
+  __shared__ long long s_begin[kMaxCached];
+  const bool cached = n_jobs <= kMaxCached;
+  if (cached)
+    for (int i = threadIdx.x; i < n_jobs; i += blockDim.x) s_begin[i] = jobs[i].begin;
+  __syncthreads();
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
-  for (long long tid = blockIdx.x; tid < total_tiles; tid += gridDim.x) {
-    int lo = 0, hi = n_jobs - 1;
-    while (lo < hi) {
-      const int mid = (lo + hi + 1) >> 1;
-      if (jobs[mid].begin <= tid) lo = mid; else hi = mid - 1;
+  // a block owns a contiguous run of tiles: consecutive tiles mostly belong to the same job
+  const long long per = (total_tiles + gridDim.x - 1) / gridDim.x;
+  const long long t_begin = (long long)blockIdx.x * per, t_end = min(total_tiles, t_begin + per);
+  int cur = -1;
+  long long cur_lo = 0, cur_hi = 0;
+  for (long long tid = t_begin; tid < t_end; ++tid) {
+    if (tid < cur_lo || tid >= cur_hi) {
+      int lo = 0, hi = n_jobs - 1;
+      while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        const long long b = cached ? s_begin[mid] : jobs[mid].begin;
+        if (b <= tid) lo = mid; else hi = mid - 1;
+      }
+      cur = lo;
+      cur_lo = cached ? s_begin[lo] : jobs[lo].begin;
+      cur_hi = lo + 1 < n_jobs ? (cached ? s_begin[lo + 1] : jobs[lo + 1].begin) : total_tiles;
     }
-    const vdn_pack_job& a = jobs[lo];
+    const vdn_pack_job& a = jobs[cur];
     const int tiles_ci = (a.cin + 31) >> 5, tiles_co = (a.cout + 31) >> 5;
-    int r = (int)(tid - a.begin);
+    int r = (int)(tid - cur_lo);
     const int co0 = (r % tiles_co) * 32;
     r /= tiles_co;
     const int ci0 = (r % tiles_ci) * 32;
