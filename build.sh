@@ -16,5 +16,5 @@ for f in $PKG/csrc/*.cu; do
   fi
 done
 for p in "${pids[@]}"; do wait $p; done
-nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $PKG/libvdn.so $OBJ/*.o
+nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $PKG/libvdn.so $OBJ/*.o -ldl
 echo "built $PKG/libvdn.so"

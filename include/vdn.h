@@ -40,6 +40,9 @@ int vdn_version(void);
 const char* vdn_last_error(void);
 /* kernels launched (or recorded into a CUDA graph under capture) by this library so far */
 unsigned long long vdn_launch_count(void);
+/* Test / tool hook: set (enable != 0) or clear one experiment switch by its VDN_* name.
+ * Product code never reads the process environment; without this call every switch has its compiled-in default. */
+int vdn_debug_set(const char* name, int value, int enable);
 
 /* ---------------------------------------------------------------------------------
  * Weight repacking (fp32 reference layout -> bf16 K-major GEMM operand).
@@ -233,6 +236,27 @@ int vdn_mha_temporal_bwd(const void* qkv, const void* o, const void* d_o, const 
                          int H, int W, void* stream);
 
 /* ---------------------------------------------------------------------------------
+ * MultiheadAttention with the reference's OPTIONAL inputs, and RelativePositionBias (modules.py:285-326, :330-390).
+ * Dead inside Unet3D (PreNorm drops kwargs, modules.py:146-148) - the fused kernels above do not carry them - but
+ * live when the module is called directly (test_modules.py:242-271). Literal semantics:
+ *   attn = softmax_j(q k^T / sqrt(dim)); focus_present_mask[b] != 0: off-diagonal entries are REPLACED, after the
+ *   softmax, by finfo(float32).min (:307-316); pos_bias [heads][S][S] is ADDED after the softmax (:320-321);
+ *   copy_v != 0 is the all-focus early return out(v) (:291-292): o = v.
+ * qkv rows are [3][heads][dim] (q | k | v), o rows [heads][dim]; dtype VDN_BF16 or VDN_F32; dim in {8,16,32,64}.
+ * Token t of sequence s is row (s / inner) * S * inner + (s % inner) + t * inner: inner = 1 for (..., S, C) inputs,
+ * inner = H*W for the temporal view 'b f h w c -> b (h w) f c' of a (B,F,H,W,C) tensor (unet3d.py:86-96).
+ * mask_b: device bytes [n_seq / seqs_per_batch] or NULL.
+ *
+ * vdn_rel_pos_bias: out[h][i][j] = embedding[bucket(i - j)][h] with the static 32 / 128 bucket parameters that
+ * RelativePositionBias.__call__ uses whatever its constructor got (modules.py:386); buckets_out (int32 [n][n],
+ * optional) returns the ids (integer work, bit-exact).
+ * --------------------------------------------------------------------------------- */
+int vdn_mha_core_ext_fwd(const void* qkv, void* o, int dtype, int heads, int dim, int n_seq, int S, int inner,
+                         const unsigned char* mask_b, int seqs_per_batch, const float* pos_bias, int copy_v,
+                         void* stream);
+int vdn_rel_pos_bias(const float* embedding, int n, int heads, float* out, int* buckets_out, void* stream);
+
+/* ---------------------------------------------------------------------------------
  * Small layers. init conv: nnx.Conv(channels, dim, (1,k,k)) on x fp32 (B,Cin,F,H,W) (unet3d.py:110-115,
  * :280-282) -> bf16 (B*F,H,W,Cout); w fp32 [k*k][Cin][Cout]. final conv: nnx.Conv(dim, out, 1)
  * (unet3d.py:251): h bf16 [P][C] -> fp32 [P][Co]. time MLP: SinusoidalPosEmb -> Linear -> gelu(tanh) ->
@@ -305,6 +329,48 @@ int vdn_countdown(int* t_dev, int B, void* stream);
 int vdn_colsum(const void* dy, float* db, long P, int C, void* stream);
 int vdn_add_bf16(const void* a, const void* b, void* out, long n, void* stream);
 int vdn_adam_ema(float* p, const float* g, float* m, float* v, float* ema, const float* hp_dev, long n, void* stream);
+/* Global-norm clip folded into the same update (utils.py:127-152, `max_grad_norm` of the trainer configs):
+ * vdn_grad_sqnorm writes out[0] = sum g^2 of the flat gradient (after the all-reduce); vdn_adam_ema_clip reads
+ * hp_dev[9] = max_grad_norm (0 = off) and hp_dev[10] = the reference's epsilon (1e-6):
+ * l2 = sqrt(out[0] * grad_scale^2 + eps), g *= min(max_grad_norm / (l2 + eps), 1). */
+int vdn_grad_sqnorm(const float* g, long n, float* out, void* stream);
+int vdn_adam_ema_clip(float* p, const float* g, float* m, float* v, float* ema, const float* hp_dev,
+                      const float* sqnorm_dev, long n, void* stream);
+
+/* ---------------------------------------------------------------------------------
+ * Scratch sizes. Every buffer (operands, results, scratch) is allocated and owned by the caller (XLA allocates
+ * scratch as an extra result of the custom call); these return the BYTES of the scratch argument of the
+ * entry point of the same name. Ops not listed need none.
+ * --------------------------------------------------------------------------------- */
+size_t vdn_sla_core_fwd_workspace(int n_img, int N);       /* ws of vdn_sla_core_fwd / vdn_sla_fused_fwd */
+size_t vdn_sla_core_bwd_workspace(int n_img);              /* dctx */
+size_t vdn_gn_silu_bwd_workspace(int B, int C);            /* T_ws */
+size_t vdn_mha_core_bwd_workspace(long P);                 /* D_ws */
+size_t vdn_time_heads_bwd_workspace(int B, int ss_ld);     /* de_ws */
+size_t vdn_time_mlp_bwd_workspace(int B, int dim);         /* dh1_ws */
+size_t vdn_tapgemm_workspace(const vdn_tapgemm_desc* d);   /* 0: operands stream through shared memory / TMEM */
+
+/* ---------------------------------------------------------------------------------
+ * Data-parallel gradient exchange. The reference shards the batch over the `data`
+ * mesh axis and GSPMD inserts the gradient all-reduce of the pjit'd train step (trainer.py:307-326,363-364);
+ * here it is explicit: one communicator per process (one process per GPU), sum-reduce of one contiguous bucket
+ * of the flat gradient, enqueued on `stream` (CUDA-graph capturable). The mean's 1/world is folded into
+ * vdn_adam_ema (hp_dev[8]). NCCL is resolved at run time; without it these return VDN_E_ARCH.
+ *   id exchange: rank 0 calls vdn_comm_unique_id(id_host) (vdn_comm_unique_id_bytes() bytes) and ships the bytes
+ *   to every rank out of band (torch.distributed / MPI / a file); every rank then calls vdn_comm_init.
+ *   max_ctas > 0 caps the SMs NCCL may occupy (the reduction overlaps the backward pass).
+ * --------------------------------------------------------------------------------- */
+int vdn_comm_unique_id_bytes(void);
+int vdn_comm_unique_id(void* id_host);
+int vdn_comm_init(void** comm_out, const void* id_host, int rank, int world, int max_ctas);
+int vdn_comm_world(const void* comm, int* rank, int* world);
+int vdn_allreduce_bucket(void* comm, void* buf, long count, int dtype, void* stream);
+int vdn_comm_destroy(void* comm);
+
+/* Library-owned state: cached TMA descriptors (keyed by pointer + shape; hits / misses since load) and
+ * communicators. vdn_shutdown releases both; the library never owns device memory. */
+int vdn_tmap_cache_stats(unsigned long long* hits, unsigned long long* misses);
+int vdn_shutdown(void);
 
 #ifdef __cplusplus
 }

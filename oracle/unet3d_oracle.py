@@ -141,17 +141,17 @@ def relative_position_bias(p: Params, prefix: str, n: int) -> torch.Tensor:
     return emb.permute(2, 0, 1)
 
 
-def block(p: Params, prefix: str, x: torch.Tensor, scale_shift=None) -> torch.Tensor:
+def block(p: Params, prefix: str, x: torch.Tensor, scale_shift=None, groups: int = GROUPS) -> torch.Tensor:
     """modules.py:171-179."""
     x = conv_khw(x, p[prefix + ".proj.kernel"], p[prefix + ".proj.bias"])
-    x = group_norm(x, p[prefix + ".norm.scale"], p[prefix + ".norm.bias"])
+    x = group_norm(x, p[prefix + ".norm.scale"], p[prefix + ".norm.bias"], groups)
     if scale_shift is not None:
         scale, shift = scale_shift
         x = x * (scale + 1) + shift
     return F.silu(x)
 
 
-def resnet_block(p: Params, prefix: str, x: torch.Tensor, t_emb: Optional[torch.Tensor]) -> torch.Tensor:
+def resnet_block(p: Params, prefix: str, x: torch.Tensor, t_emb: Optional[torch.Tensor], groups: int = GROUPS) -> torch.Tensor:
     """modules.py:226-243."""
     scale_shift = None
     if (prefix + ".mlp.layers.1.kernel") in p:
@@ -160,8 +160,8 @@ def resnet_block(p: Params, prefix: str, x: torch.Tensor, t_emb: Optional[torch.
         e = layer_norm(e, p[prefix + ".norm_1.scale"], p[prefix + ".norm_1.bias"])
         e = e[:, None, None, None, :]
         scale_shift = torch.chunk(e, 2, dim=-1)
-    h = block(p, prefix + ".block_1", x, scale_shift)
-    h = block(p, prefix + ".block_2", h)
+    h = block(p, prefix + ".block_1", x, scale_shift, groups)
+    h = block(p, prefix + ".block_2", h, None, groups)
     if (prefix + ".res_conv.kernel") in p:
         s = conv1x1(x, p[prefix + ".res_conv.kernel"], p[prefix + ".res_conv.bias"])
     else:
@@ -229,9 +229,19 @@ def sla_residual(p: Params, prefix: str, x: torch.Tensor) -> torch.Tensor:
 # --------------------------------------------------------------------------------------
 # unet3d.py
 # --------------------------------------------------------------------------------------
-def unet3d_forward(p: Params, x: torch.Tensor, time: torch.Tensor, dim: int, dim_mults=(1, 2, 4, 8)) -> torch.Tensor:
-    """unet3d.py:262-387, unconditional (has_cond False). x (B,C,F,H,W), time (B,) int -> (B,F,H,W,C)."""
+def unet3d_forward(p: Params, x: torch.Tensor, time: torch.Tensor, dim: int, dim_mults=(1, 2, 4, 8),
+                   resnet_groups: int = GROUPS, use_sparse_linear_attn: bool = True) -> torch.Tensor:
+    """unet3d.py:262-387, unconditional (has_cond False). x (B,C,F,H,W), time (B,) int -> (B,F,H,W,C).
+    resnet_groups -> every GroupNorm (unet3d.py:156); use_sparse_linear_attn=False puts Identity() in the spatial
+    attention slots (unet3d.py:179-181,230-231)."""
     dtype = x.dtype
+
+    def res(pp, prefix, xx, tt):
+        return resnet_block(pp, prefix, xx, tt, resnet_groups)
+
+    def sla(pp, prefix, xx):
+        return sla_residual(pp, prefix, xx) if use_sparse_linear_attn else xx
+
     n_res = len(dim_mults)
     x = x.permute(0, 2, 3, 4, 1)  # :280
     x = conv_khw(x, p["init_conv.kernel"], p["init_conv.bias"])  # :282
@@ -243,34 +253,35 @@ def unet3d_forward(p: Params, x: torch.Tensor, time: torch.Tensor, dim: int, dim
     t = t @ p["time_mlp.layers.3.kernel"] + p["time_mlp.layers.3.bias"]
     hs = []
     for l in range(n_res):  # :303-314
-        x = resnet_block(p, f"downs.{l}.0", x, t)
-        x = resnet_block(p, f"downs.{l}.1", x, t)
-        x = sla_residual(p, f"downs.{l}.2", x)
+        x = res(p, f"downs.{l}.0", x, t)
+        x = res(p, f"downs.{l}.1", x, t)
+        x = sla(p, f"downs.{l}.2", x)
         x = temporal_attention(p, f"downs.{l}.3", x)
         hs.append(x)
         if l < n_res - 1:
             x = conv_khw(x, p[f"downs.{l}.4.kernel"], p[f"downs.{l}.4.bias"], stride=2)
-    x = resnet_block(p, "mid_block1", x, t)  # :320
+    x = res(p, "mid_block1", x, t)  # :320
     x = spatial_attention(p, "mid_spatial_attn", x)  # :324
     x = temporal_attention(p, "mid_temporal_attn", x)  # :328
-    x = resnet_block(p, "mid_block2", x, t)  # :334
+    x = res(p, "mid_block2", x, t)  # :334
     for i in range(n_res):  # :337-370
         x = torch.cat([x, hs.pop()], dim=-1)
-        x = resnet_block(p, f"ups.{i}.0", x, t)
-        x = resnet_block(p, f"ups.{i}.1", x, t)
-        x = sla_residual(p, f"ups.{i}.2", x)
+        x = res(p, f"ups.{i}.0", x, t)
+        x = res(p, f"ups.{i}.1", x, t)
+        x = sla(p, f"ups.{i}.2", x)
         x = temporal_attention(p, f"ups.{i}.3", x)
         if i < n_res - 1:
             x = conv_transpose_k4s2(x, p[f"ups.{i}.4.kernel"], p[f"ups.{i}.4.bias"])
     x = torch.cat([x, r], dim=-1)  # :377
-    x = resnet_block(p, "final_conv.layers.0", x, None)  # :250 (no time embedding)
+    x = res(p, "final_conv.layers.0", x, None)  # :250 (no time embedding)
     return conv1x1(x, p["final_conv.layers.1.kernel"], p["final_conv.layers.1.bias"])  # :251
 
 
 # --------------------------------------------------------------------------------------
 # parameter construction (flax init distributions; NOT bit-identical to nnx.Rngs(0))
 # --------------------------------------------------------------------------------------
-def param_shapes(dim: int, channels: int, dim_mults=(1, 2, 4, 8), init_kernel_size: int = 7) -> Dict[str, tuple]:
+def param_shapes(dim: int, channels: int, dim_mults=(1, 2, 4, 8), init_kernel_size: int = 7,
+                 use_sparse_linear_attn: bool = True) -> Dict[str, tuple]:
     """Names and shapes of the Unet3D state (unet3d.py:58-252), in creation order."""
     s: Dict[str, tuple] = {}
     time_dim = dim * 4
@@ -286,6 +297,8 @@ def param_shapes(dim: int, channels: int, dim_mults=(1, 2, 4, 8), init_kernel_si
         s[prefix + ".fn.fn.fn.out.bias"] = (c,)
 
     def sla(prefix, c):
+        if not use_sparse_linear_attn:
+            return
         s[prefix + ".fn.norm.scale"] = (c,)
         s[prefix + ".fn.norm.bias"] = (c,)
         for n in ("q", "k", "v"):
@@ -349,13 +362,13 @@ def param_shapes(dim: int, channels: int, dim_mults=(1, 2, 4, 8), init_kernel_si
 
 
 def init_params(dim: int, channels: int, seed: int = 3, dtype=torch.float32, perturb: float = 0.0,
-                dim_mults=(1, 2, 4, 8)) -> Params:
+                dim_mults=(1, 2, 4, 8), use_sparse_linear_attn: bool = True) -> Params:
     """flax default initialisers: kernels lecun_normal (truncated normal, std sqrt(1/fan_in)),
     biases 0, norm scale 1 / bias 0, embedding normal(std 1/sqrt(features))... `perturb` > 0 adds
     N(0, perturb) to biases and norm parameters so that parity tests exercise them."""
     g = torch.Generator().manual_seed(seed)
     p: Params = {}
-    for name, shape in param_shapes(dim, channels, dim_mults).items():
+    for name, shape in param_shapes(dim, channels, dim_mults, use_sparse_linear_attn=use_sparse_linear_attn).items():
         leaf = name.rsplit(".", 1)[1]
         if leaf == "kernel":
             if ".out.kernel" in name and len(shape) == 3 and shape[0] == HEADS:

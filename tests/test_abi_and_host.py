@@ -128,3 +128,90 @@ def test_checkpoint_bridge_round_trip(tmp_path):
     other = Unet3D(dim=32, channels=1, rngs=2)
     other.load_state_dict(got_ema)
     assert np.array_equal(other.state_dict()["init_conv.bias"], ema["init_conv.bias"])
+
+
+def _mnist_file(tmp_path, frames=15, seqs=5, hw=32):
+    rng = np.random.default_rng(0)
+    path = str(tmp_path / "mnist.npy")
+    np.save(path, rng.integers(0, 256, (frames, seqs, hw, hw)).astype(np.uint8))
+    return path
+
+
+def test_moving_mnist_matches_reference_behaviour(tmp_path):
+    """test_datasets.py:35-103 carried over: length, (c, f, h, w) float32 items at the ORIGINAL size (the transform is
+    never applied), zero padding / truncation / pass-through of the frame axis, raw 0..255 values (no rescaling)."""
+    from video_diffusion_nnx_b200.data import MovingMNIST
+
+    path = _mnist_file(tmp_path)
+    raw = np.load(path)
+    ds = MovingMNIST(file_path=path, image_size=64, num_frames=20, channels=1, force_num_frames=True)
+    assert len(ds) == 5 and ds.image_size == 64 and ds.channnels == 1
+    assert ds.cast_num_frames_fn.keywords["frames"] == 20
+    item = ds[0]
+    assert isinstance(item, np.ndarray) and item.shape == (1, 20, 32, 32) and item.dtype == np.float32
+    assert np.array_equal(item[0, :15], raw[:, 0].astype(np.float32)) and not item[0, 15:].any()
+    assert item.max() > 1.0  # raw pixel values: the reference does not divide by 255
+    assert MovingMNIST(path, 64, num_frames=25)[0].shape[1] == 25
+    assert MovingMNIST(path, 64, num_frames=10)[3].shape[1] == 10
+    assert np.array_equal(MovingMNIST(path, 64, num_frames=10)[3][0], raw[:10, 3].astype(np.float32))
+    assert MovingMNIST(path, 64, num_frames=20, force_num_frames=False)[0].shape[1] == 15
+
+
+def test_training_batches_shard_the_global_batch(tmp_path):
+    """Two ranks with the same seed see disjoint halves of the same shuffled global batches (trainer.py:307-309)."""
+    from video_diffusion_nnx_b200.data import MovingMNIST, training_batches
+
+    ds = MovingMNIST(_mnist_file(tmp_path, seqs=12), 32, num_frames=4)
+    it0 = training_batches(ds, 2, seed=5, rank=0, world=2, device=None)
+    it1 = training_batches(ds, 2, seed=5, rank=1, world=2, device=None)
+    whole = training_batches(ds, 4, seed=5, rank=0, world=1, device=None)
+    for _ in range(7):  # crosses an epoch boundary (3 global batches per epoch)
+        a, b, w = next(it0), next(it1), next(whole)
+        assert a.shape == (2, 1, 4, 32, 32) and torch_equal(torch_cat(a, b), w)
+
+
+def torch_cat(a, b):
+    import torch
+
+    return torch.cat([a, b])
+
+
+def torch_equal(a, b):
+    import torch
+
+    return torch.equal(a, b)
+
+
+def test_checkpoint_tree_is_the_diffusion_state(tmp_path):
+    """The reference checkpoints nnx.split(GaussianDiffusion) (trainer.py:136, 600; utils.py:486): `denoise_fn/...`
+    leaves plus the ten schedule tables. Save -> load -> GaussianDiffusion.load_state_dict round trip on the host,
+    including changed (trained) tables and the '/value' leaf spelling."""
+    from video_diffusion_nnx_b200 import checkpoint as ck
+    from video_diffusion_nnx_b200.gaussian_diffusion import GaussianDiffusion
+    from video_diffusion_nnx_b200.unet3d import Unet3D
+
+    net = Unet3D(dim=32, channels=1, rngs=1)
+    gd = GaussianDiffusion(net, image_size=64, num_frames=2, channels=1, timesteps=50, loss_type="l2")
+    state = gd.state_dict()
+    assert len(state) == len(net.reference_param_shapes()) + 10
+    assert "denoise_fn.downs.0.0.block_1.proj.kernel" in state and state["sqrt_alphas_cumprod"].shape == (50,)
+    trained = dict(state)
+    trained["sqrt_alphas_cumprod"] = state["sqrt_alphas_cumprod"] * 0.5  # as if Adam had moved the table (C9)
+    ema = {k: v + 1.0 for k, v in trained.items()}
+    for suffix in (False, True):
+        path = str(tmp_path / f"ck{int(suffix)}.npz")
+        ck.save_checkpoint(path, trained, ema, step=3, value_suffix=suffix)
+        with np.load(path) as z:
+            keys = set(z.files)
+        want = "model/denoise_fn/init_conv/kernel" + ("/value" if suffix else "")
+        assert want in keys and ("ema_params/posterior_variance" + ("/value" if suffix else "")) in keys
+        got, step = ck.load_checkpoint(path)
+        got_ema, _ = ck.load_checkpoint(path, load_ema_params=True)
+        assert step == 3 and set(got) == set(trained)
+        net2 = Unet3D(dim=32, channels=1, rngs=9)
+        gd2 = GaussianDiffusion(net2, image_size=64, num_frames=2, channels=1, timesteps=50, loss_type="l2")
+        gd2.load_state_dict(got_ema)
+        back = gd2.state_dict()
+        assert all(np.array_equal(back[k], ema[k]) for k in ema)
+        net2.load_state_dict(got)  # a bare Unet3D accepts the prefixed tree and ignores the tables
+        assert np.array_equal(net2.state_dict()["init_conv.kernel"], trained["denoise_fn.init_conv.kernel"])

@@ -1,0 +1,195 @@
+"""Parity of the configuration bench.py actually times: config_v2_2 at per-GPU batch 4, 10 frames, 64x64, CUDA-graph
+replay of the whole step with the side streams / stream priorities on (TrainStep(use_graph=True)), against the live
+CPU oracle on the same weights, clips, timesteps and noise - loss, predicted noise, global and per-tensor gradients -
+plus graph replay == eager launch order within split-K atomics noise. Also the constructor options that change the
+graph (resnet_groups, use_sparse_linear_attn=False) and the fused Adam + EMA (+ global-norm clip) kernel against
+torch's Adam on identical gradients (the optimizer arithmetic itself, free of bf16 gradient noise).
+
+Tolerances (bf16 tensor-core path vs the fp32 oracle; stated in DESIGN.md section 2): predicted noise rel-L2 2e-2,
+loss 1e-2, global gradient rel-L2 3e-2; graph vs eager 2e-3 (atomics order only); Adam kernel 2e-6."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel_l2(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
+
+
+def _oracle_loss_grads(p, x, t, noise, dim, Fr, S, T, **kw):
+    from oracle import diffusion_oracle as D
+    from oracle import unet3d_oracle as U
+
+    for v in p.values():
+        v.requires_grad_(True)
+        v.grad = None
+    cap = {}
+
+    def fwd(xx, tt):
+        cap["eps"] = U.unet3d_forward(p, xx, tt, dim, **kw)
+        return cap["eps"]
+
+    gdo = D.GaussianDiffusionOracle(fwd, image_size=S, num_frames=Fr, channels=1, timesteps=T, loss_type="l2")
+    loss = gdo(x, t, noise)
+    loss.backward()
+    return loss.item(), cap["eps"].detach(), {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in p.items()}
+
+
+def _grad_errors(net, grads_ref, flat_grad):
+    got = net.state_dict(flat=flat_grad)
+    num = den = 0.0
+    worst = []
+    gmax = max(g.norm().item() for g in grads_ref.values())
+    for k, ref in grads_ref.items():
+        g = torch.from_numpy(got[k]).double()
+        num += (g - ref.double()).pow(2).sum().item()
+        den += ref.double().pow(2).sum().item()
+        if ref.norm().item() > 1e-3 * gmax:
+            worst.append((_rel_l2(g, ref), k))
+    worst.sort(reverse=True)
+    return (num / den) ** 0.5, worst
+
+
+def test_benchmarked_train_step_v2_2_b4_graph_vs_oracle_and_eager():
+    from oracle import unet3d_oracle as U
+    from video_diffusion_nnx_b200.gaussian_diffusion import GaussianDiffusion
+    from video_diffusion_nnx_b200.trainer import TrainStep
+    from video_diffusion_nnx_b200.unet3d import Unet3D
+
+    dim, B, Fr, S, T = 32, 4, 10, 64, 1000  # configs/config_v2_2.yaml, per-GPU batch of bench.py
+    p = U.init_params(dim, 1, seed=3, perturb=0.05)
+    rng = np.random.default_rng(21)
+    x = torch.from_numpy(rng.random((B, 1, Fr, S, S), dtype=np.float32))
+    t = torch.from_numpy(rng.integers(0, T, (B,)).astype(np.int32))
+    noise = torch.from_numpy(rng.standard_normal((B, 1, Fr, S, S)).astype(np.float32))
+    loss_ref, eps_ref, grads_ref = _oracle_loss_grads(p, x, t, noise, dim, Fr, S, T)
+
+    res = {}
+    for use_graph in (True, False):
+        net = Unet3D(dim=dim, channels=1)
+        net.load_state_dict({k: v.detach().numpy() for k, v in p.items()})
+        gd = GaussianDiffusion(net, image_size=S, num_frames=Fr, channels=1, timesteps=T, loss_type="l2")
+        ts = TrainStep(gd, batch_size=B, train_lr=1e-4, use_graph=use_graph)
+        ts.x.copy_(x)
+        ts.t.copy_(t)
+        ts.noise.copy_(noise)
+        loss = ts.step_device(0)  # graph: eager warm-up on a snapshot, capture, ONE replay from the restored weights
+        torch.cuda.synchronize()
+        if use_graph:
+            assert ts._graph is not None and ts.graph_launches_per_step == 1
+        res[use_graph] = (float(loss.item()), ts.eng.out.detach().cpu().clone(), net.store.grad.detach().clone(), net)
+
+    for use_graph, (loss, eps, grad, net) in res.items():
+        e_eps, e_loss = _rel_l2(eps, eps_ref), abs(loss - loss_ref) / loss_ref
+        glob, worst = _grad_errors(net, grads_ref, grad)
+        print(f"graph={use_graph}: loss {loss:.6f} vs {loss_ref:.6f} (rel {e_loss:.2e}); eps rel-L2 {e_eps:.2e}; "
+              f"global grad rel-L2 {glob:.2e}; worst tensors {[(f'{r:.2e}', k) for r, k in worst[:4]]}")
+        assert e_eps < 2e-2 and e_loss < 1e-2 and glob < 3e-2
+        assert all(r < 0.1 for r, _ in worst)
+    # graph replay (side streams, priorities) and the eager launch order compute the same step
+    (lg, eg, gg, _), (le, ee, ge, _) = res[True], res[False]
+    assert abs(lg - le) / le < 1e-4 and _rel_l2(eg, ee) < 1e-4
+    assert _rel_l2(gg.cpu(), ge.cpu()) < 2e-3
+
+
+@pytest.mark.parametrize("groups,use_sla", [(4, True), (16, True), (8, False)])
+def test_constructor_options_change_the_graph_like_the_reference(groups, use_sla):
+    """resnet_groups (unet3d.py:156 -> every GroupNorm) and use_sparse_linear_attn=False (Identity in the spatial
+    attention slots, unet3d.py:179-181,230-231): loss, predicted noise and gradients against the oracle."""
+    from oracle import unet3d_oracle as U
+    from video_diffusion_nnx_b200.gaussian_diffusion import GaussianDiffusion
+    from video_diffusion_nnx_b200.trainer import TrainStep
+    from video_diffusion_nnx_b200.unet3d import Unet3D
+
+    dim, B, Fr, S, T = 32, 2, 2, 64, 200
+    p = U.init_params(dim, 1, seed=5, perturb=0.05, use_sparse_linear_attn=use_sla)
+    rng = np.random.default_rng(3)
+    x = torch.from_numpy(rng.random((B, 1, Fr, S, S), dtype=np.float32))
+    t = torch.from_numpy(rng.integers(0, T, (B,)).astype(np.int32))
+    noise = torch.from_numpy(rng.standard_normal((B, 1, Fr, S, S)).astype(np.float32))
+    loss_ref, eps_ref, grads_ref = _oracle_loss_grads(p, x, t, noise, dim, Fr, S, T, resnet_groups=groups,
+                                                      use_sparse_linear_attn=use_sla)
+    net = Unet3D(dim=dim, channels=1, resnet_groups=groups, use_sparse_linear_attn=use_sla)
+    assert set(net.reference_param_shapes()) == set(p)
+    net.load_state_dict({k: v.detach().numpy() for k, v in p.items()})
+    gd = GaussianDiffusion(net, image_size=S, num_frames=Fr, channels=1, timesteps=T, loss_type="l2")
+    ts = TrainStep(gd, batch_size=B, use_graph=False)
+    loss = ts.loss_and_grad(x.cuda(), t.cuda(), noise.cuda())
+    torch.cuda.synchronize()
+    glob, worst = _grad_errors(net, grads_ref, net.store.grad)
+    e_eps = _rel_l2(ts.eng.out.cpu(), eps_ref)
+    print(f"groups={groups} sla={use_sla}: loss {loss.item():.6f} vs {loss_ref:.6f}; eps {e_eps:.2e}; grad {glob:.2e}")
+    assert abs(loss.item() - loss_ref) / loss_ref < 1e-2 and e_eps < 2e-2 and glob < 3e-2
+
+
+@pytest.mark.parametrize("max_norm", [0.0, 0.5])
+def test_fused_adam_ema_clip_kernel_matches_torch_adam_on_identical_gradients(max_norm):
+    """trainer.py:367-382 (optax.adam defaults + EMA) and utils.py:127-152 (global-norm clip) as ONE kernel, against
+    torch.optim.Adam driven with the same gradients: three steps, bias corrections, EMA on steps 1 and 2."""
+    from video_diffusion_nnx_b200 import ops
+
+    n, lr, decay, world = 100_003, 3e-4, 0.99, 2
+    g = torch.Generator(device="cuda").manual_seed(0)
+    p = torch.randn(n, device="cuda", generator=g)
+    m, v, ema = torch.zeros_like(p), torch.zeros_like(p), p.clone()
+    pr = p.clone().requires_grad_(True)
+    opt = torch.optim.Adam([pr], lr=lr, betas=(0.9, 0.999), eps=1e-8)
+    ema_r = p.clone()
+    sq = torch.zeros(1, device="cuda")
+    for c in range(1, 4):
+        grad_sum = torch.randn(n, device="cuda", generator=g) * (10.0 if c == 2 else 0.01)  # the all-reduced SUM
+        hp = torch.tensor([lr, 0.9, 0.999, 1e-8, 1 - 0.9 ** c, 1 - 0.999 ** c, decay, float(c >= 2), 1.0 / world,
+                           max_norm, 1e-6, 0, 0, 0, 0, 0], device="cuda")
+        if max_norm > 0:
+            ops.grad_sqnorm(grad_sum, sq)
+            ops.adam_ema(p, grad_sum, m, v, ema, hp, sqnorm=sq)
+        else:
+            ops.adam_ema(p, grad_sum, m, v, ema, hp)
+        gm = grad_sum / world  # the mean gradient the reference's pjit step sees
+        if max_norm > 0:
+            l2 = torch.sqrt((gm.double() ** 2).sum() + 1e-6)
+            gm = gm * min(max_norm / (l2.item() + 1e-6), 1.0)
+        pr.grad = gm.clone()
+        opt.step()
+        if c >= 2:
+            ema_r = decay * ema_r + (1 - decay) * pr.detach()
+    torch.cuda.synchronize()
+    assert _rel_l2(p - ema, pr.detach() - ema_r) < 1e-3
+    assert ((p - pr.detach()).abs().max() / lr).item() < 2e-3  # in units of one Adam step
+    assert (ema - ema_r).abs().max().item() < 1e-6
+
+
+def test_train_then_sample_uses_the_updated_weights():
+    """Every engine of a Unet3D packs its own bf16 operands: after optimizer steps the cached sampler (engine + captured
+    graph) must see the NEW weights. train -> sample == fresh model loaded with the trained state -> sample."""
+    from oracle import unet3d_oracle as U
+    from video_diffusion_nnx_b200.gaussian_diffusion import GaussianDiffusion
+    from video_diffusion_nnx_b200.trainer import TrainStep
+    from video_diffusion_nnx_b200.unet3d import Unet3D
+
+    p = U.init_params(32, 1, seed=3, perturb=0.05)
+    net = Unet3D(dim=32, channels=1)
+    net.load_state_dict({k: v.numpy() for k, v in p.items()})
+    gd = GaussianDiffusion(net, image_size=64, num_frames=2, channels=1, timesteps=6, loss_type="l2")
+    before = gd.p_sample_loop((2,), 5).clone()          # builds + caches the sampler graph on the initial weights
+    ts = TrainStep(gd, batch_size=2, train_lr=5e-2, use_graph=True)  # large steps: the weights really move
+    rng = np.random.default_rng(0)
+    for i in range(3):
+        ts.step(torch.from_numpy(rng.random((2, 1, 2, 64, 64), dtype=np.float32)), 100 + i, i)
+    after = gd.p_sample_loop((2,), 5).clone()            # cached sampler, weights changed underneath it
+    net.train(False)
+    fresh = Unet3D(dim=32, channels=1)
+    fresh.load_state_dict(net.state_dict())
+    gd2 = GaussianDiffusion(fresh, image_size=64, num_frames=2, channels=1, timesteps=6, loss_type="l2")
+    want = gd2.p_sample_loop((2,), 5)
+    torch.cuda.synchronize()
+    assert _rel_l2(after, before) > 1e-2                  # training changed the samples ...
+    assert _rel_l2(after, want) < 1e-3                    # ... and the cached sampler tracks the trained weights
+    # (not bit-equal: the GroupNorm partial sums are accumulated with float atomics, whose order varies)
+    # eval-mode forward through a cached inference engine as well
+    x = torch.from_numpy(rng.standard_normal((2, 1, 2, 64, 64)).astype(np.float32)).cuda()
+    tt = torch.tensor([3, 1], dtype=torch.int32).cuda()
+    assert _rel_l2(net(x, tt), fresh(x, tt)) < 1e-3

@@ -39,16 +39,12 @@ def _rel(a, b):
 
 @pytest.fixture(params=[None, "1", "3", "7"])
 def rc_grid(request):
-    old = os.environ.get("VDN_RC_GRID")
-    if request.param is None:
-        os.environ.pop("VDN_RC_GRID", None)
-    else:
-        os.environ["VDN_RC_GRID"] = request.param
+    from video_diffusion_nnx_b200 import _lib
+
+    if request.param is not None:
+        _lib.debug_set("VDN_RC_GRID", int(request.param))
     yield request.param
-    if old is None:
-        os.environ.pop("VDN_RC_GRID", None)
-    else:
-        os.environ["VDN_RC_GRID"] = old
+    _lib.debug_clear("VDN_RC_GRID")
 
 
 @pytest.mark.parametrize("B,Fr,H,W,n_src,cout,c", [(2, 2, 64, 64, 1, 32, 32), (2, 3, 64, 64, 2, 32, 32),

@@ -39,19 +39,14 @@ def _rel(a, b):
 
 @pytest.fixture(params=[None, "1", "3"])
 def slab_env(request):
-    keys = ("VDN_SLAB_GRID", "VDN_SLAB_MIN_ITEMS")
-    old = {k: os.environ.get(k) for k in keys}
-    os.environ["VDN_SLAB_MIN_ITEMS"] = "1"
-    if request.param is None:
-        os.environ.pop("VDN_SLAB_GRID", None)
-    else:
-        os.environ["VDN_SLAB_GRID"] = request.param
+    from video_diffusion_nnx_b200 import _lib
+
+    _lib.debug_set("VDN_SLAB_MIN_ITEMS", 1)
+    if request.param is not None:
+        _lib.debug_set("VDN_SLAB_GRID", int(request.param))
     yield request.param
-    for k, v in old.items():
-        if v is None:
-            os.environ.pop(k, None)
-        else:
-            os.environ[k] = v
+    _lib.debug_clear("VDN_SLAB_GRID")
+    _lib.debug_clear("VDN_SLAB_MIN_ITEMS")
 
 
 # (B, Fr, H, W, n_src, c, cout): every supported width, R = 4 and R = 2 groups, 64- and 128-column tiles,

@@ -124,18 +124,12 @@ def _ln_ref(x, gamma, beta, eps=1e-6):
 def gn_bwd_mode(request):
     """gn_silu_bwd variants: the default two-kernel version, the opt-in single-launch version with the per-sample
     grid barrier (VDN_GN_FUSED=1), and - through a larger sample - the multi-chunk blocks of the two-kernel version."""
-    import os
+    from video_diffusion_nnx_b200 import _lib
 
-    old = os.environ.get("VDN_GN_FUSED")
     if request.param == "fused":
-        os.environ["VDN_GN_FUSED"] = "1"
-    else:
-        os.environ.pop("VDN_GN_FUSED", None)
+        _lib.debug_set("VDN_GN_FUSED", 1)
     yield request.param
-    if old is None:
-        os.environ.pop("VDN_GN_FUSED", None)
-    else:
-        os.environ["VDN_GN_FUSED"] = old
+    _lib.debug_clear("VDN_GN_FUSED")
 
 
 @pytest.mark.parametrize("B,R,Cc,with_ss", [(2, 512, 32, True), (3, 160, 64, False), (2, 96, 256, True), (1, 64, 1024, True)])

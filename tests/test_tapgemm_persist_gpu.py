@@ -32,19 +32,14 @@ def _rel(a, b):
 
 @pytest.fixture(params=[None, "1", "5"])
 def persist_env(request):
-    keys = ("VDN_PERSIST_GRID", "VDN_PERSIST_MIN_ITEMS")
-    old = {k: os.environ.get(k) for k in keys}
-    os.environ["VDN_PERSIST_MIN_ITEMS"] = "1"
-    if request.param is None:
-        os.environ.pop("VDN_PERSIST_GRID", None)
-    else:
-        os.environ["VDN_PERSIST_GRID"] = request.param
+    from video_diffusion_nnx_b200 import _lib
+
+    _lib.debug_set("VDN_PERSIST_MIN_ITEMS", 1)
+    if request.param is not None:
+        _lib.debug_set("VDN_PERSIST_GRID", int(request.param))
     yield request.param
-    for k, v in old.items():
-        if v is None:
-            os.environ.pop(k, None)
-        else:
-            os.environ[k] = v
+    _lib.debug_clear("VDN_PERSIST_GRID")
+    _lib.debug_clear("VDN_PERSIST_MIN_ITEMS")
 
 
 # (n_img, H, W, n_src, c, cout): 256-, 128-, 64- and 32-column tiles (four / two / one 128-byte sub-tiles, one

@@ -81,8 +81,9 @@ def test_three_adam_ema_steps_match_the_oracle():
         rel, erel = (num / den) ** 0.5, (enum / max(eden, 1e-30)) ** 0.5
         print(f"graph={use_graph}: losses {losses} vs {ref_losses}; update rel-L2 {rel:.3e}, EMA-update rel-L2 {erel:.3e}")
         # Adam normalises each gradient element, so elements whose gradient is bf16 noise move in a random direction:
-        # the bound is on the whole update vector
-        assert rel < 0.25 and erel < 0.25
+        # the bound is on the whole update vector (measured 8-10 %). The optimizer arithmetic itself is checked to
+        # 1e-3 of a step against torch's Adam on identical gradients in test_bench_path_parity_gpu.py.
+        assert rel < 0.15 and erel < 0.15
 
 
 def test_device_prefetcher_keeps_order_and_values():

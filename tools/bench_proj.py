@@ -6,7 +6,7 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from video_diffusion_nnx_b200 import ops  # noqa: E402
+from video_diffusion_nnx_b200 import _lib, ops  # noqa: E402
 
 
 def time_proj(n_img, H, W, C, N, res, nbuf=4, n=16):
@@ -47,6 +47,7 @@ def time_proj(n_img, H, W, C, N, res, nbuf=4, n=16):
 
 if __name__ == "__main__":
     tag = "generic" if os.environ.get("VDN_NO_PERSIST") else "persist"
+    _lib.apply_env_switches()
     for name, n_img, HW, shapes in (("v2_3x L0", 64, 128, [(128, 768, 0), (256, 128, 1), (768, 128, 1), (128, 256, 0), (256, 128, 0)]),
                                     ("v2_3x L1", 64, 64, [(256, 768, 0), (256, 256, 1), (768, 256, 1)]),
                                     ("v2_2 L0", 40, 64, [(32, 768, 0), (256, 32, 1), (768, 32, 1), (32, 256, 0)]),

@@ -7,7 +7,7 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from video_diffusion_nnx_b200 import ops  # noqa: E402
+from video_diffusion_nnx_b200 import _lib, ops  # noqa: E402
 
 dev = "cuda"
 
@@ -60,6 +60,7 @@ for name, *shp in shapes:
             continue
         if S:
             os.environ["VDN_RC_S"], os.environ["VDN_RC_CPS"] = str(S), str(cps)
+        _lib.apply_env_switches()
         try:
             us, gbs = bench(*shp)
             row.append(f"{tag}: {us:6.1f} us {gbs:6.0f} GB/s")

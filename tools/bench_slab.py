@@ -6,7 +6,7 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from video_diffusion_nnx_b200 import ops  # noqa: E402
+from video_diffusion_nnx_b200 import _lib, ops  # noqa: E402
 
 
 def time_conv(n_img, H, W, C, N, nbuf=8, n=32, gn=False):
@@ -52,6 +52,7 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "gn":
         for gn, dbg in ((False, "0"), (True, "0"), (True, "16"), (True, "32"), (True, "48")):
             os.environ["VDN_SLAB_DBG"] = dbg
+            _lib.apply_env_switches()
             us, tf = time_conv(64, 128, 128, 128, 128, gn=gn)
             print(f"gn={gn} dbg={dbg} (16: no atomics, 32: no accumulation): {us:8.1f} us {tf:7.1f} TF/s", flush=True)
         sys.exit(0)
@@ -66,5 +67,6 @@ if __name__ == "__main__":
             for k in ("VDN_SLAB_BK", "VDN_SLAB_DBG", "VDN_SLAB_S", "VDN_SLAB_MIN_ITEMS", "VDN_SLAB_GRID"):
                 os.environ.pop(k, None)
             os.environ.update(env)
+            _lib.apply_env_switches()
             us, tf = time_conv(*shp)
             print(f"{shp} {str(env):40s} {us:8.1f} us {tf:7.1f} TF/s", flush=True)

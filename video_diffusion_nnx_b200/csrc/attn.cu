@@ -653,7 +653,7 @@ extern "C" int vdn_sla_core_fwd(const void* qkv, void* tok_out, float* ctx, floa
   const int per_al = (per + kSlaTile - 1) / kSlaTile * kSlaTile;
   float* ctx_part = ws;
   float* ms_part = ws + (size_t)n_img * kHeads * ns * 1024;
-  static const bool scalar = getenv("VDN_SLA_SCALAR") != nullptr;  // CUDA-core kernels (A/B comparison only)
+  const bool scalar = tune_on("VDN_SLA_SCALAR");  // CUDA-core kernels (A/B comparison only)
   int rc;
   if (scalar) {
     sla_ctx_partial_kernel<<<dim3(ns, kHeads, n_img), 256, 0, st>>>(reinterpret_cast<const bf16*>(qkv), N, per_al,
@@ -708,7 +708,7 @@ extern "C" int vdn_sla_core_bwd(const void* qkv, const void* d_tok, const float*
   const int ns = sla_splits(N, n_img);
   const int per = (N + ns - 1) / ns;
   const int per_al = (per + kSlaTile - 1) / kSlaTile * kSlaTile;
-  static const bool scalar = getenv("VDN_SLA_SCALAR") != nullptr;
+  const bool scalar = tune_on("VDN_SLA_SCALAR");
   int rc;
   if (scalar) {
     sla_dctx_kernel<<<dim3(ns, kHeads, n_img), 256, 0, st>>>(reinterpret_cast<const bf16*>(qkv),

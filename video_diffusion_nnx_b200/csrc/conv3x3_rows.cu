@@ -365,8 +365,7 @@ static int launch_rowconv(const RowConvMaps& maps, const RowConvArgs& a, int gri
 static long long* g_rc_trace = nullptr;
 
 bool rowconv_applicable(const vdn_tapgemm_desc* d, const void* residual, const float* gn_sums) {
-  static const bool off = getenv("VDN_NO_ROWCONV") != nullptr;
-  if (off) return false;
+  if (tune_on("VDN_NO_ROWCONV")) return false;
   if (d->kind != VDN_TAP_UNIT || d->n_taps != 9 || d->out_dtype != VDN_BF16) return false;
   if (d->W != 64 && d->W != 32) return false;
   const int TR = kRcTileM / d->W;
@@ -421,8 +420,8 @@ int rowconv_launch(const vdn_tapgemm_desc* d, const void* src0, const void* src1
     S = 4;
     while (S > 2 && smem_for(S) > 220 * 1024) --S;
   }
-  if (const char* e = getenv("VDN_RC_S")) S = std::max(2, std::min(kRcMaxStages, atoi(e)));
-  if (const char* e = getenv("VDN_RC_CPS")) cps = std::max(1, std::min(4, atoi(e)));
+  if (tune_is_set("VDN_RC_S")) S = std::max(2, std::min(kRcMaxStages, tune_int("VDN_RC_S", S)));
+  if (tune_is_set("VDN_RC_CPS")) cps = std::max(1, std::min(4, tune_int("VDN_RC_CPS", cps)));
   VDN_REQUIRE(smem_for(S) <= 224 * 1024, VDN_E_SHAPE, "conv3x3_rows: shared memory %d B exceeds the SM", smem_for(S));
   a.S = S;
   a.region_bytes = (S * a.TR + a.TR - 1) * a.row_bytes;
@@ -455,7 +454,7 @@ int rowconv_launch(const vdn_tapgemm_desc* d, const void* src0, const void* src1
                   (!out2 || (reinterpret_cast<uintptr_t>(out2) & 15) == 0) && (!bias || (reinterpret_cast<uintptr_t>(bias) & 15) == 0),
               VDN_E_ALIGN, "conv3x3_rows: out/residual/bias must be 16B aligned");
   int grid = std::min(a.n_tiles, num_sms() * cps);
-  if (const char* e = getenv("VDN_RC_GRID")) grid = std::max(1, std::min(a.n_tiles, atoi(e)));  // tests: long runs per CTA
+  if (tune_is_set("VDN_RC_GRID")) grid = std::max(1, std::min(a.n_tiles, tune_int("VDN_RC_GRID", grid)));  // tests: long runs per CTA
   const int smem = smem_for(S);
   if (KC == 64) return launch_rowconv<64, 64, 1>(maps, a, grid, smem, st);
   if (N == 32 && d->n_src == 1) return launch_rowconv<32, 32, 1>(maps, a, grid, smem, st);

@@ -381,8 +381,7 @@ __global__ void __launch_bounds__(kSlThreads) conv3x3_slab_kernel(const __grid_c
 }
 
 static int sl_env_int(const char* name, int dflt) {
-  const char* e = getenv(name);
-  return e ? atoi(e) : dflt;
+  return tune_int(name, dflt);
 }
 
 // Geometry shared by applicable() and launch(): BN column tile, R tiles per group.
@@ -409,8 +408,7 @@ static bool slab_geometry(const vdn_tapgemm_desc* d, int* BN, int* R) {
 }
 
 bool slabconv_applicable(const vdn_tapgemm_desc* d, const void* residual, const float* gn_sums) {
-  static const bool off = getenv("VDN_NO_SLABCONV") != nullptr;
-  if (off) return false;
+  if (tune_on("VDN_NO_SLABCONV")) return false;
   if (d->kind != VDN_TAP_UNIT || d->n_taps != 9 || d->out_dtype != VDN_BF16) return false;
   if (d->src_c < 64 || d->src_c % 32 != 0) return false;
   int BN, R;
@@ -481,7 +479,7 @@ int slabconv_launch(const vdn_tapgemm_desc* d, const void* src0, const void* src
   int S = kSlMaxStages;
   while (S > 2 && 1024 + S * a.stage_bytes + stg_bytes > 224 * 1024) --S;
   S = std::min(S, std::max(2, a.n_src * a.chunks * 3));
-  if (const char* e = getenv("VDN_SLAB_S")) S = std::max(2, std::min(kSlMaxStages, atoi(e)));
+  if (tune_is_set("VDN_SLAB_S")) S = std::max(2, std::min(kSlMaxStages, tune_int("VDN_SLAB_S", S)));
   const int smem = 1024 + S * a.stage_bytes + stg_bytes;
   VDN_REQUIRE(smem <= 224 * 1024, VDN_E_SHAPE, "conv3x3_slab: shared memory %d B exceeds the SM", smem);
   a.S = S;
@@ -534,7 +532,7 @@ int slabconv_launch(const vdn_tapgemm_desc* d, const void* src0, const void* src
   // CTAs per SM: limited by TMEM columns and shared memory
   const int cps = std::max(1, std::min(512 / a.tmem_cols, (227 * 1024) / (smem + 1024)));
   int grid = std::min(a.n_items, num_sms() * cps);
-  if (const char* e = getenv("VDN_SLAB_GRID")) grid = std::max(1, std::min(a.n_items, atoi(e)));  // tests: long runs per CTA
+  if (tune_is_set("VDN_SLAB_GRID")) grid = std::max(1, std::min(a.n_items, tune_int("VDN_SLAB_GRID", grid)));  // tests: long runs per CTA
   cudaError_t le = kSlBK == 32
                        ? launch_pdl(conv3x3_slab_kernel<32>, dim3(grid), dim3(kSlThreads), (size_t)smem, st, 1, maps, a)
                        : launch_pdl(conv3x3_slab_kernel<16>, dim3(grid), dim3(kSlThreads), (size_t)smem, st, 1, maps, a);

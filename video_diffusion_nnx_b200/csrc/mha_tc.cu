@@ -351,7 +351,7 @@ extern "C" int vdn_mha_temporal_tc_fwd(const void* x, const void* w_hm, const fl
                                        float* lse, int B, int F, int H, int W, int C, void* stream) {
   VDN_REQUIRE(x && w_hm && o && B > 0 && H > 0 && W > 0, VDN_E_SHAPE, "mha_tc: bad args");
   VDN_REQUIRE(vdn_mha_temporal_tc_supported(F, C), VDN_E_SHAPE, "mha_tc: F=%d C=%d not instantiated", F, C);
-  static const bool force_tcgen05 = getenv("VDN_MHA_TC_FWD") != nullptr;  // A/B comparison only
+  const bool force_tcgen05 = tune_on("VDN_MHA_TC_FWD");  // A/B comparison only
   if (C == 32 && !(force_tcgen05 && (F == 10 || F == 16)))
     return vdn::mha_temporal_mma_fwd_launch(x, w_hm, bias_hm, o, qkv, lse, B, F, H, W, reinterpret_cast<cudaStream_t>(stream));
   const int PX = std::min(128 / F, H * W);  // pixels per 128-row tile (12 for F = 10, 8 for F = 16)
@@ -613,7 +613,7 @@ extern "C" int vdn_colsum(const void* dy, float* db, long P, int C, void* stream
 extern "C" int vdn_mha_temporal_tc_bwd(const void* qkv, const void* d_o, const float* lse, void* dqkv, float* dbias,
                                        int B, int F, int H, int W, void* stream) {
   VDN_REQUIRE(qkv && d_o && lse && dqkv && F >= 1 && F <= 16, VDN_E_SHAPE, "mha_tc_bwd: bad args (F <= 16)");
-  static const bool use_tcgen05 = getenv("VDN_MHA_TC_BWD") != nullptr;  // block-diagonal tcgen05 kernel (A/B only)
+  const bool use_tcgen05 = tune_on("VDN_MHA_TC_BWD");  // block-diagonal tcgen05 kernel (A/B only)
   if (!use_tcgen05)
   {
     // (accumulating the bias column sums inside the MMA kernel costs more than the separate pass: measured

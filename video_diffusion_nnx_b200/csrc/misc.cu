@@ -791,11 +791,18 @@ __global__ void add_bf16_kernel(const bf16* __restrict__ a, const bf16* __restri
 // Fused Adam (optax.adam defaults, bias-corrected) + EMA (trainer.py:367-382) over the flat state.
 // hp (device): {lr, b1, b2, eps, 1-b1^t, 1-b2^t, ema_decay, do_ema, grad_scale}
 // ---------------------------------------------------------------------------------------
+// Optional global-norm clip (utils.py:127-152): with hp[9] = max_grad_norm > 0 and sq = sum g^2 over the raw flat
+// gradient, l2 = sqrt(sq * gs^2 + hp[10]) and every gradient is scaled by min(max_grad_norm / (l2 + hp[10]), 1).
 __global__ void adam_ema_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
-                                float* __restrict__ v, float* __restrict__ ema, const float* __restrict__ hp, long n) {
+                                float* __restrict__ v, float* __restrict__ ema, const float* __restrict__ hp,
+                                const float* __restrict__ sq, long n) {
   const float lr = hp[0], b1 = hp[1], b2 = hp[2], eps = hp[3], bc1 = hp[4], bc2 = hp[5], decay = hp[6];
   const bool do_ema = hp[7] != 0.f;
-  const float gs = hp[8];
+  float gs = hp[8];
+  if (sq != nullptr && hp[9] > 0.f) {
+    const float l2 = sqrtf(sq[0] * gs * gs + hp[10]);
+    gs *= fminf(hp[9] / (l2 + hp[10]), 1.f);
+  }
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
     const float gi = g[i] * gs;
     const float mi = b1 * m[i] + (1.f - b1) * gi;
@@ -865,7 +872,7 @@ extern "C" int vdn_init_conv_fwd(const float* x, const float* w, const float* bi
                                  int H, int W, int Cout, int ks, void* stream) {
   VDN_REQUIRE(H % kIT == 0 && W % kIT == 0 && Cout % 32 == 0 && (ks & 1) && ks <= 7 && Cin >= 1 && Cin <= 4, VDN_E_SHAPE,
               "init_conv_fwd: unsupported shape H=%d W=%d Cout=%d ks=%d Cin=%d", H, W, Cout, ks, Cin);
-  static const bool generic_only = getenv("VDN_INIT_CONV_GENERIC") != nullptr;
+  const bool generic_only = tune_on("VDN_INIT_CONV_GENERIC");
   if (ks == kI7 && H % kI7TH == 0 && W % kI7TW == 0 && !generic_only) {
     const size_t smem7 = (size_t)(kI7 * kI7 * Cin * Cout + Cin * (kI7TH + kI7 - 1) * 48) * sizeof(float);
     static bool cfg7 = false;
@@ -893,7 +900,7 @@ extern "C" int vdn_init_conv_wgrad(const float* x, const void* dy, float* dw, fl
                                    int H, int W, int Cout, int ks, void* stream) {
   VDN_REQUIRE(H % kIT == 0 && W % kIT == 0 && Cout % 32 == 0 && (ks & 1) && ks <= 7 && Cin >= 1 && Cin <= 3, VDN_E_SHAPE,
               "init_conv_wgrad: unsupported shape");
-  static const bool generic_only = getenv("VDN_INIT_CONV_GENERIC") != nullptr;
+  const bool generic_only = tune_on("VDN_INIT_CONV_GENERIC");
   if (ks == kI7 && !generic_only && (Cout <= 128 ? (Cout == 32 || Cout == 64 || Cout == 128) : Cout % 128 == 0)) {
     const int cb = std::min(Cout, 128);
     const int hs7 = kIT + kI7 - 1;
@@ -1055,6 +1062,43 @@ extern "C" int vdn_countdown(int* t_dev, int B, void* stream) {
 
 extern "C" int vdn_adam_ema(float* p, const float* g, float* m, float* v, float* ema, const float* hp_dev, long n,
                             void* stream) {
-  adam_ema_kernel<<<ew_grid(n), 256, 0, ST(stream)>>>(p, g, m, v, ema, hp_dev, n);
+  adam_ema_kernel<<<ew_grid(n), 256, 0, ST(stream)>>>(p, g, m, v, ema, hp_dev, nullptr, n);
   return check_launch("adam_ema");
+}
+
+// sum of squares of a flat fp32 buffer, accumulated (+=) into out[0]: block reduction + one atomic per block
+__global__ void __launch_bounds__(256) sqnorm_kernel(const float* __restrict__ g, long n, float* __restrict__ out) {
+  __shared__ float red[8];
+  float acc = 0.f;
+  const long n4 = n >> 2;
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
+    const float4 q = g4[i];
+    acc = fmaf(q.x, q.x, fmaf(q.y, q.y, fmaf(q.z, q.z, fmaf(q.w, q.w, acc))));
+  }
+  if (blockIdx.x == 0)
+    for (long i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) acc = fmaf(g[i], g[i], acc);
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    float t = red[threadIdx.x];
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) t += __shfl_xor_sync(0xffu, t, o);
+    if (threadIdx.x == 0) atomicAdd(out, t);
+  }
+}
+
+extern "C" int vdn_grad_sqnorm(const float* g, long n, float* out, void* stream) {
+  VDN_REQUIRE(g && out && n > 0 && (reinterpret_cast<uintptr_t>(g) & 15) == 0, VDN_E_SHAPE, "grad_sqnorm: bad args");
+  cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float), ST(stream));
+  VDN_REQUIRE(e == cudaSuccess, VDN_E_CUDA, "grad_sqnorm memset: %s", cudaGetErrorString(e));
+  sqnorm_kernel<<<std::min<long>(148 * 4, (n / 4 + 255) / 256 + 1), 256, 0, ST(stream)>>>(g, n, out);
+  return check_launch("grad_sqnorm");
+}
+
+extern "C" int vdn_adam_ema_clip(float* p, const float* g, float* m, float* v, float* ema, const float* hp_dev,
+                                 const float* sqnorm_dev, long n, void* stream) {
+  adam_ema_kernel<<<ew_grid(n), 256, 0, ST(stream)>>>(p, g, m, v, ema, hp_dev, sqnorm_dev, n);
+  return check_launch("adam_ema_clip");
 }

@@ -798,7 +798,7 @@ static int cluster_for(int want, int* grid_x) {
   // Measured on B200 (profiles/r1_microbench_sweep.txt): launching these short kernels as thread-block clusters costs
   // more (co-scheduling of 8 CTAs per GPC) than the DSMEM pre-reduction saves in L2 atomics - gn_silu_bwd 38.8 us with
   // clusters of 8, 30.5 us without. The cluster path stays selectable (VDN_NORM_CLUSTER=2|4|8) but is off by default.
-  static const int cmax = getenv("VDN_NORM_CLUSTER") ? atoi(getenv("VDN_NORM_CLUSTER")) : 1;
+  const int cmax = tune_int("VDN_NORM_CLUSTER", 1);
   int c = 1;
   while (c < cmax && c * 2 <= want) c *= 2;
   *grid_x = (want + c - 1) / c * c;
@@ -888,10 +888,10 @@ extern "C" int vdn_gn_silu_bwd(const void* dy, const void* x_raw, const float* g
     // (VDN_GN_FUSED=1): measured 23.7 us against 32.9 us for the two kernels at the 64x64 level of config_v2_2 in
     // isolation, but no gain on the training step (6.87 vs 6.89 ms) - a grid that needs every SM cannot overlap with
     // the weight-gradient GEMMs of the side streams, which is where the two-kernel version hides its latency.
-    const char* fe = getenv("VDN_GN_FUSED");
+    const bool fe = tune_on("VDN_GN_FUSED");
     // VDN_GN_FUSED=1: every sample that fits; VDN_GN_FUSED_MAX=<elements per sample>: only samples up to that size
-    static const long fused_max = getenv("VDN_GN_FUSED_MAX") ? atol(getenv("VDN_GN_FUSED_MAX")) : 0;
-    const bool fused_off = !(fe && fe[0] == '1') && !((long)rows_per_sample * C <= fused_max);
+    const long fused_max = tune_int("VDN_GN_FUSED_MAX", 0);
+    const bool fused_off = !fe && !((long)rows_per_sample * C <= fused_max);
     const int cps = B <= kFusedMaxB ? num_sms() / B : 0;  // CTAs per sample; cps * B <= number of SMs
     if (!fused_off && cps >= 1 && kFusedThreads % (C / 8) == 0) {
       const int rpc = (rows_per_sample + cps - 1) / cps;
@@ -920,7 +920,7 @@ extern "C" int vdn_gn_silu_bwd(const void* dy, const void* x_raw, const float* g
   // chunks per block: 1 until the launch exceeds ~2 waves of 8 blocks per SM, then up to 8 (large samples)
   const long blocks1 = (long)grid_x_for(rows_per_sample, pl_n * kVecPerThread) * B;
   int iters = (int)std::max<long>(1, std::min<long>(8, blocks1 / (2 * 8 * num_sms())));
-  if (const char* ie = getenv("VDN_GN_ITERS")) iters = std::max(1, std::min(16, atoi(ie)));  // experiments
+  if (tune_is_set("VDN_GN_ITERS")) iters = std::max(1, std::min(16, tune_int("VDN_GN_ITERS", iters)));  // experiments
   cl = cluster_for(grid_x_for(rows_per_sample, pl_n * kVecPerThread * iters), &gx);
   const size_t smem_r = (6 * C + kNormThreads * 16) * sizeof(float);
   cudaError_t le = iters > 1 ? launch_pdl(gn_bwd_reduce_kernel<true>, dim3(gx, B), dim3(kNormThreads), (size_t)(smem_r), st, cl, a, reinterpret_cast<const bf16*>(dy), T_ws, iters)

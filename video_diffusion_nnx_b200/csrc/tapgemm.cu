@@ -971,8 +971,7 @@ static int launch_tapgemm_persist(const TapMaps& maps, const TapArgs& args, int 
 }
 
 static int tg_env_int(const char* name, int dflt) {
-  const char* e = getenv(name);
-  return e ? atoi(e) : dflt;
+  return tune_int(name, dflt);
 }
 
 }  // namespace vdn
@@ -1006,12 +1005,12 @@ extern "C" int vdn_tapgemm(const vdn_tapgemm_desc* d, const void* src0, const vo
     // Short-K GEMMs (e.g. the 32 -> 256 / 768 projections) are all epilogue: a 256-column tile holds 256 of the
     // SM's 512 TMEM columns, so only two CTAs are resident and nothing hides their load -> MMA -> store chain.
     // Narrower tiles cost a few extra reads of the (tiny) A tile and buy 4-8 resident CTAs.
-    static const int smallk_bn = getenv("VDN_BN_SMALLK") ? atoi(getenv("VDN_BN_SMALLK")) : 128;
+    const int smallk_bn = tune_int("VDN_BN_SMALLK", 128);
     const int ktot = d->n_taps * d->n_src * d->src_c;
     if (ktot <= 64 && smallk_bn >= 32 && a.BN > smallk_bn && d->n_out % smallk_bn == 0) a.BN = smallk_bn;
   }
-  if (const char* e = getenv("VDN_BN")) {  // tuning override (experiments only)
-    const int v = atoi(e);
+  if (tune_is_set("VDN_BN")) {  // tuning override (experiments only)
+    const int v = tune_int("VDN_BN", 0);
     if (v >= 16 && v <= 256 && d->n_out % v == 0) a.BN = v;
   }
   if (d->split_col > 0) {
@@ -1105,7 +1104,7 @@ extern "C" int vdn_tapgemm(const vdn_tapgemm_desc* d, const void* src0, const vo
   const int ctas_per_sm = std::min(6, ceil_div(n_ctas, num_sms()));
   const int budget = (200 * 1024) / ctas_per_sm;
   a.stages = std::max(2, std::min(std::min(kMaxStages, budget / stage_bytes), std::max(n_steps, 2)));
-  if (const char* e = getenv("VDN_STAGES")) a.stages = std::max(1, std::min(kMaxStages, atoi(e)));
+  if (tune_is_set("VDN_STAGES")) a.stages = std::max(1, std::min(kMaxStages, tune_int("VDN_STAGES", a.stages)));
   int cols = 32;
   while (cols < a.BN) cols *= 2;
   a.tmem_cols = cols;
@@ -1130,7 +1129,7 @@ extern "C" int vdn_tapgemm(const vdn_tapgemm_desc* d, const void* src0, const vo
     const bool shape_ok = !gn_sums && !a.out_f32 && !a.scatter && a.BN >= 32 && (a.BN & (a.BN - 1)) == 0 && !narrow_res &&
                           n_steps <= tg_env_int("VDN_PERSIST_MAX_STEPS", 16) &&
                           items >= (long)tg_env_int("VDN_PERSIST_MIN_ITEMS", 3 * num_sms());
-    static const bool persist_off = getenv("VDN_NO_PERSIST") != nullptr;
+    const bool persist_off = tune_on("VDN_NO_PERSIST");
     if (shape_ok && !persist_off) {
       TapArgs p = a;
       p.n_ntiles = d->n_out / a.BN;
@@ -1161,7 +1160,7 @@ extern "C" int vdn_tapgemm(const vdn_tapgemm_desc* d, const void* src0, const vo
         const int psmem = 1024 + S * stage_bytes + p.stg_bufs * buf_bytes;
         const int cps = std::max(1, std::min(512 / p.tmem_cols, (227 * 1024) / (psmem + 1024)));
         int grid = (int)std::min<long>(items, (long)num_sms() * cps);
-        if (const char* e = getenv("VDN_PERSIST_GRID")) grid = std::max(1, std::min((int)items, atoi(e)));
+        if (tune_is_set("VDN_PERSIST_GRID")) grid = std::max(1, std::min((int)items, tune_int("VDN_PERSIST_GRID", grid)));
         const bool has_res = residual != nullptr || residual2 != nullptr;
         if (BK == 64) return has_res ? launch_tapgemm_persist<64, true>(maps, p, psmem, grid, st) : launch_tapgemm_persist<64, false>(maps, p, psmem, grid, st);
         if (BK == 32) return has_res ? launch_tapgemm_persist<32, true>(maps, p, psmem, grid, st) : launch_tapgemm_persist<32, false>(maps, p, psmem, grid, st);

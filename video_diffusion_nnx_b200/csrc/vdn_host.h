@@ -8,8 +8,20 @@
 
 namespace vdn {
 
+// Experiment / test switches (the "VDN_*" names of DESIGN.md section 7). Product code never reads the process
+// environment on a launch path: a switch keeps its compiled-in default unless a test or tool sets it through the
+// C ABI (vdn_debug_set). Only a -DVDN_DEBUG build also seeds the table from environment variables of the same names.
+bool tune_is_set(const char* name);
+int tune_int(const char* name, int dflt);  // the value if set, else dflt
+bool tune_on(const char* name);            // set and non-zero
+
 int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                      const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes);
+
+int encode_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                    const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes);
+void tmap_cache_clear();
+void comm_shutdown();  // comm.cu
 
 // conv3x3_rows.cu: persistent row-ring (1,3,3) conv; applicable() decides, launch() has vdn_tapgemm's contract
 bool rowconv_applicable(const vdn_tapgemm_desc* d, const void* residual, const float* gn_sums);

@@ -408,11 +408,11 @@ extern "C" int vdn_wgrad_bias(int kind, const void* src0, const void* src1, cons
   const int base_ctas = m_tiles * n_tiles;
   // split K (pixels) over CTAs to fill the machine, but keep >= 4 K steps per split: every split adds a
   // full set of fp32 reductions on the output tile (128-bit red.v4.f32 where the output row is contiguous).
-  static const int min_k = getenv("VDN_WG_MINK") ? std::max(1, atoi(getenv("VDN_WG_MINK"))) : 4;
+  const int min_k = std::max(1, tune_int("VDN_WG_MINK", 4));
   // CTAs per SM to aim for: 1 for the small problems of config_v2_2 (the weight gradients run on a side stream next to
   // the dependency chain; fewer, longer CTAs leave the chain more of the machine: 6.81 -> 6.75 ms per step), 2 once the
   // GEMM is large enough to be throughput bound by itself (v2_3x: 81.7 vs 84.8 ms per step)
-  static const int fill_env = getenv("VDN_WG_FILL") ? std::max(1, atoi(getenv("VDN_WG_FILL"))) : 0;
+  const int fill_env = tune_is_set("VDN_WG_FILL") ? std::max(1, tune_int("VDN_WG_FILL", 0)) : 0;
   const double work = (double)P * a.atoms_total * a.cw * Cn;
   const int fill = fill_env ? fill_env : (work >= 2e10 ? 2 : 1);
   int splits = std::max(1, std::min(std::max(1, a.n_pix_tiles / min_k), (fill * num_sms() + base_ctas - 1) / base_ctas));

@@ -14,7 +14,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
 
-from . import ops
+from . import _lib, ops
 from .ops import TAPS_1x1, TAPS_3x3, TAPS_4x4, VDN_TAP_DOWN, VDN_TAP_UNIT, VDN_TAP_UP
 
 HEADS = 8
@@ -29,7 +29,7 @@ F32 = torch.float32
 # parameters
 # ------------------------------------------------------------------------------------------
 def internal_param_spec(dim: int, channels: int, dim_mults=(1, 2, 4, 8), init_kernel_size: int = 7,
-                        out_dim: Optional[int] = None) -> List[Tuple[str, tuple]]:
+                        out_dim: Optional[int] = None, use_sla: bool = True) -> List[Tuple[str, tuple]]:
     """Internal flat layout. q/k/v kernels are stored fused as [C][768] (q | k | v) so that one
     GEMM produces qkv; state_dict()/load_state_dict() translate to the reference's nnx paths."""
     s: List[Tuple[str, tuple]] = []
@@ -41,6 +41,8 @@ def internal_param_spec(dim: int, channels: int, dim_mults=(1, 2, 4, 8), init_ke
                   (p + ".qkv.bias", (3 * HD,)), (p + ".out.kernel", (HD, c)), (p + ".out.bias", (c,))])
 
     def sla(p, c):
+        if not use_sla:  # use_sparse_linear_attn=False: the slot holds an Identity (unet3d.py:179-181,230-231)
+            return
         s.extend([(p + ".norm.scale", (c,)), (p + ".norm.bias", (c,)), (p + ".qkv.kernel", (c, 3 * HD)),
                   (p + ".to_out.kernel", (HD, c))])
 
@@ -111,6 +113,18 @@ class ParamStore:
         self.total = off
         self.flat = torch.zeros(off, dtype=F32, device=device)
         self.grad = torch.zeros(off, dtype=F32, device=device) if with_grad else None
+        # bumped by every writer of `flat` (optimizer step, state upload): engines compare it with the version their
+        # packed bf16 GEMM operands were built from and repack lazily (UnetEngine.sync_weights)
+        self.version = 0
+
+    def ensure_grad(self) -> None:
+        """Adds the gradient buffer in place (the store object, and with it every engine / captured graph that holds
+        views of `flat`, stays valid)."""
+        if self.grad is None:
+            self.grad = torch.zeros(self.total, dtype=F32, device=self.flat.device)
+
+    def bump(self) -> None:
+        self.version += 1
 
     def view(self, name: str) -> torch.Tensor:
         off, shape = self.offsets[name]
@@ -171,7 +185,7 @@ class GemmConv:
 
     def fwd(self, srcs, out, residual=None, gn_sums=None, rows_per_sample=0, out_dtype=BF16):
         return ops.tapgemm(VDN_TAP_UNIT, srcs, self.wp, self.taps, bias=self.bias, residual=residual, out=out,
-                           gn_sums=gn_sums, gn_groups=GROUPS if gn_sums is not None else 0,
+                           gn_sums=gn_sums, gn_groups=self.eng.groups if gn_sums is not None else 0,
                            rows_per_sample=rows_per_sample, out_dtype=out_dtype)
 
     def dgrad(self, dy, outs, residuals=None):
@@ -229,11 +243,11 @@ class ResBlock:
             s = srcs[0]
         self.conv1.fwd(srcs, self.a_raw, gn_sums=self.sums1, rows_per_sample=self.rows)
         ops.gn_silu_fwd(self.a_raw, self.sums1, self.p["block_1.norm.scale"], self.p["block_1.norm.bias"], self._ss(),
-                        self.a, B, self.rows, self.cout)
+                        self.a, B, self.rows, self.cout, G=eng.groups)
         self.conv2.fwd([self.a], self.b_raw, gn_sums=self.sums2, rows_per_sample=self.rows)
         eng.join(hres)
         ops.resblock_tail_fwd(self.b_raw, self.sums2, self.p["block_2.norm.scale"], self.p["block_2.norm.bias"], s,
-                              self.p["norm_2.scale"], self.p["norm_2.bias"], self.out, B, self.rows, self.cout)
+                              self.p["norm_2.scale"], self.p["norm_2.bias"], self.out, B, self.rows, self.cout, G=eng.groups)
         return self.out
 
     def backward(self, dout, extra=None):
@@ -252,7 +266,7 @@ class ResBlock:
         db_raw = pool.get(shape)
         ops.gn_silu_bwd(dout, self.b_raw, self.sums2, self.p["block_2.norm.scale"], self.p["block_2.norm.bias"], None,
                         T, db_raw, self.g["block_2.norm.scale"], self.g["block_2.norm.bias"], None, B, self.rows, C,
-                        dconv_bias=self.conv2.dbias)
+                        G=eng.groups, dconv_bias=self.conv2.dbias)
         # weight gradients are off the critical path: they run on the side stream, overlapped with the
         # data-gradient chain below, and are joined before their operands go back to the pool
         h2 = eng.side(lambda: self.conv2.wgrad([self.a], db_raw, bias_done=True))
@@ -262,7 +276,7 @@ class ResBlock:
         dss = eng.dss[:, self.ss_off:self.ss_off + 2 * C] if self.ss_off is not None else None
         ops.gn_silu_bwd(da, self.a_raw, self.sums1, self.p["block_1.norm.scale"], self.p["block_1.norm.bias"],
                         self._ss(), T, da_raw, self.g["block_1.norm.scale"], self.g["block_1.norm.bias"], dss, B,
-                        self.rows, C, dconv_bias=self.conv1.dbias)
+                        self.rows, C, G=eng.groups, dconv_bias=self.conv1.dbias)
         pool.put(da)
         pool.put(T)
         h1 = eng.side(lambda: self.conv1.wgrad(self.srcs, da_raw, bias_done=True))
@@ -303,8 +317,7 @@ class MHABlock:
         # training engines at C >= 64: the projection runs as a tap-GEMM (full tensor-core rate, qkv has to be
         # materialised for the backward anyway) and the F x F core as a register-resident warp-MMA kernel
         # (VDN_MHA_SPLIT_FWD=0: the single-kernel tcgen05 version, which is a latency chain per head)
-        import os
-        self.split_fwd = (self.fused and eng.training and C >= 64 and os.environ.get("VDN_MHA_SPLIT_FWD", "1") != "0")
+        self.split_fwd = (self.fused and eng.training and C >= 64 and _lib.host_flag("VDN_MHA_SPLIT_FWD", "1") != "0")
         need_qkv = eng.training or not self.fused
         self.qkv = eng.new((n_img, H, W, 3 * HD)) if need_qkv else None
         self.o = None if self.folded else eng.new((n_img, H, W, HD))
@@ -525,18 +538,19 @@ class UnetEngine:
                 main.wait_event(h)
 
     def __init__(self, store: ParamStore, *, dim: int, channels: int, dim_mults=(1, 2, 4, 8), init_kernel_size=7,
-                 B: int, F: int, H: int, W: int, training: bool, out_dim: Optional[int] = None):
+                 B: int, F: int, H: int, W: int, training: bool, out_dim: Optional[int] = None, groups: int = GROUPS,
+                 use_sla: bool = True):
         self.store, self.device, self.training = store, store.flat.device, training
         self.dim, self.channels, self.B, self.F, self.H, self.W = dim, channels, B, F, H, W
         self.out_dim = channels if out_dim is None else out_dim
         self.ks = init_kernel_size
+        self.groups, self.use_sla = groups, use_sla
         self.pack_jobs = []
         self.extra_packers = []
         self.pool = _Pool(self.device)
         # second stream for the weight-gradient GEMMs (see side() / join()); VDN_NO_OVERLAP=1 serialises them
-        import os
         self.side_stream = (torch.cuda.Stream(device=self.device)
-                            if self.device.type == "cuda" and not os.environ.get("VDN_NO_OVERLAP") else None)
+                            if self.device.type == "cuda" and not _lib.host_flag("VDN_NO_OVERLAP") else None)
         self.side_stream2 = torch.cuda.Stream(device=self.device) if self.side_stream is not None else None
         self._gn_slots: List[torch.Tensor] = []
         self._gn_count = 0
@@ -554,7 +568,7 @@ class UnetEngine:
         self.n_res = n
         # count GroupNorm slots first (2 per ResnetBlock) so one buffer can be zeroed per forward
         n_blocks = 4 * n + 2 + 1
-        self.gn_all = torch.zeros(n_blocks * 2, ops.GN_REPLICAS, B, GROUPS, 2, dtype=F32, device=self.device)
+        self.gn_all = torch.zeros(n_blocks * 2, ops.GN_REPLICAS, B, groups, 2, dtype=F32, device=self.device)
 
         self.h0 = self.new((n_img, H, W, dim))
         self.init_attn = MHABlock(self, "init_temporal_attn", dim, n_img, H, W, 0)
@@ -563,7 +577,7 @@ class UnetEngine:
         for l, (ci, co) in enumerate(in_out):
             blk = [ResBlock(self, f"downs.{l}.0", 1, ci, co, n_img, h, w),
                    ResBlock(self, f"downs.{l}.1", 1, co, co, n_img, h, w),
-                   SLABlock(self, f"downs.{l}.2", co, n_img, h, w),
+                   SLABlock(self, f"downs.{l}.2", co, n_img, h, w) if use_sla else None,
                    MHABlock(self, f"downs.{l}.3", co, n_img, h, w, 0),
                    DownConv(self, f"downs.{l}.4", co, n_img, h, w) if l < n - 1 else None]
             self.downs.append(blk)
@@ -577,7 +591,7 @@ class UnetEngine:
         for i, (ci, co) in enumerate(reversed(in_out)):
             blk = [ResBlock(self, f"ups.{i}.0", 2, co, ci, n_img, h, w),
                    ResBlock(self, f"ups.{i}.1", 1, ci, ci, n_img, h, w),
-                   SLABlock(self, f"ups.{i}.2", ci, n_img, h, w),
+                   SLABlock(self, f"ups.{i}.2", ci, n_img, h, w) if use_sla else None,
                    MHABlock(self, f"ups.{i}.3", ci, n_img, h, w, 0),
                    UpConv(self, f"ups.{i}.4", ci, n_img, h, w) if i < n - 1 else None]
             self.ups.append(blk)
@@ -611,6 +625,7 @@ class UnetEngine:
         self.n_heads = len(entries)
         self.x_in = None
         self.pack_table, self.n_pack_jobs, self.pack_total = ops.make_pack_table(self.pack_jobs, self.device)
+        self.packed_version = -1
         self.repack()
 
     # -- allocation helpers ------------------------------------------------------------------
@@ -640,6 +655,15 @@ class UnetEngine:
         ops.pack_batched(self.pack_table, self.n_pack_jobs, self.pack_total)
         for f in self.extra_packers:
             f()
+        self.packed_version = self.store.version
+
+    def sync_weights(self) -> bool:
+        """Repack if the master weights changed since this engine's operands were packed (another engine's optimizer
+        step, a state upload). Call before launching a forward eagerly or replaying a captured graph of one."""
+        if self.packed_version != self.store.version:
+            self.repack()
+            return True
+        return False
 
     # -- forward -----------------------------------------------------------------------------
     def forward(self, x: torch.Tensor, time: torch.Tensor) -> torch.Tensor:
@@ -647,6 +671,8 @@ class UnetEngine:
         st = self.store
         B, Fr, H, W = self.B, self.F, self.H, self.W
         self.x_in = x
+        if not torch.cuda.is_current_stream_capturing():
+            self.sync_weights()
         self.gn_all.zero_()
 
         def time_path():  # latency-bound tiny kernels: overlapped with the init conv / init attention
@@ -665,7 +691,8 @@ class UnetEngine:
         for b1, b2, sla, mha, down in self.downs:
             h = b1.forward([h])
             h = b2.forward([h])
-            h = sla.forward(h)
+            if sla is not None:
+                h = sla.forward(h)
             h = mha.forward(h)
             skips.append(h)
             if down is not None:
@@ -677,7 +704,8 @@ class UnetEngine:
         for b1, b2, sla, mha, up in self.ups:
             h = b1.forward([h, skips.pop()])
             h = b2.forward([h])
-            h = sla.forward(h)
+            if sla is not None:
+                h = sla.forward(h)
             h = mha.forward(h)
             if up is not None:
                 h = up.forward(h)
@@ -723,7 +751,8 @@ class UnetEngine:
                 if up is not None:
                     step(up.backward)
                 step(mha.backward)
-                step(sla.backward)
+                if sla is not None:
+                    step(sla.backward)
                 step(b2.backward)
                 d2, dsk = b1.backward(S["d"])
                 pool.put(S["d"])
@@ -746,7 +775,8 @@ class UnetEngine:
                     pool.put(S["d"])
                     S["d"] = acc
                 step(mha.backward)
-                step(sla.backward)
+                if sla is not None:
+                    step(sla.backward)
                 step(b2.backward)
                 step(b1.backward, extra=S["dr"] if l == 0 else None)
             return f

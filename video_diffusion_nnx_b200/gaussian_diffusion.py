@@ -67,6 +67,13 @@ def as_key(key) -> Key:
     return key if isinstance(key, Key) else Key(int(key))
 
 
+def randint_from_key(key: Key, high: int, n: int) -> torch.Tensor:
+    """n int32 draws from [0, high) as a pure function of the key (stands in for jax.random.randint,
+    gaussian_diffusion.py:496); host tensor. One seed-folding rule for every caller."""
+    g = torch.Generator(device="cpu").manual_seed((key.seed * 7919 + key.stream) % (2 ** 63))
+    return torch.randint(0, high, (n,), generator=g, dtype=torch.int32)
+
+
 class GaussianDiffusion:
     def __init__(self, denoise_fn, *, image_size: int, num_frames: int, text_use_bert_cls: bool = False,
                  channels: int = 3, timesteps: int = 1000, loss_type: str = "l1", use_dynamic_thres: bool = False,
@@ -97,6 +104,30 @@ class GaussianDiffusion:
     @property
     def device(self):
         return self.denoise_fn.device
+
+    # ---- state exchange (the tree `nnx.split(GaussianDiffusion)` gives: trainer.py:136, utils.py:486) ----------
+    def state_dict(self, flat: Optional[torch.Tensor] = None) -> Dict[str, np.ndarray]:
+        """`denoise_fn.<Unet3D nnx path>` leaves (from the device store, or from another flat buffer of the same layout
+        such as the EMA copy) + the ten schedule tables: what the reference checkpoints per tree."""
+        from .checkpoint import diffusion_state
+
+        return diffusion_state(self.denoise_fn.state_dict(flat), self._host_tables)
+
+    def load_state_dict(self, state: Dict[str, "np.ndarray | torch.Tensor"]) -> None:
+        """Loads a reference-named state: Unet3D leaves (with or without the `denoise_fn.` prefix) and, when present,
+        the schedule tables - the reference Adam-updates them, so a trained checkpoint's tables differ
+        from the closed form and sampling must use the checkpoint's."""
+        from .checkpoint import split_diffusion_state
+
+        state = {k: (v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)) for k, v in state.items()}
+        unet, sched = split_diffusion_state(state)
+        self.denoise_fn.load_state_dict(unet)
+        for name, arr in sched.items():
+            if arr.shape != (self.num_timesteps,):
+                raise ValueError(f"{name}: expected shape ({self.num_timesteps},), got {arr.shape}")
+            self._host_tables[name] = arr.astype(np.float32)
+            if name in self._dev_tables:  # in place: captured sampler / training graphs hold this address
+                self._dev_tables[name].copy_(torch.from_numpy(self._host_tables[name]))
 
     def _f32(self, x):
         return x.to(device=self.device, dtype=torch.float32).contiguous()
@@ -144,8 +175,7 @@ class GaussianDiffusion:
             "expected (b, c, f, h, w) matching the configured channels / frames / size"
         key = as_key(key)
         _, t_key, loss_key = key.split(3)
-        g = torch.Generator(device="cpu").manual_seed(t_key.seed * 7919 + t_key.stream)
-        t = torch.randint(0, self.num_timesteps, (B,), generator=g, dtype=torch.int32)
+        t = randint_from_key(t_key, self.num_timesteps, B)
         return self.p_losses(x, t, loss_key, *args, _normalize=True, **kwargs)
 
     def _extract(self, name: str, t) -> torch.Tensor:
@@ -218,6 +248,10 @@ class GaussianDiffusion:
         """gaussian_diffusion.py:264-320. The T host iterations replay ONE captured CUDA graph
         (Unet forward + Philox z + posterior update); `sample_offset` is the global index of this
         shard's first sample, so a sharded batch draws the same noise as the unsharded one."""
+        if cond is not None or cond_scale != 1.0:
+            # the reference's loop ignores both (gaussian_diffusion.py:301,316 never pass them on); an unconditional
+            # model has nothing to scale, so anything but the defaults is a caller error here
+            raise NotImplementedError("conditioning is outside the accelerated hot path (cond must be None, cond_scale 1.0)")
         key = as_key(key)
         B = shape[0]
         shape = (B, self.channels, self.num_frames, self.image_size, self.image_size)
@@ -250,6 +284,7 @@ class GaussianDiffusion:
                   "prm": torch.zeros(3, dtype=torch.int64, device=self.device), "graph": None}
             self._samplers[B] = st
         eng, img, t_dev, z, nxt = st["eng"], st["img"], st["t"], st["z"], st["nxt"]
+        eng.sync_weights()  # a training step / state upload since the last call: repack before replaying the graph
         img.copy_(self._normal(shape, init_key, sample_offset * per_sample))
         tabs = [self.table(n) for n in ("sqrt_recip_alphas_cumprod", "sqrt_recipm1_alphas_cumprod",
                                         "posterior_mean_coef1", "posterior_mean_coef2",

@@ -43,9 +43,10 @@ def pack_weight(src: torch.Tensor, dst: torch.Tensor, taps: int, cin: int, cout:
           "vdn_pack_weight")
 
 
-# timing experiments only (tools/whatif.sh): VDN_SKIP="gn_bwd,wgrad,..." turns the named wrappers into no-ops so
-# that the step-time contribution of a kernel family can be read off (results are wrong, of course)
-_SKIP = set(filter(None, os.environ.get("VDN_SKIP", "").split(",")))
+# timing experiments only (tools/whatif.sh, which opts in with VDN_DEBUG=1): VDN_SKIP="gn_bwd,wgrad,..." turns the
+# named wrappers into no-ops so that the step-time contribution of a kernel family can be read off (results are
+# wrong, of course). Empty in every product / test / bench process.
+_SKIP = set(filter(None, (_lib.host_flag("VDN_SKIP", "") or "").split(",")))
 
 
 def tapgemm(kind: int, srcs: Sequence[torch.Tensor], wp: torch.Tensor, taps, *, bias=None, residual=None,
@@ -162,9 +163,6 @@ def mha_core_bwd(qkv, o, d_o, lse, D_ws, dqkv, mode, B, F, HW):
                                stream_ptr()), "vdn_mha_core_bwd")
 
 
-lib.vdn_sla_workspace_floats.restype = C.c_size_t
-
-
 def sla_workspace_floats(n_img, N) -> int:
     return int(lib.vdn_sla_workspace_floats(n_img, N))
 
@@ -275,9 +273,19 @@ def add_bf16(a, b, out):
     check(lib.vdn_add_bf16(ptr(a), ptr(b), ptr(out), C.c_long(a.numel()), stream_ptr()), "vdn_add_bf16")
 
 
-def adam_ema(p, g, m, v, ema, hp):
-    check(lib.vdn_adam_ema(ptr(p), ptr(g), ptr(m), ptr(v), ptr(ema), ptr(hp), C.c_long(p.numel()), stream_ptr()),
-          "vdn_adam_ema")
+def adam_ema(p, g, m, v, ema, hp, sqnorm=None):
+    """Fused optax.adam + EMA over the flat state; with `sqnorm` (device scalar from grad_sqnorm) the global-norm
+    clip of utils.py:127-152 is applied first (hp[9] = max_grad_norm, hp[10] = epsilon)."""
+    if sqnorm is None:
+        check(lib.vdn_adam_ema(ptr(p), ptr(g), ptr(m), ptr(v), ptr(ema), ptr(hp), p.numel(), stream_ptr()), "vdn_adam_ema")
+    else:
+        check(lib.vdn_adam_ema_clip(ptr(p), ptr(g), ptr(m), ptr(v), ptr(ema), ptr(hp), ptr(sqnorm), p.numel(),
+                                    stream_ptr()), "vdn_adam_ema_clip")
+
+
+def grad_sqnorm(g, out):
+    """out[0] = sum g^2 (fp32 device scalar)."""
+    check(lib.vdn_grad_sqnorm(ptr(g), g.numel(), ptr(out), stream_ptr()), "vdn_grad_sqnorm")
 
 
 def randn(out, seed: int, subseq: int = 0, elem_offset: int = 0):

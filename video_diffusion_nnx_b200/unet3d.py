@@ -35,17 +35,32 @@ class Unet3D:
                  resnet_groups: int = 8, log_dims: bool = False, device="cuda"):
         if cond_dim is not None or use_bert_text_cond:
             raise NotImplementedError("text conditioning is outside the accelerated hot path (SURVEY.md C7)")
-        if attn_heads != HEADS or attn_dim_head != DIM_HEAD or resnet_groups != 8 or not use_sparse_linear_attn:
-            raise NotImplementedError("only attn_heads=8, attn_dim_head=32, resnet_groups=8, sparse linear attention")
-        if init_dim not in (None, dim) or init_kernel_size % 2 != 1 or dim % 32 != 0:
-            raise NotImplementedError("init_dim must equal dim, init_kernel_size odd, dim a multiple of 32")
+        if attn_heads != HEADS or attn_dim_head != DIM_HEAD:
+            raise NotImplementedError("the fused attention kernels are built for attn_heads=8, attn_dim_head=32 (every "
+                                      "reference config; SpatialLinearAttention hard-codes D=32 too, unet3d.py:174,225)")
+        if init_dim not in (None, dim):
+            # the reference cannot run this either: final_conv's block is built for 2*dim input channels
+            # (unet3d.py:249-250) while the concat at :377 delivers dim + init_dim
+            raise NotImplementedError("init_dim != dim: the reference's own final block (2*dim inputs) rejects it")
+        if init_kernel_size % 2 != 1 or dim % 32 != 0:
+            raise NotImplementedError("init_kernel_size must be odd (unet3d.py:105) and dim a multiple of 32")
+        if block_type != "resnet":
+            raise NotImplementedError("block_type is accepted and ignored by the reference; only 'resnet' exists")
+        # GroupNorm groups (modules.py:167): channels per group must be a power of two >= 2 at every level
+        cmin = dim * min([1] + list(dim_mults))
+        cpg = cmin // resnet_groups if resnet_groups > 0 and cmin % resnet_groups == 0 else 0
+        if cpg < 2 or (cpg & (cpg - 1)) != 0 or (resnet_groups & (resnet_groups - 1)) != 0:
+            raise NotImplementedError("resnet_groups must be a power of two leaving >= 2 channels per group")
+        self.resnet_groups = resnet_groups
+        self.use_sparse_linear_attn = bool(use_sparse_linear_attn)
         self.dim, self.channels, self.dim_mults = dim, channels, tuple(dim_mults)
         self.out_dim = channels if out_dim is None else out_dim
         self.init_kernel_size = init_kernel_size
         self.log_dims = log_dims
         self.has_cond = False
         self.device = torch.device(device)
-        self.spec = internal_param_spec(dim, channels, self.dim_mults, init_kernel_size, self.out_dim)
+        self.spec = internal_param_spec(dim, channels, self.dim_mults, init_kernel_size, self.out_dim,
+                                        self.use_sparse_linear_attn)
         self.store: Optional[ParamStore] = None
         self._engines: Dict[tuple, UnetEngine] = {}
         self._host_state = self._init_state(_seed_of(rngs))
@@ -103,6 +118,8 @@ class Unet3D:
             s[p + ".fn.fn.fn.out.bias"] = (c,)
 
         def sla(p, c):
+            if not self.use_sparse_linear_attn:  # Identity() holds no state (unet3d.py:179-181)
+                return
             s[p + ".fn.norm.scale"] = (c,)
             s[p + ".fn.norm.bias"] = (c,)
             for n in ("q", "k", "v"):
@@ -178,7 +195,12 @@ class Unet3D:
         return n, None
 
     def load_state_dict(self, state: Dict[str, "np.ndarray | torch.Tensor"]) -> None:
-        """Load reference-named arrays (flax layouts) into the flat device store."""
+        """Load reference-named arrays (flax layouts) into the flat device store. Keys may carry the `denoise_fn.`
+        prefix of the reference's checkpoint tree (the trainer splits the GaussianDiffusion module, trainer.py:136);
+        the schedule tables of such a tree are ignored here (GaussianDiffusion.load_state_dict takes them)."""
+        from .checkpoint import split_diffusion_state
+
+        state, _ = split_diffusion_state(dict(state))
         shapes = self.reference_param_shapes()
         missing = [k for k in shapes if k not in state]
         if missing:
@@ -211,8 +233,7 @@ class Unet3D:
             off, shape = st.offsets[name]
             flat[off:off + bufs[name].size] = bufs[name].ravel()
         st.flat.copy_(torch.from_numpy(flat))
-        for e in self._engines.values():
-            e.repack()
+        st.bump()  # every engine (and every sampler graph built on one) repacks before its next forward
 
     def state_dict(self, flat: Optional[torch.Tensor] = None) -> Dict[str, np.ndarray]:
         """Reference-named numpy arrays (flax layouts) read back from the device store (or from another
@@ -244,16 +265,13 @@ class Unet3D:
         return self.train(False)
 
     def _ensure_store(self, with_grad: bool) -> None:
-        if self.store is None or (with_grad and self.store.grad is None):
+        if self.store is None:
             if not torch.cuda.is_available():
                 raise RuntimeError("Unet3D needs a CUDA device (sm_100a); there is no CPU fallback")
-            old = self.store
             self.store = ParamStore(self.spec, self.device, with_grad)
-            if old is not None:
-                self.store.flat.copy_(old.flat)
-                self._engines.clear()
-            else:
-                self._upload()
+            self._upload()
+        elif with_grad:
+            self.store.ensure_grad()  # in place: existing engines / sampler graphs keep pointing at the same store
 
     def engine(self, B: int, F: int, H: int, W: int, training: Optional[bool] = None) -> UnetEngine:
         training = self.training if training is None else training
@@ -262,7 +280,8 @@ class Unet3D:
         if key not in self._engines:
             self._engines[key] = UnetEngine(self.store, dim=self.dim, channels=self.channels, dim_mults=self.dim_mults,
                                             init_kernel_size=self.init_kernel_size, B=B, F=F, H=H, W=W,
-                                            training=training, out_dim=self.out_dim)
+                                            training=training, out_dim=self.out_dim, groups=self.resnet_groups,
+                                            use_sla=self.use_sparse_linear_attn)
         return self._engines[key]
 
     def __call__(self, x: torch.Tensor, time: torch.Tensor, cond=None, null_cond_prob: float = 0.0,
