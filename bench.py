@@ -125,11 +125,11 @@ class ClockSampler:
                 "reasons": sorted(self.reasons), "samples": len(sm), "how": self.how}
 
 
-def run_reference(args):
-    """The reference's own algorithm on the host cores (oracle port; JAX is not installable here)."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
+def _cpu_train_sampler(batch, steps, warmup, sample_steps):
+    """The reference's algorithm on the host cores (oracle port of the JAX code; JAX is not installable here):
+    `steps` timed training steps of `batch` clips = p_losses value_and_grad + optax-style Adam + the EMA rule
+    (trainer.py:337-382), then `sample_steps` timed p_sample steps of one clip (gaussian_diffusion.py:231-261).
+    Returns (clips/s, s per training step, frames/s of a full T-step loop, cores)."""
     import torch
 
     from oracle import diffusion_oracle as D
@@ -144,135 +144,168 @@ def run_reference(args):
     gd = D.GaussianDiffusionOracle(lambda xx, tt: U.unet3d_forward(p, xx, tt, CFG["dim"]), image_size=CFG["size"],
                                    num_frames=CFG["frames"], channels=CFG["channels"], timesteps=CFG["timesteps"],
                                    loss_type=CFG["loss"])
-    Bs = 1  # bounded sample: one clip per step
-    x = torch.rand(Bs, 1, CFG["frames"], CFG["size"], CFG["size"])
+    opt = torch.optim.Adam(list(p.values()), lr=CFG["lr"], betas=(0.9, 0.999), eps=1e-8)
+    ema = {k: v.detach().clone() for k, v in p.items()}
+    x = torch.rand(batch, 1, CFG["frames"], CFG["size"], CFG["size"])
+    n = [0]
 
     def step():
-        for v in p.values():
-            v.grad = None
-        t = torch.randint(0, CFG["timesteps"], (Bs,), dtype=torch.int32)
+        opt.zero_grad()
+        t = torch.randint(0, CFG["timesteps"], (batch,), dtype=torch.int32)
         loss = gd(x, t, torch.randn_like(x))
         loss.backward()
+        for v in p.values():
+            if v.grad is None:
+                v.grad = torch.zeros_like(v)
+        opt.step()
+        n[0] += 1
+        if n[0] % CFG["update_ema_every"] == 0:
+            with torch.no_grad():
+                for k in ema:
+                    ema[k].mul_(CFG["ema_decay"]).add_(p[k].detach(), alpha=1 - CFG["ema_decay"])
         return loss.item()
 
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         step()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(steps):
         step()
-    dt = time.perf_counter() - t0
-    val = Bs * args.steps / dt
-    line = {"impl": "reference",
-            "metric": "train clips/sec (Unet3D config_v2_2 p_losses fwd+bwd+allreduce+Adam/EMA, device-timed)",
-            "value": val, "unit": "clips/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    fps = None
+    if sample_steps > 0:
+        with torch.no_grad():
+            img = torch.randn(1, 1, CFG["frames"], CFG["size"], CFG["size"])
+            tt = torch.full((1,), CFG["timesteps"] - 1, dtype=torch.int32)
+            gd.p_sample(img, tt, torch.randn_like(img))
+            t1 = time.perf_counter()
+            for _ in range(sample_steps):
+                img = gd.p_sample(img, tt, torch.randn_like(img))
+            ds = (time.perf_counter() - t1) / sample_steps
+        fps = CFG["frames"] / (ds * CFG["timesteps"])
+    return batch / dt, dt, fps, cores
+
+
+def run_reference(args):
+    """--impl reference: the reference's own algorithm on the box's host cores (oracle port; rank 0 alone)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    os.environ.pop("OMP_NUM_THREADS", None)
+    B = CFG["per_gpu_batch"]
+    val, dt, fps, cores = _cpu_train_sampler(B, args.steps, args.warmup, 2)
+    sample = (f"{args.steps} steps x {B} clips (one rank's shard of the workload), p_losses fwd+bwd + Adam + EMA, torch fp32 "
+              f"oracle port of the JAX reference on {cores} host threads")
+    line = {"impl": "reference", "metric": metric_name("v2_2"), "value": val, "unit": "clips/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"configs/config_v2_2.yaml training step: Unet3D dim 32, 1 ch, 10 frames, 64x64, "
-                                   f"T=1000, L2, Adam+EMA; per-GPU batch {CFG['per_gpu_batch']}, global batch "
-                                   f"{CFG['per_gpu_batch'] * args.gpus}",
-                       "parallelism": f"dp{args.gpus}", "global_batch": CFG["per_gpu_batch"] * args.gpus,
-                       "note": "reference arm = the reference's algorithm on the host CPU cores (oracle port; JAX is not "
-                               "installable in this image); each step is a bounded sample of the workload: 1 clip, fwd+bwd"},
-            "cpu_baseline": {"value": val, "unit": "clips/s", "cores": cores, "kind": "port",
-                             "sample": f"{args.steps} steps x 1 clip, fwd+bwd (no optimizer), torch fp32 oracle port of the JAX reference"},
-            "e2e": {"value": val, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+            "config": workload_config(B, args.gpus),
+            "cpu_baseline": {"value": val, "unit": "clips/s", "cores": cores, "kind": "port", "sample": sample,
+                             "sampling": {"value": fps, "unit": "frames/s",
+                                          "sample": "2 p_sample steps of 1 clip, extrapolated to the T=1000 loop"}},
+            "e2e": {"value": val, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "JAX / flax are not installable in this image (DESIGN.md section 6): the arm is the CPU restatement of the "
+                    "reference (kind = port), each step a bounded sample of the workload: one rank's batch of "
+                    f"{B} clips with the optimizer"}
     print(json.dumps(line), flush=True)
 
 
-def cpu_baseline_sample():
-    import torch
-
-    from oracle import diffusion_oracle as D
-    from oracle import unet3d_oracle as U
-
-    cores = os.cpu_count()
-    torch.set_num_threads(cores)
-    p = U.init_params(CFG["dim"], CFG["channels"])
-    for v in p.values():
-        v.requires_grad_(True)
-    gd = D.GaussianDiffusionOracle(lambda xx, tt: U.unet3d_forward(p, xx, tt, CFG["dim"]), image_size=CFG["size"],
-                                   num_frames=CFG["frames"], channels=CFG["channels"], timesteps=CFG["timesteps"],
-                                   loss_type=CFG["loss"])
-    x = torch.rand(1, 1, CFG["frames"], CFG["size"], CFG["size"])
-    ts = []
-    for i in range(9):
-        t = torch.randint(0, CFG["timesteps"], (1,), dtype=torch.int32)
-        t0 = time.perf_counter()
-        loss = gd(x, t, torch.randn_like(x))
-        loss.backward()
-        ts.append(time.perf_counter() - t0)
-    best = sorted(ts[1:])[len(ts[1:]) // 2]
-    return {"value": 1.0 / best, "unit": "clips/s", "cores": cores, "kind": "port",
-            "sample": "median of 8 training steps (fwd+bwd) of 1 clip after 1 warm-up (~10 s of CPU work), torch fp32 "
-                      "oracle port of the JAX reference on all host cores"}
+def cpu_baseline_subprocess():
+    """The CPU baseline leg, run in a fresh process with a clean threading environment BEFORE any process group
+    exists (torchrun exports OMP_NUM_THREADS=1, and ranks waiting in a NCCL barrier would spin on their GPUs)."""
+    env = {k: v for k, v in os.environ.items() if k not in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "RANK", "WORLD_SIZE",
+                                                            "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT")}
+    env["CUDA_VISIBLE_DEVICES"] = ""
+    try:
+        out = subprocess.run([sys.executable, os.path.abspath(__file__), "--cpu-baseline-worker"], env=env,
+                             capture_output=True, text=True, timeout=600).stdout.strip().splitlines()
+        return json.loads(out[-1])
+    except Exception as e:  # the baseline is a reported number, never a reason to lose the bench line
+        return {"value": None, "unit": "clips/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e!r}"}
 
 
-def conv_roofline(torch, ops, pk):
-    """Times the dominant tensor-core kernel class of the step - the (1,3,3) implicit-GEMM conv of the
-    64x64 level (M = B*F*64*64 = 163840 pixels, 32 -> 32 channels, K = 288) - in isolation with CUDA
-    events, rotating over enough distinct buffers to exceed L2."""
+def cpu_baseline_worker():
+    B = CFG["per_gpu_batch"]
+    val, dt, fps, cores = _cpu_train_sampler(B, 3, 1, 2)
+    print(json.dumps({"value": val, "unit": "clips/s", "cores": cores, "kind": "port",
+                      "sample": f"3 training steps of {B} clips after 1 warm-up (~{4 * dt:.0f} s of CPU work): p_losses "
+                                "fwd+bwd + Adam + EMA, torch fp32 oracle port of the JAX reference on all host cores",
+                      "sampling": {"value": fps, "unit": "frames/s",
+                                   "sample": "2 p_sample steps of 1 clip, extrapolated to the T=1000 loop"}}), flush=True)
+
+
+def metric_name(workload):
+    return f"train clips/sec (Unet3D config_{workload} p_losses fwd+bwd+allreduce+Adam/EMA, device-timed)"
+
+
+def workload_config(B, world):
+    return {"workload": f"{WORKLOAD_NAME} training step: Unet3D dim {CFG['dim']}, 1 ch, {CFG['frames']} frames, "
+                        f"{CFG['size']}x{CFG['size']}, T=1000, L2, Adam+EMA; per-GPU batch {B}, global batch {B * world}",
+            "parallelism": f"dp{world}", "global_batch": B * world,
+            "l2": "no explicit flush: one step streams > 2 GB of activations / saved tensors, far beyond the 126 MB L2",
+            "timing": "CUDA events on the launch stream around K CUDA-graph-replayed steps, max over ranks"}
+
+
+def conv_roofline(torch, ops, pk, level=0, with_traffic=False):
+    """Times one (1,3,3) implicit-GEMM conv + bias + GroupNorm partial sums of the step at resolution level `level`
+    (0: 64x64 / dim channels ... 3: 8x8 / 8*dim channels for config_v2_2) in isolation with CUDA events, replayed from a
+    CUDA graph that rotates over enough distinct (input, weights, output) sets to exceed the 126 MB L2."""
     dev = "cuda"
-    n_img, H, W, C = CFG["per_gpu_batch"] * CFG["frames"], CFG["size"], CFG["size"], CFG["dim"]
-    nbuf = 16  # 16 x (10.5 MB in + 10.5 MB out) = 336 MB > 126 MB L2
+    n_img = CFG["per_gpu_batch"] * CFG["frames"]
+    H = W = CFG["size"] >> level
+    C = CFG["dim"] << level
+    per_set = n_img * H * W * C * 2 * 2 + 9 * C * C * 2
+    nbuf = max(4, min(128, int(260e6 // per_set) + 1))  # > 2 x L2 in rotation
     xs = [torch.randn(n_img, H, W, C, device=dev).to(torch.bfloat16) for _ in range(nbuf)]
     outs = [torch.empty(n_img, H, W, C, device=dev, dtype=torch.bfloat16) for _ in range(nbuf)]
-    w = torch.randn(9, C, C, device=dev) * (9 * C) ** -0.5
-    wp = torch.empty(C, 9 * C, dtype=torch.bfloat16, device=dev)
-    ops.pack_weight(w, wp, 9, C, C, 0)
+    wps = []
+    for _ in range(nbuf):
+        w = torch.randn(9, C, C, device=dev) * (9 * C) ** -0.5
+        wp = torch.empty(C, 9 * C, dtype=torch.bfloat16, device=dev)
+        ops.pack_weight(w, wp, 9, C, C, 0)
+        wps.append(wp)
     bias = torch.zeros(C, device=dev)
     sums = torch.zeros(ops.GN_REPLICAS, CFG["per_gpu_batch"], 8, 2, device=dev)
     rows = CFG["frames"] * H * W
 
     def run(i):
-        ops.tapgemm(ops.VDN_TAP_UNIT, [xs[i % nbuf]], wp, ops.TAPS_3x3, bias=bias, out=outs[i % nbuf], gn_sums=sums,
-                    gn_groups=8, rows_per_sample=rows)
+        ops.tapgemm(ops.VDN_TAP_UNIT, [xs[i % nbuf]], wps[i % nbuf], ops.TAPS_3x3, bias=bias, out=outs[i % nbuf],
+                    gn_sums=sums, gn_groups=8, rows_per_sample=rows)
 
-    for i in range(8):
-        run(i)
-    torch.cuda.synchronize()
-    # the launches are replayed from a CUDA graph: per-call host work (descriptor encode, ctypes) is ~20 us,
-    # longer than the kernel, and must not be what is timed
-    n = 64
-    side = torch.cuda.Stream()
-    side.wait_stream(torch.cuda.current_stream())
-    graph = torch.cuda.CUDAGraph()
-    with torch.cuda.stream(side):
-        with torch.cuda.graph(graph, stream=side):
-            for i in range(n):
-                run(i)
-    torch.cuda.current_stream().wait_stream(side)
-    graph.replay()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    graph.replay()
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / n
+    n0 = ops.lib.vdn_launch_count()
+    run(0)
+    assert ops.lib.vdn_launch_count() == n0 + 1
+    # the launches are replayed from a CUDA graph: per-call host work (ctypes) is longer than the kernel
+    us = _graph_time_us(torch, run, n=max(64, nbuf), warm=8)
+    ms = us * 1e-3
     M = n_img * H * W
     flops = 2.0 * M * C * 9 * C
     bytes_alg = 2.0 * M * C * 2 + 9 * C * C * 2
     tf = flops / (ms * 1e-3) / 1e12
     gbs = bytes_alg / (ms * 1e-3) / 1e9
-    # the dim-32 layer is below the ridge (AI = flops/bytes ~ 144 FLOP/B < 212): HBM is the binding roofline there;
-    # the dim-128 layer of the v2_3x workload (AI 576) is bound by the tensor pipe
+    # below the ridge (AI = flops/bytes < ~250 FLOP/B: the dim-32 level, AI 144) HBM is the binding roofline; the
+    # small-M levels (AI 570-1000) and every level of the v2_3x workload are bound by the tensor pipe
     ridge = pk["tf_burst"] * 1e3 / pk["hbm"]
     tensor_bound = flops / bytes_alg > ridge
     traffic = None
     tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-    if os.path.exists(tp) and C == 32:  # dram bytes per launch of this kernel from the committed `ncu --set full` capture
+    if with_traffic and os.path.exists(tp):  # dram bytes per launch of this kernel from the committed `ncu --set full` capture
         td = json.load(open(tp))
-        traffic = td["dram_bytes_read"] + td["dram_bytes_write"]
-    name = (f"conv(1,3,3) {C}->{C} @{H}x{W} (M={M},N={C},K={9 * C}) "
-            + ("conv3x3_rows_kernel<32,32,1>" if C == 32 else "conv3x3_slab_kernel<32>"))
+        key = f"conv_l{level}_c{C}"
+        if key in td:
+            traffic = td[key]["dram_bytes_read"] + td[key]["dram_bytes_write"]
+    kern = {32: "conv3x3_rows_kernel<32,32,1>", 64: "conv3x3_rows_kernel<64,64,1>"}.get(C, "tapgemm_kernel<64>")
+    if CFG["dim"] >= 128:
+        kern = "conv3x3_slab_kernel<32>"
+    name = f"conv(1,3,3) {C}->{C} @{H}x{W} (M={M},N={C},K={9 * C}) {kern}"
     r = {"kernel": name, "bound": "tensor" if tensor_bound else "hbm"}
     if tensor_bound:
         r.update(achieved=tf, peak=pk["tf_burst"], unit="TFLOP/s", frac=tf / pk["tf_burst"], traffic=traffic,
-                 algorithmic_flops=flops, hbm_gbs=gbs)
+                 algorithmic_flops=flops, algorithmic_bytes=bytes_alg, hbm_gbs=gbs)
     else:
         r.update(achieved=gbs, peak=pk["hbm"], unit="GB/s", frac=gbs / pk["hbm"], traffic=traffic,
                  algorithmic_bytes=bytes_alg, tensor_tflops=tf, tensor_frac_of_burst=tf / pk["tf_burst"])
-    r.update(us_per_launch=ms * 1e3, peak_source=pk["src"])
+    r.update(us_per_launch=ms * 1e3, peak_source=pk["src"], buffers_in_rotation=nbuf,
+             l2="inputs, weights and outputs rotate over sets larger than L2 between launches")
     return r
 
 
@@ -354,6 +387,52 @@ def extra_rooflines(torch, ops, pk):
     return out
 
 
+def parity_block(torch, ops, gd, net, B):
+    """Loss and predicted noise of the benchmarked model (the weights the timed steps left behind) against the CPU
+    oracle on one batch of the benchmark's own shape, in the same job. bf16 = the timed tensor-core path; fp32 = the
+    fp32-grade operand path (bf16 x 3 split operands, fp32 activations; gate 1e-3, BASELINE.json north_star)."""
+    import numpy as np
+
+    from oracle import diffusion_oracle as D
+    from oracle import unet3d_oracle as U
+
+    rng = np.random.default_rng(99)
+    shape = (B, CFG["channels"], CFG["frames"], CFG["size"], CFG["size"])
+    x = torch.from_numpy(rng.random(shape, dtype=np.float32))
+    t = torch.from_numpy(rng.integers(0, CFG["timesteps"], (B,)).astype(np.int32))
+    noise = torch.from_numpy(rng.standard_normal(shape).astype(np.float32))
+    p = {k: torch.from_numpy(v) for k, v in net.state_dict().items()}
+    cap = {}
+
+    def fwd(xx, tt):
+        cap["eps"] = U.unet3d_forward(p, xx, tt, CFG["dim"])
+        return cap["eps"]
+
+    torch.set_num_threads(os.cpu_count())
+    with torch.no_grad():
+        gdo = D.GaussianDiffusionOracle(fwd, image_size=CFG["size"], num_frames=CFG["frames"], channels=CFG["channels"],
+                                        timesteps=CFG["timesteps"], loss_type=CFG["loss"])
+        loss_ref = float(gdo(x, t, noise).item())
+    eps_ref = cap["eps"].double()
+
+    def rel(a):
+        return float(((a.double().cpu() - eps_ref).norm() / eps_ref.norm()).item())
+
+    out = {"oracle": "torch fp32 CPU restatement of the reference (oracle/), same weights / clips / t / noise",
+           "batch": B, "loss_oracle": loss_ref}
+    net.train(False)
+    xn = gd.q_sample(x.cuda() * 2 - 1, t.cuda(), noise=noise.cuda())
+    eps = net(xn, t.cuda())
+    loss = float(gd.p_losses(x.cuda() * 2 - 1, t.cuda(), noise=noise.cuda()).item())
+    out["bf16"] = {"loss_rel_err": abs(loss - loss_ref) / loss_ref, "eps_rel_l2": rel(eps), "tolerance": 2e-2}
+    if hasattr(net, "forward_fp32"):
+        eps32 = net.forward_fp32(xn, t.cuda())
+        d = eps32.permute(0, 4, 1, 2, 3) - noise.cuda()
+        loss32 = float((d * d).mean().item())
+        out["fp32"] = {"loss_rel_err": abs(loss32 - loss_ref) / loss_ref, "eps_rel_l2": rel(eps32), "tolerance": 1e-3}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -363,33 +442,49 @@ def main():
     ap.add_argument("--batch", type=int, default=CFG["per_gpu_batch"], help="per-GPU batch")
     ap.add_argument("--no-sampling", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-rooflines", action="store_true")
     ap.add_argument("--sample-timesteps", type=int, default=CFG["timesteps"])
     ap.add_argument("--sample-batch", type=int, default=16,
                     help="samples per GPU in the sampling metric (16 = the reference default, gaussian_diffusion.py:323)")
     ap.add_argument("--workload", default="v2_2", choices=["v2_2", "v2_3x"])
+    ap.add_argument("--headline", default="train", choices=["train", "sampling"],
+                    help="which of BASELINE.json's two metrics is the line's top-level metric / value")
+    ap.add_argument("--cpu-baseline-worker", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
     select_workload(args.workload)
+    if args.cpu_baseline_worker:
+        return cpu_baseline_worker()
     if args.workload == "v2_3x":  # big model: short sampling run (extrapolated to T), small sample batch
         args.sample_timesteps = min(args.sample_timesteps, 20)
         args.sample_batch = min(args.sample_batch, 4)
         args.no_cpu_baseline = True
+        args.no_parity = True
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
         return run_reference(args)
 
-    import torch
-    import torch.distributed as dist
-
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # CPU baseline first: rank 0, in a fresh process with all host cores, before CUDA / NCCL exist in this job (the
+    # other ranks wait in the process-group rendezvous, asleep on a socket - not spinning on their GPUs)
+    cpu_base = None
+    if rank == 0 and not args.no_cpu_baseline:
+        cpu_base = cpu_baseline_subprocess()
+
+    import datetime
+
+    import torch
+    import torch.distributed as dist
+
     torch.cuda.set_device(local)
     pg = None
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(minutes=20))
         pg = dist.group.WORLD
 
-    from video_diffusion_nnx_b200 import _lib, ops
+    from video_diffusion_nnx_b200 import ops
     from video_diffusion_nnx_b200.gaussian_diffusion import GaussianDiffusion
     from video_diffusion_nnx_b200.trainer import TrainStep
     from video_diffusion_nnx_b200.unet3d import Unet3D
@@ -413,6 +508,12 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(v):
+        tv = torch.tensor([v], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tv, op=dist.ReduceOp.MAX)
+        return float(tv.item())
+
     # ---------------- device-resident timing (`value`) ----------------
     x_dev = torch.rand(shape, generator=g).to(dev)
     t_all = torch.randint(0, CFG["timesteps"], (K + Wm + 2, B), generator=g, dtype=torch.int32).to(dev)
@@ -420,7 +521,7 @@ def main():
     ts.t.copy_(t_all[0])
     ops.randn(ts.noise, 7 + rank, 0)
     ts.step_device(0)  # eager warm-up pass (state restored) + graph capture + one replayed step
-    # kernels of libvdn in one replayed step (counted by the library while the step's graphs were captured) + the
+    # kernels of libvdn in one replayed step (counted by the library while the step's graph was captured) + the
     # noise kernel launched per step below
     launches_per_step = ts.launches_per_step + 1
     for i in range(Wm):
@@ -437,13 +538,8 @@ def main():
             ts.step_device(1 + Wm + i)
         e1.record()
         barrier()
-    ms = e0.elapsed_time(e1)
     loss_last = float(ts.loss.item())
-    tms = torch.tensor([ms], device=dev)
-    if world > 1:
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-    ms = float(tms.item())
-    ms_per_step = ms / K
+    ms_per_step = max_over_ranks(e0.elapsed_time(e1)) / K
     value = world * B / (ms_per_step * 1e-3)
 
     # ---------------- end-to-end through the public API (`e2e`) ----------------
@@ -456,32 +552,22 @@ def main():
         loss = ts.step(hosts[i % 4], 1000 + i, 3000 + i)
         _ = float(loss.item())  # device -> host read of the step's result, every step
     barrier()
-    e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * K / float(te.item())
+    e2e_value = world * B * K / max_over_ranks(time.perf_counter() - t0)
     h2d = hosts[0].numel() * 4 + B * 4 + 16 * 4
     d2h = 4
 
     line = None
     if rank == 0:
-        act_mb = sum(t.numel() * t.element_size() for t in ts.eng.__dict__.values() if isinstance(t, torch.Tensor)) / 1e6
         line = {
-            "metric": f"train clips/sec (Unet3D config_{args.workload} p_losses fwd+bwd+allreduce+Adam/EMA, device-timed)",
-            "value": value, "unit": "clips/s", "n_gpus": world, "steps": K, "warmup": Wm,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"{WORKLOAD_NAME} training step: Unet3D dim {CFG['dim']}, 1 ch, {CFG['frames']} frames, "
-                                   f"{CFG['size']}x{CFG['size']}, T=1000, L2, Adam+EMA; per-GPU batch {B}, global batch {B * world}",
-                       "parallelism": f"dp{world}", "global_batch": B * world,
-                       "l2": "no explicit flush: one step streams > 2 GB of activations / saved tensors, far beyond the 126 MB L2",
-                       "timing": "CUDA events on the launch stream around K CUDA-graph-replayed steps, max over ranks"},
+            "metric": metric_name(args.workload), "value": value, "unit": "clips/s", "n_gpus": world, "steps": K,
+            "warmup": Wm, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic", "config": workload_config(B, world),
             "loss_last": loss_last,
             "e2e": {"value": e2e_value, "unit": "clips/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "how": "TrainStep.step(pinned host batch, key, step) + loss.item() every step, wall clock"},
             "gpu_launches": int(launches_per_step * K),
             "launches_per_step": int(launches_per_step),
+            "graph_launches_per_step": ts.graph_launches_per_step,
             "clocks": clk.summary(),
             "train_tflops": value * TRAIN_GFLOP_PER_CLIP / 1e3,
             "train_frac_of_sustained_bf16_peak": value / world * TRAIN_GFLOP_PER_CLIP / 1e3 / pk["tf_sust"],
@@ -494,34 +580,60 @@ def main():
         T = args.sample_timesteps
         gd.p_sample_loop((sb,), 11, sample_offset=rank * sb, timesteps=4)  # warm-up + capture path
         barrier()
+        n0 = ops.lib.vdn_launch_count()
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s0.record()
-        vid = gd.p_sample_loop((sb,), 12, sample_offset=rank * sb, timesteps=T)
-        s1.record()
+        with ClockSampler(local) as sclk:
+            s0.record()
+            vid = gd.p_sample_loop((sb,), 12, sample_offset=rank * sb, timesteps=T)
+            s1.record()
+            barrier()
+        sms = max_over_ranks(s0.elapsed_time(s1))
+        # end to end through the public API: the loop above plus the device -> host read of the generated clips
         barrier()
-        sms = torch.tensor([s0.elapsed_time(s1)], device=dev)
-        if world > 1:
-            dist.all_reduce(sms, op=dist.ReduceOp.MAX)
+        w0 = time.perf_counter()
+        vid_host = gd.p_sample_loop((sb,), 13, sample_offset=rank * sb, timesteps=T).cpu()
+        s_e2e = max_over_ranks(time.perf_counter() - w0)
         if rank == 0:
-            fps = world * sb * CFG["frames"] / (float(sms.item()) * 1e-3) * (CFG["timesteps"] / T) / (CFG["timesteps"] / T)
-            fps_full = world * sb * CFG["frames"] / (float(sms.item()) * 1e-3 * CFG["timesteps"] / T)
+            scale = CFG["timesteps"] / T
+            fps_full = world * sb * CFG["frames"] / (sms * 1e-3 * scale)
+            eng = gd._samplers[sb]["eng"]
+            n_eager = int(ops.lib.vdn_launch_count() - n0)  # init noise etc.; the timestep graph replays are on top
             line["sampling"] = {"metric": f"sampling frames/sec (p_sample_loop, T=1000, config_{args.workload})", "value": fps_full,
-                                "unit": "frames/s", "timesteps_run": T, "ms_per_timestep": float(sms.item()) / T,
+                                "unit": "frames/s", "timesteps_run": T, "ms_per_timestep": sms / T,
                                 "sample_batch_per_gpu": sb, "finite": bool(torch.isfinite(vid).all().item()),
+                                "e2e": {"value": world * sb * CFG["frames"] / (s_e2e * scale), "unit": "frames/s",
+                                        "h2d_bytes_per_step": 24, "d2h_bytes_per_step": vid_host.numel() * 4},
                                 "sampling_tflops": fps_full * FWD_GFLOP_PER_CLIP / CFG["frames"] * CFG["timesteps"] / 1e3,
                                 "frac_of_sustained_bf16_peak": fps_full / world * FWD_GFLOP_PER_CLIP / CFG["frames"]
-                                * CFG["timesteps"] / 1e3 / pk["tf_sust"]}
-            del fps
+                                * CFG["timesteps"] / 1e3 / pk["tf_sust"], "clocks": sclk.summary(),
+                                "eager_launches": n_eager}
+            del eng
 
-    if rank == 0:
-        line["roofline"] = conv_roofline(torch, ops, pk)
-        line["roofline_kernels"] = extra_rooflines(torch, ops, pk)
-        if not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline_sample()
-        print(json.dumps(line), flush=True)
-    if world > 1:
+    if world > 1:  # the rest is rank 0's alone: leave the process group first so that nobody spins in a barrier
         dist.barrier()
         dist.destroy_process_group()
+    if rank != 0:
+        return
+    if args.headline == "sampling" and "sampling" in line:
+        smp = line["sampling"]
+        train = {k: line[k] for k in ("metric", "value", "unit", "ms_per_step", "e2e", "gpu_launches", "launches_per_step",
+                                      "clocks", "loss_last")}
+        line.update(metric=smp["metric"], value=smp["value"], unit=smp["unit"], ms_per_step=smp["ms_per_timestep"],
+                    e2e=smp["e2e"], clocks=smp["clocks"], steps=smp["timesteps_run"], training=train)
+        line["config"]["workload"] = (f"{WORKLOAD_NAME} p_sample_loop, T=1000 ({smp['timesteps_run']} timesteps run): Unet3D dim "
+                                      f"{CFG['dim']}, {CFG['frames']} frames, {CFG['size']}x{CFG['size']}; {smp['sample_batch_per_gpu']} samples per GPU")
+    if not args.no_rooflines:
+        small = args.workload == "v2_2"
+        # the dominant kernel of the step by the committed launch list (profiles/): the small-M tap-GEMM convs of the
+        # 16x16 / 8x8 levels (tapgemm_kernel<64>); the full-resolution conv and three more kernels follow
+        line["roofline"] = conv_roofline(torch, ops, pk, level=3 if small else 0, with_traffic=True)
+        extra = [conv_roofline(torch, ops, pk, level=2), conv_roofline(torch, ops, pk, level=0, with_traffic=True)] if small else []
+        line["roofline_kernels"] = extra + extra_rooflines(torch, ops, pk)
+    if not args.no_parity:
+        line["parity"] = parity_block(torch, ops, gd, net, B)
+    if cpu_base is not None:
+        line["cpu_baseline"] = cpu_base
+    print(json.dumps(line), flush=True)
 
 
 if __name__ == "__main__":

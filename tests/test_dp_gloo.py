@@ -36,6 +36,23 @@ def _worker(rank, world, port, q):
     want = torch.stack(gathered).mean(0)
     ok = torch.allclose(grad, want, atol=1e-6)
     lo, hi = shard_range(8, world, rank)
+    # timesteps are drawn for the GLOBAL batch from the key and sliced per rank (trainer.TrainStep.draw): the shards
+    # tile a single process's draw, and different ranks get different timesteps
+    from video_diffusion_nnx_b200.gaussian_diffusion import Key, randint_from_key
+
+    t_all = randint_from_key(Key(77, 3), 1000, 8)
+    mine_t = t_all[lo:hi].clone()
+    got_t = [torch.zeros(hi - lo, dtype=torch.int32) for _ in range(world)]
+    dist.all_gather(got_t, mine_t)
+    ok = ok and torch.equal(torch.cat(got_t), t_all) and not torch.equal(got_t[0], got_t[1])
+    # the NCCL unique id of the C-ABI communicator travels over any torch.distributed backend
+    from video_diffusion_nnx_b200.trainer import Communicator
+
+    box = [Communicator.new_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    ids = [None] * world
+    dist.all_gather_object(ids, box[0])
+    ok = ok and len(box[0]) == 128 and ids[0] == ids[1]
     q.put((rank, bool(ok), (lo, hi)))
     dist.destroy_process_group()
 

@@ -44,7 +44,33 @@ def run(batch, pg, lo, hi, graph):
     return init, losses, net.store.flat.clone()
 
 
-ok = True
+def draws_match():
+    """TrainStep.step under DP draws t / noise for the GLOBAL batch and slices its shard (the reference's pjit step
+    draws once and shards): the gathered shard draws must equal a single process's draws on the whole batch, bit for bit."""
+    lo, hi = shard_range(G, world, rank)
+    net = Unet3D(dim=32, channels=1, rngs=0)
+    gd = GaussianDiffusion(net, image_size=S, num_frames=Fr, channels=1, timesteps=T, loss_type="l2")
+    step = TrainStep(gd, batch_size=b, use_graph=False, process_group=dist.group.WORLD)
+    step.draw(1234)
+    torch.cuda.synchronize()
+    t_all = [torch.empty_like(step.t) for _ in range(world)]
+    n_all = [torch.empty_like(step.noise) for _ in range(world)]
+    dist.all_gather(t_all, step.t)
+    dist.all_gather(n_all, step.noise)
+    good = True
+    if rank == 0:
+        net1 = Unet3D(dim=32, channels=1, rngs=0)
+        gd1 = GaussianDiffusion(net1, image_size=S, num_frames=Fr, channels=1, timesteps=T, loss_type="l2")
+        full = TrainStep(gd1, batch_size=G, use_graph=False)
+        full.draw(1234)
+        torch.cuda.synchronize()
+        good = torch.equal(torch.cat(t_all), full.t) and torch.equal(torch.cat(n_all), full.noise)
+        print(f"DP draws equal the full-batch draws: {good}; shard timesteps differ across ranks: "
+              f"{not torch.equal(t_all[0], t_all[-1])}", flush=True)
+    return good
+
+
+ok = draws_match()
 for graph in (False, True):
     lo, hi = shard_range(G, world, rank)
     init, losses, flat = run(b, dist.group.WORLD, lo, hi, graph)
