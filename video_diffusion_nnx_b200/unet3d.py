@@ -49,8 +49,9 @@ class Unet3D:
         # GroupNorm groups (modules.py:167): channels per group must be a power of two >= 2 at every level
         cmin = dim * min([1] + list(dim_mults))
         cpg = cmin // resnet_groups if resnet_groups > 0 and cmin % resnet_groups == 0 else 0
-        if cpg < 2 or (cpg & (cpg - 1)) != 0 or (resnet_groups & (resnet_groups - 1)) != 0:
-            raise NotImplementedError("resnet_groups must be a power of two leaving >= 2 channels per group")
+        if cpg < 2 or (cpg & (cpg - 1)) != 0 or resnet_groups not in (2, 4, 8):
+            # the conv epilogues keep at most 8 (sum, sum-of-squares) pairs per column tile
+            raise NotImplementedError("resnet_groups must be 2, 4 or 8 (every reference config uses 8)")
         self.resnet_groups = resnet_groups
         self.use_sparse_linear_attn = bool(use_sparse_linear_attn)
         self.dim, self.channels, self.dim_mults = dim, channels, tuple(dim_mults)
