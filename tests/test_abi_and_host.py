@@ -215,3 +215,36 @@ def test_checkpoint_tree_is_the_diffusion_state(tmp_path):
         assert all(np.array_equal(back[k], ema[k]) for k in ema)
         net2.load_state_dict(got)  # a bare Unet3D accepts the prefixed tree and ignores the tables
         assert np.array_equal(net2.state_dict()["init_conv.kernel"], trained["denoise_fn.init_conv.kernel"])
+
+
+def test_ffi_shim_builds_and_names_real_entry_points():
+    """ffi/vdn_ffi.cc compiles everywhere (stub form without jaxlib's headers); every FFI target it announces maps to
+    a C-ABI entry point that include/vdn.h declares and libvdn.so exports."""
+    from video_diffusion_nnx_b200 import _lib, jax_ffi
+
+    assert os.path.exists(jax_ffi.FFI_LIB_PATH), "run build() first"
+    lib = ctypes.CDLL(jax_ffi.FFI_LIB_PATH)
+    names = jax_ffi._targets(lib)
+    assert len(names) >= 35 and len(set(names)) == len(names)
+    alias = {"vdn_wgrad": "vdn_wgrad_bias", "vdn_mha_temporal_fwd": "vdn_mha_temporal_tc_fwd",
+             "vdn_mha_temporal_bwd": "vdn_mha_temporal_tc_bwd"}
+    for n in names:
+        assert alias.get(n, n) in _lib.PROTOTYPES, n
+    src = open(os.path.join(ROOT, "ffi", "vdn_ffi.cc")).read()
+    for n in names:
+        assert f"XLA_FFI_DEFINE_HANDLER_SYMBOL({n}_ffi" in src, n
+    lib.vdn_ffi_available.restype = ctypes.c_int
+    if not lib.vdn_ffi_available():  # no jaxlib here: register() must refuse loudly, not fall back
+        with pytest.raises(RuntimeError):
+            jax_ffi.register()
+
+
+def test_every_prototype_has_argtypes():
+    from video_diffusion_nnx_b200 import _lib
+
+    assert len(_lib.PROTOTYPES) >= 60
+    for name, (ret, argt) in _lib.PROTOTYPES.items():
+        fn = getattr(_lib.lib, name)
+        assert fn.argtypes is not None and list(fn.argtypes) == argt, name
+    with pytest.raises(ctypes.ArgumentError):
+        _lib.lib.vdn_randn(None, "not a number", 0, 0, 0, None)
