@@ -10,7 +10,9 @@ Follows gaussian_diffusion.py:77-98 (schedule tables), :120-136 (predict_start_f
 
 Pinned by the reference's own known answers (gaussian_diffusion_test.py:88-109,111-123,135-158,
 175-189,191-210; utils_test.py:102-110,121-131) in tests/test_oracle_known_answers.py.
-The Unet numerics themselves are PARITY UNPINNED (see oracle/unet3d_oracle.py).
+Also pinned by executing the reference's own gaussian_diffusion.py / utils.py over oracle/refshim
+(tests/test_oracle_vs_reference_code.py: every method at 1e-9, the ten schedule tables bit-identical in
+float32). For the Unet numerics see the PARITY PIN paragraph of oracle/unet3d_oracle.py.
 
 jax.random (threefry) streams cannot be reproduced here, so every random draw (t, noise, the
 per-step z of p_sample) is an explicit input.

@@ -3,11 +3,20 @@
 This file is NOT part of the product. Only tests/, __graft_entry__.smoke() and bench.py's
 cpu_baseline / --impl reference legs may import it, and only as the checker / CPU baseline.
 
-PARITY UNPINNED for the Unet numerics: the reference (maxsonate/video-diffusion-nnx) is
-flax.nnx/JAX code, jax/flax are not installable in this image, and the reference's own tests
-assert shapes only (test_unet3d.py:24,48; test_modules.py). What IS pinned: every closed-form
-known-answer the reference tests hold for this path (tests/test_oracle_known_answers.py), and the
-framework semantics below re-derived from definition in numpy (tests/test_oracle_semantics.py).
+PARITY PIN. The reference (maxsonate/video-diffusion-nnx) is flax.nnx / JAX code; jax / flax are not installable in
+this image and the reference's own tests assert shapes only (test_unet3d.py:24,48; test_modules.py). What pins this
+oracle:
+  1. THE REFERENCE'S OWN PYTHON, EXECUTED HERE: tests/golden/make_ref_golden.py imports /root/reference/modules.py,
+     unet3d.py, gaussian_diffusion.py and utils.py unmodified over oracle/refshim (a numpy restatement of the jax /
+     flax.nnx calls they make) and records the Unet3D forward, the diffusion methods, the stand-alone modules and the
+     state tree; tests/test_oracle_vs_reference_code.py holds this oracle to those fixtures at 1e-9 (float64). That
+     pins graph wiring, argument plumbing, dead-code behaviours, the diffusion algebra, names / shapes / count of the
+     parameters - everything a re-reading can get wrong.
+  2. every closed-form known answer the reference's tests hold for this path (tests/test_oracle_known_answers.py);
+  3. the flax layer semantics re-derived from definition in numpy (tests/test_oracle_semantics.py).
+What remains UNPINNED: the numerics INSIDE the flax layers and jax.nn functions as XLA evaluates them (conv
+accumulation order, transcendental implementations) - restated from the public flax / jax definitions, twice, by
+different routes (torch calls here, explicit dilate / pad / shifted-slice matmuls in refshim).
 
 Restates, in plain PyTorch on CPU (fp32 or fp64), the EFFECTIVE graph of
   unet3d.py:262-387   Unet3D.__call__
