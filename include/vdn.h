@@ -338,6 +338,31 @@ int vdn_adam_ema_clip(float* p, const float* g, float* m, float* v, float* ema, 
                       const float* sqnorm_dev, long n, void* stream);
 
 /* ---------------------------------------------------------------------------------
+ * fp32-grade forward path (north_star: loss and predicted noise within 1e-3 of the fp32 reference; modules.py computes
+ * in float32 throughout). Activations stay fp32; every GEMM is a split-bf16 product on the SAME tcgen05 tap-GEMM:
+ *   x w ~= [x_hi | x_lo] [w_hi ; w_hi] + x_hi w_lo,  hi = bf16(v), lo = bf16(v - hi)
+ * = vdn_tapgemm with the (hi, lo) pair as its two K-concatenated sources and fp32 output, then a second vdn_tapgemm
+ * accumulating through the residual operand. These entry points supply the rest: the split (with optional channel
+ * concat of two sources, unet3d.py:346,377), GroupNorm statistics / apply + SiLU (modules.py:171-179), the ResnetBlock
+ * tail (modules.py:241-242), the SpatialLinearAttention core (modules.py:105-123), init / final convs
+ * (unet3d.py:110-115, :251). The MultiheadAttention core is vdn_mha_core_ext_fwd with dtype VDN_F32.
+ * sums: double [B][G][2] = (sum x, sum x^2). Forward only.
+ * --------------------------------------------------------------------------------- */
+/* weights: hi = float(bf16(w)), lo = w - hi as fp32 tensors, the sources vdn_pack_weight packs into w_hi / w_lo */
+int vdn_f32_hilo(const float* src, float* hi, float* lo, long n, void* stream);
+int vdn_f32_split(const float* src0, const float* src1, void* hi, void* lo, long P, int C0, int C1, void* stream);
+int vdn_f32_gn_stats(const float* x, double* sums, int B, int rows_per_sample, int C, int G, void* stream);
+int vdn_f32_gn_silu(const float* x, const double* sums, const float* gamma, const float* beta, const float* scale_shift,
+                    int ss_ld, float* out, int B, int rows_per_sample, int C, int G, void* stream);
+int vdn_f32_tail(const float* b_raw, const double* sums, const float* gamma, const float* beta, const float* s,
+                 const float* ln_gamma, const float* ln_beta, float* out, int B, int rows_per_sample, int C, int G,
+                 void* stream);
+int vdn_f32_sla_core(const float* qkv, float* tok_out, float* ctx, int n_img, int N, void* stream);
+int vdn_f32_init_conv(const float* x, const float* w, const float* bias, float* out, int B, int Cin, int F, int H, int W,
+                      int Cout, int ks, void* stream);
+int vdn_f32_final_conv(const float* h, const float* w, const float* bias, float* out, long P, int C, int Co, void* stream);
+
+/* ---------------------------------------------------------------------------------
  * Scratch sizes. Every buffer (operands, results, scratch) is allocated and owned by the caller (XLA allocates
  * scratch as an extra result of the custom call); these return the BYTES of the scratch argument of the
  * entry point of the same name. Ops not listed need none.

@@ -32,7 +32,14 @@ class Unet3D:
     def __init__(self, dim: int, rngs=0, dim_mults=(1, 2, 4, 8), cond_dim=None, out_dim=None, channels: int = 3,
                  attn_heads: int = 8, attn_dim_head: int = 32, use_bert_text_cond: bool = False, init_dim=None,
                  init_kernel_size: int = 7, use_sparse_linear_attn: bool = True, block_type: str = "resnet",
-                 resnet_groups: int = 8, log_dims: bool = False, device="cuda"):
+                 resnet_groups: int = 8, log_dims: bool = False, device="cuda", precision: str = "bf16"):
+        """Reference constructor arguments (unet3d.py:58-75) + `device` and `precision`: "bf16" = the tensor-core
+        throughput path (bf16 activations / operands, fp32 accumulation), "fp32" = the fp32-grade forward path
+        (engine_f32.py: fp32 activations, split-bf16 operands on the same tcgen05 kernels; forward only, used for
+        evaluation / parity at the reference's own float32 precision)."""
+        if precision not in ("bf16", "fp32"):
+            raise ValueError("precision must be 'bf16' or 'fp32'")
+        self.precision = precision
         if cond_dim is not None or use_bert_text_cond:
             raise NotImplementedError("text conditioning is outside the accelerated hot path (SURVEY.md C7)")
         if attn_heads != HEADS or attn_dim_head != DIM_HEAD:
@@ -64,6 +71,7 @@ class Unet3D:
                                         self.use_sparse_linear_attn)
         self.store: Optional[ParamStore] = None
         self._engines: Dict[tuple, UnetEngine] = {}
+        self._f32_engines: Dict[tuple, object] = {}
         self._host_state = self._init_state(_seed_of(rngs))
         self.training = False
 
@@ -295,7 +303,22 @@ class Unet3D:
         B, _, Fr, H, W = x.shape
         x = x.to(device=self.device, dtype=torch.float32).contiguous()
         time = time.to(device=self.device, dtype=torch.int32).contiguous()
+        if self.precision == "fp32" and not self.training:
+            return self.forward_fp32(x, time)
         return self.engine(B, Fr, H, W).forward(x, time)
+
+    def forward_fp32(self, x: torch.Tensor, time: torch.Tensor) -> torch.Tensor:
+        """The same forward at the reference's float32 precision (engine_f32.F32Engine): (b c f h w) -> (b f h w c)."""
+        from .engine_f32 import F32Engine
+
+        B, _, Fr, H, W = x.shape
+        x = x.to(device=self.device, dtype=torch.float32).contiguous()
+        time = time.to(device=self.device, dtype=torch.int32).contiguous()
+        self._ensure_store(False)
+        key = (B, Fr, H, W)
+        if key not in self._f32_engines:
+            self._f32_engines[key] = F32Engine(self, B, Fr, H, W)
+        return self._f32_engines[key].forward(x, time)
 
     def forward_with_cond_scale(self, *args, cond_scale: float = 2.0, **kwargs):
         """unet3d.py:254-260: without conditioning this is exactly one forward."""
