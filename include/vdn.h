@@ -106,6 +106,8 @@ int vdn_tapgemm(const vdn_tapgemm_desc* d, const void* src0, const void* src1, c
 /* Debug only: device buffer of 8*3*64 int64 that the row-ring (1,3,3) conv kernel stamps with clock64()
  * for its first 8 CTAs (producer / MMA / epilogue timelines); NULL switches it off. */
 void vdn_debug_rowconv_trace(void* dev_buf);
+/* Same for the generic tap-GEMM kernel: 4 x 64 int64 (producer 0 / producer 1 / MMA issuer per K step; epilogue). */
+void vdn_debug_tapgemm_trace(void* dev_buf);
 
 int vdn_tapgemm_ref(const vdn_tapgemm_desc* d, const void* src0, const void* src1, const void* wp,
                     const float* bias, const void* residual, const void* residual2, void* out, void* out2,

@@ -917,9 +917,13 @@ extern "C" int vdn_gn_silu_bwd(const void* dy, const void* x_raw, const float* g
   }
   const int pl_n = kNormThreads / (C / 8);
   int gx, cl;
-  // chunks per block: 1 until the launch exceeds ~2 waves of 8 blocks per SM, then up to 8 (large samples)
+  // Chunks per block. These kernels hold two blocks per SM (register budget), i.e. 296 blocks in flight, and a block
+  // is three dependent global round trips (statistics, data, atomics): more than ~1.4 waves of one-chunk blocks costs
+  // more than folding the extra waves into the blocks (measured, tools/tune_gn.py, 64x64 / 32x32 levels of
+  // config_v2_2: 640 blocks 32.8 us with 1 chunk, 26.6 us with 3; 320 blocks 24.6 -> 20.8 us; at <= 160 blocks extra
+  // chunks only lengthen the one wave). Up to 8 for large samples.
   const long blocks1 = (long)grid_x_for(rows_per_sample, pl_n * kVecPerThread) * B;
-  int iters = (int)std::max<long>(1, std::min<long>(8, blocks1 / (2 * 8 * num_sms())));
+  int iters = (int)std::max<long>(1, std::min<long>(8, (2 * blocks1 + 213) / (2 * 213)));
   if (tune_is_set("VDN_GN_ITERS")) iters = std::max(1, std::min(16, tune_int("VDN_GN_ITERS", iters)));  // experiments
   cl = cluster_for(grid_x_for(rows_per_sample, pl_n * kVecPerThread * iters), &gx);
   const size_t smem_r = (6 * C + kNormThreads * 16) * sizeof(float);

@@ -22,7 +22,13 @@ namespace vdn {
 
 constexpr int kTileM = 128;
 constexpr int kMaxStages = 8;
-constexpr int kGemmThreads = 192;
+// Epilogue warps of the one-tile kernel: 4 (one per TMEM lane quarter). Eight (two per quarter, half the columns each)
+// drain a tile faster - 9.8 instead of 11.4 us on the 8x8-level conv - but 320 threads x 130 registers leave room for
+// ONE CTA per SM, and every launch with more CTAs than SMs lost its co-resident partner (16x16 level 11.8 -> 16.2 us,
+// training step 6.69 -> 7.34 ms): not kept.
+constexpr int kEpiWarps = 4;
+constexpr int kEpiThreads = 32 * kEpiWarps;
+constexpr int kGemmThreads = 64 + kEpiThreads;     // warps: 0 TMA producer, 1 MMA issuer, 2.. epilogue
 
 struct TapMaps {
   CUtensorMap a[4];
@@ -52,6 +58,7 @@ struct TapArgs {
   float* gn_sums;
   int gn_groups, cpg, rows_per_sample, n_samples;
   int n_ntiles, n_items, stg_bufs;  // persistent kernel: (M tile, N tile) items, staging buffers
+  long long* trace;  // debug (vdn_debug_tapgemm_trace): clock64 stamps of CTA (0,0): [4][64] = producer0 / producer1 / MMA / epilogue
 };
 
 // ---------------------------------------------------------------------------------------
@@ -102,7 +109,7 @@ __device__ __forceinline__ void gn_accumulate16_warp(const float (&v)[16], bool 
 }
 
 template <int BK>
-__global__ void __launch_bounds__(kGemmThreads) tapgemm_kernel(const __grid_constant__ TapMaps maps,
+__global__ void __launch_bounds__(kGemmThreads, 4) tapgemm_kernel(const __grid_constant__ TapMaps maps,
                                                                const TapArgs args) {
   constexpr int kSwizzle = BK * 2;                 // bytes per smem row == swizzle span
   constexpr int kABytes = kTileM * BK * 2;         // 16 KB / 8 KB / 4 KB
@@ -114,7 +121,8 @@ __global__ void __launch_bounds__(kGemmThreads) tapgemm_kernel(const __grid_cons
   __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
   __shared__ __align__(8) uint64_t tmem_full_bar;
   __shared__ uint32_t tmem_base_smem;
-  __shared__ float s_gn[4][16];  // per epilogue warp: (sum, sumsq) of up to 8 groups of this N tile
+  __shared__ float s_gn[kEpiWarps][16];  // per epilogue warp: (sum, sumsq) of up to 8 groups of this N tile
+  __shared__ float s_bias[256];  // bias row of this N tile
 
   // warp-uniform role index (shfl broadcast): keeps the producer / MMA loops on the uniform datapath
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
@@ -153,29 +161,34 @@ __global__ void __launch_bounds__(kGemmThreads) tapgemm_kernel(const __grid_cons
 
   if (warp == 0) {
     // ================= TMA producer =================
-    // One elected lane issues; `elect_one` (not `lane == 0`) lets the compiler treat the region as a single
-    // thread, so descriptors / coordinates stay in uniform registers instead of per-instruction waterfall loops.
+    // One elected lane per producer warp issues; `elect_one` (not `lane == 0`) lets the compiler treat the region as a
+    // single thread, so descriptors / coordinates stay in uniform registers instead of per-instruction waterfall loops.
     if (elect_one()) {
+      // one producer thread: a second producer warp on alternate steps measured no gain - the K loop is bound by the
+      // tensor pipe (220 cycles per step against a 208-cycle floor, tools/trace_tapgemm.py)
       const int hw = args.H * args.W;
       const int n0 = m0 / hw;
       const int rem = m0 - n0 * hw;
       const int y0 = rem / args.W;
       const int x0 = rem - y0 * args.W;
       const uint32_t tx_bytes = (uint32_t)(kABytes + BN * BK * 2);
-      int st = 0, kcol = 0;
+      int st = 0, kcol = 0, step = 0;
       uint32_t ph = 1u;  // parity to wait for on the empty barrier of the slot
       for (int t = 0; t < args.n_taps; ++t) {
         const int cx = x0 + args.tap_dx[t];
         const int cy = y0 + args.tap_dy[t];
         for (int s = 0; s < args.n_src; ++s) {
           const CUtensorMap* am = &maps.a[args.tap_map[t] + s];
-          for (int c = 0; c < args.chunks; ++c) {
-            mbar_wait(&empty_bar[st], ph);
-            uint8_t* sa = smem + st * stage_bytes;
-            uint8_t* sb = sa + kABytes;
-            mbar_expect_tx(&full_bar[st], tx_bytes);
-            tma_load_4d(sa, am, &full_bar[st], c * BK, cx, cy, n0);
-            tma_load_2d(sb, &maps.b, &full_bar[st], kcol, n_tile * BN);
+          for (int c = 0; c < args.chunks; ++c, ++step) {
+            {
+              mbar_wait(&empty_bar[st], ph);
+              if (args.trace && blockIdx.x == 0 && blockIdx.y == 0 && step < 64) args.trace[(step & 1) * 64 + step] = clock64();
+              uint8_t* sa = smem + st * stage_bytes;
+              uint8_t* sb = sa + kABytes;
+              mbar_expect_tx(&full_bar[st], tx_bytes);
+              tma_load_4d(sa, am, &full_bar[st], c * BK, cx, cy, n0);
+              tma_load_2d(sb, &maps.b, &full_bar[st], kcol, n_tile * BN);
+            }
             kcol += BK;
             if (++st == S) {
               st = 0;
@@ -199,6 +212,7 @@ __global__ void __launch_bounds__(kGemmThreads) tapgemm_kernel(const __grid_cons
       uint32_t a_lo = a_lo0;
       for (int it = 0; it < n_steps; ++it) {
         mbar_wait(&full_bar[st], ph);
+        if (args.trace && blockIdx.x == 0 && blockIdx.y == 0 && it < 64) args.trace[2 * 64 + it] = clock64();
         tc_fence_after();
         const uint32_t b_lo = a_lo + (uint32_t)(kABytes >> 4);
 #pragma unroll
@@ -219,18 +233,29 @@ __global__ void __launch_bounds__(kGemmThreads) tapgemm_kernel(const __grid_cons
     }
     __syncwarp();
   } else {
-    // ================= epilogue (warps 2..5) =================
+    // ================= epilogue (warps 2..) =================
+    // A one-tile CTA has nothing to overlap its epilogue with: on the 36-step K loops of the 8x8 level it used to be
+    // 6900 of the CTA's 16200 cycles (tools/trace_tapgemm.py) - bias loads from global memory behind every TMEM load,
+    // a TMEM wait per 32 columns, divisions in the write-out loop. Now the bias row of the tile is staged in shared
+    // memory while the K loop runs, the TMEM load of the next 32 columns is in flight while the current 32 are
+    // processed, and the write-out indexes with shifts. (With kEpiWarps = 8, two warps share a TMEM lane quarter and
+    // drain half of the columns each.)
+    const int ew = warp - 2;       // 0..kEpiWarps-1
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    const int chalf = ew >> 2;     // which half of the columns (kEpiWarps = 8, tiles of >= 64 columns)
     const int r = quarter * 32 + lane;
     const int m = m0 + r;
     const bool valid = m < args.M;
-    const int et = threadIdx.x - 64;  // epilogue thread id 0..127
-    if (et < 64) s_gn[et >> 4][et & 15] = 0.f;
-    asm volatile("bar.sync 1, 128;" ::: "memory");
+    const int et = threadIdx.x - 64;  // epilogue thread id 0..255
+    const int col_base = n_tile * BN;
+    if (et < 16 * kEpiWarps) s_gn[et >> 4][et & 15] = 0.f;
+    for (int c = et; c < BN; c += kEpiThreads) s_bias[c] = args.bias ? __ldg(args.bias + col_base + c) : 0.f;
+    asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+    if (args.trace && blockIdx.x == 0 && blockIdx.y == 0 && et == 0) args.trace[3 * 64 + 0] = clock64();
     mbar_wait(&tmem_full_bar, 0);
+    if (args.trace && blockIdx.x == 0 && blockIdx.y == 0 && et == 0) args.trace[3 * 64 + 1] = clock64();
     tc_fence_after();
 
-    const int col_base = n_tile * BN;
     uint8_t* outp;
     const uint8_t* resp;
     int ld, col_o;
@@ -276,78 +301,104 @@ __global__ void __launch_bounds__(kGemmThreads) tapgemm_kernel(const __grid_cons
     const int pitch = BN * esz + 16;          // smem row pitch of the staged tile (bytes)
     uint8_t* srow = smem + (size_t)r * pitch;
     const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    // columns of this warp: half of the tile (tiles below 64 columns are drained by the first warp of the quarter)
+    const bool halves = kEpiWarps == 8 && BN >= 64;
+    const int cb = halves ? chalf * (BN >> 1) : 0;
+    const int ce = halves ? cb + (BN >> 1) : (chalf == 0 ? BN : 0);
 
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      uint32_t raw[32];
-      const bool wide = (BN - c0) >= 32;
-      if (wide) {
-        tmem_ld_32x32(taddr + (uint32_t)c0, raw);
-      } else {
-        tmem_ld_32x16(taddr + (uint32_t)c0, *reinterpret_cast<uint32_t(*)[16]>(&raw[0]));
+    // processes 16 consecutive accumulator columns starting at tile column cl
+    auto process16 = [&](const uint32_t* raw16, int cl) {
+      float v[16];
+      const int cg = col_base + cl;  // global output column of v[0]
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw16[j]) + s_bias[cl + j];
+      if (gn_on) {
+        const int cpg = args.cpg;
+        if (gn_wide) {
+          // per-thread partial sums over the whole tile (four independent chains per 16 columns), ONE 16-shuffle
+          // warp reduction after the column loop: a shuffle reduction per chunk sits on the serial path of the epilogue
+          float p1[4], p2[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float x = valid ? v[q] : 0.f;
+            p1[q] = x;
+            p2[q] = x * x;
+          }
+#pragma unroll
+          for (int j = 4; j < 16; ++j) {
+            const float x = valid ? v[j] : 0.f;
+            p1[j & 3] += x;
+            p2[j & 3] = fmaf(x, x, p2[j & 3]);
+          }
+          const float s1 = (p1[0] + p1[1]) + (p1[2] + p1[3]), s2 = (p2[0] + p2[1]) + (p2[2] + p2[3]);
+          const int g = cl >> cpg_log;  // group within this N tile (warp-uniform)
+#pragma unroll
+          for (int gi = 0; gi < 8; ++gi)
+            if (gi == g) {
+              ga[2 * gi] += s1;
+              ga[2 * gi + 1] += s2;
+            }
+        } else if (gn_cta) {
+          float* slot = &s_gn[ew][2 * (cg / cpg - g_tile0)];
+          if (cpg >= 16) gn_accumulate16_warp<16>(v, valid, slot, lane);
+          else if (cpg == 8) gn_accumulate16_warp<8>(v, valid, slot, lane);
+          else if (cpg == 4) gn_accumulate16_warp<4>(v, valid, slot, lane);
+          else gn_accumulate16_warp<2>(v, valid, slot, lane);
+        } else {
+          float* base = gdst + 2 * (cg / cpg);
+          if (cpg >= 16) gn_accumulate16<16>(v, valid, base, 0, lane);
+          else if (cpg == 8) gn_accumulate16<8>(v, valid, base, 0, lane);
+          else if (cpg == 4) gn_accumulate16<4>(v, valid, base, 0, lane);
+          else gn_accumulate16<2>(v, valid, base, 0, lane);
+        }
       }
-      tmem_ld_wait();
+      if (staged) {
+        if (args.out_f32) {
+          float4* sp = reinterpret_cast<float4*>(srow + cl * 4);
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        if (h == 1 && !wide) break;
-        float v[16];
-        const int cl = c0 + h * 16;        // column inside the tile
-        const int cg = col_base + cl;      // global output column of v[0]
+          for (int j = 0; j < 4; ++j) sp[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        } else {
+          uint4* sp = reinterpret_cast<uint4*>(srow + cl * 2);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[h * 16 + j]);
-        if (args.bias) {
-#pragma unroll
-          for (int j = 0; j < 16; j += 4) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(args.bias + cg + j));
-            v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+          for (int j = 0; j < 2; ++j) {
+            uint4 q;
+            q.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
+            q.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+            q.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+            q.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+            sp[j] = q;
           }
         }
-        if (gn_on) {
-          const int cpg = args.cpg;
-          if (gn_wide) {
-            // per-thread partial sums over the whole tile (four independent chains per 16 columns), ONE 16-shuffle
-            // warp reduction after the column loop: a shuffle reduction per chunk sits on the serial path of the epilogue
-            float p1[4], p2[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const float x = valid ? v[q] : 0.f;
-              p1[q] = x;
-              p2[q] = x * x;
-            }
-#pragma unroll
-            for (int j = 4; j < 16; ++j) {
-              const float x = valid ? v[j] : 0.f;
-              p1[j & 3] += x;
-              p2[j & 3] = fmaf(x, x, p2[j & 3]);
-            }
-            const float s1 = (p1[0] + p1[1]) + (p1[2] + p1[3]), s2 = (p2[0] + p2[1]) + (p2[2] + p2[3]);
-            const int g = cl >> cpg_log;  // group within this N tile (warp-uniform)
-#pragma unroll
-            for (int gi = 0; gi < 8; ++gi)
-              if (gi == g) {
-                ga[2 * gi] += s1;
-                ga[2 * gi + 1] += s2;
-              }
-          } else if (gn_cta) {
-            float* slot = &s_gn[warp - 2][2 * (cg / cpg - g_tile0)];
-            if (cpg >= 16) gn_accumulate16_warp<16>(v, valid, slot, lane);
-            else if (cpg == 8) gn_accumulate16_warp<8>(v, valid, slot, lane);
-            else if (cpg == 4) gn_accumulate16_warp<4>(v, valid, slot, lane);
-            else gn_accumulate16_warp<2>(v, valid, slot, lane);
-          } else {
-            float* base = gdst + 2 * (cg / cpg);
-            if (cpg >= 16) gn_accumulate16<16>(v, valid, base, 0, lane);
-            else if (cpg == 8) gn_accumulate16<8>(v, valid, base, 0, lane);
-            else if (cpg == 4) gn_accumulate16<4>(v, valid, base, 0, lane);
-            else gn_accumulate16<2>(v, valid, base, 0, lane);
-          }
-        }
-        if (staged) {
+      } else {
+        const long eoff = orow * ld + (col_o + cl);
+        if (resp && valid) {
           if (args.out_f32) {
-            float4* sp = reinterpret_cast<float4*>(srow + cl * 4);
+            const float4* rp = reinterpret_cast<const float4*>(resp + eoff * 4);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) sp[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            for (int j = 0; j < 4; ++j) {
+              const float4 q = rp[j];
+              v[4 * j] += q.x; v[4 * j + 1] += q.y; v[4 * j + 2] += q.z; v[4 * j + 3] += q.w;
+            }
           } else {
-            uint4* sp = reinterpret_cast<uint4*>(srow + cl * 2);
+            const uint4* rp = reinterpret_cast<const uint4*>(resp + eoff * 2);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              const uint4 q = rp[j];
+              float2 f;
+              f = unpack_bf16x2(q.x); v[8 * j + 0] += f.x; v[8 * j + 1] += f.y;
+              f = unpack_bf16x2(q.y); v[8 * j + 2] += f.x; v[8 * j + 3] += f.y;
+              f = unpack_bf16x2(q.z); v[8 * j + 4] += f.x; v[8 * j + 5] += f.y;
+              f = unpack_bf16x2(q.w); v[8 * j + 6] += f.x; v[8 * j + 7] += f.y;
+            }
+          }
+        }
+        if (valid) {
+          if (args.out_f32) {
+            float4* op = reinterpret_cast<float4*>(outp + eoff * 4);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          } else {
+            uint4* op = reinterpret_cast<uint4*>(outp + eoff * 2);
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
               uint4 q;
@@ -355,64 +406,48 @@ __global__ void __launch_bounds__(kGemmThreads) tapgemm_kernel(const __grid_cons
               q.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
               q.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
               q.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
-              sp[j] = q;
-            }
-          }
-        } else {
-          const long eoff = orow * ld + (col_o + cl);
-          if (resp && valid) {
-            if (args.out_f32) {
-              const float4* rp = reinterpret_cast<const float4*>(resp + eoff * 4);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float4 q = rp[j];
-                v[4 * j] += q.x; v[4 * j + 1] += q.y; v[4 * j + 2] += q.z; v[4 * j + 3] += q.w;
-              }
-            } else {
-              const uint4* rp = reinterpret_cast<const uint4*>(resp + eoff * 2);
-#pragma unroll
-              for (int j = 0; j < 2; ++j) {
-                const uint4 q = rp[j];
-                float2 f;
-                f = unpack_bf16x2(q.x); v[8 * j + 0] += f.x; v[8 * j + 1] += f.y;
-                f = unpack_bf16x2(q.y); v[8 * j + 2] += f.x; v[8 * j + 3] += f.y;
-                f = unpack_bf16x2(q.z); v[8 * j + 4] += f.x; v[8 * j + 5] += f.y;
-                f = unpack_bf16x2(q.w); v[8 * j + 6] += f.x; v[8 * j + 7] += f.y;
-              }
-            }
-          }
-          if (valid) {
-            if (args.out_f32) {
-              float4* op = reinterpret_cast<float4*>(outp + eoff * 4);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-            } else {
-              uint4* op = reinterpret_cast<uint4*>(outp + eoff * 2);
-#pragma unroll
-              for (int j = 0; j < 2; ++j) {
-                uint4 q;
-                q.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
-                q.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
-                q.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
-                q.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
-                op[j] = q;
-              }
+              op[j] = q;
             }
           }
         }
       }
+    };
+
+    if (cb < ce) {
+      // software pipeline over 16-column chunks: the TMEM load of the next chunk is in flight while the current one is
+      // processed. (Two 32-column buffers would be one TMEM instruction fewer per pair, but cost 32 more registers: at
+      // 130 registers only two CTAs fit on an SM instead of four, and every launch with more CTAs than SMs slowed down -
+      // training step 6.69 -> 6.99 ms. This version stays within the register budget of four co-resident CTAs.)
+      uint32_t raw_a[16], raw_b[16];
+      tmem_ld_32x16(taddr + (uint32_t)cb, raw_a);
+      for (int c0 = cb; c0 < ce; c0 += 32) {
+        tmem_ld_wait();
+        const bool two = c0 + 16 < ce;
+        if (two) tmem_ld_32x16(taddr + (uint32_t)(c0 + 16), raw_b);
+        process16(raw_a, c0);
+        if (two) {
+          tmem_ld_wait();
+          if (c0 + 32 < ce) tmem_ld_32x16(taddr + (uint32_t)(c0 + 32), raw_a);
+          process16(raw_b, c0 + 16);
+        }
+      }
     }
+    if (args.trace && blockIdx.x == 0 && blockIdx.y == 0 && et == 0) args.trace[3 * 64 + 4] = clock64();
     if (gn_wide) {
       const float tot = warp_sum16(ga, lane);
-      if ((lane & 1) == 0) s_gn[warp - 2][lane >> 1] = tot;
+      if ((lane & 1) == 0) s_gn[ew][lane >> 1] = tot;
     }
     if (staged) {
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+      if (args.trace && blockIdx.x == 0 && blockIdx.y == 0 && et == 0) args.trace[3 * 64 + 5] = clock64();
       // coalesced write-out: consecutive threads store consecutive 16-byte segments of a row
       const int spr = (BN * esz) >> 4;  // 16B segments per row
       const int total = kTileM * spr;
-      for (int idx = et; idx < total; idx += 128) {
-        const int rr = idx / spr, sg = idx - rr * spr;
+      const bool spr_pow2 = (spr & (spr - 1)) == 0;
+      const int spr_log = 31 - __clz(spr);
+      for (int idx = et; idx < total; idx += kEpiThreads) {
+        const int rr = spr_pow2 ? (idx >> spr_log) : idx / spr;
+        const int sg = idx - rr * spr;
         const int mm = m0 + rr;
         if (mm >= args.M) break;
         uint4 q = *reinterpret_cast<const uint4*>(smem + (size_t)rr * pitch + sg * 16);
@@ -434,17 +469,24 @@ __global__ void __launch_bounds__(kGemmThreads) tapgemm_kernel(const __grid_cons
         }
         *reinterpret_cast<uint4*>(outp + goff) = q;
       }
-      if (gn_cta && et < 2 * ((BN + args.cpg - 1) / args.cpg))
-        atomicAdd(gdst + 2 * g_tile0 + et, s_gn[0][et] + s_gn[1][et] + s_gn[2][et] + s_gn[3][et]);
+      if (args.trace && blockIdx.x == 0 && blockIdx.y == 0 && et == 0) args.trace[3 * 64 + 6] = clock64();
+      if (gn_cta && et < 2 * ((BN + args.cpg - 1) / args.cpg)) {
+        float tot = 0.f;
+#pragma unroll
+        for (int w8 = 0; w8 < kEpiWarps; ++w8) tot += s_gn[w8][et];
+        atomicAdd(gdst + 2 * g_tile0 + et, tot);
+      }
     }
   }
 
+  if (args.trace && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 64) args.trace[3 * 64 + 2] = clock64();
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, (uint32_t)args.tmem_cols);
   }
+  if (args.trace && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) args.trace[3 * 64 + 3] = clock64();
 }
 
 
@@ -970,6 +1012,8 @@ static int launch_tapgemm_persist(const TapMaps& maps, const TapArgs& args, int 
   return check_launch("tapgemm_persist_kernel");
 }
 
+static long long* g_tg_trace = nullptr;
+
 static int tg_env_int(const char* name, int dflt) {
   return tune_int(name, dflt);
 }
@@ -1043,6 +1087,7 @@ extern "C" int vdn_tapgemm(const vdn_tapgemm_desc* d, const void* src0, const vo
   a.rows_per_sample = d->rows_per_sample > 0 ? d->rows_per_sample : 1;
   a.n_samples = std::max(1, a.M / a.rows_per_sample);
   if (!gn_sums) a.gn_sums = nullptr;
+  a.trace = g_tg_trace;
   VDN_REQUIRE(!(gn_sums && residual), VDN_E_SHAPE, "tapgemm: gn_sums and residual are mutually exclusive");
 
   TapMaps maps;
@@ -1173,6 +1218,8 @@ extern "C" int vdn_tapgemm(const vdn_tapgemm_desc* d, const void* src0, const vo
   if (BK == 32) return launch_tapgemm<32>(maps, a, smem_bytes, st);
   return launch_tapgemm<16>(maps, a, smem_bytes, st);
 }
+
+extern "C" void vdn_debug_tapgemm_trace(void* dev_buf) { vdn::g_tg_trace = reinterpret_cast<long long*>(dev_buf); }
 
 extern "C" int vdn_tapgemm_ref(const vdn_tapgemm_desc* d, const void* src0, const void* src1, const void* wp,
                                const float* bias, const void* residual, const void* residual2, void* out,
