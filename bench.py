@@ -450,6 +450,8 @@ def main():
     ap.add_argument("--workload", default="v2_2", choices=["v2_2", "v2_3x"])
     ap.add_argument("--headline", default="train", choices=["train", "sampling"],
                     help="which of BASELINE.json's two metrics is the line's top-level metric / value")
+    ap.add_argument("--bucket-mb", type=float, default=None, help="gradient bucket size (MB) of the DP exchange")
+    ap.add_argument("--comm-ctas", type=int, default=None, help="cap on the CTAs NCCL may use for the gradient exchange")
     ap.add_argument("--cpu-baseline-worker", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
     select_workload(args.workload)
@@ -498,7 +500,9 @@ def main():
     ts = TrainStep(gd, batch_size=B, train_lr=CFG["lr"], lr_decay_start_step=CFG["lr_decay_start_step"],
                    lr_decay_steps=CFG["lr_decay_steps"], lr_decay_coeff=CFG["lr_decay_coeff"],
                    step_start_ema=0, update_ema_every=CFG["update_ema_every"], ema_decay=CFG["ema_decay"],
-                   use_graph=True, process_group=pg)
+                   use_graph=True, process_group=pg,
+                   **({"bucket_bytes": int(args.bucket_mb * (1 << 20))} if args.bucket_mb else {}),
+                   **({"comm_max_ctas": args.comm_ctas} if args.comm_ctas is not None else {}))
     shape = (B, CFG["channels"], CFG["frames"], CFG["size"], CFG["size"])
     g = torch.Generator().manual_seed(1234 + rank)
     K, Wm = args.steps, args.warmup

@@ -151,7 +151,7 @@ class TrainStep:
                  lr_decay_start_step: int = 0, lr_decay_steps: int = 0, lr_decay_coeff: float = 1.0,
                  step_start_ema: int = 2000, update_ema_every: int = 10, ema_decay: float = 0.9999,
                  max_grad_norm: Optional[float] = None, use_graph: bool = True, process_group=None,
-                 comm: Optional[Communicator] = None, comm_max_ctas: int = 16, bucket_bytes: int = 16 << 20):
+                 comm: Optional[Communicator] = None, comm_max_ctas: int = 4, bucket_bytes: int = 4 << 20):
         """batch_size is the PER-RANK batch (the shard of trainer.py:307-309). `process_group`: a torch.distributed
         group used only to exchange the NCCL unique id; `comm`: an existing Communicator instead."""
         self.gd = diffusion
