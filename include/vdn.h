@@ -101,12 +101,21 @@ typedef struct {
 int vdn_tapgemm(const vdn_tapgemm_desc* d, const void* src0, const void* src1, const void* wp, const float* bias,
                 const void* residual, const void* residual2, void* out, void* out2, float* gn_sums, void* stream);
 
+/* Same, with caller-owned scratch of >= vdn_tapgemm_workspace(d) bytes (16-byte aligned; contents undefined before and
+ * after; not to be shared by launches that may run concurrently on different streams). With it, launches whose output
+ * has too few 128-row tiles to fill the SMs (the 8x8 level of config_v2_2) split the K loop over thread-block clusters
+ * and reduce through the scratch; launches that need no scratch ignore it. workspace == NULL: as vdn_tapgemm. */
+int vdn_tapgemm_ws(const vdn_tapgemm_desc* d, const void* src0, const void* src1, const void* wp, const float* bias,
+                   const void* residual, const void* residual2, void* out, void* out2, float* gn_sums, void* workspace,
+                   size_t workspace_bytes, void* stream);
+
 /* Reference (non tensor-core) implementation of the same contract, used only by the GPU
  * tests to localise faults. Not on any product path. */
 /* Debug only: device buffer of 8*3*64 int64 that the row-ring (1,3,3) conv kernel stamps with clock64()
  * for its first 8 CTAs (producer / MMA / epilogue timelines); NULL switches it off. */
 void vdn_debug_rowconv_trace(void* dev_buf);
-/* Same for the generic tap-GEMM kernel: 4 x 64 int64 (producer 0 / producer 1 / MMA issuer per K step; epilogue). */
+/* Same for the generic / split-K tap-GEMM kernels: 1024 int64 = 4 x 64 clock64 stamps of CTA 0 (producer 0 / producer 1 /
+ * MMA issuer per K step; epilogue), then [256][3] global-timer stamps (prologue done, predecessor complete, exit) per CTA. */
 void vdn_debug_tapgemm_trace(void* dev_buf);
 
 int vdn_tapgemm_ref(const vdn_tapgemm_desc* d, const void* src0, const void* src1, const void* wp,
@@ -375,7 +384,7 @@ size_t vdn_gn_silu_bwd_workspace(int B, int C);            /* T_ws */
 size_t vdn_mha_core_bwd_workspace(long P);                 /* D_ws */
 size_t vdn_time_heads_bwd_workspace(int B, int ss_ld);     /* de_ws */
 size_t vdn_time_mlp_bwd_workspace(int B, int dim);         /* dh1_ws */
-size_t vdn_tapgemm_workspace(const vdn_tapgemm_desc* d);   /* 0: operands stream through shared memory / TMEM */
+size_t vdn_tapgemm_workspace(const vdn_tapgemm_desc* d);   /* scratch of vdn_tapgemm_ws; 0 when the launch does not split K */
 
 /* ---------------------------------------------------------------------------------
  * Data-parallel gradient exchange. The reference shards the batch over the `data`

@@ -20,14 +20,14 @@ ops.pack_weight(w, wp, 9, C, C, 0)
 out = torch.empty(n_img, H, H, C, dtype=torch.bfloat16, device=dev)
 bias = torch.zeros(C, device=dev)
 sums = torch.zeros(ops.GN_REPLICAS, 4, 8, 2, device=dev)
-trace = torch.zeros(4 * 64, dtype=torch.int64, device=dev)
+trace = torch.zeros(1024, dtype=torch.int64, device=dev)
 for rep in range(3):
     trace.zero_()
     lib.vdn_debug_tapgemm_trace(trace.data_ptr())
     ops.tapgemm(ops.VDN_TAP_UNIT, [x], wp, ops.TAPS_3x3, bias=bias, out=out, gn_sums=sums, gn_groups=8, rows_per_sample=10 * H * H)
     torch.cuda.synchronize()
     lib.vdn_debug_tapgemm_trace(None)
-tr = trace.view(4, 64).cpu()
+tr = trace[:256].view(4, 64).cpu()
 t0 = int(min(v for v in tr.flatten().tolist() if v))
 p0 = [(i, int(v) - t0) for i, v in enumerate(tr[0].tolist()) if v]
 p1 = [(i, int(v) - t0) for i, v in enumerate(tr[1].tolist()) if v]

@@ -615,6 +615,8 @@ static SeqMap make_seqmap(int mode, int B, int F, int HW) {
 
 extern "C" int vdn_mha_core_fwd(const void* qkv, void* o, float* lse, int mode, int B, int F, int HW, void* stream) {
   VDN_REQUIRE(qkv && o && lse && B > 0 && F > 0 && HW > 0 && (mode == 0 || mode == 1), VDN_E_SHAPE, "mha_core_fwd: bad args");
+  if (mode == 1 && mha_spatial_mma_applicable(HW) && !tune_on("VDN_MHA_SPATIAL_SCALAR"))
+    return mha_spatial_mma_fwd_launch(qkv, o, lse, B * F, HW, reinterpret_cast<cudaStream_t>(stream));
   const SeqMap m = make_seqmap(mode, B, F, HW);
   const long total = m.n_seq * m.S * kHeads * 2;
   mha_core_fwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
@@ -625,6 +627,8 @@ extern "C" int vdn_mha_core_fwd(const void* qkv, void* o, float* lse, int mode, 
 extern "C" int vdn_mha_core_bwd(const void* qkv, const void* o, const void* d_o, const float* lse, float* D_ws,
                                 void* dqkv, int mode, int B, int F, int HW, void* stream) {
   VDN_REQUIRE(qkv && o && d_o && lse && D_ws && dqkv && (mode == 0 || mode == 1), VDN_E_SHAPE, "mha_core_bwd: bad args");
+  if (mode == 1 && mha_spatial_mma_applicable(HW) && !tune_on("VDN_MHA_SPATIAL_SCALAR"))
+    return mha_spatial_mma_bwd_launch(qkv, o, d_o, lse, dqkv, B * F, HW, reinterpret_cast<cudaStream_t>(stream));
   const SeqMap m = make_seqmap(mode, B, F, HW);
   const long total = m.n_seq * m.S * kHeads * 2;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);

@@ -253,4 +253,3 @@ extern "C" size_t vdn_gn_silu_bwd_workspace(int B, int C) { return (size_t)B * C
 extern "C" size_t vdn_mha_core_bwd_workspace(long P) { return (size_t)P * 8 * sizeof(float); }
 extern "C" size_t vdn_time_heads_bwd_workspace(int B, int ss_ld) { return (size_t)B * ss_ld * sizeof(float); }
 extern "C" size_t vdn_time_mlp_bwd_workspace(int B, int dim) { return (size_t)B * 4 * dim * sizeof(float); }
-extern "C" size_t vdn_tapgemm_workspace(const vdn_tapgemm_desc*) { return 0; }

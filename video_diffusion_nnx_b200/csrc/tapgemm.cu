@@ -26,9 +26,9 @@ constexpr int kMaxStages = 8;
 // drain a tile faster - 9.8 instead of 11.4 us on the 8x8-level conv - but 320 threads x 130 registers leave room for
 // ONE CTA per SM, and every launch with more CTAs than SMs lost its co-resident partner (16x16 level 11.8 -> 16.2 us,
 // training step 6.69 -> 7.34 ms): not kept.
-constexpr int kEpiWarps = 4;
-constexpr int kEpiThreads = 32 * kEpiWarps;
-constexpr int kGemmThreads = 64 + kEpiThreads;     // warps: 0 TMA producer, 1 MMA issuer, 2.. epilogue
+// Both exist as template instances: EW = 4 with four co-resident CTAs per SM for launches with more CTAs than SMs, EW = 8
+// with one CTA per SM (no register cap, no spills) for launches that cannot fill the SMs anyway (the small-M levels).
+constexpr int kEpiWarpsWide = 8;
 
 struct TapMaps {
   CUtensorMap a[4];
@@ -58,7 +58,10 @@ struct TapArgs {
   float* gn_sums;
   int gn_groups, cpg, rows_per_sample, n_samples;
   int n_ntiles, n_items, stg_bufs;  // persistent kernel: (M tile, N tile) items, staging buffers
-  long long* trace;  // debug (vdn_debug_tapgemm_trace): clock64 stamps of CTA (0,0): [4][64] = producer0 / producer1 / MMA / epilogue
+  int splits;        // split-K kernel: K ranges per output tile = cluster size along z
+  float* ws;         // split-K kernel: fp32 partial tiles [splits][m_tiles][n_tiles][128][BN]
+  long long* trace;  // debug (vdn_debug_tapgemm_trace), 1024 entries: clock64 stamps of CTA (0,0): [4][64] = producer0 / producer1 / MMA /
+                     // epilogue, then [256][3] global-timer stamps (prologue done, predecessor complete, exit) of the first 256 CTAs
 };
 
 // ---------------------------------------------------------------------------------------
@@ -108,9 +111,10 @@ __device__ __forceinline__ void gn_accumulate16_warp(const float (&v)[16], bool 
   }
 }
 
-template <int BK>
-__global__ void __launch_bounds__(kGemmThreads, 4) tapgemm_kernel(const __grid_constant__ TapMaps maps,
-                                                               const TapArgs args) {
+template <int BK, int kEpiWarps>
+__global__ void __launch_bounds__(64 + 32 * kEpiWarps, kEpiWarps == 8 ? 1 : 4)
+tapgemm_kernel(const __grid_constant__ TapMaps maps, const TapArgs args) {
+  constexpr int kEpiThreads = 32 * kEpiWarps;      // warps: 0 TMA producer, 1 MMA issuer, 2.. epilogue
   constexpr int kSwizzle = BK * 2;                 // bytes per smem row == swizzle span
   constexpr int kABytes = kTileM * BK * 2;         // 16 KB / 8 KB / 4 KB
   constexpr uint32_t kLayout = umma_layout_type(kSwizzle);
@@ -157,7 +161,12 @@ __global__ void __launch_bounds__(kGemmThreads, 4) tapgemm_kernel(const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  // debug timeline of every CTA (global timer, ns): prologue done / predecessor complete / exit
+  const int trace_cta = blockIdx.y * gridDim.x + blockIdx.x;
+  const bool trace_on = args.trace != nullptr && threadIdx.x == 0 && trace_cta < 256;
+  if (trace_on) args.trace[256 + 3 * trace_cta] = (long long)globaltimer_ns();
   pdl_wait();  // the prologue above overlapped the previous kernel's tail; global memory is touched below
+  if (trace_on) args.trace[256 + 3 * trace_cta + 1] = (long long)globaltimer_ns();
 
   if (warp == 0) {
     // ================= TMA producer =================
@@ -487,6 +496,7 @@ __global__ void __launch_bounds__(kGemmThreads, 4) tapgemm_kernel(const __grid_c
     tmem_dealloc(tmem_base, (uint32_t)args.tmem_cols);
   }
   if (args.trace && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) args.trace[3 * 64 + 3] = clock64();
+  if (trace_on) args.trace[256 + 3 * trace_cta + 2] = (long long)globaltimer_ns();
 }
 
 
@@ -778,6 +788,311 @@ __global__ void __launch_bounds__(kPersistThreads) tapgemm_persist_kernel(const 
 }
 
 // ---------------------------------------------------------------------------------------
+// Split-K variant for the small-M levels (the 8x8 level of config_v2_2: M = 2560 = 20 row tiles against 148 SMs).
+// With one CTA per output tile those launches either leave half of the SMs idle or cut N into 64-column tiles,
+// which re-reads every activation tile N/64 times from L2 (the K loop then runs at the L2 -> SM rate of the chip,
+// tools/probe_smallm.py) and still leaves each CTA a 36-step serial K loop plus a full epilogue.
+// Here an output tile of 128 x BN (BN = 128 where N allows) belongs to a thread-block CLUSTER of `splits` CTAs, each
+// of which runs 1/splits of the K steps. The partial accumulators meet in an L2-resident fp32 workspace (plain
+// coalescable stores; DSMEM moves ~20 B/clk per SM and is far slower than L2 for 64 KB tiles), one cluster barrier
+// (release / acquire covers the global stores; the hardware co-schedules a cluster, so waiting is deadlock-free
+// whatever else shares the GPU), then every CTA finalises its own slice of the tile's ROWS: sum of the partials,
+// bias, GroupNorm partial sums, residual, conversion, store - the epilogue is split `splits` ways as well.
+// Warps: 0 TMA producer, 1 MMA issuer, 2-9 epilogue (two per TMEM lane quarter).
+// ---------------------------------------------------------------------------------------
+constexpr int kSplitEpiThreads = 256;
+constexpr int kSplitThreads = 64 + kSplitEpiThreads;
+
+template <int BK>
+__global__ void __launch_bounds__(kSplitThreads, 1) tapgemm_splitk_kernel(const __grid_constant__ TapMaps maps,
+                                                                         const TapArgs args) {
+  constexpr int kSwizzle = BK * 2;
+  constexpr int kABytes = kTileM * BK * 2;
+  constexpr uint32_t kLayout = umma_layout_type(kSwizzle);
+  constexpr uint32_t kSBO = 8 * kSwizzle;
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t tmem_full_bar;
+  __shared__ uint32_t tmem_base_smem;
+  __shared__ float s_gn[16];      // (sum, sumsq) of up to 8 groups of this N tile
+  __shared__ __align__(16) float s_bias[256];
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const int BN = args.BN;
+  const int b_bytes = (BN * BK * 2 + 1023) & ~1023;
+  const int stage_bytes = kABytes + b_bytes;
+  uint8_t* smem = smem_raw + (((smem_u32(smem_raw) + 1023u) & ~1023u) - smem_u32(smem_raw));
+
+  const int n_tile = blockIdx.x;
+  const int m_tile = blockIdx.y;
+  const int m0 = m_tile * kTileM;
+  const int split = blockIdx.z;  // == rank in the (1, 1, splits) cluster
+  const int S = args.stages;
+  const int n_steps = args.n_taps * args.n_src * args.chunks;
+  const int k_begin = (int)(((long)n_steps * split) / args.splits);
+  const int k_end = (int)(((long)n_steps * (split + 1)) / args.splits);
+  const int col_base = n_tile * BN;
+
+  pdl_trigger();
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < args.n_maps; ++i) tma_prefetch_desc(&maps.a[i]);
+    tma_prefetch_desc(&maps.b);
+    for (int s = 0; s < S; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&tmem_full_bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(&tmem_base_smem, (uint32_t)args.tmem_cols);
+    tmem_relinquish();
+  }
+  if (threadIdx.x < 16) s_gn[threadIdx.x] = 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+  const int trace_cta = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+  const bool trace_on = args.trace != nullptr && threadIdx.x == 0 && trace_cta < 256;
+  if (trace_on) args.trace[256 + 3 * trace_cta] = (long long)globaltimer_ns();
+  pdl_wait();
+  if (trace_on) args.trace[256 + 3 * trace_cta + 1] = (long long)globaltimer_ns();
+  const bool trace0 = args.trace != nullptr && trace_cta == 0;
+
+  float* part = args.ws + ((((size_t)split * gridDim.y + m_tile) * gridDim.x + n_tile) * kTileM) * BN;
+
+  if (warp == 0) {
+    // ================= TMA producer: K steps [k_begin, k_end) of the (tap, source, chunk) sequence =================
+    if (elect_one()) {
+      const int hw = args.H * args.W;
+      const int n0 = m0 / hw;
+      const int rem = m0 - n0 * hw;
+      const int y0 = rem / args.W;
+      const int x0 = rem - y0 * args.W;
+      const uint32_t tx_bytes = (uint32_t)(kABytes + BN * BK * 2);
+      const int per_tap = args.n_src * args.chunks;
+      int t = k_begin / per_tap;
+      int r2 = k_begin - t * per_tap;
+      int sidx = r2 / args.chunks;
+      int c = r2 - sidx * args.chunks;
+      int kcol = k_begin * BK;
+      int st = 0;
+      uint32_t ph = 1u;
+      for (int step = k_begin; step < k_end; ++step) {
+        mbar_wait(&empty_bar[st], ph);
+        uint8_t* sa = smem + st * stage_bytes;
+        mbar_expect_tx(&full_bar[st], tx_bytes);
+        tma_load_4d(sa, &maps.a[args.tap_map[t] + sidx], &full_bar[st], c * BK, x0 + args.tap_dx[t], y0 + args.tap_dy[t], n0);
+        tma_load_2d(sa + kABytes, &maps.b, &full_bar[st], kcol, col_base);
+        kcol += BK;
+        if (++c == args.chunks) {
+          c = 0;
+          if (++sidx == args.n_src) {
+            sidx = 0;
+            ++t;
+          }
+        }
+        if (++st == S) {
+          st = 0;
+          ph ^= 1u;
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (elect_one()) {
+      const uint32_t idesc = umma_idesc_bf16(kTileM, BN, 0, 0);
+      const uint32_t desc_hi = (kSBO >> 4) | (1u << 14) | (kLayout << 29);
+      const uint32_t stage16 = (uint32_t)stage_bytes >> 4;
+      const uint32_t a_lo0 = (smem_u32(smem) >> 4) | (1u << 16);
+      int st = 0;
+      uint32_t ph = 0u;
+      uint32_t a_lo = a_lo0;
+      const int n_my = k_end - k_begin;
+      for (int it = 0; it < n_my; ++it) {
+        mbar_wait(&full_bar[st], ph);
+        if (trace0 && it < 64) args.trace[2 * 64 + it] = clock64();
+        tc_fence_after();
+        const uint32_t b_lo = a_lo + (uint32_t)(kABytes >> 4);
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k)
+          umma_bf16(tmem_base, (static_cast<uint64_t>(desc_hi) << 32) | (a_lo + 2u * k),
+                    (static_cast<uint64_t>(desc_hi) << 32) | (b_lo + 2u * k), idesc, (it | k) != 0 ? 1u : 0u);
+        tc_commit(&empty_bar[st]);
+        a_lo += stage16;
+        if (++st == S) {
+          st = 0;
+          ph ^= 1u;
+          a_lo = a_lo0;
+        }
+      }
+      tc_commit(&tmem_full_bar);
+    }
+    __syncwarp();
+  } else {
+    // ================= epilogue, part 1: accumulator -> fp32 partial tile in the workspace =================
+    const int ew = warp - 2;
+    const int quarter = warp & 3;
+    const int chalf = ew >> 2;
+    const int r = quarter * 32 + lane;
+    const int et = threadIdx.x - 64;
+    for (int cc = et; cc < BN; cc += kSplitEpiThreads) s_bias[cc] = args.bias ? __ldg(args.bias + col_base + cc) : 0.f;
+    const int cb = BN >= 32 ? chalf * (BN >> 1) : 0;
+    const int ce = BN >= 32 ? cb + (BN >> 1) : (chalf == 0 ? BN : 0);
+    if (trace0 && et == 0) args.trace[3 * 64 + 0] = clock64();
+    mbar_wait(&tmem_full_bar, 0);
+    if (trace0 && et == 0) args.trace[3 * 64 + 1] = clock64();
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    float4* prow = reinterpret_cast<float4*>(part + (size_t)r * BN);
+    auto dump16 = [&](const uint32_t (&raw)[16], int cl) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        __stcg(prow + (cl >> 2) + j, make_float4(__uint_as_float(raw[4 * j]), __uint_as_float(raw[4 * j + 1]),
+                                                 __uint_as_float(raw[4 * j + 2]), __uint_as_float(raw[4 * j + 3])));
+    };
+    if (cb < ce) {
+      uint32_t raw_a[16], raw_b[16];
+      tmem_ld_32x16(taddr + (uint32_t)cb, raw_a);
+      for (int c0 = cb; c0 < ce; c0 += 32) {
+        tmem_ld_wait();
+        const bool two = c0 + 16 < ce;
+        if (two) tmem_ld_32x16(taddr + (uint32_t)(c0 + 16), raw_b);
+        dump16(raw_a, c0);
+        if (two) {
+          tmem_ld_wait();
+          if (c0 + 32 < ce) tmem_ld_32x16(taddr + (uint32_t)(c0 + 32), raw_a);
+          dump16(raw_b, c0 + 16);
+        }
+      }
+    }
+    if (trace0 && et == 0) args.trace[3 * 64 + 4] = clock64();
+  }
+
+  // every partial of this tile is in the workspace once all CTAs of the cluster have passed the barrier
+  tc_fence_before();
+  cluster_sync_all();
+
+  if (warp >= 2) {
+    // ================= epilogue, part 2: this CTA's row slice of the tile =================
+    const int et = threadIdx.x - 64;
+    if (trace0 && et == 0) args.trace[3 * 64 + 5] = clock64();
+    const int splits = args.splits;
+    const int row_lo = split == 0 ? 0 : ((kTileM * split) / splits) & ~7;
+    const int row_hi = split == splits - 1 ? kTileM : ((kTileM * (split + 1)) / splits) & ~7;
+    const int chunks_log = 31 - __clz(BN >> 2);  // 16-byte fp32 chunks per row (BN is a power of two)
+    const int chunk = et & ((1 << chunks_log) - 1);
+    const int rows_per_pass = kSplitEpiThreads >> chunks_log;
+    const int row_in_pass = et >> chunks_log;
+    uint8_t* outp;
+    const uint8_t* resp;
+    int ld, col_o;
+    if (args.split_col > 0 && col_base >= args.split_col) {
+      outp = reinterpret_cast<uint8_t*>(args.out2);
+      resp = reinterpret_cast<const uint8_t*>(args.res2);
+      ld = args.ld_out2;
+      col_o = col_base - args.split_col;
+    } else {
+      outp = reinterpret_cast<uint8_t*>(args.out);
+      resp = reinterpret_cast<const uint8_t*>(args.res);
+      ld = args.ld_out;
+      col_o = col_base;
+    }
+    const size_t tile_stride = (size_t)gridDim.y * gridDim.x * kTileM * BN;  // floats between partials of one tile
+    const float* tile0 = args.ws + (((size_t)m_tile * gridDim.x + n_tile) * kTileM) * BN + chunk * 4;
+    const float4 b4 = *reinterpret_cast<const float4*>(&s_bias[chunk * 4]);
+    float s1 = 0.f, s2 = 0.f;
+    for (int row = row_lo + row_in_pass; row < row_hi; row += 2 * rows_per_pass) {
+      // two rows per iteration: 2 * splits independent 16-byte loads in flight per thread
+      const int rowb = row + rows_per_pass;
+      const bool has_b = rowb < row_hi;
+      float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = va;
+      float4 pa[4], pb[4];
+#pragma unroll
+      for (int p = 0; p < 4; ++p)
+        if (p < splits) {
+          pa[p] = __ldcg(reinterpret_cast<const float4*>(tile0 + p * tile_stride + (size_t)row * BN));
+          if (has_b) pb[p] = __ldcg(reinterpret_cast<const float4*>(tile0 + p * tile_stride + (size_t)rowb * BN));
+        }
+#pragma unroll
+      for (int p = 0; p < 4; ++p)
+        if (p < splits) {
+          va.x += pa[p].x; va.y += pa[p].y; va.z += pa[p].z; va.w += pa[p].w;
+          if (has_b) { vb.x += pb[p].x; vb.y += pb[p].y; vb.z += pb[p].z; vb.w += pb[p].w; }
+        }
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int rr = h ? rowb : row;
+        if (h && !has_b) break;
+        const int m = m0 + rr;
+        if (m >= args.M) continue;
+        float4 v = h ? vb : va;
+        v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
+        s1 += (v.x + v.y) + (v.z + v.w);
+        s2 += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+        const size_t eoff = (size_t)m * ld + col_o + chunk * 4;
+        if (args.out_f32) {
+          if (resp) {
+            const float4 q = *reinterpret_cast<const float4*>(resp + eoff * 4);
+            v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
+          }
+          *reinterpret_cast<float4*>(outp + eoff * 4) = v;
+        } else {
+          if (resp) {
+            const uint2 q = *reinterpret_cast<const uint2*>(resp + eoff * 2);
+            const float2 q0 = unpack_bf16x2(q.x), q1 = unpack_bf16x2(q.y);
+            v.x += q0.x; v.y += q0.y; v.z += q1.x; v.w += q1.y;
+          }
+          uint2 o;
+          o.x = pack_bf16x2(v.x, v.y);
+          o.y = pack_bf16x2(v.z, v.w);
+          *reinterpret_cast<uint2*>(outp + eoff * 2) = o;
+        }
+      }
+    }
+    if (args.gn_sums != nullptr) {
+      // GroupNorm partial sums: the thread's four columns lie in one group; lanes of the same group form aligned runs
+      const int cpg = args.cpg;
+      int run = cpg >> 2;               // lanes per group within a row segment
+      if (run > 32) run = 32;
+      const int lanes_per_row = 1 << chunks_log;
+      if (run > lanes_per_row && cpg < BN) run = lanes_per_row;
+      for (int o = 1; o < run; o <<= 1) {
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+      }
+      if ((lane & (run - 1)) == 0) {
+        const int g = (chunk * 4) / cpg;  // group within this N tile
+        atomicAdd(&s_gn[2 * g], s1);
+        atomicAdd(&s_gn[2 * g + 1], s2);
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(kSplitEpiThreads) : "memory");
+      const int groups_here = (BN + cpg - 1) / cpg;
+      if (et < 2 * groups_here) {
+        const int sample = min(m0, args.M - 1) / args.rows_per_sample;
+        const int rep = m_tile % kGnReplicas;
+        float* gdst = args.gn_sums + ((long)(rep * args.n_samples + sample) * args.gn_groups) * 2 + 2 * (col_base / cpg);
+        atomicAdd(gdst + et, s_gn[et]);
+      }
+    }
+    if (trace0 && et == 0) args.trace[3 * 64 + 6] = clock64();
+  }
+
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)args.tmem_cols);
+  }
+  if (trace0 && threadIdx.x == 0) args.trace[3 * 64 + 3] = clock64();
+  if (trace_on) args.trace[256 + 3 * trace_cta + 2] = (long long)globaltimer_ns();
+}
+
+// ---------------------------------------------------------------------------------------
 // Reference kernel (CUDA cores, one thread per output element). Test-only.
 // ---------------------------------------------------------------------------------------
 struct RefArgs {
@@ -970,12 +1285,17 @@ static int validate_desc(const vdn_tapgemm_desc* d) {
 
 // N tile: as wide as possible (fewer re-reads of the A tile) while still giving every SM a CTA - but not below
 // 64 columns when N allows it: 32-column tiles re-read A eight times at the 8x8 level and measured slower.
-static int pick_bn(int N, int m_tiles) {
+// A launch that reaches at least half of the SMs with 128-column (or narrower) tiles stops there: it runs the
+// 8-epilogue-warp instance with one CTA per SM, and halving the tile again to get past 148 CTAs doubles the L2 reads of
+// the activations for a second, partial wave (16x16 level, 128 -> 128: 80 CTAs x BN 128 = 9.4 us, 160 x BN 64 = 11.1 us).
+static int pick_bn(int N, int m_tiles, int n_steps) {
   int best = -1;
   for (int bn = 256; bn >= (N >= 64 && N % 64 == 0 ? 64 : 32); bn >>= 1) {
     if (bn > N || N % bn != 0) continue;
     if (best < 0) best = bn;
-    if (m_tiles * (N / bn) >= num_sms()) return bn;
+    const int ctas = m_tiles * (N / bn);
+    if (ctas >= num_sms()) return bn;
+    if (n_steps >= 8 && bn <= 128 && bn >= 64 && 2 * ctas >= num_sms()) return bn;
     best = bn;
   }
   if (best > 0) return best;
@@ -983,16 +1303,16 @@ static int pick_bn(int N, int m_tiles) {
   return 16;
 }
 
-template <int BK>
+template <int BK, int EW>
 static int launch_tapgemm(const TapMaps& maps, const TapArgs& args, int smem_bytes, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(tapgemm_kernel<BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(tapgemm_kernel<BK, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     VDN_REQUIRE(e == cudaSuccess, VDN_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     configured = true;
   }
   dim3 grid(args.N / args.BN, ceil_div(args.M, kTileM));
-  cudaError_t le = launch_pdl(tapgemm_kernel<BK>, grid, dim3(kGemmThreads), (size_t)smem_bytes, st, 1, maps, args);
+  cudaError_t le = launch_pdl(tapgemm_kernel<BK, EW>, grid, dim3(64 + 32 * EW), (size_t)smem_bytes, st, 1, maps, args);
   VDN_REQUIRE(le == cudaSuccess, VDN_E_CUDA, "tapgemm launch: %s", cudaGetErrorString(le));
   return check_launch("tapgemm_kernel");
 }
@@ -1012,6 +1332,82 @@ static int launch_tapgemm_persist(const TapMaps& maps, const TapArgs& args, int 
   return check_launch("tapgemm_persist_kernel");
 }
 
+template <int BK>
+static int launch_tapgemm_splitk(const TapMaps& maps, const TapArgs& args, int smem_bytes, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(tapgemm_splitk_kernel<BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024);
+    VDN_REQUIRE(e == cudaSuccess, VDN_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(args.N / args.BN, ceil_div(args.M, kTileM), args.splits);
+  cfg.blockDim = dim3(kSplitThreads);
+  cfg.dynamicSmemBytes = (size_t)smem_bytes;
+  cfg.stream = st;
+  cudaLaunchAttribute at[2];
+  int n = 0;
+  at[n].id = cudaLaunchAttributeClusterDimension;
+  at[n].val.clusterDim.x = 1;
+  at[n].val.clusterDim.y = 1;
+  at[n].val.clusterDim.z = (unsigned)args.splits;
+  ++n;
+  if (pdl_enabled()) {
+    at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = at;
+  cfg.numAttrs = n;
+  cudaError_t le = cudaLaunchKernelEx(&cfg, tapgemm_splitk_kernel<BK>, maps, args);
+  VDN_REQUIRE(le == cudaSuccess, VDN_E_CUDA, "tapgemm_splitk launch: %s", cudaGetErrorString(le));
+  return check_launch("tapgemm_splitk_kernel");
+}
+
+// Split-K plan of a launch (tapgemm_splitk_kernel): N tile width and number of K ranges, or false when the launch has
+// enough output tiles to fill the SMs on its own / too few K steps to split / an epilogue the kernel does not have.
+struct SplitPlan {
+  int bn, splits;
+};
+static bool splitk_plan(const vdn_tapgemm_desc* d, SplitPlan* plan) {
+  // Opt-in (tests / tools set VDN_SPLITK): measured slower than the one-tile-per-CTA kernel at config_v2_2's 8x8 level -
+  // the K loop shrinks from 7500 to 3100 cycles, but the partial tiles' trip through L2 (64 KB out, cluster barrier,
+  // 60 KB back in) costs 12000 cycles against the 3500-cycle epilogue it replaces (tools/probe_smallm.py).
+  if (!tune_on("VDN_SPLITK")) return false;
+  if (d->kind == VDN_TAP_UP) return false;
+  const int C = d->src_c;
+  const int BK = (C % 64 == 0) ? 64 : (C % 32 == 0) ? 32 : 16;
+  const int n_steps = d->n_taps * d->n_src * (C / BK);
+  const int M = d->n_img * d->H * d->W;
+  const int m_tiles = ceil_div(M, kTileM);
+  const int N = d->n_out;
+  if (d->gn_groups > 0) {
+    const int cpg = N / d->gn_groups;
+    if (cpg < 4 || (cpg & (cpg - 1)) != 0 || d->rows_per_sample % kTileM != 0) return false;
+  }
+  const int max_splits = std::min(4, tune_int("VDN_SPLITK_S", 4));
+  double best = 1e30;
+  for (int bn = 128; bn >= 32; bn >>= 1) {
+    if (tune_is_set("VDN_SPLITK_BN") && bn != tune_int("VDN_SPLITK_BN", bn)) continue;
+    if (N % bn != 0) continue;
+    if (d->split_col > 0 && d->split_col % bn != 0) continue;
+    if (d->gn_groups > 0 && bn / (N / d->gn_groups) > 8) continue;
+    const int tiles = m_tiles * (N / bn);
+    const int splits = std::min(max_splits, num_sms() / std::max(1, tiles));
+    if (splits < 2 || n_steps / splits < 3) continue;
+    // cycles: K loop = max(tensor pipe, L2 -> SM operand traffic of the whole launch at ~10 KB/clk), + reduction
+    const double mma = (bn == 128 ? 67.0 : bn == 64 ? 52.0 : 42.5) * (BK / 16) * ceil_div(n_steps, splits);
+    const double traffic = (double)tiles * n_steps * (kTileM + bn) * BK * 2 / 10000.0;
+    const double cost = std::max(mma, traffic) + 8.0 * bn + 600.0;
+    if (cost < best) {
+      best = cost;
+      plan->bn = bn;
+      plan->splits = splits;
+    }
+  }
+  return best < 1e30;
+}
+
 static long long* g_tg_trace = nullptr;
 
 static int tg_env_int(const char* name, int dflt) {
@@ -1022,9 +1418,22 @@ static int tg_env_int(const char* name, int dflt) {
 
 using namespace vdn;
 
+extern "C" size_t vdn_tapgemm_workspace(const vdn_tapgemm_desc* d) {
+  SplitPlan plan;
+  if (!d || validate_desc(d) != VDN_OK || !splitk_plan(d, &plan)) return 0;
+  const int m_tiles = ceil_div(d->n_img * d->H * d->W, kTileM);
+  return (size_t)plan.splits * m_tiles * kTileM * d->n_out * sizeof(float);
+}
+
 extern "C" int vdn_tapgemm(const vdn_tapgemm_desc* d, const void* src0, const void* src1, const void* wp,
                            const float* bias, const void* residual, const void* residual2, void* out, void* out2,
                            float* gn_sums, void* stream) {
+  return vdn_tapgemm_ws(d, src0, src1, wp, bias, residual, residual2, out, out2, gn_sums, nullptr, 0, stream);
+}
+
+extern "C" int vdn_tapgemm_ws(const vdn_tapgemm_desc* d, const void* src0, const void* src1, const void* wp,
+                              const float* bias, const void* residual, const void* residual2, void* out, void* out2,
+                              float* gn_sums, void* workspace, size_t workspace_bytes, void* stream) {
   int rc = validate_desc(d);
   if (rc) return rc;
   VDN_REQUIRE(src0 && wp && out, VDN_E_SHAPE, "tapgemm: null operand");
@@ -1044,7 +1453,7 @@ extern "C" int vdn_tapgemm(const vdn_tapgemm_desc* d, const void* src0, const vo
   memset(&a, 0, sizeof(a));
   a.M = d->n_img * d->H * d->W;
   a.N = d->n_out;
-  a.BN = pick_bn(d->n_out, ceil_div(a.M, kTileM));
+  a.BN = pick_bn(d->n_out, ceil_div(a.M, kTileM), d->n_taps * d->n_src * (C / BK));
   {
     // Short-K GEMMs (e.g. the 32 -> 256 / 768 projections) are all epilogue: a 256-column tile holds 256 of the
     // SM's 512 TMEM columns, so only two CTAs are resident and nothing hides their load -> MMA -> store chain.
@@ -1163,6 +1572,33 @@ extern "C" int vdn_tapgemm(const vdn_tapgemm_desc* d, const void* src0, const vo
 
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
 
+  // ---- split-K variant: small-M launches, when the caller provides the scratch (see tapgemm_splitk_kernel) ----
+  {
+    SplitPlan plan;
+    if (workspace && splitk_plan(d, &plan)) {
+      const size_t need = (size_t)plan.splits * ceil_div(a.M, kTileM) * kTileM * d->n_out * sizeof(float);
+      VDN_REQUIRE(workspace_bytes >= need, VDN_E_SHAPE, "tapgemm: workspace of %zu bytes, %zu needed", workspace_bytes, need);
+      VDN_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, VDN_E_ALIGN, "tapgemm: workspace must be 16B aligned");
+      TapArgs p = a;
+      p.BN = plan.bn;
+      p.splits = plan.splits;
+      p.ws = reinterpret_cast<float*>(workspace);
+      p.tmem_cols = std::max(32, plan.bn);
+      const uint64_t ktot = (uint64_t)d->n_taps * d->n_src * C;
+      const uint64_t dims[2] = {ktot, (uint64_t)d->n_out};
+      const uint64_t str[1] = {ktot * 2};
+      const uint32_t bbox[2] = {(uint32_t)BK, (uint32_t)plan.bn};
+      rc = encode_tmap_bf16(&maps.b, wp, 2, dims, str, bbox, swz);
+      if (rc) return rc;
+      const int sb = a_bytes + ((plan.bn * BK * 2 + 1023) & ~1023);
+      p.stages = std::max(2, std::min(std::min(kMaxStages, (200 * 1024) / sb), ceil_div(n_steps, plan.splits)));
+      const int ssmem = p.stages * sb + 1024;
+      if (BK == 64) return launch_tapgemm_splitk<64>(maps, p, ssmem, st);
+      if (BK == 32) return launch_tapgemm_splitk<32>(maps, p, ssmem, st);
+      return launch_tapgemm_splitk<16>(maps, p, ssmem, st);
+    }
+  }
+
   // ---- persistent variant: many tiles per SM and a short K loop (see tapgemm_persist_kernel) ----
   {
     const int m_tiles = ceil_div(a.M, kTileM);
@@ -1214,9 +1650,17 @@ extern "C" int vdn_tapgemm(const vdn_tapgemm_desc* d, const void* src0, const vo
     }
   }
 
-  if (BK == 64) return launch_tapgemm<64>(maps, a, smem_bytes, st);
-  if (BK == 32) return launch_tapgemm<32>(maps, a, smem_bytes, st);
-  return launch_tapgemm<16>(maps, a, smem_bytes, st);
+  // launches that cannot fill the SMs anyway run the 8-epilogue-warp instance (one CTA per SM, no register cap)
+  bool wide_epi = n_ctas <= num_sms() && a.BN >= 64;
+  if (tune_is_set("VDN_EW")) wide_epi = tune_int("VDN_EW", 4) == 8;
+  if (wide_epi) {
+    if (BK == 64) return launch_tapgemm<64, kEpiWarpsWide>(maps, a, smem_bytes, st);
+    if (BK == 32) return launch_tapgemm<32, kEpiWarpsWide>(maps, a, smem_bytes, st);
+    return launch_tapgemm<16, kEpiWarpsWide>(maps, a, smem_bytes, st);
+  }
+  if (BK == 64) return launch_tapgemm<64, 4>(maps, a, smem_bytes, st);
+  if (BK == 32) return launch_tapgemm<32, 4>(maps, a, smem_bytes, st);
+  return launch_tapgemm<16, 4>(maps, a, smem_bytes, st);
 }
 
 extern "C" void vdn_debug_tapgemm_trace(void* dev_buf) { vdn::g_tg_trace = reinterpret_cast<long long*>(dev_buf); }

@@ -109,6 +109,11 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
 // ----------------------------------------------------------------------------
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 
 // ----------------------------------------------------------------------------
 // thread-block clusters: barrier + distributed shared memory reads

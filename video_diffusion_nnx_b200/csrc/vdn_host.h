@@ -53,6 +53,12 @@ int mha_temporal_mma_bwd_launch(const void* qkv, const void* d_o, const float* l
 int mha_temporal_mma_fwd_launch(const void* x, const void* w_hm, const float* bias_hm, void* o, void* qkv, float* lse,
                                 int B, int F, int H, int W, cudaStream_t st);
 
+// mha_spatial_mma.cu: mid-block spatial attention core (sequences of HW = 64k tokens) on warp-level MMAs
+bool mha_spatial_mma_applicable(int HW);
+int mha_spatial_mma_fwd_launch(const void* qkv, void* o, float* lse, int n_seq, int S, cudaStream_t st);
+int mha_spatial_mma_bwd_launch(const void* qkv, const void* o, const void* d_o, const float* lse, void* dqkv, int n_seq,
+                               int S, cudaStream_t st);
+
 int sla_ctx_fused_launch(const void* x, const void* w_qkv, int N, int tokens_per_split, int n_split, float* ctx_part,
                          float* ms_part, int n_img, cudaStream_t st);
 int sla_apply_fused_launch(const void* x, const void* w_qkv, const void* w_out, const float* ctx, void* out, int n_img,

@@ -415,7 +415,10 @@ extern "C" int vdn_wgrad_bias(int kind, const void* src0, const void* src1, cons
   const int fill_env = tune_is_set("VDN_WG_FILL") ? std::max(1, tune_int("VDN_WG_FILL", 0)) : 0;
   const double work = (double)P * a.atoms_total * a.cw * Cn;
   const int fill = fill_env ? fill_env : (work >= 2e10 ? 2 : 1);
-  int splits = std::max(1, std::min(std::max(1, a.n_pix_tiles / min_k), (fill * num_sms() + base_ctas - 1) / base_ctas));
+  // never past `fill` CTAs per SM: shared memory admits one (or two) CTAs per SM, so 150 CTAs are two waves - the whole
+  // launch then takes as long as 296 would (the 3 x 50 splits of the 64x64-level conv, the 18 x 2 x 5 of the 8x8 level)
+  const int want = tune_on("VDN_WG_CEIL") ? (fill * num_sms() + base_ctas - 1) / base_ctas : (fill * num_sms()) / base_ctas;
+  int splits = std::max(1, std::min(std::max(1, a.n_pix_tiles / min_k), want));
   a.tiles_per_split = ceil_div(a.n_pix_tiles, splits);
   splits = ceil_div(a.n_pix_tiles, a.tiles_per_split);
   const int a_bytes = a.atoms_per_tile * kKPix * a.cw * 2;

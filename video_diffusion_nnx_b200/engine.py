@@ -179,23 +179,39 @@ class GemmConv:
             self.dw = st.gview(wname)
             self.dbias = st.gview(bname) if bname else None
         self.flip = [nt - 1 - t for t in range(nt)]
+        self._ws_bytes = {}
         eng.pack_jobs.append((self.w, self.wp, nt, self.cin, self.cout, 0, None))
         if self.wd is not None:
             eng.pack_jobs.append((self.w, self.wd, nt, self.cin, self.cout, 1, self.flip))
 
+    def _ws(self, x, n_src, n_out, split_col=0, gn_groups=0, rows_per_sample=0):
+        """Split-K scratch of this launch (vdn_tapgemm_ws) from the engine's per-stream-lane buffer, or None."""
+        n_img, H, W, C = x.shape
+        key = (n_img, H, W, C, n_src, n_out, split_col, gn_groups, rows_per_sample)
+        nbytes = self._ws_bytes.get(key)
+        if nbytes is None:
+            nbytes = ops.tapgemm_workspace_bytes(VDN_TAP_UNIT, n_img, H, W, n_src, C, self.taps, n_out,
+                                                 split_col=split_col, gn_groups=gn_groups,
+                                                 rows_per_sample=rows_per_sample)
+            self._ws_bytes[key] = nbytes
+        return self.eng.splitk_ws(nbytes) if nbytes else None
+
     def fwd(self, srcs, out, residual=None, gn_sums=None, rows_per_sample=0, out_dtype=BF16):
+        groups = self.eng.groups if gn_sums is not None else 0
         return ops.tapgemm(VDN_TAP_UNIT, srcs, self.wp, self.taps, bias=self.bias, residual=residual, out=out,
-                           gn_sums=gn_sums, gn_groups=self.eng.groups if gn_sums is not None else 0,
-                           rows_per_sample=rows_per_sample, out_dtype=out_dtype)
+                           gn_sums=gn_sums, gn_groups=groups, rows_per_sample=rows_per_sample, out_dtype=out_dtype,
+                           workspace=self._ws(srcs[0], len(srcs), self.cout, gn_groups=groups,
+                                              rows_per_sample=rows_per_sample))
 
     def dgrad(self, dy, outs, residuals=None):
         """dsrc(s) = dy (*) W^T (+ residuals). outs: 1 or 2 tensors (concat split)."""
         r = residuals or [None] * len(outs)
         if len(outs) == 1:
-            ops.tapgemm(VDN_TAP_UNIT, [dy], self.wd, self.taps, residual=r[0], out=outs[0])
+            ops.tapgemm(VDN_TAP_UNIT, [dy], self.wd, self.taps, residual=r[0], out=outs[0],
+                        workspace=self._ws(dy, 1, self.cin))
         else:
             ops.tapgemm(VDN_TAP_UNIT, [dy], self.wd, self.taps, residual=r[0], residual2=r[1], out=outs[0],
-                        out2=outs[1], split_col=self.c_src)
+                        out2=outs[1], split_col=self.c_src, workspace=self._ws(dy, 1, self.cin, split_col=self.c_src))
 
     def wgrad(self, srcs, dy, bias_done=False):
         # the bias gradient (column sums of dy) rides on the weight-gradient GEMM (spare "ones" M atom)
@@ -525,11 +541,25 @@ class UnetEngine:
         ev = torch.cuda.Event()
         ev.record(main)
         stream.wait_event(ev)
-        with torch.cuda.stream(stream):
-            fn()
-            done = torch.cuda.Event()
-            done.record(stream)
+        prev_lane, self._lane = self._lane, lane + 1
+        try:
+            with torch.cuda.stream(stream):
+                fn()
+                done = torch.cuda.Event()
+                done.record(stream)
+        finally:
+            self._lane = prev_lane
         return done
+
+    def splitk_ws(self, nbytes: int) -> torch.Tensor:
+        """Scratch for split-K tap-GEMM launches of the CURRENT stream lane (main / side / side 2): launches of one
+        lane are stream-ordered, so they can share one L2-resident buffer; lanes run concurrently and must not."""
+        buf = self._splitk_ws.get(self._lane)
+        if buf is None or buf.numel() < nbytes:
+            assert not torch.cuda.is_current_stream_capturing(), "split-K scratch must exist before graph capture"
+            buf = torch.empty(max(nbytes, 8 << 20), dtype=torch.uint8, device=self.device)
+            self._splitk_ws[self._lane] = buf
+        return buf
 
     def join(self, *handles):
         main = torch.cuda.current_stream()
@@ -541,6 +571,7 @@ class UnetEngine:
                  B: int, F: int, H: int, W: int, training: bool, out_dim: Optional[int] = None, groups: int = GROUPS,
                  use_sla: bool = True):
         self.store, self.device, self.training = store, store.flat.device, training
+        self._lane, self._splitk_ws = 0, {}
         self.dim, self.channels, self.B, self.F, self.H, self.W = dim, channels, B, F, H, W
         self.out_dim = channels if out_dim is None else out_dim
         self.ks = init_kernel_size

@@ -51,7 +51,9 @@ _SKIP = set(filter(None, (_lib.host_flag("VDN_SKIP", "") or "").split(",")))
 
 def tapgemm(kind: int, srcs: Sequence[torch.Tensor], wp: torch.Tensor, taps, *, bias=None, residual=None,
             residual2=None, out=None, out2=None, split_col: int = 0, gn_sums=None, gn_groups: int = 0, rows_per_sample: int = 0,
-            py: int = 0, px: int = 0, out_dtype=torch.bfloat16, ref: bool = False) -> torch.Tensor:
+            py: int = 0, px: int = 0, out_dtype=torch.bfloat16, ref: bool = False, workspace=None) -> torch.Tensor:
+    """`workspace`: optional scratch tensor of >= tapgemm_workspace_bytes(...) bytes (vdn_tapgemm_ws): lets small-M
+    launches split their K loop over thread-block clusters. Not to be shared by launches that may run concurrently."""
     x0 = srcs[0]
     assert x0.dtype == torch.bfloat16 and x0.is_contiguous() and x0.dim() == 4
     n_img, Hs, Ws, Csrc = x0.shape
@@ -73,10 +75,27 @@ def tapgemm(kind: int, srcs: Sequence[torch.Tensor], wp: torch.Tensor, taps, *, 
     if out is None:
         oh, ow = (2 * H, 2 * W) if kind == VDN_TAP_UP else (H, W)
         out = torch.empty((n_img, oh, ow, split_col if split_col else n_out), dtype=out_dtype, device=x0.device)
+    if workspace is not None and not ref:
+        check(lib.vdn_tapgemm_ws(C.byref(d), ptr(x0), ptr(srcs[1]) if len(srcs) > 1 else None, ptr(wp), ptr(bias),
+                                 ptr(residual), ptr(residual2), ptr(out), ptr(out2), ptr(gn_sums), ptr(workspace),
+                                 workspace.numel() * workspace.element_size(), stream_ptr()), "vdn_tapgemm_ws")
+        return out
     fn = lib.vdn_tapgemm_ref if ref else lib.vdn_tapgemm
     check(fn(C.byref(d), ptr(x0), ptr(srcs[1]) if len(srcs) > 1 else None, ptr(wp), ptr(bias), ptr(residual),
              ptr(residual2), ptr(out), ptr(out2), ptr(gn_sums), stream_ptr()), "vdn_tapgemm")
     return out
+
+
+def tapgemm_workspace_bytes(kind: int, n_img: int, H: int, W: int, n_src: int, src_c: int, taps, n_out: int, *,
+                            split_col: int = 0, gn_groups: int = 0, rows_per_sample: int = 0) -> int:
+    """Scratch bytes vdn_tapgemm_ws wants for this launch (0: the launch does not split its K loop)."""
+    d = TapGemmDesc()
+    d.kind, d.n_img, d.H, d.W = kind, n_img, H, W
+    d.n_src, d.src_c, d.n_taps = n_src, src_c, len(taps)
+    for i, (dy, dx) in enumerate(taps):
+        d.tap_dy[i], d.tap_dx[i] = dy, dx
+    d.n_out, d.split_col, d.gn_groups, d.rows_per_sample = n_out, split_col, gn_groups, rows_per_sample
+    return int(lib.vdn_tapgemm_workspace(C.byref(d)))
 
 
 # ------------------------------------------------------------------------------------------
