@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(kWgThreads) wgrad_kernel(const __grid_constant
       const int id = atom0 + (valid ? ai : 0);
       const int chunk = id % a.chunks;
       const int src = (id / a.chunks) % a.n_src;
-      const int tap = id / (a.chunks * a.n_src);
+      const int tap = min(id / (a.chunks * a.n_src), a.n_taps - 1);  // the ones-only tile has no tap of its own
       const long row = (long)src * a.src_c + chunk * a.cw + (r % a.cw);
       float* orow = a.out + a.tap_perm[tap] * a.tap_stride + row * a.row_stride + (long)(n_tile * a.BN) * a.col_stride;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
@@ -391,9 +391,11 @@ extern "C" int vdn_wgrad_bias(int kind, const void* src0, const void* src1, cons
     }
   }
 
-  const int m_tiles = ceil_div(a.atoms_total, a.atoms_per_tile);
+  int m_tiles = ceil_div(a.atoms_total, a.atoms_per_tile);
   const int n_tiles = Cn / a.BN;
-  // bias gradient: through a ones atom when the last M tile has a spare slot and the gradient is the N side
+  // bias gradient: through a ones atom when the gradient is the N side - in the spare slot of the last M tile, or, when
+  // the atoms fill their tiles exactly (1x1 projections of 128 / 256 channels), in an extra M tile that holds nothing
+  // else: one more CTA column of a launch-latency-bound GEMM instead of a separate column-sum launch (26 per step)
   a.dbias = nullptr;
   a.ones_tile = -1;
   bool bias_by_colsum = false;
@@ -401,6 +403,10 @@ extern "C" int vdn_wgrad_bias(int kind, const void* src0, const void* src1, cons
     if (!swap && a.atoms_total % a.atoms_per_tile != 0) {
       a.dbias = dbias;
       a.ones_tile = m_tiles - 1;
+    } else if (!swap && !tune_on("VDN_WG_COLSUM")) {
+      a.dbias = dbias;
+      a.ones_tile = m_tiles;
+      m_tiles += 1;
     } else {
       bias_by_colsum = true;
     }
