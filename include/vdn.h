@@ -118,6 +118,10 @@ void vdn_debug_rowconv_trace(void* dev_buf);
  * MMA issuer per K step; epilogue), then [256][3] global-timer stamps (prologue done, predecessor complete, exit) per CTA. */
 void vdn_debug_tapgemm_trace(void* dev_buf);
 
+/* Generic timeline hook (tools only): device buffer of >= 1024 int64 that kernels with a timeline stamp with clock64()
+ * (mha_folded_tc: per tile of CTA 0, 8 stamps = tile start, x landed, Y ready, y staged, core done, O ready, stored). */
+void vdn_debug_trace_buffer(void* dev_buf);
+
 int vdn_tapgemm_ref(const vdn_tapgemm_desc* d, const void* src0, const void* src1, const void* wp,
                     const float* bias, const void* residual, const void* residual2, void* out, void* out2,
                     float* gn_sums, void* stream);

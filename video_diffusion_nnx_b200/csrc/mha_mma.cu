@@ -765,5 +765,8 @@ extern "C" int vdn_mha_temporal_folded_fwd(const void* x, const void* fa, const 
                                            void* stream) {
   VDN_REQUIRE(x && fa && fu && fm && fb && out && B > 0 && H > 0 && W > 0, VDN_E_SHAPE, "mha_temporal_folded_fwd: bad args");
   VDN_REQUIRE(C == 32 && F >= 1 && F <= 16, VDN_E_SHAPE, "mha_temporal_folded_fwd: C=%d F=%d unsupported (C == 32, F <= 16)", C, F);
+  // the shared-weight GEMMs on tcgen05 (mha_folded_tc.cu); VDN_MHA_FOLDED_MMA=1 keeps the all-mma.sync kernel
+  if (mha_folded_tc_applicable(F, H * W) && !tune_on("VDN_MHA_FOLDED_MMA"))
+    return mha_folded_tc_launch(x, fa, fu, fm, fb, out, B, F, H, W, reinterpret_cast<cudaStream_t>(stream));
   return mha_temporal_folded_fwd_launch(x, fa, fu, fm, fb, out, B, F, H, W, reinterpret_cast<cudaStream_t>(stream));
 }

@@ -229,6 +229,12 @@ extern "C" int vdn_debug_set(const char* name, int value, int enable) {
   vdn::tune_store(name, enable ? value : vdn::kTuneUnset);
   return VDN_OK;
 }
+// Debug: device buffer (>= 1024 int64) that kernels with a timeline hook stamp with clock64(); NULL switches it off.
+static long long* g_debug_trace = nullptr;
+namespace vdn {
+long long* debug_trace_ptr() { return g_debug_trace; }
+}
+extern "C" void vdn_debug_trace_buffer(void* dev_buf) { g_debug_trace = reinterpret_cast<long long*>(dev_buf); }
 // Number of kernels this library has launched (or recorded into a CUDA graph) in this process.
 extern "C" unsigned long long vdn_launch_count(void) { return vdn::g_launches.load(); }
 extern "C" const char* vdn_last_error(void) { return vdn::g_err; }

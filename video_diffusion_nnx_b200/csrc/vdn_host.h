@@ -21,6 +21,7 @@ int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_
 int encode_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                     const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes);
 void tmap_cache_clear();
+long long* debug_trace_ptr();  // runtime.cu: vdn_debug_trace_buffer (NULL unless a tool set it)
 void comm_shutdown();  // comm.cu
 
 // conv3x3_rows.cu: persistent row-ring (1,3,3) conv; applicable() decides, launch() has vdn_tapgemm's contract
@@ -58,6 +59,11 @@ bool mha_spatial_mma_applicable(int HW);
 int mha_spatial_mma_fwd_launch(const void* qkv, void* o, float* lse, int n_seq, int S, cudaStream_t st);
 int mha_spatial_mma_bwd_launch(const void* qkv, const void* o, const void* d_o, const float* lse, void* dqkv, int n_seq,
                                int S, cudaStream_t st);
+
+// mha_folded_tc.cu: folded temporal attention block (inference, C = 32) with its shared-weight GEMMs on tcgen05
+bool mha_folded_tc_applicable(int F, int HW);
+int mha_folded_tc_launch(const void* x, const void* fa, const float* fu, const void* fm, const float* fb, void* out, int B,
+                         int F, int H, int W, cudaStream_t st);
 
 int sla_ctx_fused_launch(const void* x, const void* w_qkv, int N, int tokens_per_split, int n_split, float* ctx_part,
                          float* ms_part, int n_img, cudaStream_t st);
