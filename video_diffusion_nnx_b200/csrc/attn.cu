@@ -700,6 +700,11 @@ extern "C" int vdn_sla_fused_fwd(const void* x, const void* w_qkv, const void* w
   sla_ctx_merge_kernel<<<n_img * kHeads, 256, 0, st>>>(ctx_part, ms_part, ns, ctx, kstat);
   rc = check_launch("sla_ctx_merge");
   if (rc) return rc;
+  // apply pass as two tcgen05 GEMMs around a thread-local feature softmax (sla_apply_tc.cu); the split partials in ws
+  // are dead after the merge, so the folded per-image matrices (16 KB each) take their place.
+  // VDN_SLA_APPLY_MMA=1 keeps the all-mma.sync kernel.
+  if (sla_apply_tc_applicable(N) && !tune_on("VDN_SLA_APPLY_MMA"))
+    return sla_apply_tc_launch(x, w_qkv, w_out, ctx, ws, out, n_img, N, st);
   return sla_apply_fused_launch(x, w_qkv, w_out, ctx, out, n_img, N, st);
 }
 

@@ -65,6 +65,12 @@ bool mha_folded_tc_applicable(int F, int HW);
 int mha_folded_tc_launch(const void* x, const void* fa, const float* fu, const void* fm, const float* fb, void* out, int B,
                          int F, int H, int W, cudaStream_t st);
 
+// sla_apply_tc.cu: apply pass of the fused SpatialLinearAttention forward (inference, C = 32) on tcgen05
+bool sla_apply_tc_applicable(int N);
+size_t sla_apply_tc_scratch_bytes(int n_img);
+int sla_apply_tc_launch(const void* x, const void* w_qkv, const void* w_out, const float* ctx, void* gt_ws, void* out,
+                        int n_img, int N, cudaStream_t st);
+
 int sla_ctx_fused_launch(const void* x, const void* w_qkv, int N, int tokens_per_split, int n_split, float* ctx_part,
                          float* ms_part, int n_img, cudaStream_t st);
 int sla_apply_fused_launch(const void* x, const void* w_qkv, const void* w_out, const float* ctx, void* out, int n_img,
