@@ -34,6 +34,7 @@ struct TapMaps {
   CUtensorMap a[4];
   CUtensorMap b;
   CUtensorMap o[2];  // persistent kernel only: outputs [M][ld] (second: columns >= split_col), box (min(BN,64), 128)
+  CUtensorMap r[2];  // persistent kernel with a residual: the residual tensors, same geometry as o[]
 };
 
 struct TapArgs {
@@ -527,6 +528,7 @@ __global__ void __launch_bounds__(kPersistThreads) tapgemm_persist_kernel(const 
   __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
   __shared__ __align__(8) uint64_t tfull_bar[2];
   __shared__ __align__(8) uint64_t tempty_bar[2];
+  __shared__ __align__(8) uint64_t rfull_bar[2];  // residual tile landed in staging buffer b (kRes)
   __shared__ uint32_t tmem_base_smem;
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
@@ -551,6 +553,7 @@ __global__ void __launch_bounds__(kPersistThreads) tapgemm_persist_kernel(const 
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tfull_bar[b], 1);
       mbar_init(&tempty_bar[b], kPersistEpiThreads);
+      mbar_init(&rfull_bar[b], 1);
     }
     mbar_fence_init();
   }
@@ -653,56 +656,60 @@ __global__ void __launch_bounds__(kPersistThreads) tapgemm_persist_kernel(const 
     const int row_b = subw * 2;                // 64 or 128 bytes
     const int sub_bytes = kTileM * row_b;
     const int buf_bytes = n_sub * sub_bytes;
-    const int cpr = row_b >> 4;                // 16-byte chunks per staged row (4 or 8)
     // chunk position of chunk c of row r: 128-byte rows XOR (r & 7), 64-byte rows XOR ((r >> 1) & 3)
     const uint32_t swz = row_b == 128 ? (uint32_t)(r & 7) : (uint32_t)((r >> 1) & 3);
     // columns of this warp: half of the tile (32-column tiles are drained by the first warp of the quarter alone)
     const int cb = BN >= 64 ? chalf * (BN >> 1) : 0;
     const int ce = BN >= 64 ? cb + (BN >> 1) : (chalf == 0 ? BN : 0);
+    // Residual operand (kRes): the residual TILE is fetched by TMA into the staging buffer the item will use, one
+    // item ahead, in the same swizzled layout the output tile is staged in; the epilogue adds the accumulator to it in
+    // place and the tile leaves through the TMA store like every other tile. (Per-thread 16-byte residual loads put
+    // 2.2 us of exposed latency on every tile of the K = 256 -> 32 projections of the 64x64 level: 27.8 us with a
+    // residual against 17.2 us without; residual == out stays legal - a tile is read before it is written.)
+    auto fetch_residual = [&](int it, int jj) {  // called by ONE thread, after the buffer's previous store has been read
+      if constexpr (kRes) {
+        const int cbase = (it % args.n_ntiles) * BN;
+        const int mm0 = (it / args.n_ntiles) * kTileM;
+        const bool second = args.split_col > 0 && cbase >= args.split_col;
+        const CUtensorMap* rm = second ? &maps.r[1] : &maps.r[0];
+        const int co = second ? cbase - args.split_col : cbase;
+        const int b = jj & 1;
+        uint8_t* dst = stg + (args.stg_bufs > 1 ? b * buf_bytes : 0);
+        mbar_expect_tx(&rfull_bar[b], (uint32_t)buf_bytes);
+        for (int sub = 0; sub < n_sub; ++sub) tma_load_2d(dst + sub * sub_bytes, rm, &rfull_bar[b], co + sub * subw, mm0);
+      }
+    };
+    if (kRes && et == 0 && (int)blockIdx.x < args.n_items) fetch_residual(blockIdx.x, 0);
     int j = 0;
     for (int item = blockIdx.x; item < args.n_items; item += gridDim.x, ++j) {
       const int n_tile = item % args.n_ntiles;
       const int m0 = (item / args.n_ntiles) * kTileM;
       const int col_base = n_tile * BN;
-      uint8_t* outp;
-      const uint8_t* resp;
       const CUtensorMap* omap;
-      int ld, col_o;
+      int col_o;
       if (args.split_col > 0 && col_base >= args.split_col) {
-        outp = reinterpret_cast<uint8_t*>(args.out2);
-        resp = kRes ? reinterpret_cast<const uint8_t*>(args.res2) : nullptr;
-        ld = args.ld_out2;
         col_o = col_base - args.split_col;
         omap = &maps.o[1];
       } else {
-        outp = reinterpret_cast<uint8_t*>(args.out);
-        resp = kRes ? reinterpret_cast<const uint8_t*>(args.res) : nullptr;
-        ld = args.ld_out;
         col_o = col_base;
         omap = &maps.o[0];
       }
       const int buf = j & 1;
       uint8_t* sbuf = stg + (args.stg_bufs > 1 ? buf * buf_bytes : 0);
-      // residual operand: this thread's (up to 16) 16-byte segments of the tile - in the coalesced order of the
-      // write-out below - are requested NOW, so that their latency overlaps the wait for the accumulator
-      const int spr_log = 31 - __clz(BN >> 3);  // log2(16-byte segments per output row)
-      const int nseg = BN >> 4;                 // segments per thread per tile (128 rows * BN/8 segments / 256 threads)
-      uint4 rq[kRes ? 16 : 1];
-      if (kRes && resp) {
-#pragma unroll
-        for (int u = 0; u < (kRes ? 16 : 0); ++u) {
-          const int idx = et + u * kPersistEpiThreads;
-          const int rr = idx >> spr_log, sg = idx & ((1 << spr_log) - 1);
-          if (u < nseg && m0 + rr < args.M)
-            rq[u] = *reinterpret_cast<const uint4*>(resp + ((long)(m0 + rr) * ld + col_o) * 2 + sg * 16);
-        }
-      }
       // the TMA store that last read this staging buffer must have finished reading it
       if (et == 0) {
-        if (args.stg_bufs > 1) bulk_wait_read_1(); else bulk_wait_read_0();
+        if constexpr (kRes) {
+          // the OTHER buffer receives the next item's residual now: its last store (item j-1) must be through with it
+          bulk_wait_read_0();
+          const int nitem = item + (int)gridDim.x;
+          if (nitem < args.n_items && args.stg_bufs > 1) fetch_residual(nitem, j + 1);
+        } else {
+          if (args.stg_bufs > 1) bulk_wait_read_1(); else bulk_wait_read_0();
+        }
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
       mbar_wait(&tfull_bar[buf], (uint32_t)(j >> 1) & 1u);
+      if constexpr (kRes) mbar_wait(&rfull_bar[buf], (uint32_t)(j >> 1) & 1u);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * BN);
       auto process = [&](const uint32_t (&raw)[32], int c0) {
@@ -724,12 +731,21 @@ __global__ void __launch_bounds__(kPersistThreads) tapgemm_persist_kernel(const 
           const uint32_t c16 = (uint32_t)(cl - sub * subw) >> 3;  // first 16-byte chunk of these 16 columns
 #pragma unroll
           for (int q = 0; q < 2; ++q) {
+            uint4* slot = reinterpret_cast<uint4*>(rowp + (((c16 + q) ^ swz) << 4));
+            if constexpr (kRes) {
+              const uint4 rv = *slot;
+              float2 f;
+              f = unpack_bf16x2(rv.x); v[8 * q + 0] += f.x; v[8 * q + 1] += f.y;
+              f = unpack_bf16x2(rv.y); v[8 * q + 2] += f.x; v[8 * q + 3] += f.y;
+              f = unpack_bf16x2(rv.z); v[8 * q + 4] += f.x; v[8 * q + 5] += f.y;
+              f = unpack_bf16x2(rv.w); v[8 * q + 6] += f.x; v[8 * q + 7] += f.y;
+            }
             uint4 u;
             u.x = pack_bf16x2(v[8 * q + 0], v[8 * q + 1]);
             u.y = pack_bf16x2(v[8 * q + 2], v[8 * q + 3]);
             u.z = pack_bf16x2(v[8 * q + 4], v[8 * q + 5]);
             u.w = pack_bf16x2(v[8 * q + 6], v[8 * q + 7]);
-            *reinterpret_cast<uint4*>(rowp + (((c16 + q) ^ swz) << 4)) = u;
+            *slot = u;
           }
         }
       };
@@ -750,29 +766,18 @@ __global__ void __launch_bounds__(kPersistThreads) tapgemm_persist_kernel(const 
       }
       tc_fence_before();
       mbar_arrive(&tempty_bar[buf]);  // accumulator buffer is free for item j+2
-      if (!resp) fence_proxy_async_smem();
+      fence_proxy_async_smem();
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (!resp) {
-        if (et == 0) {
-          for (int sub = 0; sub < n_sub; ++sub) tma_store_2d(omap, sbuf + sub * sub_bytes, col_o + sub * subw, m0);
-          bulk_commit();
-        }
-      } else if constexpr (kRes) {
-        // residual add + store by the threads: consecutive threads take consecutive 16-byte segments of a row
-#pragma unroll
-        for (int u = 0; u < 16; ++u) {
-          const int idx = et + u * kPersistEpiThreads;
-          const int rr = idx >> spr_log, sg = idx & ((1 << spr_log) - 1);
-          if (u >= nseg || m0 + rr >= args.M) continue;
-          const int sub = sg / cpr, c16 = sg - sub * cpr;
-          const uint32_t rsw = row_b == 128 ? (uint32_t)(rr & 7) : (uint32_t)((rr >> 1) & 3);
-          uint4 q = *reinterpret_cast<const uint4*>(sbuf + sub * sub_bytes + rr * row_b + (((uint32_t)c16 ^ rsw) << 4));
-          float2 x, y;
-          x = unpack_bf16x2(q.x); y = unpack_bf16x2(rq[u].x); q.x = pack_bf16x2(x.x + y.x, x.y + y.y);
-          x = unpack_bf16x2(q.y); y = unpack_bf16x2(rq[u].y); q.y = pack_bf16x2(x.x + y.x, x.y + y.y);
-          x = unpack_bf16x2(q.z); y = unpack_bf16x2(rq[u].z); q.z = pack_bf16x2(x.x + y.x, x.y + y.y);
-          x = unpack_bf16x2(q.w); y = unpack_bf16x2(rq[u].w); q.w = pack_bf16x2(x.x + y.x, x.y + y.y);
-          *reinterpret_cast<uint4*>(outp + ((long)(m0 + rr) * ld + col_o) * 2 + sg * 16) = q;
+      if (et == 0) {
+        for (int sub = 0; sub < n_sub; ++sub) tma_store_2d(omap, sbuf + sub * sub_bytes, col_o + sub * subw, m0);
+        bulk_commit();
+        if constexpr (kRes) {
+          // single staging buffer: the next item's residual goes into this buffer once the store has read it
+          const int nitem = item + (int)gridDim.x;
+          if (args.stg_bufs == 1 && nitem < args.n_items) {
+            bulk_wait_read_0();
+            fetch_residual(nitem, j + 1);
+          }
         }
       }
     }
@@ -1603,13 +1608,16 @@ extern "C" int vdn_tapgemm_ws(const vdn_tapgemm_desc* d, const void* src0, const
   {
     const int m_tiles = ceil_div(a.M, kTileM);
     const long items = (long)m_tiles * (d->n_out / a.BN);
-    // 32-column tiles with a residual measured slower than the one-tile-per-CTA kernel (27.6 vs 23.6 us at K = 256,
-    // 163840 pixels); tests lower VDN_PERSIST_MIN_ITEMS and still reach that combination
-    const bool narrow_res = a.BN < 64 && (residual || residual2) && tg_env_int("VDN_PERSIST_MIN_ITEMS", 3 * num_sms()) > 1 &&
-                            !tg_env_int("VDN_PERSIST_NARROW_RES", 0);
+    // From one item per SM on (measured on the training step: 444 -> 148 items = 6.32 -> 6.25 ms). Narrow tiles with a
+    // residual used to stay on the one-tile kernel (per-thread residual loads: 27.6 vs 23.6 us at K = 256 -> 32, 163840
+    // pixels); with the residual tile arriving by TMA the persistent kernel does it in 20.3 us. VDN_PERSIST_NARROW_RES=0
+    // restores the old routing.
+    const int persist_min_items = tg_env_int("VDN_PERSIST_MIN_ITEMS", num_sms());
+    const bool narrow_res = a.BN < 64 && (residual || residual2) && persist_min_items > 1 &&
+                            tg_env_int("VDN_PERSIST_NARROW_RES", 1) == 0;
     const bool shape_ok = !gn_sums && !a.out_f32 && !a.scatter && a.BN >= 32 && (a.BN & (a.BN - 1)) == 0 && !narrow_res &&
-                          n_steps <= tg_env_int("VDN_PERSIST_MAX_STEPS", 16) &&
-                          items >= (long)tg_env_int("VDN_PERSIST_MIN_ITEMS", 3 * num_sms());
+                          n_steps <= tg_env_int("VDN_PERSIST_MAX_STEPS", 12) &&
+                          items >= (long)persist_min_items;
     const bool persist_off = tune_on("VDN_NO_PERSIST");
     if (shape_ok && !persist_off) {
       TapArgs p = a;
@@ -1632,17 +1640,30 @@ extern "C" int vdn_tapgemm_ws(const vdn_tapgemm_desc* d, const void* src0, const
         const uint64_t str0[1] = {(uint64_t)a.ld_out * 2};
         rc = encode_tmap_bf16(&maps.o[0], out, 2, dims0, str0, obox, subw * 2);
         if (rc) return rc;
+        if (residual) {
+          rc = encode_tmap_bf16(&maps.r[0], residual, 2, dims0, str0, obox, subw * 2);
+          if (rc) return rc;
+        }
         if (d->split_col > 0) {
           const uint64_t dims1[2] = {(uint64_t)a.ld_out2, Mrows};
           const uint64_t str1[1] = {(uint64_t)a.ld_out2 * 2};
           rc = encode_tmap_bf16(&maps.o[1], out2, 2, dims1, str1, obox, subw * 2);
           if (rc) return rc;
+          if (residual2) {
+            rc = encode_tmap_bf16(&maps.r[1], residual2, 2, dims1, str1, obox, subw * 2);
+            if (rc) return rc;
+          }
         }
         const int psmem = 1024 + S * stage_bytes + p.stg_bufs * buf_bytes;
         const int cps = std::max(1, std::min(512 / p.tmem_cols, (227 * 1024) / (psmem + 1024)));
         int grid = (int)std::min<long>(items, (long)num_sms() * cps);
         if (tune_is_set("VDN_PERSIST_GRID")) grid = std::max(1, std::min((int)items, tune_int("VDN_PERSIST_GRID", grid)));
         const bool has_res = residual != nullptr || residual2 != nullptr;
+        VDN_REQUIRE(!has_res || (residual != nullptr && (d->split_col == 0 || residual2 != nullptr)), VDN_E_SHAPE,
+                    "tapgemm: a split output needs both residuals or none");
+        VDN_REQUIRE(!has_res || ((reinterpret_cast<uintptr_t>(residual) & 15) == 0 &&
+                                 (!residual2 || (reinterpret_cast<uintptr_t>(residual2) & 15) == 0)),
+                    VDN_E_ALIGN, "tapgemm: residual must be 16B aligned");
         if (BK == 64) return has_res ? launch_tapgemm_persist<64, true>(maps, p, psmem, grid, st) : launch_tapgemm_persist<64, false>(maps, p, psmem, grid, st);
         if (BK == 32) return has_res ? launch_tapgemm_persist<32, true>(maps, p, psmem, grid, st) : launch_tapgemm_persist<32, false>(maps, p, psmem, grid, st);
         return has_res ? launch_tapgemm_persist<16, true>(maps, p, psmem, grid, st) : launch_tapgemm_persist<16, false>(maps, p, psmem, grid, st);
