@@ -59,6 +59,7 @@ struct TapArgs {
   float* gn_sums;
   int gn_groups, cpg, rows_per_sample, n_samples;
   int n_ntiles, n_items, stg_bufs;  // persistent kernel: (M tile, N tile) items, staging buffers
+  int res_tma;       // generic kernel: byte offset (in dynamic smem) of the TMA-fetched residual tile, or 0
   int splits;        // split-K kernel: K ranges per output tile = cluster size along z
   float* ws;         // split-K kernel: fp32 partial tiles [splits][m_tiles][n_tiles][128][BN]
   long long* trace;  // debug (vdn_debug_tapgemm_trace), 1024 entries: clock64 stamps of CTA (0,0): [4][64] = producer0 / producer1 / MMA /
@@ -125,6 +126,7 @@ tapgemm_kernel(const __grid_constant__ TapMaps maps, const TapArgs args) {
   __shared__ __align__(8) uint64_t full_bar[kMaxStages];
   __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
   __shared__ __align__(8) uint64_t tmem_full_bar;
+  __shared__ __align__(8) uint64_t res_bar;  // residual tile landed (args.res_tma)
   __shared__ uint32_t tmem_base_smem;
   __shared__ float s_gn[kEpiWarps][16];  // per epilogue warp: (sum, sumsq) of up to 8 groups of this N tile
   __shared__ float s_bias[256];  // bias row of this N tile
@@ -152,6 +154,7 @@ tapgemm_kernel(const __grid_constant__ TapMaps maps, const TapArgs args) {
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(&tmem_full_bar, 1);
+    mbar_init(&res_bar, 1);
     mbar_fence_init();
   }
   if (warp == 1) {
@@ -182,6 +185,14 @@ tapgemm_kernel(const __grid_constant__ TapMaps maps, const TapArgs args) {
       const int y0 = rem / args.W;
       const int x0 = rem - y0 * args.W;
       const uint32_t tx_bytes = (uint32_t)(kABytes + BN * BK * 2);
+      if (args.res_tma) {
+        // the residual tile [128 rows][BN] (plain row-major) travels while the K loop runs; per-thread residual loads in
+        // the write-out loop cost 2.6 - 4.3 us per launch at the 8x8 / 16x16 levels
+        const int cb0 = n_tile * BN;
+        const bool second = args.split_col > 0 && cb0 >= args.split_col;
+        mbar_expect_tx(&res_bar, (uint32_t)(kTileM * BN * 2));
+        tma_load_2d(smem + args.res_tma, second ? &maps.r[1] : &maps.r[0], &res_bar, second ? cb0 - args.split_col : cb0, m0);
+      }
       int st = 0, kcol = 0, step = 0;
       uint32_t ph = 1u;  // parity to wait for on the empty barrier of the slot
       for (int t = 0; t < args.n_taps; ++t) {
@@ -449,6 +460,7 @@ tapgemm_kernel(const __grid_constant__ TapMaps maps, const TapArgs args) {
     }
     if (staged) {
       asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+      if (args.res_tma) mbar_wait(&res_bar, 0);
       if (args.trace && blockIdx.x == 0 && blockIdx.y == 0 && et == 0) args.trace[3 * 64 + 5] = clock64();
       // coalesced write-out: consecutive threads store consecutive 16-byte segments of a row
       const int spr = (BN * esz) >> 4;  // 16B segments per row
@@ -463,7 +475,8 @@ tapgemm_kernel(const __grid_constant__ TapMaps maps, const TapArgs args) {
         uint4 q = *reinterpret_cast<const uint4*>(smem + (size_t)rr * pitch + sg * 16);
         const long goff = ((long)mm * ld + col_o) * esz + sg * 16;
         if (resp) {
-          const uint4 rq = *reinterpret_cast<const uint4*>(resp + goff);
+          const uint4 rq = args.res_tma ? *reinterpret_cast<const uint4*>(smem + args.res_tma + (size_t)rr * (BN * 2) + sg * 16)
+                                        : *reinterpret_cast<const uint4*>(resp + goff);
           if (args.out_f32) {
             q.x = __float_as_uint(__uint_as_float(q.x) + __uint_as_float(rq.x));
             q.y = __float_as_uint(__uint_as_float(q.y) + __uint_as_float(rq.y));
@@ -1674,10 +1687,35 @@ extern "C" int vdn_tapgemm_ws(const vdn_tapgemm_desc* d, const void* src0, const
   // launches that cannot fill the SMs anyway run the 8-epilogue-warp instance (one CTA per SM, no register cap)
   bool wide_epi = n_ctas <= num_sms() && a.BN >= 64;
   if (tune_is_set("VDN_EW")) wide_epi = tune_int("VDN_EW", 4) == 8;
+  int smem_launch = smem_bytes;
+  if (wide_epi && residual && !a.out_f32 && !a.scatter && (d->split_col == 0 || residual2) && !tune_on("VDN_NO_RES_TMA")) {
+    // residual tile by TMA into its own shared-memory region behind the pipeline stages / the staged output tile
+    const int res_bytes = kTileM * a.BN * 2;
+    // the pipeline gives up stages to make room (a one-CTA-per-SM launch had taken all 200 KB for them)
+    const int max_stages = (200 * 1024 - 1024 - 128 - res_bytes) / stage_bytes;
+    if (max_stages >= 3 && !tune_is_set("VDN_STAGES")) a.stages = std::min(a.stages, max_stages);
+    const int off = (std::max(a.stages * stage_bytes, tile_bytes) + 127) & ~127;
+    if (off + res_bytes + 1024 <= 200 * 1024) {
+      const uint64_t Mrows = (uint64_t)a.M;
+      const uint32_t rbox[2] = {(uint32_t)a.BN, (uint32_t)kTileM};
+      const uint64_t dims0[2] = {(uint64_t)a.ld_out, Mrows};
+      const uint64_t str0[1] = {(uint64_t)a.ld_out * 2};
+      rc = encode_tmap_bf16(&maps.r[0], residual, 2, dims0, str0, rbox, 0);
+      if (rc) return rc;
+      if (d->split_col > 0) {
+        const uint64_t dims1[2] = {(uint64_t)a.ld_out2, Mrows};
+        const uint64_t str1[1] = {(uint64_t)a.ld_out2 * 2};
+        rc = encode_tmap_bf16(&maps.r[1], residual2, 2, dims1, str1, rbox, 0);
+        if (rc) return rc;
+      }
+      a.res_tma = off;
+      smem_launch = off + res_bytes + 1024;
+    }
+  }
   if (wide_epi) {
-    if (BK == 64) return launch_tapgemm<64, kEpiWarpsWide>(maps, a, smem_bytes, st);
-    if (BK == 32) return launch_tapgemm<32, kEpiWarpsWide>(maps, a, smem_bytes, st);
-    return launch_tapgemm<16, kEpiWarpsWide>(maps, a, smem_bytes, st);
+    if (BK == 64) return launch_tapgemm<64, kEpiWarpsWide>(maps, a, smem_launch, st);
+    if (BK == 32) return launch_tapgemm<32, kEpiWarpsWide>(maps, a, smem_launch, st);
+    return launch_tapgemm<16, kEpiWarpsWide>(maps, a, smem_launch, st);
   }
   if (BK == 64) return launch_tapgemm<64, 4>(maps, a, smem_bytes, st);
   if (BK == 32) return launch_tapgemm<32, 4>(maps, a, smem_bytes, st);
