@@ -293,7 +293,7 @@ def conv_roofline(torch, ops, pk, level=0, with_traffic=False):
         key = f"conv_l{level}_c{C}"
         if key in td:
             traffic = td[key]["dram_bytes_read"] + td[key]["dram_bytes_write"]
-    kern = {32: "conv3x3_rows_kernel<32,32,1>", 64: "conv3x3_rows_kernel<64,64,1>"}.get(C, "tapgemm_kernel<64>")
+    kern = {32: "conv3x3_rows_kernel<32,32,1>", 64: "conv3x3_rows_kernel<64,64,1>"}.get(C, "tapgemm_kernel<64,8>")
     if CFG["dim"] >= 128:
         kern = "conv3x3_slab_kernel<32>"
     name = f"conv(1,3,3) {C}->{C} @{H}x{W} (M={M},N={C},K={9 * C}) {kern}"
@@ -307,6 +307,37 @@ def conv_roofline(torch, ops, pk, level=0, with_traffic=False):
     r.update(us_per_launch=ms * 1e3, peak_source=pk["src"], buffers_in_rotation=nbuf,
              l2="inputs, weights and outputs rotate over sets larger than L2 between launches")
     return r
+
+
+def wgrad_roofline(torch, ops, pk):
+    """The step's dominant kernel by the committed launch list (profiles/r2_final_launches_train_v2_2_b4.summary.txt:
+    wgrad_kernel<0>, 90 launches = 15.7 % of the kernel time) on the instance that takes most of its time: the weight
+    (+ bias) gradient of a q|k|v projection at the full-resolution level, dW[C][768] = x^T dqkv over all P pixels -
+    one pass over the 768-channel gradient tensor, HBM bound. Timed live, dqkv rotating over sets larger than L2."""
+    dev, bf = "cuda", torch.bfloat16
+    B, Fr, S, C = CFG["per_gpu_batch"], CFG["frames"], CFG["size"], CFG["dim"]
+    n_img, P = B * Fr, B * Fr * S * S
+    nb = max(2, int(300e6 // (P * 768 * 2)) + 1)
+    x = torch.randn(n_img, S, S, C, device=dev).to(bf)
+    gs = [torch.randn(n_img, S, S, 768, device=dev).to(bf) for _ in range(nb)]
+    dw = torch.zeros(1, C, 768, device=dev)
+    db = torch.zeros(768, device=dev)
+    us = _graph_time_us(torch, lambda i: ops.wgrad(ops.VDN_TAP_UNIT, [x], gs[i % nb], dw, ops.TAPS_1x1, dbias=db), n=16)
+    bytes_alg = 2.0 * P * (C + 768) + 2 * 4.0 * C * 768
+    flops = 2.0 * P * C * 768
+    gbs = bytes_alg / (us * 1e-6) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tp):
+        td = json.load(open(tp)).get("wgrad_qkv_l0")
+        if td:
+            traffic = td["dram_bytes_read"] + td["dram_bytes_write"]
+    return {"kernel": f"q|k|v projection weight + bias gradient {C}x768 over {P} pixels (wgrad_kernel<0>, split-K over 24 pixel ranges)",
+            "bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"], "traffic": traffic,
+            "algorithmic_bytes": bytes_alg, "algorithmic_flops": flops, "tensor_tflops": flops / (us * 1e-6) / 1e12,
+            "us_per_launch": us, "peak_source": pk["src"], "buffers_in_rotation": nb,
+            "share_of_step_kernel_time": 0.157, "launch_list": "profiles/r2_final_launches_train_v2_2_b4.summary.txt",
+            "l2": "the gradient tensors rotate over sets larger than L2 between launches"}
 
 
 def _graph_time_us(torch, run, n=32, warm=4):
@@ -630,8 +661,15 @@ def main():
         small = args.workload == "v2_2"
         # the dominant kernel of the step by the committed launch list (profiles/): the small-M tap-GEMM convs of the
         # 16x16 / 8x8 levels (tapgemm_kernel<64>); the full-resolution conv and three more kernels follow
-        line["roofline"] = conv_roofline(torch, ops, pk, level=3 if small else 0, with_traffic=True)
-        extra = [conv_roofline(torch, ops, pk, level=2), conv_roofline(torch, ops, pk, level=0, with_traffic=True)] if small else []
+        if small:
+            # dominant kernel of the step by name: wgrad_kernel<0>; then the conv of the small-M levels (the generic
+            # tap-GEMM, second by share and the kernel furthest below its roofline), the 16x16 and 64x64 convs, ...
+            line["roofline"] = wgrad_roofline(torch, ops, pk)
+            extra = [conv_roofline(torch, ops, pk, level=3, with_traffic=True), conv_roofline(torch, ops, pk, level=2),
+                     conv_roofline(torch, ops, pk, level=0, with_traffic=True)]
+        else:
+            line["roofline"] = conv_roofline(torch, ops, pk, level=0, with_traffic=True)
+            extra = []
         line["roofline_kernels"] = extra + extra_rooflines(torch, ops, pk)
     if not args.no_parity:
         line["parity"] = parity_block(torch, ops, gd, net, B)

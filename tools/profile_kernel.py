@@ -37,6 +37,11 @@ if what in ("conv_l0", "conv_l3", "qkv_l0", "conv_v23x_l0", "conv_v23x_l1"):
         else:
             ops.tapgemm(ops.VDN_TAP_UNIT, [x], wp, taps, bias=bias, out=out, gn_sums=sums, gn_groups=8,
                         rows_per_sample=F * H * H)
+elif what == "wgrad_qkv_l0":  # weight + bias gradient of a q|k|v projection at the 64x64 level (the bench's `roofline`)
+    x, g = bf(B * F, 64, 64, 32), bf(B * F, 64, 64, 768)
+    dw, db = torch.zeros(1, 32, 768, device=dev), torch.zeros(768, device=dev)
+    for _ in range(5):
+        ops.wgrad(ops.VDN_TAP_UNIT, [x], g, dw, ops.TAPS_1x1, dbias=db)
 elif what == "wgrad_l0":
     x, g = bf(B * F, 64, 64, 32), bf(B * F, 64, 64, 32)
     dw = torch.zeros(9, 32, 32, device=dev)
