@@ -590,12 +590,15 @@ __global__ void __launch_bounds__(256) sla_bwd_tokens_kernel(const bf16* __restr
 }
 
 // Token splits per frame for the context / dcontext passes: at most 32, and no more than needed to give every SM
-// ~4 blocks (n_img frames x splits): every split writes a 32 KB partial per frame that the merge pass re-reads,
+// its resident blocks (n_img frames x splits): every split writes a 32 KB partial per frame that the merge pass re-reads,
 // which at large batch (n_img = 160) was more traffic than the input itself.
 static int sla_splits(int N, int n_img) {
   int per = std::max(kSlaTile, ((N + 31) / 32 + kSlaTile - 1) / kSlaTile * kSlaTile);  // <= 32 splits
   const int max_splits = std::max(1, (N + per - 1) / per);
-  const int want = std::max(1, (148 * 4 + n_img - 1) / std::max(1, n_img));
+  // the context kernels keep three blocks of 256 threads resident per SM (74 registers): fill exactly one wave. (Four per
+  // SM with a ceiling gave 600 blocks for the 444 slots at 40 frames - 1.35 waves; 5.98 vs 6.04 ms per training step.)
+  const int per_sm = tune_int("VDN_SLA_BLOCKS_PER_SM", 3);
+  const int want = std::max(1, (148 * per_sm) / std::max(1, n_img));
   return std::min(max_splits, want);
 }
 

@@ -105,7 +105,7 @@ __device__ __forceinline__ void store_rows(const float (&o)[4][4], bf16* row_lo,
 }
 
 // grid: blocks of 8 warps = the 8 heads of one pixel; a block walks pixels blockIdx.x, +gridDim.x, ...
-__global__ void __launch_bounds__(256) mha_temporal_mma_bwd_kernel(const bf16* __restrict__ qkv,
+__global__ void __launch_bounds__(256, 4) mha_temporal_mma_bwd_kernel(const bf16* __restrict__ qkv,
                                                                    const bf16* __restrict__ d_o,
                                                                    const float* __restrict__ lse,
                                                                    bf16* __restrict__ dqkv, int B, int F, long HW) {
@@ -121,8 +121,6 @@ __global__ void __launch_bounds__(256) mha_temporal_mma_bwd_kernel(const bf16* _
     const long b = pix / HW, p = pix - b * HW;
     const long row0 = b * F * HW + p;          // token f lives at row0 + f*HW
     const long r_lo = row0 + (long)g * HW, r_hi = row0 + (long)(g + 8) * HW;
-    const bf16* qb = qkv + row0 * 768 + h * 32;
-    const bf16* gb = d_o + row0 * 256 + h * 32;
     // ---- 16-byte chunk operands (rows g / g+8) ----
     uint4 q_lo = zero4, q_hi = zero4, k_lo = zero4, k_hi = zero4, vv_lo = zero4, vv_hi = zero4, g_lo = zero4, g_hi = zero4;
     float L_lo = 0.f, L_hi = 0.f;
@@ -142,11 +140,25 @@ __global__ void __launch_bounds__(256) mha_temporal_mma_bwd_kernel(const bf16* _
       g_hi = __ldg(reinterpret_cast<const uint4*>(d_o + r_hi * 256 + h * 32) + j);
       L_hi = __ldg(lse + r_hi * 8 + h);
     }
-    // ---- token-word operands (contraction over tokens) ----
-    TokWords wq, wk, wg;
-    load_tokwords(wq, qb, HW * 768, F, g, j);
-    load_tokwords(wk, qb + 256, HW * 768, F, g, j);
-    load_tokwords(wg, gb, HW * 256, F, g, j);
+    // ---- operands that contract over TOKENS (K for dQ, Q for dK, dO for dV) are the 8x8-tile transposes of the chunk
+    //      registers already loaded (movmatrix), as in the forward kernel's P V: 24 register shuffles instead of 24
+    //      four-byte global loads, their address arithmetic and the byte permutes; n-tile t then holds the features of
+    //      chunk register t, so the products land in the chunk layout and leave with 16-byte stores ----
+    auto times_tokens = [&](uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, const uint4& lo, const uint4& hi,
+                            bf16* dst_lo, bf16* dst_hi) {
+      const uint32_t bt[4][2] = {{movmatrix_trans(lo.x), movmatrix_trans(hi.x)}, {movmatrix_trans(lo.y), movmatrix_trans(hi.y)},
+                                 {movmatrix_trans(lo.z), movmatrix_trans(hi.z)}, {movmatrix_trans(lo.w), movmatrix_trans(hi.w)}};
+      uint32_t u_lo[4], u_hi[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        float c[4] = {0.f, 0.f, 0.f, 0.f};
+        mma16816(c, a0, a1, a2, a3, bt[t][0], bt[t][1]);
+        u_lo[t] = pack_bf16x2(c[0], c[1]);
+        u_hi[t] = pack_bf16x2(c[2], c[3]);
+      }
+      if (v_lo) reinterpret_cast<uint4*>(dst_lo)[j] = make_uint4(u_lo[0], u_lo[1], u_lo[2], u_lo[3]);
+      if (v_hi) reinterpret_cast<uint4*>(dst_hi)[j] = make_uint4(u_hi[0], u_hi[1], u_hi[2], u_hi[3]);
+    };
 
     // ---- query-major pass: P, dS (rows = query tokens g / g+8, columns = key tokens) ----
     float S[2][4], dP[2][4];
@@ -175,9 +187,9 @@ __global__ void __launch_bounds__(256) mha_temporal_mma_bwd_kernel(const bf16* _
         dS[t][i] = S[t][i] * (dP[t][i] - D_lo) * scale;
         dS[t][2 + i] = S[t][2 + i] * (dP[t][2 + i] - D_hi) * scale;
       }
-    float o[4][4];
-    frag_times_tokens(dS, wk, o);  // dQ = dS K
-    store_rows(o, dqkv + r_lo * 768 + h * 32, dqkv + r_hi * 768 + h * 32, v_lo, v_hi, j);
+    // dQ = dS K
+    times_tokens(pack_bf16x2(dS[0][0], dS[0][1]), pack_bf16x2(dS[0][2], dS[0][3]), pack_bf16x2(dS[1][0], dS[1][1]),
+                 pack_bf16x2(dS[1][2], dS[1][3]), k_lo, k_hi, dqkv + r_lo * 768 + h * 32, dqkv + r_hi * 768 + h * 32);
 
     // ---- key-major operands: P^T and dS^T are the 8x8-tile transposes of the query-major fragments
     //      (movmatrix), A fragment = {T(q0-7 x k0-7), T(q0-7 x k8-15), T(q8-15 x k0-7), T(q8-15 x k8-15)} ----
@@ -190,10 +202,9 @@ __global__ void __launch_bounds__(256) mha_temporal_mma_bwd_kernel(const bf16* _
     dsT[1] = movmatrix_trans(pack_bf16x2(dS[1][0], dS[1][1]));
     dsT[2] = movmatrix_trans(pack_bf16x2(dS[0][2], dS[0][3]));
     dsT[3] = movmatrix_trans(pack_bf16x2(dS[1][2], dS[1][3]));
-    afrag_times_tokens(dsT, wq, o);  // dK = dS^T Q
-    store_rows(o, dqkv + r_lo * 768 + 256 + h * 32, dqkv + r_hi * 768 + 256 + h * 32, v_lo, v_hi, j);
-    afrag_times_tokens(pT, wg, o);   // dV = P^T dO
-    store_rows(o, dqkv + r_lo * 768 + 512 + h * 32, dqkv + r_hi * 768 + 512 + h * 32, v_lo, v_hi, j);
+    // dK = dS^T Q, dV = P^T dO
+    times_tokens(dsT[0], dsT[1], dsT[2], dsT[3], q_lo, q_hi, dqkv + r_lo * 768 + 256 + h * 32, dqkv + r_hi * 768 + 256 + h * 32);
+    times_tokens(pT[0], pT[1], pT[2], pT[3], g_lo, g_hi, dqkv + r_lo * 768 + 512 + h * 32, dqkv + r_hi * 768 + 512 + h * 32);
   }
 }
 
@@ -409,7 +420,7 @@ int mha_temporal_mma_fwd_launch(const void* x, const void* w_hm, const float* bi
                                 int B, int F, int H, int W, cudaStream_t st) {
   const long HW = (long)H * W;
   const long n_pix = (long)B * HW;
-  const int grid = (int)std::min<long>(n_pix, 148L * 16);
+  const int grid = (int)std::min<long>(n_pix, 148L * tune_int("VDN_MHA_FWD_CTAS", 16));
   const size_t smem_t = (size_t)8 * 3 * kProjWords * 32 * 4, smem_i = smem_t;
   static bool cfg = false;
   if (!cfg) {
@@ -733,7 +744,7 @@ int mha_temporal_mma_bwd_launch(const void* qkv, const void* d_o, const float* l
                                 int W, cudaStream_t st) {
   const long HW = (long)H * W;
   const long n_pix = (long)B * HW;
-  const int grid = (int)std::min<long>(n_pix, 148L * 16);
+  const int grid = (int)std::min<long>(n_pix, 148L * tune_int("VDN_MHA_BWD_CTAS", 4));  // = the four resident CTAs per SM (64 registers)
   cudaError_t le = launch_pdl(mha_temporal_mma_bwd_kernel, dim3(grid), dim3(256), (size_t)0, st, 1,
                               reinterpret_cast<const bf16*>(qkv), reinterpret_cast<const bf16*>(d_o), lse,
                               reinterpret_cast<bf16*>(dqkv), B, F, HW);
