@@ -10,7 +10,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from video_diffusion_nnx_b200 import ops  # noqa: E402
-from video_diffusion_nnx_b200._lib import debug_switches  # noqa: E402
+from video_diffusion_nnx_b200._lib import debug_switches, set_host_flag  # noqa: E402
 from video_diffusion_nnx_b200.gaussian_diffusion import GaussianDiffusion  # noqa: E402
 from video_diffusion_nnx_b200.trainer import TrainStep  # noqa: E402
 from video_diffusion_nnx_b200.unet3d import Unet3D  # noqa: E402
@@ -47,9 +47,16 @@ def measure(sw, n=30):
 
 sets = sys.argv[1:] or [""]
 for spec in sets:
-    sw = {}
+    sw, host = {}, {}
     for kv in filter(None, spec.split(",")):
         k, v = kv.split("=")
-        sw[k] = int(v)
+        if k.startswith("HOST_"):  # Python-side engine switch (e.g. HOST_VDN_DEFER_JOINS=0)
+            host[k[5:]] = v
+        else:
+            sw[k] = int(v)
+    for k, v in host.items():
+        set_host_flag(k, v)
     ms, loss = measure(sw)
+    for k in host:
+        set_host_flag(k, None)
     print(f"{spec or '(defaults)':60s} {ms:7.3f} ms/step  {B / ms * 1e3:7.1f} clips/s  loss {loss:.4f}", flush=True)

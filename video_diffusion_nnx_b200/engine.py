@@ -151,6 +151,7 @@ class _Pool:
     def __init__(self, device):
         self.device = device
         self.free: Dict[tuple, List[torch.Tensor]] = {}
+        self.deferred: Optional[List[torch.Tensor]] = None
 
     def get(self, shape, dtype=BF16) -> torch.Tensor:
         key = (tuple(shape), dtype)
@@ -160,7 +161,15 @@ class _Pool:
         return torch.empty(shape, dtype=dtype, device=self.device)
 
     def put(self, t: torch.Tensor) -> None:
+        if self.deferred is not None:  # inside a backward stage with deferred joins: recycled at the end of the stage
+            self.deferred.append(t)
+            return
         self.free.setdefault((tuple(t.shape), t.dtype), []).append(t)
+
+    def release_deferred(self) -> None:
+        bufs, self.deferred = self.deferred or [], None
+        for t in bufs:
+            self.put(t)
 
 
 class GemmConv:
@@ -307,7 +316,7 @@ class ResBlock:
         else:
             eng.join(hln)
             self.conv1.dgrad(da_raw, dsrc, residuals=[ds])
-        eng.join(h2, h1, hr)
+        eng.join_later(h2, h1, hr)
         pool.put(db_raw)
         pool.put(ds)
         pool.put(da_raw)
@@ -399,7 +408,7 @@ class MHABlock:
         hq = eng.side(lambda: self.qkv_proj.wgrad([self.x], dqkv))
         dx = pool.get(self.x.shape)
         self.qkv_proj.dgrad(dqkv, [dx], residuals=[dout])
-        eng.join(ho, hq)  # dout belongs to the caller, dqkv to the pool
+        eng.join_later(ho, hq)  # dout belongs to the caller, dqkv to the pool
         pool.put(dqkv)
         return dx
 
@@ -446,7 +455,7 @@ class SLABlock:
         hq = eng.side(lambda: self.qkv_proj.wgrad([self.x], dqkv))
         dx = pool.get(self.x.shape)
         self.qkv_proj.dgrad(dqkv, [dx], residuals=[dout])
-        eng.join(ho, hq)
+        eng.join_later(ho, hq)
         pool.put(dqkv)
         return dx
 
@@ -484,7 +493,7 @@ class DownConv:
         hw = self.eng.side(lambda: ops.wgrad(VDN_TAP_DOWN, [self.x], dy, self.dw, TAPS_4x4, dbias=self.dbias))
         for py, px, shifts, _, wd in self.cls:
             ops.tapgemm(VDN_TAP_UP, [dy], wd, shifts, residual=acc, out=acc, py=py, px=px)
-        self.eng.join(hw)
+        self.eng.join_later(hw)
         return acc
 
 
@@ -522,7 +531,7 @@ class UpConv:
         hw = self.eng.side(lambda: ops.wgrad(VDN_TAP_UP, [self.x], dy, self.dw, TAPS_4x4, dbias=self.dbias))
         dx = pool.get(self.x.shape)
         ops.tapgemm(VDN_TAP_DOWN, [dy], self.wd, TAPS_4x4, out=dx)
-        self.eng.join(hw)
+        self.eng.join_later(hw)
         return dx
 
 
@@ -567,11 +576,33 @@ class UnetEngine:
             if h is not None:
                 main.wait_event(h)
 
+    def join_later(self, *handles):
+        """Join of side-stream work whose RESULTS the dependency chain does not need (weight gradients): inside a
+        backward stage the wait moves to the end of the stage, together with the recycling of every scratch buffer the
+        stage released - the chain no longer stalls behind a weight-gradient GEMM at the end of every block (180 GB of
+        HBM pay for the extra live buffers). Outside a stage it is a plain join."""
+        if self.pool.deferred is None:
+            self.join(*handles)
+        else:
+            self._pending.extend(h for h in handles if h is not None)
+
+    def begin_stage(self):
+        if self.defer_joins:
+            self.pool.deferred = []
+
+    def end_stage(self):
+        if self.pool.deferred is not None:
+            self.join(*self._pending)
+            self._pending.clear()
+            self.pool.release_deferred()
+
     def __init__(self, store: ParamStore, *, dim: int, channels: int, dim_mults=(1, 2, 4, 8), init_kernel_size=7,
                  B: int, F: int, H: int, W: int, training: bool, out_dim: Optional[int] = None, groups: int = GROUPS,
                  use_sla: bool = True):
         self.store, self.device, self.training = store, store.flat.device, training
         self._lane, self._splitk_ws = 0, {}
+        self._pending = []
+        self.defer_joins = _lib.host_flag("VDN_DEFER_JOINS", "1") != "0"
         self.dim, self.channels, self.B, self.F, self.H, self.W = dim, channels, B, F, H, W
         self.out_dim = channels if out_dim is None else out_dim
         self.ks = init_kernel_size
@@ -835,6 +866,16 @@ class UnetEngine:
         stages += [("mid", st_mid)]
         stages += [(f"downs.{l}", make_down(l)) for l in reversed(range(n))]
         stages += [("late", st_late)]
+        def staged(fn):
+            def run():
+                self.begin_stage()
+                try:
+                    fn()
+                finally:
+                    self.end_stage()
+            return run
+
+        stages = [(nm, staged(fn)) for nm, fn in stages]
         self._bw_state = S
         return stages
 
