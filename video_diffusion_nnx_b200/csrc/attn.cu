@@ -595,9 +595,10 @@ __global__ void __launch_bounds__(256) sla_bwd_tokens_kernel(const bf16* __restr
 static int sla_splits(int N, int n_img) {
   int per = std::max(kSlaTile, ((N + 31) / 32 + kSlaTile - 1) / kSlaTile * kSlaTile);  // <= 32 splits
   const int max_splits = std::max(1, (N + per - 1) / per);
-  // the context kernels keep three blocks of 256 threads resident per SM (74 registers): fill exactly one wave. (Four per
-  // SM with a ceiling gave 600 blocks for the 444 slots at 40 frames - 1.35 waves; 5.98 vs 6.04 ms per training step.)
-  const int per_sm = tune_int("VDN_SLA_BLOCKS_PER_SM", 3);
+  // the context kernels keep two blocks of 256 threads resident per SM (92 - 97 registers with the double-buffered
+  // operand words): fill exactly one wave. (Four per SM with a ceiling gave 600 blocks at 40 frames - a wave and a
+  // half; 5.84 vs 6.04 ms per training step.)
+  const int per_sm = tune_int("VDN_SLA_BLOCKS_PER_SM", 2);
   const int want = std::max(1, (148 * per_sm) / std::max(1, n_img));
   return std::min(max_splits, want);
 }

@@ -372,19 +372,33 @@ __global__ void __launch_bounds__(256) sla_ctx_partial_mma_kernel(const bf16* __
       srow[u][i] = 0.f;
     }
   const uint32_t* base = reinterpret_cast<const uint32_t*>(qkv + (long)img * N * kSmQKV + h * kSmDh);
+  // the words of the NEXT 16-token group are requested before the current group is processed (register double buffer):
+  // one group per iteration left every warp a load round trip per 8 MMAs
+  uint32_t nkw[2][4], nvw0[4], nvw1[4];
+  auto fetch = [&](int n0) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int n = min(n0 + 4 * j + c, n_end - 1);
+      const uint32_t* row = base + (long)n * (kSmQKV / 2);
+      nkw[0][c] = __ldg(row + kSmHD / 2 + g);
+      nkw[1][c] = __ldg(row + kSmHD / 2 + 8 + g);
+      nvw0[c] = __ldg(row + kSmHD + g);
+      nvw1[c] = __ldg(row + kSmHD + 8 + g);
+    }
+  };
+  if (n_begin < n_end) fetch(n_begin);
   for (int n0 = n_begin; n0 < n_end; n0 += 16) {
     uint32_t kw[2][4], vw0[4], vw1[4];
     bool valid[4];
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-      const int n = n0 + 4 * j + c;
-      valid[c] = n < n_end;
-      const uint32_t* row = base + (long)(valid[c] ? n : n_end - 1) * (kSmQKV / 2);
-      kw[0][c] = __ldg(row + kSmHD / 2 + g);
-      kw[1][c] = __ldg(row + kSmHD / 2 + 8 + g);
-      vw0[c] = __ldg(row + kSmHD + g);
-      vw1[c] = __ldg(row + kSmHD + 8 + g);
+      valid[c] = n0 + 4 * j + c < n_end;
+      kw[0][c] = nkw[0][c];
+      kw[1][c] = nkw[1][c];
+      vw0[c] = nvw0[c];
+      vw1[c] = nvw1[c];
     }
+    if (n0 + 16 < n_end) fetch(n0 + 16);
     float kf[2][2][4];
 #pragma unroll
     for (int u = 0; u < 2; ++u)
@@ -446,19 +460,30 @@ __global__ void __launch_bounds__(256) sla_dctx_mma_kernel(const bf16* __restric
   tokacc_zero(acc);
   const uint32_t* qbase = reinterpret_cast<const uint32_t*>(qkv + (long)img * N * kSmQKV + h * kSmDh);
   const uint32_t* gbase = reinterpret_cast<const uint32_t*>(dtok + (long)img * N * kSmHD + h * kSmDh);
+  uint32_t nqw[2][4], ngw0[4], ngw1[4];  // next group's words (register double buffer, see sla_ctx_partial_mma_kernel)
+  auto fetch = [&](int n0) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const long nn = min(n0 + 4 * j + c, n_end - 1);
+      nqw[0][c] = __ldg(qbase + nn * (kSmQKV / 2) + g);
+      nqw[1][c] = __ldg(qbase + nn * (kSmQKV / 2) + 8 + g);
+      ngw0[c] = __ldg(gbase + nn * (kSmHD / 2) + g);
+      ngw1[c] = __ldg(gbase + nn * (kSmHD / 2) + 8 + g);
+    }
+  };
+  if (n_begin < n_end) fetch(n_begin);
   for (int n0 = n_begin; n0 < n_end; n0 += 16) {
     uint32_t qw[2][4], gw0[4], gw1[4];
     bool valid[4];
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-      const int n = n0 + 4 * j + c;
-      valid[c] = n < n_end;
-      const long nn = valid[c] ? n : n_end - 1;
-      qw[0][c] = __ldg(qbase + nn * (kSmQKV / 2) + g);
-      qw[1][c] = __ldg(qbase + nn * (kSmQKV / 2) + 8 + g);
-      gw0[c] = __ldg(gbase + nn * (kSmHD / 2) + g);
-      gw1[c] = __ldg(gbase + nn * (kSmHD / 2) + 8 + g);
+      valid[c] = n0 + 4 * j + c < n_end;
+      qw[0][c] = nqw[0][c];
+      qw[1][c] = nqw[1][c];
+      gw0[c] = ngw0[c];
+      gw1[c] = ngw1[c];
     }
+    if (n0 + 16 < n_end) fetch(n0 + 16);
     float qf[2][2][4];
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
