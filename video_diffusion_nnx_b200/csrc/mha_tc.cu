@@ -352,6 +352,9 @@ extern "C" int vdn_mha_temporal_tc_fwd(const void* x, const void* w_hm, const fl
   VDN_REQUIRE(x && w_hm && o && B > 0 && H > 0 && W > 0, VDN_E_SHAPE, "mha_tc: bad args");
   VDN_REQUIRE(vdn_mha_temporal_tc_supported(F, C), VDN_E_SHAPE, "mha_tc: F=%d C=%d not instantiated", F, C);
   const bool force_tcgen05 = tune_on("VDN_MHA_TC_FWD");  // A/B comparison only
+  // training forward (q|k|v and lse kept for the backward): projection on tcgen05, F x F core on warp-level MMAs
+  if (C == 32 && qkv && lse && vdn::mha_train_tc_applicable(F, H * W) && !tune_on("VDN_MHA_TRAIN_MMA") && !force_tcgen05)
+    return vdn::mha_train_tc_launch(x, w_hm, bias_hm, o, qkv, lse, B, F, H, W, reinterpret_cast<cudaStream_t>(stream));
   if (C == 32 && !(force_tcgen05 && (F == 10 || F == 16)))
     return vdn::mha_temporal_mma_fwd_launch(x, w_hm, bias_hm, o, qkv, lse, B, F, H, W, reinterpret_cast<cudaStream_t>(stream));
   const int PX = std::min(128 / F, H * W);  // pixels per 128-row tile (12 for F = 10, 8 for F = 16)

@@ -65,6 +65,11 @@ bool mha_folded_tc_applicable(int F, int HW);
 int mha_folded_tc_launch(const void* x, const void* fa, const float* fu, const void* fm, const float* fb, void* out, int B,
                          int F, int H, int W, cudaStream_t st);
 
+// mha_train_tc.cu: temporal attention forward of the training engines (C = 32), projection on tcgen05
+bool mha_train_tc_applicable(int F, int HW);
+int mha_train_tc_launch(const void* x, const void* w_hm, const float* bias_hm, void* o, void* qkv, float* lse, int B, int F,
+                        int H, int W, cudaStream_t st);
+
 // sla_apply_tc.cu: apply pass of the fused SpatialLinearAttention forward (inference, C = 32) on tcgen05
 bool sla_apply_tc_applicable(int N);
 size_t sla_apply_tc_scratch_bytes(int n_img);
