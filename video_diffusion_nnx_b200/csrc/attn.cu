@@ -595,11 +595,23 @@ __global__ void __launch_bounds__(256) sla_bwd_tokens_kernel(const bf16* __restr
 static int sla_splits(int N, int n_img) {
   int per = std::max(kSlaTile, ((N + 31) / 32 + kSlaTile - 1) / kSlaTile * kSlaTile);  // <= 32 splits
   const int max_splits = std::max(1, (N + per - 1) / per);
-  // the context kernels keep two blocks of 256 threads resident per SM (92 - 97 registers with the double-buffered
-  // operand words): fill exactly one wave. (Four per SM with a ceiling gave 600 blocks at 40 frames - a wave and a
-  // half; 5.84 vs 6.04 ms per training step.)
-  const int per_sm = tune_int("VDN_SLA_BLOCKS_PER_SM", 2);
-  const int want = std::max(1, (148 * per_sm) / std::max(1, n_img));
+  // The context kernels keep two blocks of 256 threads resident per SM (92 - 124 registers): take the smallest split
+  // count whose n_img x splits blocks fill whole waves of those 296 slots to >= 85 % (40 frames: 7 splits = 280 blocks;
+  // 160 frames: 5 splits = 800 blocks = 2.7 waves of 3). Four blocks per SM with a ceiling gave 600 blocks at 40 frames -
+  // a wave and a half; 5.84 vs 6.04 ms per training step.
+  const int slots = 148 * tune_int("VDN_SLA_BLOCKS_PER_SM", 2);
+  int want = 1;
+  double best = 0.0;
+  for (int sp = 1; sp <= max_splits; ++sp) {
+    const long blocks = (long)n_img * sp;
+    const long waves = (blocks + slots - 1) / slots;
+    const double eff = (double)blocks / (double)(waves * slots);
+    if (eff > best + 1e-9) {
+      best = eff;
+      want = sp;
+    }
+    if (eff >= 0.85) break;
+  }
   return std::min(max_splits, want);
 }
 
