@@ -337,7 +337,9 @@ def wgrad_roofline(torch, ops, pk):
             "algorithmic_bytes": bytes_alg, "algorithmic_flops": flops, "tensor_tflops": flops / (us * 1e-6) / 1e12,
             "us_per_launch": us, "peak_source": pk["src"], "buffers_in_rotation": nb,
             "share_of_step_kernel_time": 0.165, "launch_list": "profiles/r2_final_launches_train_v2_2_b4.summary.txt",
-            "l2": "the gradient tensors rotate over sets larger than L2 between launches"}
+            "l2": "the gradient tensors rotate over sets larger than L2 between launches",
+            "note": "dominant by kernel name; the kernel FURTHEST below its roofline is the generic tap-GEMM on the "
+                    "small-M convs (second by share): first entry of roofline_kernels"}
 
 
 def _graph_time_us(torch, run, n=32, warm=4):

@@ -181,6 +181,11 @@ int vdn_resblock_tail_fwd(const void* b_raw, const float* gn_sums, const float* 
 int vdn_gn_silu_bwd(const void* dy, const void* x_raw, const float* gn_sums, const float* gamma, const float* beta,
                     const float* scale_shift, int ss_ld, float* T_ws, void* dx_raw, float* dgamma, float* dbeta,
                     float* dss, int dss_ld, float* dconv_bias, int B, int rows_per_sample, int C, int G, void* stream);
+/* vdn_gn_silu_bwd with T_ws zeroed by the CALLER: a step's layers take slices of one buffer zeroed once, instead of a
+ * memset node per call on the dependency chain. */
+int vdn_gn_silu_bwd_acc(const void* dy, const void* x_raw, const float* gn_sums, const float* gamma, const float* beta,
+                        const float* scale_shift, int ss_ld, float* T_ws, void* dx_raw, float* dgamma, float* dbeta,
+                        float* dss, int dss_ld, float* dconv_bias, int B, int rows_per_sample, int C, int G, void* stream);
 int vdn_ln_bwd(const void* s, const void* dy, const float* ln_gamma, void* ds, float* dgamma, float* dbeta, long P,
                int C, void* stream);
 
@@ -204,6 +209,9 @@ int vdn_sla_core_fwd(const void* qkv, void* tok_out, float* ctx, float* kstat, f
                      void* stream);
 int vdn_sla_core_bwd(const void* qkv, const void* d_tok, const float* ctx, const float* kstat, float* dctx,
                      void* dqkv, int n_img, int N, void* stream);
+/* vdn_sla_core_bwd with dctx zeroed by the CALLER (see vdn_gn_silu_bwd_acc). */
+int vdn_sla_core_bwd_acc(const void* qkv, const void* d_tok, const float* ctx, const float* kstat, float* dctx,
+                         void* dqkv, int n_img, int N, void* stream);
 /* Fused SpatialLinearAttention block forward for C == 32 (modules.py:99-129 incl. the to_q/k/v and to_out 1x1
  * convs and the residual of unet3d.py:170-178): out = x + to_out(SLA(x)) with no q/k/v/tok tensor in HBM. x, out
  * bf16 [P][32]; w_qkv packed bf16 [768][32] (vdn_pack_weight mode 0 of the fused q|k|v kernel), w_out packed bf16

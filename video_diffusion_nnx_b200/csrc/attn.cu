@@ -724,12 +724,25 @@ extern "C" int vdn_sla_fused_fwd(const void* x, const void* w_qkv, const void* w
   return sla_apply_fused_launch(x, w_qkv, w_out, ctx, out, n_img, N, st);
 }
 
+static int sla_core_bwd_impl(const void* qkv, const void* d_tok, const float* ctx, const float* kstat, float* dctx,
+                             void* dqkv, int n_img, int N, void* stream, bool zero_ws);
 extern "C" int vdn_sla_core_bwd(const void* qkv, const void* d_tok, const float* ctx, const float* kstat, float* dctx,
                                 void* dqkv, int n_img, int N, void* stream) {
+  return sla_core_bwd_impl(qkv, d_tok, ctx, kstat, dctx, dqkv, n_img, N, stream, true);
+}
+// Same with dctx zeroed by the CALLER (one memset for all the blocks of a step instead of a memset node per call).
+extern "C" int vdn_sla_core_bwd_acc(const void* qkv, const void* d_tok, const float* ctx, const float* kstat, float* dctx,
+                                    void* dqkv, int n_img, int N, void* stream) {
+  return sla_core_bwd_impl(qkv, d_tok, ctx, kstat, dctx, dqkv, n_img, N, stream, false);
+}
+static int sla_core_bwd_impl(const void* qkv, const void* d_tok, const float* ctx, const float* kstat, float* dctx,
+                             void* dqkv, int n_img, int N, void* stream, bool zero_ws) {
   VDN_REQUIRE(qkv && d_tok && ctx && kstat && dctx && dqkv && n_img > 0 && N > 0, VDN_E_SHAPE, "sla_core_bwd: bad args");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  cudaError_t e = cudaMemsetAsync(dctx, 0, (size_t)n_img * kHeads * 1024 * sizeof(float), st);
-  VDN_REQUIRE(e == cudaSuccess, VDN_E_CUDA, "sla_core_bwd memset: %s", cudaGetErrorString(e));
+  if (zero_ws) {
+    cudaError_t e = cudaMemsetAsync(dctx, 0, (size_t)n_img * kHeads * 1024 * sizeof(float), st);
+    VDN_REQUIRE(e == cudaSuccess, VDN_E_CUDA, "sla_core_bwd memset: %s", cudaGetErrorString(e));
+  }
   const int ns = sla_splits(N, n_img);
   const int per = (N + ns - 1) / ns;
   const int per_al = (per + kSlaTile - 1) / kSlaTile * kSlaTile;

@@ -872,17 +872,41 @@ extern "C" int vdn_resblock_tail_fwd(const void* b_raw, const float* gn_sums, co
   return check_launch("resblock_tail_fwd");
 }
 
+static int gn_silu_bwd_impl(const void* dy, const void* x_raw, const float* gn_sums, const float* gamma, const float* beta,
+                            const float* scale_shift, int ss_ld, float* T_ws, void* dx_raw, float* dgamma, float* dbeta,
+                            float* dss, int dss_ld, float* dconv_bias, int B, int rows_per_sample, int C, int G, void* stream,
+                            bool zero_ws);
+
 extern "C" int vdn_gn_silu_bwd(const void* dy, const void* x_raw, const float* gn_sums, const float* gamma,
                                const float* beta, const float* scale_shift, int ss_ld, float* T_ws, void* dx_raw,
                                float* dgamma, float* dbeta, float* dss, int dss_ld, float* dconv_bias, int B,
                                int rows_per_sample, int C, int G, void* stream) {
+  return gn_silu_bwd_impl(dy, x_raw, gn_sums, gamma, beta, scale_shift, ss_ld, T_ws, dx_raw, dgamma, dbeta, dss, dss_ld,
+                          dconv_bias, B, rows_per_sample, C, G, stream, true);
+}
+// Same with T_ws zeroed by the CALLER (one memset for all the layers of a step instead of a memset node per call).
+extern "C" int vdn_gn_silu_bwd_acc(const void* dy, const void* x_raw, const float* gn_sums, const float* gamma,
+                                   const float* beta, const float* scale_shift, int ss_ld, float* T_ws, void* dx_raw,
+                                   float* dgamma, float* dbeta, float* dss, int dss_ld, float* dconv_bias, int B,
+                                   int rows_per_sample, int C, int G, void* stream) {
+  return gn_silu_bwd_impl(dy, x_raw, gn_sums, gamma, beta, scale_shift, ss_ld, T_ws, dx_raw, dgamma, dbeta, dss, dss_ld,
+                          dconv_bias, B, rows_per_sample, C, G, stream, false);
+}
+
+static int gn_silu_bwd_impl(const void* dy, const void* x_raw, const float* gn_sums, const float* gamma, const float* beta,
+                            const float* scale_shift, int ss_ld, float* T_ws, void* dx_raw, float* dgamma, float* dbeta,
+                            float* dss, int dss_ld, float* dconv_bias, int B, int rows_per_sample, int C, int G, void* stream,
+                            bool zero_ws) {
   int rc = check_gn("gn_silu_bwd", B, rows_per_sample, C, G);
   if (rc) return rc;
   VDN_REQUIRE(pow2(C / 8) && C / 8 <= kNormThreads, VDN_E_SHAPE, "gn_silu_bwd: C=%d must be 8 * power of two <= 2048", C);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   GnArgs a{reinterpret_cast<const bf16*>(x_raw), gn_sums, gamma, beta, scale_shift, ss_ld, B, rows_per_sample, C, G};
-  cudaError_t e = cudaMemsetAsync(T_ws, 0, (size_t)B * C * 2 * sizeof(float), st);
-  VDN_REQUIRE(e == cudaSuccess, VDN_E_CUDA, "gn_silu_bwd memset: %s", cudaGetErrorString(e));
+  cudaError_t e = cudaSuccess;
+  if (zero_ws) {
+    e = cudaMemsetAsync(T_ws, 0, (size_t)B * C * 2 * sizeof(float), st);
+    VDN_REQUIRE(e == cudaSuccess, VDN_E_CUDA, "gn_silu_bwd memset: %s", cudaGetErrorString(e));
+  }
   {
     // single-launch version when the (x, dy) slices of all samples fit in the SMs' shared memory. Opt-in
     // (VDN_GN_FUSED=1): measured 23.7 us against 32.9 us for the two kernels at the 64x64 level of config_v2_2 in

@@ -244,6 +244,7 @@ class ResBlock:
                                                          "block_2.norm.bias", "norm_2.scale", "norm_2.bias")}
         if eng.training:
             self.g = {k: st.gview(f"{prefix}.{k}") for k in self.p}
+            self.t_off = eng.reserve_zeroed(2 * eng.B * cout * 2)  # the two GroupNorm backward passes' [B][C][2] sums
         shape = (n_img, H, W, cout)
         self.a_raw, self.a, self.b_raw, self.out = (eng.new(shape) for _ in range(4))
         self.s = eng.new(shape) if self.res is not None else None
@@ -287,11 +288,11 @@ class ResBlock:
         # LayerNorm backward of the residual branch does not depend on the GroupNorm chain: side stream
         hln = eng.side(lambda: ops.ln_bwd(s, dout, self.p["norm_2.scale"], ds, self.g["norm_2.scale"],
                                           self.g["norm_2.bias"], P, C), lane=1)
-        T = pool.get((B, C, 2), F32)
+        T2, T1 = eng.zeroed(self.t_off, B * C * 2).view(B, C, 2), eng.zeroed(self.t_off + B * C * 2, B * C * 2).view(B, C, 2)
         db_raw = pool.get(shape)
         ops.gn_silu_bwd(dout, self.b_raw, self.sums2, self.p["block_2.norm.scale"], self.p["block_2.norm.bias"], None,
-                        T, db_raw, self.g["block_2.norm.scale"], self.g["block_2.norm.bias"], None, B, self.rows, C,
-                        G=eng.groups, dconv_bias=self.conv2.dbias)
+                        T2, db_raw, self.g["block_2.norm.scale"], self.g["block_2.norm.bias"], None, B, self.rows, C,
+                        G=eng.groups, dconv_bias=self.conv2.dbias, prezeroed=True)
         # weight gradients are off the critical path: they run on the side stream, overlapped with the
         # data-gradient chain below, and are joined before their operands go back to the pool
         h2 = eng.side(lambda: self.conv2.wgrad([self.a], db_raw, bias_done=True))
@@ -300,10 +301,9 @@ class ResBlock:
         da_raw = pool.get(shape)
         dss = eng.dss[:, self.ss_off:self.ss_off + 2 * C] if self.ss_off is not None else None
         ops.gn_silu_bwd(da, self.a_raw, self.sums1, self.p["block_1.norm.scale"], self.p["block_1.norm.bias"],
-                        self._ss(), T, da_raw, self.g["block_1.norm.scale"], self.g["block_1.norm.bias"], dss, B,
-                        self.rows, C, G=eng.groups, dconv_bias=self.conv1.dbias)
+                        self._ss(), T1, da_raw, self.g["block_1.norm.scale"], self.g["block_1.norm.bias"], dss, B,
+                        self.rows, C, G=eng.groups, dconv_bias=self.conv1.dbias, prezeroed=True)
         pool.put(da)
-        pool.put(T)
         h1 = eng.side(lambda: self.conv1.wgrad(self.srcs, da_raw, bias_done=True))
         sshape = (self.n_img, self.H, self.W, self.c_src)
         dsrc = [pool.get(sshape) for _ in range(self.n_src)]
@@ -426,6 +426,8 @@ class SLABlock:
         self.qkv = None if self.fused else eng.new((n_img, H, W, 3 * HD))
         self.tok = None if self.fused else eng.new((n_img, H, W, HD))
         self.ctx = eng.new((n_img, HEADS, 32, 32), F32)
+        if eng.training:
+            self.dctx_off = eng.reserve_zeroed(n_img * HEADS * 32 * 32)
         self.kstat = eng.new((n_img, HEADS, 2, 32), F32)
         self.ws = eng.shared_ws(ops.sla_workspace_floats(n_img, N))
         self.out = eng.new((n_img, H, W, C))
@@ -448,10 +450,9 @@ class SLABlock:
         dtok = pool.get(self.tok.shape)
         self.out_proj.dgrad(dout, [dtok])
         dqkv = pool.get(self.qkv.shape)
-        dctx = pool.get(self.ctx.shape, F32)
-        ops.sla_core_bwd(self.qkv, dtok, self.ctx, self.kstat, dctx, dqkv, self.n_img, self.H * self.W)
+        dctx = eng.zeroed(self.dctx_off, self.ctx.numel()).view(self.ctx.shape)
+        ops.sla_core_bwd(self.qkv, dtok, self.ctx, self.kstat, dctx, dqkv, self.n_img, self.H * self.W, prezeroed=True)
         pool.put(dtok)
-        pool.put(dctx)
         hq = eng.side(lambda: self.qkv_proj.wgrad([self.x], dqkv))
         dx = pool.get(self.x.shape)
         self.qkv_proj.dgrad(dqkv, [dx], residuals=[dout])
@@ -586,6 +587,20 @@ class UnetEngine:
         else:
             self._pending.extend(h for h in handles if h is not None)
 
+    def reserve_zeroed(self, n_floats: int) -> int:
+        """Reserves n fp32 of the per-step zeroed scratch (accumulators that kernels add into: GroupNorm backward sums,
+        SpatialLinearAttention dctx). One memset per step at the start of the backward instead of a memset node in front
+        of every consumer on the dependency chain."""
+        off = self._zeroed_total
+        self._zeroed_total += (n_floats + 63) // 64 * 64
+        return off
+
+    def zeroed(self, off: int, n_floats: int) -> torch.Tensor:
+        if self._zeroed is None or self._zeroed.numel() < self._zeroed_total:
+            assert not torch.cuda.is_current_stream_capturing(), "zeroed scratch must exist before graph capture"
+            self._zeroed = torch.zeros(self._zeroed_total, dtype=F32, device=self.device)
+        return self._zeroed[off:off + n_floats]
+
     def begin_stage(self):
         if self.defer_joins:
             self.pool.deferred = []
@@ -602,6 +617,7 @@ class UnetEngine:
         self.store, self.device, self.training = store, store.flat.device, training
         self._lane, self._splitk_ws = 0, {}
         self._pending = []
+        self._zeroed, self._zeroed_total = None, 0
         self.defer_joins = _lib.host_flag("VDN_DEFER_JOINS", "1") != "0"
         self.dim, self.channels, self.B, self.F, self.H, self.W = dim, channels, B, F, H, W
         self.out_dim = channels if out_dim is None else out_dim
@@ -800,6 +816,9 @@ class UnetEngine:
 
         def st_final():
             self.dss.zero_()
+            if self._zeroed_total:
+                self.zeroed(0, 1)  # allocate on first use
+                self._zeroed.zero_()
             dh = pool.get(self.h_last.shape)
             ops.final_conv_bwd(self.h_last, S["dout"], st.view("final_conv.1.kernel"), dh,
                                st.gview("final_conv.1.kernel"), st.gview("final_conv.1.bias"), P, self.dim, self.out_dim)

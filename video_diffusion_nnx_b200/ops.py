@@ -150,12 +150,15 @@ def resblock_tail_fwd(b_raw, sums, gamma, beta, s, ln_g, ln_b, out, B, rows, Cc,
                                     ptr(out), B, rows, Cc, G, stream_ptr()), "vdn_resblock_tail_fwd")
 
 
-def gn_silu_bwd(dy, x_raw, sums, gamma, beta, ss, T_ws, dx_raw, dgamma, dbeta, dss, B, rows, Cc, G=8, dconv_bias=None):
+def gn_silu_bwd(dy, x_raw, sums, gamma, beta, ss, T_ws, dx_raw, dgamma, dbeta, dss, B, rows, Cc, G=8, dconv_bias=None,
+                prezeroed=False):
+    """prezeroed: T_ws was zeroed by the caller (vdn_gn_silu_bwd_acc: no memset node in front of the kernels)."""
     if "gn_bwd" in _SKIP:
         return
     ss_ld = ss.stride(0) if ss is not None else 0
     dss_ld = dss.stride(0) if dss is not None else 0
-    check(lib.vdn_gn_silu_bwd(ptr(dy), ptr(x_raw), ptr(sums), ptr(gamma), ptr(beta), ptr(ss), ss_ld, ptr(T_ws),
+    fn = lib.vdn_gn_silu_bwd_acc if prezeroed else lib.vdn_gn_silu_bwd
+    check(fn(ptr(dy), ptr(x_raw), ptr(sums), ptr(gamma), ptr(beta), ptr(ss), ss_ld, ptr(T_ws),
                               ptr(dx_raw), ptr(dgamma), ptr(dbeta), ptr(dss), dss_ld, ptr(dconv_bias), B, rows, Cc, G, stream_ptr()),
           "vdn_gn_silu_bwd")
 
@@ -198,10 +201,11 @@ def sla_fused_fwd(x, w_qkv, w_out, out, ctx, kstat, ws, n_img, N, Cc):
                                 stream_ptr()), "vdn_sla_fused_fwd")
 
 
-def sla_core_bwd(qkv, d_tok, ctx, kstat, dctx, dqkv, n_img, N):
+def sla_core_bwd(qkv, d_tok, ctx, kstat, dctx, dqkv, n_img, N, prezeroed=False):
     if "sla_bwd" in _SKIP:
         return
-    check(lib.vdn_sla_core_bwd(ptr(qkv), ptr(d_tok), ptr(ctx), ptr(kstat), ptr(dctx), ptr(dqkv), n_img, N,
+    fn = lib.vdn_sla_core_bwd_acc if prezeroed else lib.vdn_sla_core_bwd
+    check(fn(ptr(qkv), ptr(d_tok), ptr(ctx), ptr(kstat), ptr(dctx), ptr(dqkv), n_img, N,
                                stream_ptr()), "vdn_sla_core_bwd")
 
 
