@@ -248,3 +248,21 @@ def test_every_prototype_has_argtypes():
         assert fn.argtypes is not None and list(fn.argtypes) == argt, name
     with pytest.raises(ctypes.ArgumentError):
         _lib.lib.vdn_randn(None, "not a number", 0, 0, 0, None)
+
+
+def test_tapgemm_workspace_is_opt_in():
+    """vdn_tapgemm_workspace is host arithmetic (no GPU): 0 for every launch by default - the cluster split-K kernel
+    behind vdn_tapgemm_ws is opt-in (measured slower) - and the partial-tile scratch of the plan
+    (splits x row tiles x 128 x N fp32) once it is switched on."""
+    from video_diffusion_nnx_b200 import ops
+    from video_diffusion_nnx_b200._lib import debug_switches
+
+    args = (ops.VDN_TAP_UNIT, 40, 8, 8, 1, 256, ops.TAPS_3x3, 256)  # the (1,3,3) 256 -> 256 conv of the 8x8 level
+    assert ops.tapgemm_workspace_bytes(*args) == 0
+    with debug_switches(VDN_SPLITK=1):
+        nbytes = ops.tapgemm_workspace_bytes(*args)
+        assert nbytes == 3 * 20 * 128 * 256 * 4  # 20 row tiles x two 128-column tiles -> 3 K ranges per tile
+        # launches that fill the SMs on their own, or have too few K steps to split, never ask for scratch
+        assert ops.tapgemm_workspace_bytes(ops.VDN_TAP_UNIT, 40, 32, 32, 1, 64, ops.TAPS_3x3, 64) == 0
+        assert ops.tapgemm_workspace_bytes(ops.VDN_TAP_UNIT, 40, 8, 8, 1, 256, ops.TAPS_1x1, 768) == 0
+    assert ops.tapgemm_workspace_bytes(*args) == 0

@@ -168,6 +168,16 @@ def test_gn_silu_fwd_bwd(gn_bwd_mode, B, R, Cc, with_ss):
     assert _rel(dbet, beta.grad) < 1e-3
     if with_ss:
         assert _rel(dss, ss.grad) < 1e-3
+    # the caller-zeroed variant (vdn_gn_silu_bwd_acc: the engine zeroes one scratch per step instead of a memset node per
+    # layer) computes the same thing when its T_ws slice is zero on entry
+    T0 = torch.zeros(B, Cc, 2, device=DEV)
+    dx0 = torch.empty_like(x)
+    dgam0, dbet0, dcb0 = torch.zeros(Cc, device=DEV), torch.zeros(Cc, device=DEV), torch.zeros(Cc, device=DEV)
+    dss0 = torch.zeros(B, 2 * Cc, device=DEV) if with_ss else None
+    ops.gn_silu_bwd(dy, x, sums, gamma.detach(), beta.detach(), ss.detach() if with_ss else None, T0, dx0, dgam0, dbet0,
+                    dss0, B, R, Cc, dconv_bias=dcb0, prezeroed=True)
+    assert _rel(dx0, dx) < 1e-2 and _rel(dgam0, dgam) < 1e-3 and _rel(dbet0, dbet) < 1e-3
+    assert _rel(T0, T) < 1e-3  # same sums (atomic order may differ)
 
 
 @pytest.mark.parametrize("B,R,Cc", [(2, 256, 32), (2, 100, 128), (1, 40, 512), (1, 24, 1024),
