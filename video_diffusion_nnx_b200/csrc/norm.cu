@@ -480,6 +480,214 @@ __global__ void __launch_bounds__(kNormThreads, 2) gn_bwd_apply_kernel(const GnA
 }
 
 // ---------------------------------------------------------------------------------------
+// GroupNorm + SiLU backward in ONE launch without any grid-level exchange, for the small samples of the 8x8 / 16x16 levels:
+// the sums a backward needs couple only the channels of one GROUP of one sample, so a CTA that owns a whole (sample, group)
+// slice - rows x cpg elements, <= 40960 - can do both passes by itself: pass 1 reads x and dy once (x stays in registers
+// as raw bf16, dz = dy * silu'(z) goes to shared memory as fp32) and accumulates T1 / T2 per channel, the block reduces
+// them (shuffles over the lanes that own the same 8 channels, then 32 warp partials through shared memory), forms the
+// group means, and pass 2 turns dz into dx with three FMAs per element. No T round trip through L2, no second launch,
+// no barrier between CTAs; grid (G, B) = 32 CTAs of 1024 threads at config_v2_2.
+// ---------------------------------------------------------------------------------------
+constexpr int kGrpThreads = 512;
+constexpr int kGrpMaxVec = 3;   // 8-channel vectors per thread
+constexpr int kGrpCluster = 4;  // CTAs (row ranges) per (sample, group): rows * cpg / 8 <= 4 * 3 * 512
+
+__global__ void __launch_bounds__(kGrpThreads, 1) gn_bwd_group_kernel(const GnArgs a, const bf16* __restrict__ dy,
+                                                                      float* __restrict__ T, bf16* __restrict__ dx,
+                                                                      float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                                      float* __restrict__ dss, int dss_ld,
+                                                                      float* __restrict__ dconv_bias) {
+  extern __shared__ __align__(16) float s_dz[];  // [nvec][8]
+  __shared__ float2 s_stat;
+  __shared__ __align__(16) float sA[32], sB[32], sK[32], sSc[32];
+  __shared__ float sT[2][32];
+  __shared__ float sM12[2];
+  __shared__ __align__(16) float sRed[kGrpThreads / 32][4][16];
+  const int g = blockIdx.x, b = blockIdx.y;
+  const int cpg = a.C / a.G, vpr = cpg >> 3, c0g = g * cpg;
+  // the (sample, group) slice is split by rows over the kGrpCluster CTAs of a cluster (blockIdx.z = rank)
+  const int rows_cta = (a.rows + kGrpCluster - 1) / kGrpCluster;
+  const int row_lo = blockIdx.z * rows_cta;
+  const int my_rows = max(0, min(a.rows, row_lo + rows_cta) - row_lo);
+  const long nvec = (long)my_rows * vpr;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int v = tid % vpr;  // kGrpThreads is a multiple of vpr: a thread always owns the same 8 channels
+  const int c0 = c0g + v * 8;
+  const long base = ((long)b * a.rows + row_lo) * a.C;
+  pdl_trigger();
+  pdl_wait();
+  uint4 xraw[kGrpMaxVec], draw[kGrpMaxVec];
+#pragma unroll
+  for (int k = 0; k < kGrpMaxVec; ++k) {
+    const long i = tid + (long)k * kGrpThreads;
+    if (i < nvec) {
+      const long off = base + (i / vpr) * a.C + c0;
+      xraw[k] = ldg16(a.x + off);
+      draw[k] = ldg16(dy + off);
+    }
+  }
+  if (warp == 0) {  // (mean, rstd) of this group: the 16 replicas of the conv epilogue's partial sums
+    float s1 = 0.f, s2 = 0.f;
+    if (lane < kGnReplicas) {
+      const float2 q = *reinterpret_cast<const float2*>(a.sums + ((long)(lane * a.B + b) * a.G + g) * 2);
+      s1 = q.x;
+      s2 = q.y;
+    }
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) {
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    if (lane == 0) {
+      const float inv_n = 1.f / ((float)a.rows * (float)cpg);
+      const float mean = s1 * inv_n;
+      s_stat = make_float2(mean, rsqrtf(fmaxf(s2 * inv_n - mean * mean, 0.f) + kEps));
+    }
+  }
+  __syncthreads();
+  const float mean = s_stat.x, rstd = s_stat.y, nm = -mean * rstd;
+  if (tid < cpg) {
+    const int c = c0g + tid;
+    const float ga = a.gamma[c], be = a.beta[c];
+    const float sc = a.ss ? a.ss[(long)b * a.ss_ld + c] + 1.f : 1.f;
+    const float sh = a.ss ? a.ss[(long)b * a.ss_ld + a.C + c] : 0.f;
+    const float A = rstd * ga;
+    sA[tid] = A * sc;
+    sB[tid] = (be - mean * A) * sc + sh;
+    sK[tid] = ga * sc;
+    sSc[tid] = sc;
+  }
+  __syncthreads();
+  float cA[8], cB[8], t1[8], t2[8];
+  load_coef8(sA, v * 8, cA);
+  load_coef8(sB, v * 8, cB);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) t1[j] = t2[j] = 0.f;
+#pragma unroll
+  for (int k = 0; k < kGrpMaxVec; ++k) {
+    const long i = tid + (long)k * kGrpThreads;
+    if (i < nvec) {
+      float xv[8], dv[8], dz[8];
+      unpack8(xraw[k], xv);
+      unpack8(draw[k], dv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float z = fmaf(xv[j], cA[j], cB[j]);
+        dz[j] = dv[j] * silu_grad_f(z);
+        const float xh = fmaf(xv[j], rstd, nm);
+        t1[j] += dz[j];
+        t2[j] = fmaf(dz[j], xh, t2[j]);
+      }
+      float4* dp = reinterpret_cast<float4*>(s_dz + i * 8);
+      dp[0] = make_float4(dz[0], dz[1], dz[2], dz[3]);
+      dp[1] = make_float4(dz[4], dz[5], dz[6], dz[7]);
+    }
+  }
+  // lanes with the same v hold partials of the same 8 channels: xor-reduce over them, then over the 32 warps
+  for (int o = vpr; o < 32; o <<= 1) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      t1[j] += __shfl_xor_sync(0xffffffffu, t1[j], o);
+      t2[j] += __shfl_xor_sync(0xffffffffu, t2[j], o);
+    }
+  }
+  if (lane < vpr) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      sRed[warp][lane][j] = t1[j];
+      sRed[warp][lane][8 + j] = t2[j];
+    }
+  }
+  __syncthreads();
+  if (tid < 2 * cpg) {
+    const int which = tid / cpg, cc = tid - which * cpg;
+    float acc = 0.f;
+#pragma unroll 8
+    for (int w = 0; w < kGrpThreads / 32; ++w) acc += sRed[w][cc >> 3][which * 8 + (cc & 7)];
+    sT[which][cc] = acc;
+  }
+  // the row ranges of the cluster's CTAs meet here: every CTA adds its peers' per-channel partials (64 floats through
+  // DSMEM) and ends up with the sums of the whole slice
+  cluster_sync_all();
+  float tot = 0.f;
+  if (tid < 2 * cpg) {
+    const float* mine = &sT[0][0] + (tid / cpg) * 32 + (tid % cpg);
+    for (uint32_t r = 0; r < (uint32_t)kGrpCluster; ++r) tot += dsmem_ld_f32(mine, r);
+  }
+  cluster_sync_all();  // every peer has read this CTA's partials
+  if (tid < 2 * cpg) sT[tid / cpg][tid % cpg] = tot;
+  __syncthreads();
+  if (warp == 0) {
+    float m1 = lane < cpg ? sK[lane] * sT[0][lane] : 0.f;
+    float m2 = lane < cpg ? sK[lane] * sT[1][lane] : 0.f;
+    m1 = warp_sum(m1);
+    m2 = warp_sum(m2);
+    if (lane == 0) {
+      const float inv_n = 1.f / ((float)a.rows * (float)cpg);
+      sM12[0] = -m1 * inv_n * rstd;  // pre-multiplied by rstd (and negated) for the FMA chain below
+      sM12[1] = -m2 * inv_n * rstd;
+    }
+    if (lane < cpg && blockIdx.z == 0) {  // per-channel results of this (sample, group): once per cluster
+      const int c = c0g + lane;
+      const float u1 = sT[0][lane], u2 = sT[1][lane], sc = sSc[lane];
+      T[((long)b * a.C + c) * 2] = u1;
+      T[((long)b * a.C + c) * 2 + 1] = u2;
+      atomicAdd(&dgamma[c], sc * u2);
+      atomicAdd(&dbeta[c], sc * u1);
+      if (dss) {
+        dss[(long)b * dss_ld + c] = a.gamma[c] * u2 + a.beta[c] * u1;  // dscale = sum dz * (xhat*gamma + beta)
+        dss[(long)b * dss_ld + a.C + c] = u1;                          // dshift
+      }
+    }
+  }
+  __syncthreads();
+  float cK[8], bs[8];
+  load_coef8(sK, v * 8, cK);
+  const float m1r = sM12[0], m2r = sM12[1];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    cK[j] *= rstd;
+    bs[j] = 0.f;
+  }
+#pragma unroll
+  for (int k = 0; k < kGrpMaxVec; ++k) {
+    const long i = tid + (long)k * kGrpThreads;
+    if (i < nvec) {
+      float xv[8], o[8];
+      unpack8(xraw[k], xv);
+      const float4* dp = reinterpret_cast<const float4*>(s_dz + i * 8);
+      const float4 d0 = dp[0], d1 = dp[1];
+      const float dz[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float xh = fmaf(xv[j], rstd, nm);
+        o[j] = fmaf(xh, m2r, fmaf(dz[j], cK[j], m1r));  // rstd * (K dz - m1 - xhat m2)
+        bs[j] += o[j];
+      }
+      store8(dx + base + (i / vpr) * a.C + c0, o);
+    }
+  }
+  if (dconv_bias) {  // column sums of dx = the gradient of the producing conv's bias
+    for (int o = vpr; o < 32; o <<= 1) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) bs[j] += __shfl_xor_sync(0xffffffffu, bs[j], o);
+    }
+    __syncthreads();  // sRed is reused
+    if (lane < vpr) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sRed[warp][lane][j] = bs[j];
+    }
+    __syncthreads();
+    if (tid < cpg) {
+      float acc = 0.f;
+#pragma unroll 8
+      for (int w = 0; w < kGrpThreads / 32; ++w) acc += sRed[w][tid >> 3][tid & 7];
+      atomicAdd(&dconv_bias[c0g + tid], acc);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // Single-launch GroupNorm+SiLU backward for samples whose (x, dy) slices fit in the shared memory of the GPU's SMs
 // (every level of config_v2_2): one CTA per SM, gridDim.x CTAs per sample. A CTA streams its slice of x and dy from
 // HBM ONCE into shared memory while accumulating T1/T2, the CTAs of a sample meet at a per-sample barrier (global
@@ -903,6 +1111,46 @@ static int gn_silu_bwd_impl(const void* dy, const void* x_raw, const float* gn_s
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   GnArgs a{reinterpret_cast<const bf16*>(x_raw), gn_sums, gamma, beta, scale_shift, ss_ld, B, rows_per_sample, C, G};
   cudaError_t e = cudaSuccess;
+  {
+    // small samples: one CTA per (sample, group) does both passes by itself (gn_bwd_group_kernel); T_ws receives the
+    // per-channel sums with plain stores, so it needs no zeroing on this path
+    const int cpg = C / G;
+    const long slice = (long)rows_per_sample * cpg;
+    const int rows_cta = (rows_per_sample + kGrpCluster - 1) / kGrpCluster;
+    if ((cpg == 8 || cpg == 16 || cpg == 32) && (long)rows_cta * cpg <= (long)kGrpMaxVec * kGrpThreads * 8 && G <= 65535 &&
+        !tune_on("VDN_GN_NO_GROUP")) {
+      const size_t smem_g = (size_t)rows_cta * cpg * sizeof(float);
+      static bool cfg_g = false;
+      if (!cfg_g) {
+        e = cudaFuncSetAttribute(gn_bwd_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        VDN_REQUIRE(e == cudaSuccess, VDN_E_CUDA, "gn_bwd_group cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        cfg_g = true;
+      }
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(G, B, kGrpCluster);
+      cfg.blockDim = dim3(kGrpThreads);
+      cfg.dynamicSmemBytes = smem_g;
+      cfg.stream = st;
+      cudaLaunchAttribute at[2];
+      int na = 0;
+      at[na].id = cudaLaunchAttributeClusterDimension;
+      at[na].val.clusterDim.x = 1;
+      at[na].val.clusterDim.y = 1;
+      at[na].val.clusterDim.z = kGrpCluster;
+      ++na;
+      if (pdl_enabled()) {
+        at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+      }
+      cfg.attrs = at;
+      cfg.numAttrs = na;
+      cudaError_t lg = cudaLaunchKernelEx(&cfg, gn_bwd_group_kernel, a, reinterpret_cast<const bf16*>(dy), T_ws,
+                                          reinterpret_cast<bf16*>(dx_raw), dgamma, dbeta, dss, dss_ld, dconv_bias);
+      VDN_REQUIRE(lg == cudaSuccess, VDN_E_CUDA, "gn_bwd_group launch: %s", cudaGetErrorString(lg));
+      return check_launch("gn_bwd_group");
+    }
+  }
   if (zero_ws) {
     e = cudaMemsetAsync(T_ws, 0, (size_t)B * C * 2 * sizeof(float), st);
     VDN_REQUIRE(e == cudaSuccess, VDN_E_CUDA, "gn_silu_bwd memset: %s", cudaGetErrorString(e));
