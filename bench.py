@@ -311,7 +311,7 @@ def conv_roofline(torch, ops, pk, level=0, with_traffic=False):
 
 def wgrad_roofline(torch, ops, pk):
     """The step's dominant kernel by the committed launch list (profiles/r2_final_launches_train_v2_2_b4.summary.txt:
-    wgrad_kernel<0>, 90 launches = 16.5 % of the kernel time) on the instance that takes most of its time: the weight
+    wgrad_kernel<0>, 90 of 486 launches = 20 % of the kernel time) on the instance that takes most of its time: the weight
     (+ bias) gradient of a q|k|v projection at the full-resolution level, dW[C][768] = x^T dqkv over all P pixels -
     one pass over the 768-channel gradient tensor, HBM bound. Timed live, dqkv rotating over sets larger than L2."""
     dev, bf = "cuda", torch.bfloat16
@@ -336,7 +336,7 @@ def wgrad_roofline(torch, ops, pk):
             "bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"], "traffic": traffic,
             "algorithmic_bytes": bytes_alg, "algorithmic_flops": flops, "tensor_tflops": flops / (us * 1e-6) / 1e12,
             "us_per_launch": us, "peak_source": pk["src"], "buffers_in_rotation": nb,
-            "share_of_step_kernel_time": 0.165, "launch_list": "profiles/r2_final_launches_train_v2_2_b4.summary.txt",
+            "share_of_step_kernel_time": 0.20, "launch_list": "profiles/r2_final_launches_train_v2_2_b4.summary.txt",
             "l2": "the gradient tensors rotate over sets larger than L2 between launches",
             "note": "dominant by kernel name; the kernel FURTHEST below its roofline is the generic tap-GEMM on the "
                     "small-M convs (second by share): first entry of roofline_kernels"}
