@@ -480,56 +480,51 @@ __global__ void __launch_bounds__(kNormThreads, 2) gn_bwd_apply_kernel(const GnA
 }
 
 // ---------------------------------------------------------------------------------------
-// GroupNorm + SiLU backward in ONE launch without any grid-level exchange, for the small samples of the 8x8 / 16x16 levels:
-// the sums a backward needs couple only the channels of one GROUP of one sample, so a CTA that owns a whole (sample, group)
-// slice - rows x cpg elements, <= 40960 - can do both passes by itself: pass 1 reads x and dy once (x stays in registers
-// as raw bf16, dz = dy * silu'(z) goes to shared memory as fp32) and accumulates T1 / T2 per channel, the block reduces
-// them (shuffles over the lanes that own the same 8 channels, then 32 warp partials through shared memory), forms the
-// group means, and pass 2 turns dz into dx with three FMAs per element. No T round trip through L2, no second launch,
-// no barrier between CTAs; grid (G, B) = 32 CTAs of 1024 threads at config_v2_2.
+// GroupNorm + SiLU backward in ONE launch without any grid-level exchange: the sums a backward needs couple only the
+// channels of one GROUP of one sample, so a thread-block cluster that owns a whole (sample, channel slice) - max(8, cpg)
+// channels = one or two groups, all rows, split by rows over the CTAs of the cluster - can do both passes by itself:
+// pass 1 reads x and dy once (dz = dy * silu'(z) goes to shared memory as fp32; x stays in registers as raw bf16 when a
+// thread owns at most 3 vectors, else it is read again in pass 2 - an L2 hit), accumulates T1 / T2 per channel, the block
+// reduces them (shuffles over the lanes that own the same 8 channels, warp partials through shared memory), the CTAs of
+// the cluster add each other's 64 floats through DSMEM, and pass 2 turns dz into dx with three FMAs per element.
+// No T round trip through L2, no second launch, no barrier between clusters; 128 CTAs at every level of config_v2_2.
 // ---------------------------------------------------------------------------------------
 constexpr int kGrpThreads = 512;
-constexpr int kGrpMaxVec = 3;   // 8-channel vectors per thread
-constexpr int kGrpCluster = 4;  // CTAs (row ranges) per (sample, group): rows * cpg / 8 <= 4 * 3 * 512
+constexpr int kGrpMaxSmem = 200 * 1024;
 
+template <int kMaxVec, bool kXRegs>
 __global__ void __launch_bounds__(kGrpThreads, 1) gn_bwd_group_kernel(const GnArgs a, const bf16* __restrict__ dy,
                                                                       float* __restrict__ T, bf16* __restrict__ dx,
                                                                       float* __restrict__ dgamma, float* __restrict__ dbeta,
                                                                       float* __restrict__ dss, int dss_ld,
                                                                       float* __restrict__ dconv_bias) {
   extern __shared__ __align__(16) float s_dz[];  // [nvec][8]
-  __shared__ float2 s_stat;
-  __shared__ __align__(16) float sA[32], sB[32], sK[32], sSc[32];
+  __shared__ float2 s_stat[2];
+  __shared__ __align__(16) float sA[32], sB[32], sK[32], sSc[32], sR[32], sNm[32], sM1[32], sM2[32];
   __shared__ float sT[2][32];
-  __shared__ float sM12[2];
   __shared__ __align__(16) float sRed[kGrpThreads / 32][4][16];
-  const int g = blockIdx.x, b = blockIdx.y;
-  const int cpg = a.C / a.G, vpr = cpg >> 3, c0g = g * cpg;
-  // the (sample, group) slice is split by rows over the kGrpCluster CTAs of a cluster (blockIdx.z = rank)
-  const int rows_cta = (a.rows + kGrpCluster - 1) / kGrpCluster;
+  const int b = blockIdx.y;
+  const int cpg = a.C / a.G;
+  const int cw = cpg < 8 ? 8 : cpg;        // channels of this slice: one group, or two groups of 4
+  const int vpr = cw >> 3, c0s = blockIdx.x * cw;
+  const int n_cl = (int)gridDim.z;         // CTAs per (sample, slice) = cluster size: row ranges
+  const int rows_cta = (a.rows + n_cl - 1) / n_cl;
   const int row_lo = blockIdx.z * rows_cta;
   const int my_rows = max(0, min(a.rows, row_lo + rows_cta) - row_lo);
   const long nvec = (long)my_rows * vpr;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int v = tid % vpr;  // kGrpThreads is a multiple of vpr: a thread always owns the same 8 channels
-  const int c0 = c0g + v * 8;
+  const int c0 = c0s + v * 8;
   const long base = ((long)b * a.rows + row_lo) * a.C;
   pdl_trigger();
   pdl_wait();
-  uint4 xraw[kGrpMaxVec], draw[kGrpMaxVec];
-#pragma unroll
-  for (int k = 0; k < kGrpMaxVec; ++k) {
-    const long i = tid + (long)k * kGrpThreads;
-    if (i < nvec) {
-      const long off = base + (i / vpr) * a.C + c0;
-      xraw[k] = ldg16(a.x + off);
-      draw[k] = ldg16(dy + off);
-    }
-  }
-  if (warp == 0) {  // (mean, rstd) of this group: the 16 replicas of the conv epilogue's partial sums
+  uint4 xraw[kXRegs ? kMaxVec : 1];
+  // pass 1 in batches of up to 4 vectors per thread: all loads of a batch are in flight before the first is consumed
+  if (warp == 0) {  // (mean, rstd) of the slice's group(s): lanes 0-15 / 16-31 add up the 16 replicas of group 0 / 1
+    const int gi = lane >> 4, g = c0s / cpg + gi;
     float s1 = 0.f, s2 = 0.f;
-    if (lane < kGnReplicas) {
-      const float2 q = *reinterpret_cast<const float2*>(a.sums + ((long)(lane * a.B + b) * a.G + g) * 2);
+    if (gi * cpg < cw) {
+      const float2 q = *reinterpret_cast<const float2*>(a.sums + ((long)((lane & 15) * a.B + b) * a.G + g) * 2);
       s1 = q.x;
       s2 = q.y;
     }
@@ -538,52 +533,71 @@ __global__ void __launch_bounds__(kGrpThreads, 1) gn_bwd_group_kernel(const GnAr
       s1 += __shfl_xor_sync(0xffffffffu, s1, o);
       s2 += __shfl_xor_sync(0xffffffffu, s2, o);
     }
-    if (lane == 0) {
+    if ((lane & 15) == 0) {
       const float inv_n = 1.f / ((float)a.rows * (float)cpg);
       const float mean = s1 * inv_n;
-      s_stat = make_float2(mean, rsqrtf(fmaxf(s2 * inv_n - mean * mean, 0.f) + kEps));
+      s_stat[gi] = make_float2(mean, rsqrtf(fmaxf(s2 * inv_n - mean * mean, 0.f) + kEps));
     }
   }
   __syncthreads();
-  const float mean = s_stat.x, rstd = s_stat.y, nm = -mean * rstd;
-  if (tid < cpg) {
-    const int c = c0g + tid;
+  if (tid < cw) {
+    const int c = c0s + tid;
+    const float2 mr = s_stat[tid / cpg];
     const float ga = a.gamma[c], be = a.beta[c];
     const float sc = a.ss ? a.ss[(long)b * a.ss_ld + c] + 1.f : 1.f;
     const float sh = a.ss ? a.ss[(long)b * a.ss_ld + a.C + c] : 0.f;
-    const float A = rstd * ga;
+    const float A = mr.y * ga;
     sA[tid] = A * sc;
-    sB[tid] = (be - mean * A) * sc + sh;
+    sB[tid] = (be - mr.x * A) * sc + sh;
     sK[tid] = ga * sc;
     sSc[tid] = sc;
+    sR[tid] = mr.y;
+    sNm[tid] = -mr.x * mr.y;
   }
   __syncthreads();
-  float cA[8], cB[8], t1[8], t2[8];
+  float cA[8], cB[8], cR[8], cN[8], t1[8], t2[8];
   load_coef8(sA, v * 8, cA);
   load_coef8(sB, v * 8, cB);
+  load_coef8(sR, v * 8, cR);
+  load_coef8(sNm, v * 8, cN);
 #pragma unroll
   for (int j = 0; j < 8; ++j) t1[j] = t2[j] = 0.f;
+  constexpr int kBatch = kMaxVec < 4 ? kMaxVec : 4;
 #pragma unroll
-  for (int k = 0; k < kGrpMaxVec; ++k) {
-    const long i = tid + (long)k * kGrpThreads;
-    if (i < nvec) {
-      float xv[8], dv[8], dz[8];
-      unpack8(xraw[k], xv);
-      unpack8(draw[k], dv);
+  for (int k0 = 0; k0 < kMaxVec; k0 += kBatch) {
+    uint4 xb[kBatch], db[kBatch];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float z = fmaf(xv[j], cA[j], cB[j]);
-        dz[j] = dv[j] * silu_grad_f(z);
-        const float xh = fmaf(xv[j], rstd, nm);
-        t1[j] += dz[j];
-        t2[j] = fmaf(dz[j], xh, t2[j]);
+    for (int q = 0; q < kBatch; ++q) {
+      const long i = tid + (long)(k0 + q) * kGrpThreads;
+      if (k0 + q < kMaxVec && i < nvec) {
+        const long off = base + (i / vpr) * a.C + c0;
+        xb[q] = ldg16(a.x + off);
+        db[q] = ldg16(dy + off);
       }
-      float4* dp = reinterpret_cast<float4*>(s_dz + i * 8);
-      dp[0] = make_float4(dz[0], dz[1], dz[2], dz[3]);
-      dp[1] = make_float4(dz[4], dz[5], dz[6], dz[7]);
+    }
+#pragma unroll
+    for (int q = 0; q < kBatch; ++q) {
+      const long i = tid + (long)(k0 + q) * kGrpThreads;
+      if (k0 + q < kMaxVec && i < nvec) {
+        if (kXRegs) xraw[k0 + q] = xb[q];
+        float xv[8], dv[8], dz[8];
+        unpack8(xb[q], xv);
+        unpack8(db[q], dv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float z = fmaf(xv[j], cA[j], cB[j]);
+          dz[j] = dv[j] * silu_grad_f(z);
+          const float xh = fmaf(xv[j], cR[j], cN[j]);
+          t1[j] += dz[j];
+          t2[j] = fmaf(dz[j], xh, t2[j]);
+        }
+        float4* dp = reinterpret_cast<float4*>(s_dz + i * 8);
+        dp[0] = make_float4(dz[0], dz[1], dz[2], dz[3]);
+        dp[1] = make_float4(dz[4], dz[5], dz[6], dz[7]);
+      }
     }
   }
-  // lanes with the same v hold partials of the same 8 channels: xor-reduce over them, then over the 32 warps
+  // lanes with the same v hold partials of the same 8 channels: xor-reduce over them, then over the warps
   for (int o = vpr; o < 32; o <<= 1) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -599,72 +613,87 @@ __global__ void __launch_bounds__(kGrpThreads, 1) gn_bwd_group_kernel(const GnAr
     }
   }
   __syncthreads();
-  if (tid < 2 * cpg) {
-    const int which = tid / cpg, cc = tid - which * cpg;
+  if (tid < 2 * cw) {
+    const int which = tid / cw, cc = tid - which * cw;
     float acc = 0.f;
 #pragma unroll 8
     for (int w = 0; w < kGrpThreads / 32; ++w) acc += sRed[w][cc >> 3][which * 8 + (cc & 7)];
     sT[which][cc] = acc;
   }
-  // the row ranges of the cluster's CTAs meet here: every CTA adds its peers' per-channel partials (64 floats through
+  // the row ranges of the cluster's CTAs meet here: every CTA adds its peers' per-channel partials (<= 64 floats through
   // DSMEM) and ends up with the sums of the whole slice
   cluster_sync_all();
   float tot = 0.f;
-  if (tid < 2 * cpg) {
-    const float* mine = &sT[0][0] + (tid / cpg) * 32 + (tid % cpg);
-    for (uint32_t r = 0; r < (uint32_t)kGrpCluster; ++r) tot += dsmem_ld_f32(mine, r);
+  if (tid < 2 * cw) {
+    const float* mine = &sT[0][0] + (tid / cw) * 32 + (tid % cw);
+    for (uint32_t r = 0; r < (uint32_t)n_cl; ++r) tot += dsmem_ld_f32(mine, r);
   }
   cluster_sync_all();  // every peer has read this CTA's partials
-  if (tid < 2 * cpg) sT[tid / cpg][tid % cpg] = tot;
+  if (tid < 2 * cw) sT[tid / cw][tid % cw] = tot;
   __syncthreads();
   if (warp == 0) {
-    float m1 = lane < cpg ? sK[lane] * sT[0][lane] : 0.f;
-    float m2 = lane < cpg ? sK[lane] * sT[1][lane] : 0.f;
-    m1 = warp_sum(m1);
-    m2 = warp_sum(m2);
-    if (lane == 0) {
-      const float inv_n = 1.f / ((float)a.rows * (float)cpg);
-      sM12[0] = -m1 * inv_n * rstd;  // pre-multiplied by rstd (and negated) for the FMA chain below
-      sM12[1] = -m2 * inv_n * rstd;
+    // group means: segmented sum over the cpg lanes of each group (cpg is a power of two >= 4)
+    float m1 = lane < cw ? sK[lane] * sT[0][lane] : 0.f;
+    float m2 = lane < cw ? sK[lane] * sT[1][lane] : 0.f;
+    for (int o = 1; o < cpg && o < 32; o <<= 1) {
+      m1 += __shfl_xor_sync(0xffffffffu, m1, o);
+      m2 += __shfl_xor_sync(0xffffffffu, m2, o);
     }
-    if (lane < cpg && blockIdx.z == 0) {  // per-channel results of this (sample, group): once per cluster
-      const int c = c0g + lane;
-      const float u1 = sT[0][lane], u2 = sT[1][lane], sc = sSc[lane];
-      T[((long)b * a.C + c) * 2] = u1;
-      T[((long)b * a.C + c) * 2 + 1] = u2;
-      atomicAdd(&dgamma[c], sc * u2);
-      atomicAdd(&dbeta[c], sc * u1);
-      if (dss) {
-        dss[(long)b * dss_ld + c] = a.gamma[c] * u2 + a.beta[c] * u1;  // dscale = sum dz * (xhat*gamma + beta)
-        dss[(long)b * dss_ld + a.C + c] = u1;                          // dshift
+    if (lane < cw) {
+      const float inv_n = 1.f / ((float)a.rows * (float)cpg);
+      sM1[lane] = -m1 * inv_n * sR[lane];  // pre-multiplied by rstd (and negated) for the FMA chain below
+      sM2[lane] = -m2 * inv_n * sR[lane];
+      if (blockIdx.z == 0) {  // per-channel results of this (sample, slice): once per cluster
+        const int c = c0s + lane;
+        const float u1 = sT[0][lane], u2 = sT[1][lane], sc = sSc[lane];
+        T[((long)b * a.C + c) * 2] = u1;
+        T[((long)b * a.C + c) * 2 + 1] = u2;
+        atomicAdd(&dgamma[c], sc * u2);
+        atomicAdd(&dbeta[c], sc * u1);
+        if (dss) {
+          dss[(long)b * dss_ld + c] = a.gamma[c] * u2 + a.beta[c] * u1;  // dscale = sum dz * (xhat*gamma + beta)
+          dss[(long)b * dss_ld + a.C + c] = u1;                          // dshift
+        }
       }
     }
   }
   __syncthreads();
-  float cK[8], bs[8];
+  float cK[8], cM1[8], cM2[8], bs[8];
   load_coef8(sK, v * 8, cK);
-  const float m1r = sM12[0], m2r = sM12[1];
+  load_coef8(sM1, v * 8, cM1);
+  load_coef8(sM2, v * 8, cM2);
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    cK[j] *= rstd;
+    cK[j] *= cR[j];
     bs[j] = 0.f;
   }
 #pragma unroll
-  for (int k = 0; k < kGrpMaxVec; ++k) {
-    const long i = tid + (long)k * kGrpThreads;
-    if (i < nvec) {
-      float xv[8], o[8];
-      unpack8(xraw[k], xv);
-      const float4* dp = reinterpret_cast<const float4*>(s_dz + i * 8);
-      const float4 d0 = dp[0], d1 = dp[1];
-      const float dz[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+  for (int k0 = 0; k0 < kMaxVec; k0 += kBatch) {
+    uint4 xb[kBatch];
+    if (!kXRegs) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float xh = fmaf(xv[j], rstd, nm);
-        o[j] = fmaf(xh, m2r, fmaf(dz[j], cK[j], m1r));  // rstd * (K dz - m1 - xhat m2)
-        bs[j] += o[j];
+      for (int q = 0; q < kBatch; ++q) {
+        const long i = tid + (long)(k0 + q) * kGrpThreads;
+        if (k0 + q < kMaxVec && i < nvec) xb[q] = ldg16(a.x + base + (i / vpr) * a.C + c0);
       }
-      store8(dx + base + (i / vpr) * a.C + c0, o);
+    }
+#pragma unroll
+    for (int q = 0; q < kBatch; ++q) {
+      const long i = tid + (long)(k0 + q) * kGrpThreads;
+      if (k0 + q < kMaxVec && i < nvec) {
+        float xv[8], o[8];
+        unpack8(kXRegs ? xraw[k0 + q] : xb[q], xv);
+        const float4* dp = reinterpret_cast<const float4*>(s_dz + i * 8);
+        const float4 d0 = dp[0], d1 = dp[1];
+        const float dz[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float xh = fmaf(xv[j], cR[j], cN[j]);
+          o[j] = fmaf(xh, cM2[j], fmaf(dz[j], cK[j], cM1[j]));  // rstd * (K dz - m1 - xhat m2)
+          bs[j] += o[j];
+        }
+        store8(dx + base + (i / vpr) * a.C + c0, o);
+      }
     }
   }
   if (dconv_bias) {  // column sums of dx = the gradient of the producing conv's bias
@@ -678,11 +707,11 @@ __global__ void __launch_bounds__(kGrpThreads, 1) gn_bwd_group_kernel(const GnAr
       for (int j = 0; j < 8; ++j) sRed[warp][lane][j] = bs[j];
     }
     __syncthreads();
-    if (tid < cpg) {
+    if (tid < cw) {
       float acc = 0.f;
 #pragma unroll 8
       for (int w = 0; w < kGrpThreads / 32; ++w) acc += sRed[w][tid >> 3][tid & 7];
-      atomicAdd(&dconv_bias[c0g + tid], acc);
+      atomicAdd(&dconv_bias[c0s + tid], acc);
     }
   }
 }
@@ -1112,22 +1141,46 @@ static int gn_silu_bwd_impl(const void* dy, const void* x_raw, const float* gn_s
   GnArgs a{reinterpret_cast<const bf16*>(x_raw), gn_sums, gamma, beta, scale_shift, ss_ld, B, rows_per_sample, C, G};
   cudaError_t e = cudaSuccess;
   {
-    // small samples: one CTA per (sample, group) does both passes by itself (gn_bwd_group_kernel); T_ws receives the
-    // per-channel sums with plain stores, so it needs no zeroing on this path
+    // one cluster per (sample, channel slice) does both passes by itself (gn_bwd_group_kernel); T_ws receives the
+    // per-channel sums with plain stores, so it needs no zeroing on this path. Cluster size 4 or 8 (row ranges): the
+    // smallest that fits a CTA's slice into 10 vectors per thread and 200 KB of shared memory, as long as the launch
+    // stays within one wave of one CTA per SM.
     const int cpg = C / G;
-    const long slice = (long)rows_per_sample * cpg;
-    const int rows_cta = (rows_per_sample + kGrpCluster - 1) / kGrpCluster;
-    if ((cpg == 8 || cpg == 16 || cpg == 32) && (long)rows_cta * cpg <= (long)kGrpMaxVec * kGrpThreads * 8 && G <= 65535 &&
-        !tune_on("VDN_GN_NO_GROUP")) {
-      const size_t smem_g = (size_t)rows_cta * cpg * sizeof(float);
+    const int cw = cpg < 8 ? 8 : cpg;
+    const int slices = C / cw;
+    int n_cl = 0, max_vec = 0;
+    if ((cpg == 4 || cpg == 8 || cpg == 16 || cpg == 32) && !tune_on("VDN_GN_NO_GROUP")) {
+      for (int cl = 4; cl <= 8; cl *= 2) {
+        const long rows_cta = (rows_per_sample + cl - 1) / cl;
+        const long nvec = rows_cta * (cw / 8);
+        const long ctas = (long)slices * B * cl;
+        if (nvec <= 10L * kGrpThreads && rows_cta * cw * 4 <= kGrpMaxSmem && ctas <= num_sms() && slices <= 65535) {
+          n_cl = cl;
+          max_vec = (int)((nvec + kGrpThreads - 1) / kGrpThreads);
+          break;
+        }
+      }
+    }
+    // Measured on the training step (tools/ab_step.py): at the 8x8 / 16x16 levels (<= 2560 rows per sample) the single
+    // launch is neutral to slightly faster (5.70 vs 5.72 ms) and saves 24 launches; at the 32x32 / 64x64 levels it is
+    // SLOWER than the two wide kernels (5.74 / 5.89 ms): 128 CTAs of 512 threads do not stream a 10 MB tensor as fast as
+    // 216 CTAs of 256, and the arithmetic of both passes sits in one kernel. Hence the row limit.
+    if (rows_per_sample > tune_int("VDN_GN_GROUP_MAXROWS", 2560)) n_cl = 0;
+    if (n_cl > 0) {
+      const long rows_cta = (rows_per_sample + n_cl - 1) / n_cl;
+      const size_t smem_g = (size_t)rows_cta * cw * sizeof(float);
+      auto kern = max_vec <= 3 ? gn_bwd_group_kernel<3, true> : max_vec <= 6 ? gn_bwd_group_kernel<6, false>
+                                                                             : gn_bwd_group_kernel<10, false>;
       static bool cfg_g = false;
       if (!cfg_g) {
-        e = cudaFuncSetAttribute(gn_bwd_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        e = cudaFuncSetAttribute(gn_bwd_group_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGrpMaxSmem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(gn_bwd_group_kernel<6, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGrpMaxSmem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(gn_bwd_group_kernel<10, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGrpMaxSmem);
         VDN_REQUIRE(e == cudaSuccess, VDN_E_CUDA, "gn_bwd_group cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         cfg_g = true;
       }
       cudaLaunchConfig_t cfg = {};
-      cfg.gridDim = dim3(G, B, kGrpCluster);
+      cfg.gridDim = dim3(slices, B, n_cl);
       cfg.blockDim = dim3(kGrpThreads);
       cfg.dynamicSmemBytes = smem_g;
       cfg.stream = st;
@@ -1136,7 +1189,7 @@ static int gn_silu_bwd_impl(const void* dy, const void* x_raw, const float* gn_s
       at[na].id = cudaLaunchAttributeClusterDimension;
       at[na].val.clusterDim.x = 1;
       at[na].val.clusterDim.y = 1;
-      at[na].val.clusterDim.z = kGrpCluster;
+      at[na].val.clusterDim.z = n_cl;
       ++na;
       if (pdl_enabled()) {
         at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -1145,7 +1198,7 @@ static int gn_silu_bwd_impl(const void* dy, const void* x_raw, const float* gn_s
       }
       cfg.attrs = at;
       cfg.numAttrs = na;
-      cudaError_t lg = cudaLaunchKernelEx(&cfg, gn_bwd_group_kernel, a, reinterpret_cast<const bf16*>(dy), T_ws,
+      cudaError_t lg = cudaLaunchKernelEx(&cfg, kern, a, reinterpret_cast<const bf16*>(dy), T_ws,
                                           reinterpret_cast<bf16*>(dx_raw), dgamma, dbeta, dss, dss_ld, dconv_bias);
       VDN_REQUIRE(lg == cudaSuccess, VDN_E_CUDA, "gn_bwd_group launch: %s", cudaGetErrorString(lg));
       return check_launch("gn_bwd_group");
